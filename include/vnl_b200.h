@@ -1,0 +1,267 @@
+/*
+ * vnl_b200.h -- C ABI of the B200-native fused MJX-style physics + imitation-reward step.
+ *
+ * This is the drop-in boundary for the hot path of talmolab/VNL-Brax-Imitation:
+ *
+ *   vnl_step   replaces  RodentTracking.step          (reference envs/rodent.py:178-239)
+ *              = PipelineEnv.pipeline_step (n_frames x mjx.step, envs/rodent.py:181)
+ *              + _get_obs / _get_traj      (envs/rodent.py:318-382)
+ *              + _calculate_reward / _calculate_termination (envs/rodent.py:241-316)
+ *              + done / NaN guard          (envs/rodent.py:207-225)
+ *   vnl_reset  replaces  RodentTracking.reset after the RNG draw
+ *              = pipeline_init (mjx.forward, envs/rodent.py:148) + obs/traj/termination
+ *              (envs/rodent.py:149-176)
+ *
+ * The reference has no FFI of its own (it is pure Python/JAX; the arithmetic lives in
+ * mujoco-mjx, reached through brax).  The binding a maintainer adds is a jax.ffi / XLA
+ * custom call whose operands are exactly the device buffers below.
+ *
+ * Conventions
+ *   - every array is a caller-allocated DEVICE buffer, fp32 / int32, batch-major contiguous
+ *     [B, n]; the library allocates nothing per call, keeps no mutable global state, only
+ *     enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises and is
+ *     CUDA-graph capturable.
+ *   - `model` and `task` are device copies of the flat blobs described below (constant
+ *     tables; pass them as operands so the caller owns their lifetime).
+ *   - return value 0 = ok, negative = argument error, positive = cudaError_t of the launch.
+ *     Numerical failure is data, not an error (nan flag -> done = 1, NaN -> 0).
+ */
+#ifndef VNL_B200_H_
+#define VNL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * Blob container: an array of 32-bit words.
+ *   words[0]            magic  (VNL_MAGIC_MODEL / VNL_MAGIC_TASK)
+ *   words[1]            version
+ *   words[2]            total number of words
+ *   words[3]            number of fields in the table
+ *   words[4 .. 63]      scalar header (ints, and floats stored by bit pattern), see enums
+ *   words[64 + 2f]      word offset of field f (16-byte aligned)   } f < VNL_MAX_FIELDS
+ *   words[64 + 2f + 1]  element count of field f                   }
+ *   words[VNL_DATA_OFF ..] data
+ * ---------------------------------------------------------------------------------------- */
+#define VNL_MAGIC_MODEL 0x4d4c4e56u /* "VNLM" */
+#define VNL_MAGIC_TASK 0x544c4e56u  /* "VNLT" */
+#define VNL_BLOB_VERSION 4
+#define VNL_TABLE_OFF 64
+#define VNL_MAX_FIELDS 96
+#define VNL_DATA_OFF (VNL_TABLE_OFF + 2 * VNL_MAX_FIELDS)
+
+/* scalar header slots of a MODEL blob (word index) */
+enum VnlModelHdr {
+  VNL_MH_NQ = 4, VNL_MH_NV, VNL_MH_NU, VNL_MH_NA, VNL_MH_NBODY, VNL_MH_NJNT, VNL_MH_NGEOM,
+  VNL_MH_NPAIR,       /* static geom pairs */
+  VNL_MH_NCON,        /* contacts always emitted (capsule pair = 2) */
+  VNL_MH_NLIMIT,      /* limited hinge joints */
+  VNL_MH_NEFC,        /* nlimit + 4 * ncon (pyramidal, condim 3) */
+  VNL_MH_SOLVER,      /* 1 = CG, 2 = Newton */
+  VNL_MH_ITERATIONS, VNL_MH_LS_ITERATIONS,
+  VNL_MH_EULERDAMP,   /* 1 = implicit joint damping in the Euler integrator */
+  VNL_MH_NM,          /* tree-sparse entries of the joint-space inertia */
+  VNL_MH_NLEVEL,      /* body-tree depth (levels below the world body) */
+  VNL_MH_MAXDEPTH,    /* longest dof ancestor chain */
+  /* floats (bit patterns) */
+  VNL_MH_TIMESTEP = 32, VNL_MH_GRAVITY_X, VNL_MH_GRAVITY_Y, VNL_MH_GRAVITY_Z,
+  VNL_MH_TOLERANCE, VNL_MH_LS_TOLERANCE, VNL_MH_IMPRATIO, VNL_MH_MEANINERTIA
+};
+
+/* fields of a MODEL blob.  i = int32, f = float32; shapes in comments */
+enum VnlModelField {
+  VNL_F_BODY_PARENTID = 0, /* i [nbody] */
+  VNL_F_BODY_ROOTID,       /* i [nbody] */
+  VNL_F_BODY_JNTADR,       /* i [nbody] */
+  VNL_F_BODY_JNTNUM,       /* i [nbody] */
+  VNL_F_BODY_DOFADR,       /* i [nbody] */
+  VNL_F_BODY_DOFNUM,       /* i [nbody] */
+  VNL_F_BODY_POS,          /* f [nbody,3] */
+  VNL_F_BODY_QUAT,         /* f [nbody,4] */
+  VNL_F_BODY_IPOS,         /* f [nbody,3] */
+  VNL_F_BODY_IQUAT,        /* f [nbody,4] */
+  VNL_F_BODY_MASS,         /* f [nbody] */
+  VNL_F_BODY_INERTIA,      /* f [nbody,3] */
+  VNL_F_BODY_INVWEIGHT0,   /* f [nbody,2] */
+  VNL_F_JNT_TYPE,          /* i [njnt] 0 free, 3 hinge */
+  VNL_F_JNT_QPOSADR,       /* i [njnt] */
+  VNL_F_JNT_DOFADR,        /* i [njnt] */
+  VNL_F_JNT_BODYID,        /* i [njnt] */
+  VNL_F_JNT_LIMITED,       /* i [njnt] */
+  VNL_F_JNT_POS,           /* f [njnt,3] */
+  VNL_F_JNT_AXIS,          /* f [njnt,3] */
+  VNL_F_JNT_STIFFNESS,     /* f [njnt] */
+  VNL_F_JNT_RANGE,         /* f [njnt,2] */
+  VNL_F_JNT_MARGIN,        /* f [njnt] */
+  VNL_F_JNT_SOLREF,        /* f [njnt,2] */
+  VNL_F_JNT_SOLIMP,        /* f [njnt,5] */
+  VNL_F_DOF_BODYID,        /* i [nv] */
+  VNL_F_DOF_JNTID,         /* i [nv] */
+  VNL_F_DOF_PARENTID,      /* i [nv] */
+  VNL_F_DOF_ARMATURE,      /* f [nv] */
+  VNL_F_DOF_DAMPING,       /* f [nv] */
+  VNL_F_DOF_INVWEIGHT0,    /* f [nv] */
+  VNL_F_QPOS0,             /* f [nq] */
+  VNL_F_QPOS_SPRING,       /* f [nq] */
+  VNL_F_GEOM_TYPE,         /* i [ngeom] */
+  VNL_F_GEOM_BODYID,       /* i [ngeom] */
+  VNL_F_GEOM_POS,          /* f [ngeom,3] */
+  VNL_F_GEOM_QUAT,         /* f [ngeom,4] */
+  VNL_F_GEOM_SIZE,         /* f [ngeom,3] */
+  VNL_F_ACT_DOFADR,        /* i [nu] */
+  VNL_F_ACT_CTRLLIMITED,   /* i [nu] */
+  VNL_F_ACT_FORCELIMITED,  /* i [nu] */
+  VNL_F_ACT_DYNTYPE,       /* i [nu] 0 none, 2 filter */
+  VNL_F_ACT_ACTADR,        /* i [nu] -1 if stateless */
+  VNL_F_ACT_GAIN,          /* f [nu] */
+  VNL_F_ACT_GEAR,          /* f [nu] */
+  VNL_F_ACT_CTRLRANGE,     /* f [nu,2] */
+  VNL_F_ACT_FORCERANGE,    /* f [nu,2] */
+  VNL_F_ACT_DYNPRM,        /* f [nu] */
+  VNL_F_PAIR_GEOM1,        /* i [npair] the plane */
+  VNL_F_PAIR_GEOM2,        /* i [npair] */
+  VNL_F_PAIR_TYPE,         /* i [npair] geom type of geom2 */
+  VNL_F_PAIR_FRICTION,     /* f [npair,5] */
+  VNL_F_PAIR_SOLREF,       /* f [npair,2] */
+  VNL_F_PAIR_SOLIMP,       /* f [npair,5] */
+  VNL_F_PAIR_INCLUDEMARGIN,/* f [npair] */
+  /* ---- derived tables used by the CUDA kernels (host-precomputed, see model_blob.py) ---- */
+  VNL_F_LEVEL_START,       /* i [nlevel+1] offsets into LEVEL_BODY (level 0 = children of world) */
+  VNL_F_LEVEL_BODY,        /* i [nbody-1] bodies sorted by depth */
+  VNL_F_DOF_MADR,          /* i [nv+1] start of dof i's row in the sparse inertia (diagonal first,
+                              then ancestors walking to the root -- MuJoCo qM order) */
+  VNL_F_M_COL,             /* i [nM] column (ancestor dof) of each sparse entry */
+  VNL_F_DOF_DEPTH,         /* i [nv] number of ancestors */
+  VNL_F_BODY_SUBTREE_END,  /* i [nbody] bodies b .. end-1 are b's subtree (ids are DFS preorder) */
+  VNL_F_LIMIT_JNT,         /* i [nlimit] joint id of each limit row */
+  VNL_F_CON_PAIR,          /* i [ncon] pair of each emitted contact */
+  VNL_F_CON_SIGN,          /* f [ncon] capsule end (+1 / -1), 0 for single-contact geoms */
+  VNL_F_GEOMC_BODY,        /* i [npair] body of geom2 */
+  VNL_F_GEOMC_POS,         /* f [npair,3] geom2 frame in its body */
+  VNL_F_GEOMC_MAT,         /* f [npair,9] */
+  VNL_F_PLANE_POS,         /* f [npair,3] plane (geom1) world frame; planes are static */
+  VNL_F_PLANE_MAT,         /* f [npair,9] */
+  VNL_F_BODY_IMAT,         /* f [nbody,9] rotation of body_iquat */
+  VNL_F_M_ROW,             /* i [nM] row (dof) of each sparse entry */
+  VNL_F_BODY_LASTDOF,      /* i [nbody] last dof of the body or of its nearest jointed ancestor, -1 if none */
+  VNL_F_DESC_ADR,          /* i [nv+1] CSR over strict descendants of each dof */
+  VNL_F_DESC_ENTRY,        /* i [nM-nv] sparse-entry index e with M_COL[e] == dof, M_ROW[e] = the descendant */
+  VNL_F_DOFLEVEL_START,    /* i [maxdepth+2] CSR of dofs grouped by ancestor count */
+  VNL_F_DOFLEVEL_DOF,      /* i [nv] */
+  VNL_F_MODEL_COUNT
+};
+
+/* scalar header slots of a TASK blob (imitation task: clip + index tables) */
+enum VnlTaskHdr {
+  VNL_TH_KIND = 4,        /* 0 = rodent (envs/rodent.py) */
+  VNL_TH_CLIP_LEN,        /* frames in the clip tables (T) */
+  VNL_TH_REF_LEN,         /* ref_traj_length (5) */
+  VNL_TH_SUB_CLIP_LEN,    /* sub_clip_length (10) */
+  VNL_TH_NTRACK,          /* tracked bodies (18) */
+  VNL_TH_NJIDX,           /* joint_names (33) */
+  VNL_TH_NAPP,            /* appendage_names (5) */
+  VNL_TH_NEE,             /* end_eff_names (4) */
+  VNL_TH_NFRAMES,         /* physics substeps per env step (5) */
+  VNL_TH_OBS_SIZE,        /* 232 */
+  VNL_TH_TRAJ_SIZE,       /* 795 */
+  VNL_TH_COM_REF_IDX,     /* column of the filtered body table used as COM reference (quirk Q4) */
+  VNL_TH_TORSO_BODY,      /* body whose xmat defines the egocentric frame (1) */
+  VNL_TH_HEALTHY_LO = 32, VNL_TH_HEALTHY_HI, VNL_TH_TERM_THRESHOLD, VNL_TH_BODY_ERR_MULT
+};
+
+enum VnlTaskField {
+  VNL_T_POSITION = 0,     /* f [T,3]      ReferenceClip.position */
+  VNL_T_QUATERNION,       /* f [T,4] */
+  VNL_T_JOINTS,           /* f [T,nq-7] */
+  VNL_T_BODY_POSITIONS,   /* f [T,ntrack,3] already filtered to walker_body_names (rodent.py:114) */
+  VNL_T_VELOCITY,         /* f [T,3] */
+  VNL_T_ANGULAR_VELOCITY, /* f [T,3] */
+  VNL_T_JOINTS_VELOCITY,  /* f [T,nv-6] */
+  VNL_T_BODY_IDXS,        /* i [ntrack]  model body ids (rodent.py:81-86) */
+  VNL_T_EE_IDX,           /* i [nee]     model body ids (rodent.py:65-70) */
+  VNL_T_APP_IDX,          /* i [napp]    model body ids (rodent.py:71-76) */
+  VNL_T_APP_REF_IDX,      /* i [napp]    app ids clamped into the filtered table (quirk Q5) */
+  VNL_T_JOINT_COL,        /* i [njidx]   joint ids clamped into the nq-7 joint columns (quirk Q6) */
+  VNL_TASK_COUNT
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Per-env state crossing the boundary.  Mirrors the leaves of the brax `State` the
+ * reference's callers read: pipeline_state.{qpos,qvel,act,
+ * qacc_warmstart,xpos,xquat,subtree_com[1],qfrc_actuator} and info.{cur_frame,sub_clip_frame}.
+ * xpos/xquat/subtree_com/qfrc_actuator lag qpos by one physics substep exactly as
+ * mjx.step leaves them (forward, then euler).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct VnlState {
+  float* qpos;           /* [B,nq] */
+  float* qvel;           /* [B,nv] */
+  float* act;            /* [B,na] */
+  float* qacc_warmstart; /* [B,nv] */
+  float* xpos;           /* [B,nbody,3] */
+  float* xquat;          /* [B,nbody,4] */
+  float* subtree_com;    /* [B,3]  subtree_com[torso] */
+  float* qfrc_actuator;  /* [B,nv] */
+  int32_t* cur_frame;      /* [B] info["cur_frame"] */
+  int32_t* sub_clip_frame; /* [B] info["sub_clip_frame"] */
+} VnlState;
+
+typedef struct VnlOutputs {
+  float* obs;     /* [B,obs_size]  State.obs (rodent.py:318-344), NaN -> 0 */
+  float* traj;    /* [B,traj_size] info["traj"] (rodent.py:346-382) */
+  float* reward;  /* [B] */
+  float* done;    /* [B] 0/1 */
+  float* metrics; /* [B,7] rcom rvel rtrunk rquat ract rapp termination_error (scaled, rodent.py:227-235) */
+  int32_t* stats; /* [B,4] solver iterations, line-search iterations, active contacts, active limits
+                     (summed over the substeps of the call); may be NULL */
+} VnlOutputs;
+
+/* One env step for B envs: `in` is read, `out` and `outputs` are written (in and out may alias
+ * buffer by buffer).  Replaces RodentTracking.step (envs/rodent.py:178-239). */
+int vnl_step(const void* model, const void* task, int B, const VnlState* in, const float* action,
+             const VnlState* out, const VnlOutputs* outputs, void* stream);
+
+/* Reset tail for B envs: qpos/qvel/cur_frame(start_frame) are read from `in` (act, ctrl and
+ * qacc_warmstart are zero as in mjx.make_data), `out` receives the mjx.forward state, obs,
+ * traj and info["termination_error"] (metrics[6]).  Replaces envs/rodent.py:148-176. */
+int vnl_reset(const void* model, const void* task, int B, const VnlState* in, const VnlState* out,
+              const VnlOutputs* outputs, void* stream);
+
+/* Physics only: `nsteps` x mjx.step (forward; euler) with a constant ctrl, no task logic.
+ * Replaces PipelineEnv.pipeline_step (envs/rodent.py:181). */
+int vnl_pipeline_step(const void* model, int B, int nsteps, const VnlState* in, const float* ctrl,
+                      const VnlState* out, int32_t* stats, void* stream);
+
+/* Stage dump of one mjx.forward for parity tests: writes the arrays listed in
+ * VNL_DUMP_* order into `dump` ([B, vnl_dump_size(model)] floats).  Test hook. */
+int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* ctrl, float* dump,
+                     void* stream);
+size_t vnl_dump_size(const void* model_host);
+
+/* Blob validation on the host (magic, version, sizes).  0 = ok. */
+int vnl_check_model(const void* model_host, size_t nbytes);
+int vnl_check_task(const void* task_host, size_t nbytes);
+
+/* The launch geometry depends on the blob's scalar header.  Blobs handed to the calls above are
+ * device buffers, so each one is registered once (host copy of the same bytes -> cached 256-byte
+ * header keyed by the device pointer); the step path then never copies or synchronises. */
+int vnl_register_blob(const void* blob_dev, const void* blob_host, size_t nbytes);
+int vnl_unregister_blob(const void* blob_dev);
+
+/* Dynamic shared memory one env's CTA needs for this model, and CTAs resident per SM. */
+int vnl_step_smem_bytes(const void* model_host);
+
+/* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
+ * size_t opaque_len)`), operand order documented in INTEGRATION.md. */
+void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+const char* vnl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VNL_B200_H_ */

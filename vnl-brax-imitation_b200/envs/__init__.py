@@ -1,0 +1,13 @@
+"""Host-side mirrors of the reference task envs (`envs/rodent.py`, ...) over the CUDA engine."""
+from .base import State  # noqa: F401
+from .rodent import RODENT_ENV_ARGS, RodentTracking, rodent_task_tables  # noqa: F401
+
+_REGISTRY = {"rodent": RodentTracking}
+
+
+def register_environment(name, cls):  # `brax.envs.register_environment` (reference train.py:65-68)
+    _REGISTRY[name] = cls
+
+
+def get_environment(name, **kwargs):  # `brax.envs.get_environment` (reference train.py:86-90)
+    return _REGISTRY[name](**kwargs)

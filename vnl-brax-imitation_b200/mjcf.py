@@ -895,3 +895,45 @@ def load_humanoid(mjcf_path: str, solver: str = "cg", iterations: int = 6, ls_it
     root = load_xml(mjcf_path)
     return compile_model(root, name="humanoid", solver=solver, iterations=iterations,
                          ls_iterations=ls_iterations, eulerdamp=False)
+
+
+# --------------------------------------------------------------------------------------
+# (de)serialisation of a compiled model -- lets hosts without the MJCF assets (the GPU
+# box has no /root/reference) rebuild the exact same tables from a small .npz
+# --------------------------------------------------------------------------------------
+_SCALARS = ("name", "nq", "nv", "nu", "na", "nbody", "njnt", "ngeom", "timestep", "tolerance", "ls_tolerance", "impratio",
+            "solver", "iterations", "ls_iterations", "eulerdamp", "meaninertia")
+
+
+def save_model(m: Model, path: str) -> None:
+    out = {f"arr_{k}": v for k, v in m.arrays.items()}
+    for k in _SCALARS:
+        out[f"s_{k}"] = np.array(getattr(m, k))
+    out["s_gravity"] = m.gravity
+    for k in ("body_names", "jnt_names", "geom_names", "act_names"):
+        out[f"n_{k}"] = np.array(getattr(m, k), dtype=object).astype(str)
+    np.savez_compressed(path, **out)
+
+
+def load_model(path: str) -> Model:
+    z = np.load(path, allow_pickle=False)
+    m = Model()
+    for k in z.files:
+        if k.startswith("arr_"):
+            m.arrays[k[4:]] = z[k]
+        elif k.startswith("n_"):
+            setattr(m, k[2:], [str(s) for s in z[k]])
+        elif k == "s_gravity":
+            m.gravity = z[k]
+        elif k.startswith("s_"):
+            v = z[k][()]
+            name = k[2:]
+            if name == "name":
+                m.name = str(v)
+            elif name == "eulerdamp":
+                m.eulerdamp = bool(v)
+            elif name in ("timestep", "tolerance", "ls_tolerance", "impratio", "meaninertia"):
+                setattr(m, name, float(v))
+            else:
+                setattr(m, name, int(v))
+    return m

@@ -1,0 +1,297 @@
+"""Serialise a compiled `mjcf.Model` / imitation task into the flat blobs of `include/vnl_b200.h`.
+
+The enum values (header slots, field ids) are parsed out of the C header at import, so the
+Python writer and the C / CUDA readers cannot drift apart.
+"""
+from __future__ import annotations
+
+import os
+import re
+from typing import Dict, List
+
+import numpy as np
+
+from . import mjcf
+
+_HEADER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "include", "vnl_b200.h")
+
+
+def _parse_header(path: str):
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    consts: Dict[str, int] = {}
+    for mm in re.finditer(r"#define\s+(VNL_\w+)\s+(0x[0-9a-fA-F]+u?|\d+)\s*$", txt, flags=re.M):
+        consts[mm.group(1)] = int(mm.group(2).rstrip("u"), 0)
+    for mm in re.finditer(r"enum\s+\w+\s*\{(.*?)\}", txt, flags=re.S):
+        val = -1
+        for item in mm.group(1).split(","):
+            item = item.strip()
+            if not item:
+                continue
+            if "=" in item:
+                nm, v = [s.strip() for s in item.split("=")]
+                val = int(v, 0)
+            else:
+                nm, val = item, val + 1
+            consts[nm] = val
+    consts["VNL_DATA_OFF"] = consts["VNL_TABLE_OFF"] + 2 * consts["VNL_MAX_FIELDS"]
+    return consts
+
+
+C = _parse_header(_HEADER)
+
+
+class _BlobWriter:
+    def __init__(self, magic: int, nfields: int):
+        self.hdr = np.zeros(C["VNL_DATA_OFF"], dtype=np.uint32)
+        self.hdr[0] = magic
+        self.hdr[1] = C["VNL_BLOB_VERSION"]
+        self.hdr[3] = nfields
+        self.chunks: List[np.ndarray] = []
+        self.off = C["VNL_DATA_OFF"]
+
+    def set_i(self, slot: str, v: int):
+        self.hdr[C[slot]] = np.uint32(np.int32(v).view(np.uint32))
+
+    def set_f(self, slot: str, v: float):
+        self.hdr[C[slot]] = np.float32(v).view(np.uint32)
+
+    def add(self, field: str, arr: np.ndarray, dtype):
+        a = np.ascontiguousarray(np.asarray(arr).astype(dtype)).reshape(-1)
+        f = C[field]
+        self.hdr[C["VNL_TABLE_OFF"] + 2 * f] = self.off
+        self.hdr[C["VNL_TABLE_OFF"] + 2 * f + 1] = a.size
+        words = a.view(np.uint32)
+        pad = (-words.size) % 4
+        if pad:
+            words = np.concatenate([words, np.zeros(pad, dtype=np.uint32)])
+        self.chunks.append(words)
+        self.off += words.size
+
+    def finish(self) -> np.ndarray:
+        self.hdr[2] = self.off
+        return np.concatenate([self.hdr] + self.chunks)
+
+
+def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
+    """Host-precomputed index tables for the CUDA kernels (tree levels, sparse-inertia
+    pattern, emitted-contact list, static geom frames)."""
+    A = m.arrays
+    nb, nv = m.nbody, m.nv
+    parent = A["body_parentid"]
+    depth = np.zeros(nb, dtype=np.int64)
+    for b in range(1, nb):
+        depth[b] = 0 if parent[b] == 0 else depth[parent[b]] + 1
+    order = sorted(range(1, nb), key=lambda b: (depth[b], b))
+    nlevel = int(depth[1:].max()) + 1 if nb > 1 else 0
+    level_start = [0]
+    for lv in range(nlevel):
+        level_start.append(level_start[-1] + int(np.sum(depth[1:] == lv)))
+    madr, mcol, ddepth = [], [], []
+    for i in range(nv):
+        madr.append(len(mcol))
+        j, d = i, 0
+        while j >= 0:
+            mcol.append(j)
+            j = A["dof_parentid"][j]
+            d += 1
+        ddepth.append(d - 1)
+    madr.append(len(mcol))
+    sub_end = np.arange(nb) + 1
+    for b in range(nb - 1, 0, -1):
+        sub_end[parent[b]] = max(sub_end[parent[b]], sub_end[b])
+    mrow = []
+    for i in range(nv):
+        mrow += [i] * (madr[i + 1] - madr[i])
+    lastdof = np.full(nb, -1, dtype=np.int64)
+    for b in range(1, nb):
+        if A["body_dofnum"][b] > 0:
+            lastdof[b] = A["body_dofadr"][b] + A["body_dofnum"][b] - 1
+        else:
+            lastdof[b] = lastdof[parent[b]]
+    desc = [[] for _ in range(nv)]
+    for e, (i, j) in enumerate(zip(mrow, mcol)):
+        if i != j:
+            desc[j].append(e)
+    desc_adr = [0]
+    for j in range(nv):
+        desc_adr.append(desc_adr[-1] + len(desc[j]))
+    desc_entry = [e for j in range(nv) for e in desc[j]]
+    maxd = int(max(ddepth)) if ddepth else 0
+    dl_start, dl_dof = [0], []
+    for dpt in range(maxd + 1):
+        dl_dof += [i for i in range(nv) if ddepth[i] == dpt]
+        dl_start.append(len(dl_dof))
+    limit_jnt = [j for j in range(m.njnt) if A["jnt_limited"][j] and A["jnt_type"][j] == mjcf.JNT_HINGE]
+    con_pair, con_sign = [], []
+    for p, t in enumerate(A["pair_type"]):
+        if t == mjcf.GEOM_CAPSULE:
+            con_pair += [p, p]
+            con_sign += [1.0, -1.0]
+        else:
+            con_pair.append(p)
+            con_sign.append(0.0)
+    g2 = A["pair_geom2"]
+    g1 = A["pair_geom1"]
+    if len(g1) and np.any(A["geom_bodyid"][g1] != 0):
+        raise NotImplementedError("planes must be attached to the world body")
+    plane_mat = np.array([mjcf.quat_to_mat(A["geom_quat"][g]).reshape(9) for g in g1]).reshape(-1, 9)
+    geom_mat = np.array([mjcf.quat_to_mat(A["geom_quat"][g]).reshape(9) for g in g2]).reshape(-1, 9)
+    return dict(level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
+                m_col=np.array(mcol), dof_depth=np.array(ddepth), body_subtree_end=sub_end,
+                limit_jnt=np.array(limit_jnt, dtype=np.int64), con_pair=np.array(con_pair, dtype=np.int64),
+                con_sign=np.array(con_sign), geomc_body=A["geom_bodyid"][g2], geomc_pos=A["geom_pos"][g2],
+                geomc_mat=geom_mat, plane_pos=A["geom_pos"][g1], plane_mat=plane_mat,
+                body_imat=np.array([mjcf.quat_to_mat(q).reshape(9) for q in A["body_iquat"]]),
+                m_row=np.array(mrow), body_lastdof=lastdof, desc_adr=np.array(desc_adr),
+                desc_entry=np.array(desc_entry, dtype=np.int64), doflevel_start=np.array(dl_start),
+                doflevel_dof=np.array(dl_dof, dtype=np.int64),
+                nlevel=nlevel, maxdepth=int(max(ddepth)) if ddepth else 0)
+
+
+_MODEL_FIELDS = [
+    ("VNL_F_BODY_PARENTID", "body_parentid", np.int32), ("VNL_F_BODY_ROOTID", "body_rootid", np.int32),
+    ("VNL_F_BODY_JNTADR", "body_jntadr", np.int32), ("VNL_F_BODY_JNTNUM", "body_jntnum", np.int32),
+    ("VNL_F_BODY_DOFADR", "body_dofadr", np.int32), ("VNL_F_BODY_DOFNUM", "body_dofnum", np.int32),
+    ("VNL_F_BODY_POS", "body_pos", np.float32), ("VNL_F_BODY_QUAT", "body_quat", np.float32),
+    ("VNL_F_BODY_IPOS", "body_ipos", np.float32), ("VNL_F_BODY_IQUAT", "body_iquat", np.float32),
+    ("VNL_F_BODY_MASS", "body_mass", np.float32), ("VNL_F_BODY_INERTIA", "body_inertia", np.float32),
+    ("VNL_F_BODY_INVWEIGHT0", "body_invweight0", np.float32),
+    ("VNL_F_JNT_TYPE", "jnt_type", np.int32), ("VNL_F_JNT_QPOSADR", "jnt_qposadr", np.int32),
+    ("VNL_F_JNT_DOFADR", "jnt_dofadr", np.int32), ("VNL_F_JNT_BODYID", "jnt_bodyid", np.int32),
+    ("VNL_F_JNT_LIMITED", "jnt_limited", np.int32), ("VNL_F_JNT_POS", "jnt_pos", np.float32),
+    ("VNL_F_JNT_AXIS", "jnt_axis", np.float32), ("VNL_F_JNT_STIFFNESS", "jnt_stiffness", np.float32),
+    ("VNL_F_JNT_RANGE", "jnt_range", np.float32), ("VNL_F_JNT_MARGIN", "jnt_margin", np.float32),
+    ("VNL_F_JNT_SOLREF", "jnt_solref", np.float32), ("VNL_F_JNT_SOLIMP", "jnt_solimp", np.float32),
+    ("VNL_F_DOF_BODYID", "dof_bodyid", np.int32), ("VNL_F_DOF_JNTID", "dof_jntid", np.int32),
+    ("VNL_F_DOF_PARENTID", "dof_parentid", np.int32), ("VNL_F_DOF_ARMATURE", "dof_armature", np.float32),
+    ("VNL_F_DOF_DAMPING", "dof_damping", np.float32), ("VNL_F_DOF_INVWEIGHT0", "dof_invweight0", np.float32),
+    ("VNL_F_QPOS0", "qpos0", np.float32), ("VNL_F_QPOS_SPRING", "qpos_spring", np.float32),
+    ("VNL_F_GEOM_TYPE", "geom_type", np.int32), ("VNL_F_GEOM_BODYID", "geom_bodyid", np.int32),
+    ("VNL_F_GEOM_POS", "geom_pos", np.float32), ("VNL_F_GEOM_QUAT", "geom_quat", np.float32),
+    ("VNL_F_GEOM_SIZE", "geom_size", np.float32),
+    ("VNL_F_ACT_DOFADR", "actuator_dofadr", np.int32), ("VNL_F_ACT_CTRLLIMITED", "actuator_ctrllimited", np.int32),
+    ("VNL_F_ACT_FORCELIMITED", "actuator_forcelimited", np.int32), ("VNL_F_ACT_DYNTYPE", "actuator_dyntype", np.int32),
+    ("VNL_F_ACT_ACTADR", "actuator_actadr", np.int32), ("VNL_F_ACT_GAIN", "actuator_gain", np.float32),
+    ("VNL_F_ACT_GEAR", "actuator_gear", np.float32), ("VNL_F_ACT_CTRLRANGE", "actuator_ctrlrange", np.float32),
+    ("VNL_F_ACT_FORCERANGE", "actuator_forcerange", np.float32), ("VNL_F_ACT_DYNPRM", "actuator_dynprm", np.float32),
+    ("VNL_F_PAIR_GEOM1", "pair_geom1", np.int32), ("VNL_F_PAIR_GEOM2", "pair_geom2", np.int32),
+    ("VNL_F_PAIR_TYPE", "pair_type", np.int32), ("VNL_F_PAIR_FRICTION", "pair_friction", np.float32),
+    ("VNL_F_PAIR_SOLREF", "pair_solref", np.float32), ("VNL_F_PAIR_SOLIMP", "pair_solimp", np.float32),
+    ("VNL_F_PAIR_INCLUDEMARGIN", "pair_includemargin", np.float32),
+]
+_DERIVED_FIELDS = [
+    ("VNL_F_LEVEL_START", "level_start", np.int32), ("VNL_F_LEVEL_BODY", "level_body", np.int32),
+    ("VNL_F_DOF_MADR", "dof_madr", np.int32), ("VNL_F_M_COL", "m_col", np.int32),
+    ("VNL_F_DOF_DEPTH", "dof_depth", np.int32), ("VNL_F_BODY_SUBTREE_END", "body_subtree_end", np.int32),
+    ("VNL_F_LIMIT_JNT", "limit_jnt", np.int32), ("VNL_F_CON_PAIR", "con_pair", np.int32),
+    ("VNL_F_CON_SIGN", "con_sign", np.float32), ("VNL_F_GEOMC_BODY", "geomc_body", np.int32),
+    ("VNL_F_GEOMC_POS", "geomc_pos", np.float32), ("VNL_F_GEOMC_MAT", "geomc_mat", np.float32),
+    ("VNL_F_PLANE_POS", "plane_pos", np.float32), ("VNL_F_PLANE_MAT", "plane_mat", np.float32),
+    ("VNL_F_BODY_IMAT", "body_imat", np.float32),
+    ("VNL_F_M_ROW", "m_row", np.int32), ("VNL_F_BODY_LASTDOF", "body_lastdof", np.int32),
+    ("VNL_F_DESC_ADR", "desc_adr", np.int32), ("VNL_F_DESC_ENTRY", "desc_entry", np.int32),
+    ("VNL_F_DOFLEVEL_START", "doflevel_start", np.int32), ("VNL_F_DOFLEVEL_DOF", "doflevel_dof", np.int32),
+]
+
+
+def model_dims(m: mjcf.Model) -> Dict[str, int]:
+    d = derived_tables(m)
+    ncon, nlimit = len(d["con_pair"]), len(d["limit_jnt"])
+    return dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom,
+                npair=len(m.arrays["pair_geom1"]), ncon=ncon, nlimit=nlimit, nefc=nlimit + 4 * ncon,
+                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"])
+
+
+def build_model_blob(m: mjcf.Model) -> np.ndarray:
+    d = derived_tables(m)
+    dims = model_dims(m)
+    w = _BlobWriter(C["VNL_MAGIC_MODEL"], C["VNL_F_MODEL_COUNT"])
+    for slot, key in [("VNL_MH_NQ", "nq"), ("VNL_MH_NV", "nv"), ("VNL_MH_NU", "nu"), ("VNL_MH_NA", "na"),
+                      ("VNL_MH_NBODY", "nbody"), ("VNL_MH_NJNT", "njnt"), ("VNL_MH_NGEOM", "ngeom"),
+                      ("VNL_MH_NPAIR", "npair"), ("VNL_MH_NCON", "ncon"), ("VNL_MH_NLIMIT", "nlimit"),
+                      ("VNL_MH_NEFC", "nefc"), ("VNL_MH_NM", "nM"), ("VNL_MH_NLEVEL", "nlevel"),
+                      ("VNL_MH_MAXDEPTH", "maxdepth")]:
+        w.set_i(slot, dims[key])
+    w.set_i("VNL_MH_SOLVER", m.solver)
+    w.set_i("VNL_MH_ITERATIONS", m.iterations)
+    w.set_i("VNL_MH_LS_ITERATIONS", m.ls_iterations)
+    w.set_i("VNL_MH_EULERDAMP", int(m.eulerdamp))
+    w.set_f("VNL_MH_TIMESTEP", m.timestep)
+    w.set_f("VNL_MH_GRAVITY_X", m.gravity[0])
+    w.set_f("VNL_MH_GRAVITY_Y", m.gravity[1])
+    w.set_f("VNL_MH_GRAVITY_Z", m.gravity[2])
+    w.set_f("VNL_MH_TOLERANCE", m.tolerance)
+    w.set_f("VNL_MH_LS_TOLERANCE", m.ls_tolerance)
+    w.set_f("VNL_MH_IMPRATIO", m.impratio)
+    w.set_f("VNL_MH_MEANINERTIA", m.meaninertia)
+    for fid, key, dt in _MODEL_FIELDS:
+        w.add(fid, m.arrays[key], dt)
+    for fid, key, dt in _DERIVED_FIELDS:
+        w.add(fid, d[key], dt)
+    return w.finish()
+
+
+def read_dims(blob: np.ndarray) -> Dict[str, int]:
+    g = lambda s: int(blob[C[s]].view(np.int32))
+    return dict(nq=g("VNL_MH_NQ"), nv=g("VNL_MH_NV"), nu=g("VNL_MH_NU"), na=g("VNL_MH_NA"),
+                nbody=g("VNL_MH_NBODY"), njnt=g("VNL_MH_NJNT"), ngeom=g("VNL_MH_NGEOM"), npair=g("VNL_MH_NPAIR"),
+                ncon=g("VNL_MH_NCON"), nlimit=g("VNL_MH_NLIMIT"), nefc=g("VNL_MH_NEFC"), nM=g("VNL_MH_NM"),
+                nlevel=g("VNL_MH_NLEVEL"), maxdepth=g("VNL_MH_MAXDEPTH"), solver=g("VNL_MH_SOLVER"),
+                iterations=g("VNL_MH_ITERATIONS"), ls_iterations=g("VNL_MH_LS_ITERATIONS"),
+                eulerdamp=g("VNL_MH_EULERDAMP"))
+
+
+def read_field(blob: np.ndarray, field: str, dtype) -> np.ndarray:
+    f = C[field]
+    off = int(blob[C["VNL_TABLE_OFF"] + 2 * f])
+    n = int(blob[C["VNL_TABLE_OFF"] + 2 * f + 1])
+    return blob[off:off + n].view(dtype)
+
+
+def read_hdr_f(blob: np.ndarray, slot: str) -> float:
+    return float(blob[C[slot]:C[slot] + 1].view(np.float32)[0])
+
+
+def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_idx: int, njoint_cols: int,
+                    clip_length: int = 250, ref_traj_length: int = 5, sub_clip_length: int = 10,
+                    healthy_z_range=(0.05, 0.5), termination_threshold: float = 5.0,
+                    body_error_multiplier: float = 1.0, n_frames: int = 5, torso_body: int = 1,
+                    obs_size: int = 0, traj_size: int = 0) -> np.ndarray:
+    """Rodent imitation task tables.  `clip.body_positions` must already be filtered to
+    `body_idxs` (`envs/rodent.py:114-115`).  The reference indexes that filtered table with
+    MODEL body ids and relies on JAX clamping out-of-range gathers; the
+    clamped indices are baked here so kernels only gather."""
+    ntrack = len(body_idxs)
+    w = _BlobWriter(C["VNL_MAGIC_TASK"], C["VNL_TASK_COUNT"])
+    w.set_i("VNL_TH_KIND", 0)
+    w.set_i("VNL_TH_CLIP_LEN", clip.position.shape[0])
+    w.set_i("VNL_TH_REF_LEN", ref_traj_length)
+    w.set_i("VNL_TH_SUB_CLIP_LEN", sub_clip_length)
+    w.set_i("VNL_TH_NTRACK", ntrack)
+    w.set_i("VNL_TH_NJIDX", len(joint_idxs))
+    w.set_i("VNL_TH_NAPP", len(app_idx))
+    w.set_i("VNL_TH_NEE", len(end_eff_idx))
+    w.set_i("VNL_TH_NFRAMES", n_frames)
+    w.set_i("VNL_TH_OBS_SIZE", obs_size)
+    w.set_i("VNL_TH_TRAJ_SIZE", traj_size)
+    w.set_i("VNL_TH_COM_REF_IDX", min(max(int(com_idx), 0), ntrack - 1))
+    w.set_i("VNL_TH_TORSO_BODY", torso_body)
+    w.set_f("VNL_TH_HEALTHY_LO", healthy_z_range[0])
+    w.set_f("VNL_TH_HEALTHY_HI", healthy_z_range[1])
+    w.set_f("VNL_TH_TERM_THRESHOLD", termination_threshold)
+    w.set_f("VNL_TH_BODY_ERR_MULT", body_error_multiplier)
+    assert clip.body_positions.shape[1] == ntrack
+    w.add("VNL_T_POSITION", clip.position, np.float32)
+    w.add("VNL_T_QUATERNION", clip.quaternion, np.float32)
+    w.add("VNL_T_JOINTS", clip.joints, np.float32)
+    w.add("VNL_T_BODY_POSITIONS", clip.body_positions, np.float32)
+    w.add("VNL_T_VELOCITY", clip.velocity, np.float32)
+    w.add("VNL_T_ANGULAR_VELOCITY", clip.angular_velocity, np.float32)
+    w.add("VNL_T_JOINTS_VELOCITY", clip.joints_velocity, np.float32)
+    w.add("VNL_T_BODY_IDXS", body_idxs, np.int32)
+    w.add("VNL_T_EE_IDX", end_eff_idx, np.int32)
+    w.add("VNL_T_APP_IDX", app_idx, np.int32)
+    w.add("VNL_T_APP_REF_IDX", np.clip(np.asarray(app_idx), 0, ntrack - 1), np.int32)
+    w.add("VNL_T_JOINT_COL", np.clip(np.asarray(joint_idxs), 0, njoint_cols - 1), np.int32)
+    return w.finish()
