@@ -133,6 +133,21 @@ int vnl_step(const void* model, const void* task, int B, const VnlState* in, con
   return (int)vnl::launch(0, p, (cudaStream_t)stream);
 }
 
+// Developer hook: vnl_step with per-phase clock64 accumulation for CTA `block` into prof[32].
+int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+                      const VnlOutputs* outputs, void* stream, long long* prof, int block) {
+  if (B <= 0 || !in || !out || !outputs || !action) return -1;
+  vnl::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc = prepare(model, task, true, p);
+  if (rc) return rc;
+  Header ht;
+  lookup(task, ht);
+  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.prof = prof; p.prof_block = block;
+  return (int)vnl::launch(0, p, (cudaStream_t)stream);
+}
+
 int vnl_reset(const void* model, const void* task, int B, const VnlState* in, const VnlState* out, const VnlOutputs* outputs,
               void* stream) {
   if (B <= 0 || !in || !out || !outputs) return -1;

@@ -30,6 +30,8 @@
 
 namespace vnl {
 
+#define PROF(c, i) do { if ((c).prof) { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); (c).prof[i] += t_ - (c).t0; (c).t0 = t_; } } } while (0)
+
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
 
 // Shared-memory layout (float offsets), identical on host and device.
@@ -50,22 +52,32 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(tmpv, d.nv);
   A(red, 2 * kMaxWarps * 12);
   A(ints, 16);
-  A(foff, VNL_F_MODEL_COUNT);
+  A(mcol8, (d.nM + 3) / 4); A(mrow8, (d.nM + 3) / 4); A(madr16, (d.nv + 2) / 2); A(dadr16, (d.nv + 2) / 2);
+  A(dent16, (d.nM - d.nv + 1) / 2); A(drow8, (d.nM - d.nv + 3) / 4); A(dls8, (d.maxdepth + 2 + 3) / 4); A(dld8, (d.nv + 3) / 4);
 #undef A
   L.total = o;
 }
 
-struct Ctx {
+// CTA-uniform context.  It lives at the start of dynamic shared memory so that the big phases can be
+// real (non-inlined) functions: one copy of each in the instruction stream instead of one per call site.
+struct __align__(16) Ctx {
   Dims d;
   Lay L;
-  float* s;            // shared memory base
+  float* s;            // shared memory base of the float arrays
   const uint32_t* mb;  // model blob (global)
-  const uint32_t* foff;
-  int tid, lane, warp, nt, nw;
-  int flip;
+  uint32_t foff[VNL_F_MODEL_COUNT];
+  const uint8_t *mcol, *mrow, *drow, *dls, *dld;
+  const uint16_t *madr, *dadr, *dent;
+  long long* prof;
+  long long t0;
+  int nt, nw;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
   __device__ __forceinline__ const float* ff(int f) const { return (const float*)(mb + foff[f]); }
 };
+constexpr int kCtxFloats = (int)((sizeof(Ctx) + 15) / 16 * 4);
+#define TID ((int)threadIdx.x)
+#define LANE ((int)(threadIdx.x & 31))
+#define WARP ((int)(threadIdx.x >> 5))
 
 // Sum N per-thread values over the CTA; every thread returns the same totals (fixed order ->
 // bit-reproducible).  One __syncthreads per call (scratch is double-buffered).
@@ -73,51 +85,54 @@ template <int N>
 __device__ __forceinline__ void block_sum(Ctx& c, float (&v)[N]) {
 #pragma unroll
   for (int n = 0; n < N; ++n) v[n] = warp_sum(v[n]);
-  float* buf = c.s + c.L.red + c.flip * (kMaxWarps * 12);
-  if (c.lane == 0) {
+  float* buf = c.s + c.L.red;
+  if (LANE == 0) {
 #pragma unroll
-    for (int n = 0; n < N; ++n) buf[c.warp * N + n] = v[n];
+    for (int n = 0; n < N; ++n) buf[WARP * N + n] = v[n];
   }
   __syncthreads();
+  const int nw = c.nw;
 #pragma unroll
   for (int n = 0; n < N; ++n) {
     float t = 0.0f;
-    for (int w = 0; w < c.nw; ++w) t += buf[w * N + n];
+#pragma unroll 1
+    for (int w = 0; w < nw; ++w) t += buf[w * N + n];
     v[n] = t;
   }
-  c.flip ^= 1;
+  __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------
 // sparse-inertia helpers
 // ---------------------------------------------------------------------------------------------
 // out = M x   (tree-sparse M, rows hold [diag, ancestors...])
-__device__ __forceinline__ void mul_m(Ctx& c, const float* x, float* out) {
-  const int* madr = c.fi(VNL_F_DOF_MADR);
-  const int* mcol = c.fi(VNL_F_M_COL);
-  const int* mrow = c.fi(VNL_F_M_ROW);
-  const int* dadr = c.fi(VNL_F_DESC_ADR);
-  const int* dent = c.fi(VNL_F_DESC_ENTRY);
+__device__ __noinline__ void mul_m(Ctx& c, const float* x, float* out) {
+  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
+  const uint16_t* dadr = c.dadr; const uint16_t* dent = c.dent; const uint8_t* drow = c.drow;
   const float* M = c.s + c.L.M;
-  for (int i = c.tid; i < c.d.nv; i += c.nt) {
-    float acc = 0.0f;
-    for (int a = madr[i]; a < madr[i + 1]; ++a) acc += M[a] * x[mcol[a]];
-    for (int k = dadr[i]; k < dadr[i + 1]; ++k) { int e = dent[k]; acc += M[e] * x[mrow[e]]; }
-    out[i] = acc;
+  for (int i = TID; i < c.d.nv; i += c.nt) {
+    float a0 = 0.0f, a1 = 0.0f;
+    int a = madr[i];
+    const int ae = madr[i + 1];
+    for (; a + 1 < ae; a += 2) { a0 += M[a] * x[mcol[a]]; a1 += M[a + 1] * x[mcol[a + 1]]; }
+    if (a < ae) a0 += M[a] * x[mcol[a]];
+    int k = dadr[i];
+    const int ke = dadr[i + 1];
+    for (; k + 1 < ke; k += 2) { a0 += M[dent[k]] * x[drow[k]]; a1 += M[dent[k + 1]] * x[drow[k + 1]]; }
+    if (k < ke) a0 += M[dent[k]] * x[drow[k]];
+    out[i] = a0 + a1;
   }
 }
 
 // L^T D L factorisation of `src` (+ dt * damping on the diagonal when `damp`), then K = L^-1.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots of L.K.
-__device__ void factor(Ctx& c, const float* src, bool damp) {
+__device__ __noinline__ void factor(Ctx& c, const float* src, bool damp) {
   const int nv = c.d.nv, nM = c.d.nM;
-  const int* madr = c.fi(VNL_F_DOF_MADR);
-  const int* mcol = c.fi(VNL_F_M_COL);
-  const int* mrow = c.fi(VNL_F_M_ROW);
+  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol; const uint8_t* mrow = c.mrow;
   float* Lf = c.s + c.L.Lf;
   float* K = c.s + c.L.K;
   const float* damping = c.ff(VNL_F_DOF_DAMPING);
-  for (int e = c.tid; e < nM; e += c.nt) {
+  for (int e = TID; e < nM; e += c.nt) {
     float v = src[e];
     if (damp && mcol[e] == mrow[e]) v += c.d.timestep * damping[mrow[e]];
     Lf[e] = v;
@@ -129,52 +144,62 @@ __device__ void factor(Ctx& c, const float* src, bool damp) {
     const int base = madr[k], dk = madr[k + 1] - base - 1;  // dk = number of ancestors
     if (dk > 0) {
       const float inv = 1.0f / Lf[base];
-      for (int a = 1 + c.warp; a <= dk; a += c.nw) {  // targets are distinct for distinct (a, cidx)
+      for (int a = 1 + WARP; a <= dk; a += c.nw) {  // targets are distinct for distinct (a, cidx)
         const int tb = madr[mcol[base + a]];
         const float t = Lf[base + a] * inv;
-        for (int cidx = c.lane; cidx <= dk - a; cidx += 32) Lf[tb + cidx] -= t * Lf[base + a + cidx];
+        for (int cidx = LANE; cidx <= dk - a; cidx += 32) Lf[tb + cidx] -= t * Lf[base + a + cidx];
       }
     }
     __syncthreads();
   }
-  // K rows are independent:  K[i][c] = -sum_{a < c} K[i][a] * Lhat[anc_a(i)][c - a],  K[i][0] = 1,
-  // with Lhat = L / diag (normalised on the fly).  1 / D goes to the diagonal slot afterwards.
-  for (int i = c.tid; i < nv; i += c.nt) {
-    const int base = madr[i], di = madr[i + 1] - base - 1;
-    K[base] = 1.0f;
-    for (int cc = 1; cc <= di; ++cc) {
-      float acc = 0.0f;
-      for (int a = 0; a < cc; ++a) {
-        const int anc = (a == 0) ? i : mcol[base + a];
-        const int ab = madr[anc];
-        acc += K[base + a] * (Lf[ab + cc - a] / Lf[ab]);
-      }
-      K[base + cc] = -acc;
-    }
+  // normalise rows: Lhat = L / diag; keep 1 / D in the diagonal slot of K
+  for (int e = TID; e < nM; e += c.nt) {
+    const int b0 = madr[mrow[e]];
+    if (e == b0) K[e] = 1.0f / Lf[e];
+    else Lf[e] = Lf[e] / Lf[b0];
   }
   __syncthreads();
-  for (int i = c.tid; i < nv; i += c.nt) K[madr[i]] = 1.0f / Lf[madr[i]];
-  __syncthreads();
+  // K = Lhat^-1 by levels of dof depth (Lhat K = I): for a dof i with ancestors anc_1..anc_d,
+  //   K[i][c] = -( Lhat[i][c] + sum_{a=1}^{c-1} Lhat[i][a] * K[anc_a(i)][c - a] ),  K[.][0] = 1 implicit
+  const uint8_t* dls = c.dls; const uint8_t* dld = c.dld;
+  for (int dl = 1; dl <= c.d.maxdepth; ++dl) {
+    const int s0 = dls[dl], n = (dls[dl + 1] - s0) * dl;
+    for (int it = TID; it < n; it += c.nt) {
+      const int i = dld[s0 + it / dl], cc = 1 + it % dl, base = madr[i];
+      float a0 = Lf[base + cc], a1 = 0.0f;
+      int a = 1;
+      for (; a + 1 < cc; a += 2) {
+        a0 += Lf[base + a] * K[madr[mcol[base + a]] + cc - a];
+        a1 += Lf[base + a + 1] * K[madr[mcol[base + a + 1]] + cc - a - 1];
+      }
+      if (a < cc) a0 += Lf[base + a] * K[madr[mcol[base + a]] + cc - a];
+      K[base + cc] = -(a0 + a1);
+    }
+    __syncthreads();
+  }
 }
 
 // x <- M^-1 x   via  K (D^-1 (K^T x));  `tmp` is nv scratch.
-__device__ __forceinline__ void solve_m(Ctx& c, const float* x, float* out, float* tmp) {
-  const int* madr = c.fi(VNL_F_DOF_MADR);
-  const int* mcol = c.fi(VNL_F_M_COL);
-  const int* mrow = c.fi(VNL_F_M_ROW);
-  const int* dadr = c.fi(VNL_F_DESC_ADR);
-  const int* dent = c.fi(VNL_F_DESC_ENTRY);
+__device__ __noinline__ void solve_m(Ctx& c, const float* x, float* out, float* tmp) {
+  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
+  const uint16_t* dadr = c.dadr; const uint16_t* dent = c.dent; const uint8_t* drow = c.drow;
   const float* K = c.s + c.L.K;
-  for (int j = c.tid; j < c.d.nv; j += c.nt) {
-    float acc = x[j];
-    for (int k = dadr[j]; k < dadr[j + 1]; ++k) { int e = dent[k]; acc += K[e] * x[mrow[e]]; }
-    tmp[j] = acc * K[madr[j]];
+  for (int j = TID; j < c.d.nv; j += c.nt) {
+    float a0 = x[j], a1 = 0.0f;
+    int k = dadr[j];
+    const int ke = dadr[j + 1];
+    for (; k + 1 < ke; k += 2) { a0 += K[dent[k]] * x[drow[k]]; a1 += K[dent[k + 1]] * x[drow[k + 1]]; }
+    if (k < ke) a0 += K[dent[k]] * x[drow[k]];
+    tmp[j] = (a0 + a1) * K[madr[j]];
   }
   __syncthreads();
-  for (int i = c.tid; i < c.d.nv; i += c.nt) {
-    float acc = tmp[i];
-    for (int a = madr[i] + 1; a < madr[i + 1]; ++a) acc += K[a] * tmp[mcol[a]];
-    out[i] = acc;
+  for (int i = TID; i < c.d.nv; i += c.nt) {
+    float a0 = tmp[i], a1 = 0.0f;
+    int a = madr[i] + 1;
+    const int ae = madr[i + 1];
+    for (; a + 1 < ae; a += 2) { a0 += K[a] * tmp[mcol[a]]; a1 += K[a + 1] * tmp[mcol[a + 1]]; }
+    if (a < ae) a0 += K[a] * tmp[mcol[a]];
+    out[i] = a0 + a1;
   }
   __syncthreads();
 }
@@ -183,21 +208,20 @@ __device__ __forceinline__ void solve_m(Ctx& c, const float* x, float* out, floa
 // constraint Jacobian products on the compact active set
 // ---------------------------------------------------------------------------------------------
 // out[row] = (J x)[row]
-__device__ __forceinline__ void jmul(Ctx& c, const float* x, float* out) {
+__device__ __noinline__ void jmul(Ctx& c, const float* x, float* out) {
   const int* ints = (const int*)(c.s + c.L.ints);
   const int nl = ints[0], nc = ints[1];
-  const int* madr = c.fi(VNL_F_DOF_MADR);
-  const int* mcol = c.fi(VNL_F_M_COL);
+  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
   const int* lastdof = c.fi(VNL_F_BODY_LASTDOF);
   const float* cdof = c.s + c.L.cdof;
   const int* cbody = (const int*)(c.s + c.L.cbody);
   const int* lim_dof = (const int*)(c.s + c.L.lim_dof);
   const float* lim_sign = c.s + c.L.lim_sign;
-  for (int k = c.warp; k < nc; k += c.nw) {
+  for (int k = WARP; k < nc; k += c.nw) {
     const int dl = lastdof[cbody[k]];
     float sacc[6] = {0, 0, 0, 0, 0, 0};
     if (dl >= 0) {
-      for (int a = madr[dl] + c.lane; a < madr[dl + 1]; a += 32) {
+      for (int a = madr[dl] + LANE; a < madr[dl + 1]; a += 32) {
         const int j = mcol[a];
         const float xj = x[j];
 #pragma unroll
@@ -206,25 +230,25 @@ __device__ __forceinline__ void jmul(Ctx& c, const float* x, float* out) {
     }
 #pragma unroll
     for (int q = 0; q < 6; ++q) sacc[q] = warp_sum(sacc[q]);
-    if (c.lane < 4) {
+    if (LANE < 4) {
       const float* fr = c.s + c.L.cframe + 9 * k;
       V3 vel = v3(sacc[3], sacc[4], sacc[5]) + cross(v3(sacc[0], sacc[1], sacc[2]), ld3(c.s + c.L.crel + 3 * k));
       const float un = dot(ld3(fr), vel);
-      const float ut = dot(ld3(fr + 3 * (1 + (c.lane >> 1))), vel);
+      const float ut = dot(ld3(fr + 3 * (1 + (LANE >> 1))), vel);
       const float mu = c.s[c.L.cmu + k];
-      out[nl + 4 * k + c.lane] = un + ut * ((c.lane & 1) ? -mu : mu);
+      out[nl + 4 * k + LANE] = un + ut * ((LANE & 1) ? -mu : mu);
     }
   }
-  for (int r = c.tid; r < nl; r += c.nt) out[r] = lim_sign[r] * x[lim_dof[r]];
+  for (int r = TID; r < nl; r += c.nt) out[r] = lim_sign[r] * x[lim_dof[r]];
 }
 
 // qfrc_con = J^T f with f[row] = -D Jaref [Jaref < 0]; returns nothing, needs a sync after.
-__device__ __forceinline__ void jtmul_force(Ctx& c, float* qfrc) {
+__device__ __noinline__ void jtmul_force(Ctx& c, float* qfrc) {
   const int* ints = (const int*)(c.s + c.L.ints);
   const int nl = ints[0], nc = ints[1];
   const float* D = c.s + c.L.efcD;
   const float* Jaref = c.s + c.L.Jaref;
-  for (int k = c.tid; k < nc; k += c.nt) {
+  for (int k = TID; k < nc; k += c.nt) {
     float f[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -245,7 +269,7 @@ __device__ __forceinline__ void jtmul_force(Ctx& c, float* qfrc) {
   const int* cbody = (const int*)(c.s + c.L.cbody);
   const int* limrow = (const int*)(c.s + c.L.limrow_of_dof);
   const float* lim_sign = c.s + c.L.lim_sign;
-  for (int i = c.tid; i < c.d.nv; i += c.nt) {
+  for (int i = TID; i < c.d.nv; i += c.nt) {
     const int b = dof_body[i], be = sub_end[b];
     const float* cd = c.s + c.L.cdof + 6 * i;
     float acc = 0.0f;
@@ -285,11 +309,11 @@ __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const f
 // ---------------------------------------------------------------------------------------------
 struct LSP { float alpha, cost, d0, d1; };
 
-__device__ void forward(Ctx& c, int* stats, float* dump) {
+__device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
   const Dims& d = c.d;
   const Lay& L = c.L;
   float* s = c.s;
-  const int tid = c.tid, nt = c.nt;
+  const int tid = TID, nt = c.nt;
   int* ints = (int*)(s + L.ints);
 
   // ---- smooth.kinematics: level-synchronous walk down the body tree --------------------------
@@ -340,6 +364,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
       __syncthreads();
     }
   }
+  PROF(c, 0);
   // ---- smooth.com_pos: xipos, root COM, cinert, cdof ------------------------------------------
   {
     const float* ipos = c.ff(VNL_F_BODY_IPOS);
@@ -350,18 +375,18 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     const int* sub_end = c.fi(VNL_F_BODY_SUBTREE_END);
     const float* mass = c.ff(VNL_F_BODY_MASS);
     // one warp per kinematic tree: subtree COM of the root = mass-weighted mean over its id range
-    for (int b = 1 + c.warp; b < d.nbody; b += c.nw) {
+    for (int b = 1 + WARP; b < d.nbody; b += c.nw) {
       if (rootid[b] != b) continue;
       float acc[4] = {0, 0, 0, 0};
-      for (int q = b + c.lane; q < sub_end[b]; q += 32) {
+      for (int q = b + LANE; q < sub_end[b]; q += 32) {
         const float mq = mass[q];
         acc[0] += s[L.xipos + 3 * q] * mq; acc[1] += s[L.xipos + 3 * q + 1] * mq; acc[2] += s[L.xipos + 3 * q + 2] * mq; acc[3] += mq;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
-      if (c.lane < 3) {
-        const float a = c.lane == 0 ? acc[0] : (c.lane == 1 ? acc[1] : acc[2]);
-        s[L.rcom + 3 * b + c.lane] = (acc[3] < VNL_MINVAL) ? s[L.xipos + 3 * b + c.lane] : a / fmaxf(acc[3], VNL_MINVAL);
+      if (LANE < 3) {
+        const float a = LANE == 0 ? acc[0] : (LANE == 1 ? acc[1] : acc[2]);
+        s[L.rcom + 3 * b + LANE] = (acc[3] < VNL_MINVAL) ? s[L.xipos + 3 * b + LANE] : a / fmaxf(acc[3], VNL_MINVAL);
       }
     }
     __syncthreads();
@@ -415,10 +440,9 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     }
     __syncthreads();
   }
+  PROF(c, 1);
   // ---- composite inertia (flat subtree sums), cvel chains ----------------------------------------
-  const int* madr = c.fi(VNL_F_DOF_MADR);
-  const int* mcol = c.fi(VNL_F_M_COL);
-  const int* mrow = c.fi(VNL_F_M_ROW);
+  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol; const uint8_t* mrow = c.mrow;
   const int* lastdof = c.fi(VNL_F_BODY_LASTDOF);
   const int* sub_end = c.fi(VNL_F_BODY_SUBTREE_END);
   const int* dof_body = c.fi(VNL_F_DOF_BODYID);
@@ -471,6 +495,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     }
     __syncthreads();
   }
+  PROF(c, 2);
   // ---- smooth.rne: cacc chains, local cfrc, subtree sums, qfrc_bias (kept in tmpv) -------------------
   {
     for (int it = tid; it < d.nbody * 6; it += nt) {
@@ -498,6 +523,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     }
     __syncthreads();
   }
+  PROF(c, 3);
   // ---- qfrc_smooth = passive - bias + actuator; act_dot ---------------------------------------------
   {
     const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
@@ -546,6 +572,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     }
     __syncthreads();
   }
+  PROF(c, 4);
   // ---- joint-space inertia (tree sparse): M[i][a] = cdof[anc_a(i)] . (crb[body_i] cdof_i) -------
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
@@ -560,15 +587,18 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
     }
     __syncthreads();
   }
+  PROF(c, 5);
   factor(c, s + L.M, false);
+  PROF(c, 6);
   solve_m(c, s + L.qfrc_smooth, s + L.qacc_smooth, s + L.tmpv);
+  PROF(c, 7);
 
   // ---- collision + constraint rows, compacted to the active set -----------------------------------
   {
     if (tid == 0) { ints[0] = 0; ints[1] = 0; }
     for (int i = tid; i < d.nv; i += nt) ((int*)(s + L.limrow_of_dof))[i] = -1;
     __syncthreads();
-    if (c.warp == 0) {
+    if (WARP == 0) {
       // joint limits (constraint._instantiate_limit_slide_hinge)
       const int* ljnt = c.fi(VNL_F_LIMIT_JNT);
       const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
@@ -579,7 +609,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
       const float* invw = c.ff(VNL_F_DOF_INVWEIGHT0);
       int base = 0;
       for (int r0 = 0; r0 < d.nlimit; r0 += 32) {
-        const int r = r0 + c.lane;
+        const int r = r0 + LANE;
         bool active = false;
         float pos = 0.0f, sign = 0.0f;
         int j = 0;
@@ -593,7 +623,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         }
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (active) {
-          const int slot = base + __popc(m & ((1u << c.lane) - 1u));
+          const int slot = base + __popc(m & ((1u << LANE) - 1u));
           const int dof = jdofadr[j];
           ((int*)(s + L.lim_dof))[slot] = dof;
           s[L.lim_sign + slot] = sign;
@@ -607,10 +637,10 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         }
         base += __popc(m);
       }
-      if (c.lane == 0) ints[0] = base;
+      if (LANE == 0) ints[0] = base;
     }
     __syncthreads();
-    if (c.warp == 0) {
+    if (WARP == 0) {
       // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
       const int nl = ints[0];
       const int* cpair = c.fi(VNL_F_CON_PAIR);
@@ -630,7 +660,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
       const float* binvw = c.ff(VNL_F_BODY_INVWEIGHT0);
       int base = 0;
       for (int c0 = 0; c0 < d.ncon; c0 += 32) {
-        const int ci = c0 + c.lane;
+        const int ci = c0 + LANE;
         bool active = false;
         float dist = 0.0f;
         V3 cp = v3(0, 0, 0), n = v3(0, 0, 1), fb = v3(0, 1, 0);
@@ -690,7 +720,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         }
         const unsigned m = __ballot_sync(0xffffffffu, active);
         if (active) {
-          const int k = base + __popc(m & ((1u << c.lane) - 1u));
+          const int k = base + __popc(m & ((1u << LANE) - 1u));
           ((int*)(s + L.cbody))[k] = body;
           const V3 rel = cp - ld3(s + L.rcom + 3 * rootid[body]);
           st3(s + L.crel + 3 * k, rel);
@@ -724,10 +754,11 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         }
         base += __popc(m);
       }
-      if (c.lane == 0) ints[1] = base;
+      if (LANE == 0) ints[1] = base;
     }
     __syncthreads();
   }
+  PROF(c, 8);
   const int nl = ints[0], nc = ints[1], nrow = nl + 4 * nc;
   if (stats && tid == 0) { stats[2] += nc; stats[3] += nl; }
 
@@ -768,6 +799,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
       cost_s = 0.5f * w[0] + 0.5f * w[1];
       __syncthreads();
     }
+    PROF(c, 9);
     const bool use_warm = cost_w < cost_s;
     if (use_warm) {
       for (int i = tid; i < d.nv; i += nt) qacc[i] = s[L.warm + i];
@@ -799,6 +831,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
       solve_m(c, grad, Mgrad, s + L.tmpv);
     };
     update();
+    PROF(c, 10);
     for (int i = tid; i < d.nv; i += nt) search[i] = -Mgrad[i];
     __syncthreads();
     while (true) {
@@ -878,6 +911,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         ++it;
       }
       lsiter += it;
+      PROF(c, 11);
       const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       const float ia = improved ? alpha : 0.0f * alpha;
@@ -898,6 +932,7 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
         for (int i = tid; i < d.nv; i += nt) search[i] = -Mgrad[i] + beta * search[i];
       }
       __syncthreads();
+      PROF(c, 12);
       ++niter;
     }
   }
@@ -910,15 +945,17 @@ __device__ void forward(Ctx& c, int* stats, float* dump) {
 // ---------------------------------------------------------------------------------------------
 // forward.euler (implicit joint damping when enabled) + _advance
 // ---------------------------------------------------------------------------------------------
-__device__ void euler(Ctx& c) {
+__device__ __noinline__ void euler(Ctx& c) {
   const Dims& d = c.d;
   const Lay& L = c.L;
   float* s = c.s;
-  const int tid = c.tid, nt = c.nt;
+  const int tid = TID, nt = c.nt;
   const float dt = d.timestep;
   float* qacc = s + L.qacc;
+  PROF(c, 13);
   if (d.eulerdamp) {
     factor(c, s + L.M, true);
+    PROF(c, 14);
     for (int i = tid; i < d.nv; i += nt) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
     __syncthreads();
     solve_m(c, s + L.grad, s + L.Mgrad, s + L.tmpv);
@@ -943,6 +980,7 @@ __device__ void euler(Ctx& c) {
     }
   }
   __syncthreads();
+  PROF(c, 15);
 }
 
 __device__ __forceinline__ float nan_to_num(float v) {
@@ -955,24 +993,44 @@ __device__ __forceinline__ float nan_to_num(float v) {
 // kernel: MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads) vnl_env_kernel(Params p) {
+__global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
   extern __shared__ __align__(16) float smem[];
   const int e = blockIdx.x;
   if (e >= p.B) return;
-  Ctx c;
-  c.s = smem;
-  c.mb = p.model;
-  c.tid = threadIdx.x; c.nt = blockDim.x; c.lane = threadIdx.x & 31; c.warp = threadIdx.x >> 5; c.nw = blockDim.x >> 5;
-  c.flip = 0;
-  c.d = p.dims;
-  make_layout(c.d, c.L);
+  Ctx& c = *reinterpret_cast<Ctx*>(smem);
+  float* s = smem + kCtxFloats;
+  const int tid = TID, nt = blockDim.x;
+  if (tid == 0) {
+    c.s = s;
+    c.mb = p.model;
+    c.nt = blockDim.x; c.nw = blockDim.x >> 5;
+    c.prof = (p.prof && blockIdx.x == p.prof_block) ? p.prof : nullptr;
+    c.t0 = clock64();
+    c.d = p.dims;
+    make_layout(c.d, c.L);
+    const Lay& L0 = c.L;
+    c.mcol = (const uint8_t*)(s + L0.mcol8); c.mrow = (const uint8_t*)(s + L0.mrow8); c.drow = (const uint8_t*)(s + L0.drow8);
+    c.dls = (const uint8_t*)(s + L0.dls8); c.dld = (const uint8_t*)(s + L0.dld8);
+    c.madr = (const uint16_t*)(s + L0.madr16); c.dadr = (const uint16_t*)(s + L0.dadr16); c.dent = (const uint16_t*)(s + L0.dent16);
+  }
+  for (int f = tid; f < VNL_F_MODEL_COUNT; f += nt) c.foff[f] = p.model[VNL_TABLE_OFF + 2 * f];
+  __syncthreads();
   const Dims& d = c.d;
   const Lay& L = c.L;
-  float* s = smem;
-  const int tid = c.tid, nt = c.nt;
-  uint32_t* foff = (uint32_t*)(s + L.foff);
-  for (int f = tid; f < VNL_F_MODEL_COUNT; f += nt) foff[f] = p.model[VNL_TABLE_OFF + 2 * f];
-  c.foff = foff;
+  {
+    uint8_t* mcol8 = (uint8_t*)(s + L.mcol8); uint8_t* mrow8 = (uint8_t*)(s + L.mrow8); uint8_t* drow8 = (uint8_t*)(s + L.drow8);
+    uint8_t* dls8 = (uint8_t*)(s + L.dls8); uint8_t* dld8 = (uint8_t*)(s + L.dld8);
+    uint16_t* madr16 = (uint16_t*)(s + L.madr16); uint16_t* dadr16 = (uint16_t*)(s + L.dadr16); uint16_t* dent16 = (uint16_t*)(s + L.dent16);
+    const int* g_mcol = vnl_field_i(p.model, VNL_F_M_COL); const int* g_mrow = vnl_field_i(p.model, VNL_F_M_ROW);
+    const int* g_madr = vnl_field_i(p.model, VNL_F_DOF_MADR); const int* g_dadr = vnl_field_i(p.model, VNL_F_DESC_ADR);
+    const int* g_dent = vnl_field_i(p.model, VNL_F_DESC_ENTRY);
+    const int* g_dls = vnl_field_i(p.model, VNL_F_DOFLEVEL_START); const int* g_dld = vnl_field_i(p.model, VNL_F_DOFLEVEL_DOF);
+    for (int i = tid; i < d.nM; i += nt) { mcol8[i] = (uint8_t)g_mcol[i]; mrow8[i] = (uint8_t)g_mrow[i]; }
+    for (int i = tid; i <= d.nv; i += nt) { madr16[i] = (uint16_t)g_madr[i]; dadr16[i] = (uint16_t)g_dadr[i]; }
+    for (int i = tid; i < d.nM - d.nv; i += nt) { const int en = g_dent[i]; dent16[i] = (uint16_t)en; drow8[i] = (uint8_t)g_mrow[en]; }
+    for (int i = tid; i < d.maxdepth + 2; i += nt) dls8[i] = (uint8_t)g_dls[i];
+    for (int i = tid; i < d.nv; i += nt) dld8[i] = (uint8_t)g_dld[i];
+  }
   int* ints = (int*)(s + L.ints);
   if (tid < 16) ints[tid] = 0;
 
@@ -1044,8 +1102,7 @@ __global__ void __launch_bounds__(kThreads) vnl_env_kernel(Params p) {
     const int* rootid = c.fi(VNL_F_BODY_ROOTID);
     for (int b = tid; b < d.nbody; b += nt)
       if (b > 0 && rootid[b] == b) st3(dump + d.dump_subtree_com + 3 * b, ld3(s + L.rcom + 3 * b));
-    const int* mrow = c.fi(VNL_F_M_ROW);
-    const int* mcol = c.fi(VNL_F_M_COL);
+    const uint8_t* mrow = c.mrow; const uint8_t* mcol = c.mcol;
     for (int i = tid; i < d.nv * d.nv; i += nt) dump[d.dump_qM + i] = 0.0f;
     __syncthreads();
     for (int q = tid; q < d.nM; q += nt) {
@@ -1218,7 +1275,7 @@ template __global__ void vnl_env_kernel<3>(Params);
 int smem_bytes(const Dims& d) {
   Lay L;
   make_layout(d, L);
-  return L.total * (int)sizeof(float);
+  return (L.total + kCtxFloats) * (int)sizeof(float);
 }
 
 cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
@@ -1226,6 +1283,11 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (err != cudaSuccess) return err;
+  // leave the rest of the unified 228 KB array to L1: the model tables are re-read from it every substep
+  int ctas = 4;
+  while (ctas > 1 && ctas * (bytes + 1024) > 227 * 1024) --ctas;
+  int pct = (ctas * (bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024);
+  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
   k<<<p.B, kThreads, bytes, stream>>>(p);
   return cudaGetLastError();
 }

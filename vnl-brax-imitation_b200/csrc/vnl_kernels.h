@@ -22,7 +22,8 @@ struct Dims {
 struct Lay {
   int qpos, qvel, act, ctrl, warm, xpos, xquat, xipos, xanchor, xaxis, rcom, cinert, crb, cdof, cdofdot, cvel, cacc, cfrc, M,
       Lf, K, qfrc_smooth, qacc_smooth, qfrc_act, act_dot, lim_dof, lim_sign, limrow_of_dof, cbody, crel, cframe, cmu, cwrench,
-      efcD, aref, Jaref, Jv, qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, red, ints, foff, total;
+      efcD, aref, Jaref, Jv, qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, red, ints, mcol8, mrow8, madr16, dadr16,
+      dent16, drow8, dls8, dld8, total;
 };
 
 struct Params {
@@ -35,6 +36,8 @@ struct Params {
   VnlOutputs outputs;
   int32_t* stats;
   float* dump;
+  long long* prof;  // optional [32] per-phase clock64 accumulators of one CTA (developer hook)
+  int prof_block;
 };
 
 int smem_bytes(const Dims& d);
