@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: rodent imitation env-steps/s (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  the reference arm: the CPU implementation of the same path
+
+A "step" is one pass of the hot path over one batch: ONE fused launch that advances every env of the rank's shard by
+one env step (5 MJX-style physics substeps + reward / obs / trajectory window / termination) and applies brax's
+AutoReset (restore the cached first state where done; `info` keeps running -- SURVEY quirk Q7).
+Workload (BASELINE.json configs[1]): rodent.xml (0.9 rescale, torque actuators, CG 6x6, pyramidal, eulerdamp),
+clip transform_snips_groom.p, 4096 envs per GPU, iid U(-1, 1) actions, weak scaling (env shards are independent,
+no data-path collective).
+
+`value`      whole-job env-steps/s with state and pre-generated actions resident in HBM (CUDA events, max over ranks).
+`e2e`        the same metric through the public env API (`RodentTracking.step`) with HOST buffers: every step copies
+             the step's actions from pinned host memory and reads obs, traj, reward and done back to pinned host memory.
+`roofline`   HBM view of the fused kernel (algorithmic bytes at the step boundary / launch time) against the measured copy
+             bandwidth; `roofline_fp32` is the binding one: algorithmic FLOPs / launch time against an FFMA
+             microkernel measured in the same run.
+`cpu_baseline` the CPU oracle (fp32 build, OpenMP over envs, all host cores) on a bounded sample, rank 0, N = 1 only.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 4096
+ENV_ARG_KEYS = ("end_eff_names", "appendage_names", "walker_body_names", "joint_names", "center_of_mass", "clip_length",
+                "sub_clip_length", "ref_traj_length", "termination_threshold")
+
+
+def pkg(name=""):
+    return importlib.import_module("vnl-brax-imitation_b200" + (("." + name) if name else ""))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# work model
+# ------------------------------------------------------------------------------------------------------------------
+def algorithmic_bytes(dims, obs_size, traj_size, ntrack):
+    """Compulsory HBM words at the step boundary, recomputed from the fields the kernel really moves."""
+    nq, nv, na, nu, nb = dims["nq"], dims["nv"], dims["na"], dims["nu"], dims["nbody"]
+    rd = nq + nv + na + nv + 3 * ntrack + nu + 2 + 1  # state, old xpos of the tracked bodies, action, 2 frame ints, done flag
+    wr = nq + nv + na + nv + 3 * nb + 4 * nb + 3 + nv + obs_size + traj_size + 1 + 1 + 7 + 2 + 4
+    return 4 * (rd + wr)
+
+
+def algorithmic_flops(dims, depth, n_frames, I, L):
+    """Work-optimal FLOPs per env step (SURVEY 8d formula), with the executed solver iterations I per substep and
+    line-search iterations L per solver iteration."""
+    nb, nv, nu, ncon, nefc, nlim, P = (dims[k] for k in ("nbody", "nv", "nu", "ncon", "nefc", "nlimit", "nM"))
+    ed = 1 if dims["eulerdamp"] else 0
+    ldl = float(np.sum(depth * (depth - 1.0)))
+    Jp = 12 * nv + 6 * nb + 45 * ncon + nlim
+    nsolve, nmul = 2 + I + ed, 3 + I
+    f = 350 * nb + 60 * nv + 10 * nb + 70 * nv + 12 * P + (1 + ed) * ldl + 250 * nb + 40 * nv + 4 * nu + 80 * ncon
+    f += Jp + 40 * nefc + nsolve * 4 * P + nmul * 4 * P + 3 * (2 * Jp + 6 * nefc)
+    f += I * (2 * Jp + 12 * nefc + (2 + 3 * L) * 8 * nefc + 12 * nv) + 6 * nv + 40
+    return n_frames * f
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self.reasons, self.stop_flag = index, period, [], set(), threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def finish(self):
+        self.stop_flag.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------------------
+def build_workload():
+    rod, mb = pkg("envs.rodent"), pkg("model_blob")
+    model, clip = rod.packaged_rodent()
+    return rod, mb, model, clip
+
+
+def initial_draws(fclip, total, lo, hi, seed=0):
+    """RodentTracking.reset draws (envs/rodent.py:123-132) for global env ids [lo, hi) out of `total`."""
+    rng = np.random.default_rng(seed)
+    start = rng.integers(0, 235, size=total).astype(np.int32)
+    noise = (1e-3 * rng.standard_normal((total, 74))).astype(np.float32)
+    s = start[lo:hi]
+    qpos = np.hstack([fclip.position[s], fclip.quaternion[s], fclip.joints[s]]).astype(np.float32) + noise[lo:hi]
+    qvel = np.hstack([fclip.velocity[s], fclip.angular_velocity[s], fclip.joints_velocity[s]]).astype(np.float32)
+    return qpos, qvel, s
+
+
+def cpu_oracle_rate(seconds_target=12.0, nthreads=0, steps=None, sample_envs=None, warmup=1):
+    """env-steps/s of the CPU oracle (fp32, OpenMP over envs) on a bounded sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle  # the reference arm / cpu_baseline leg is the one place bench.py may execute oracle/
+    rod, mb, model, clip = build_workload()
+    task, fclip, idx, obs_size, traj_size = rod.rodent_task_tables(model, clip, **{k: rod.RODENT_ENV_ARGS[k] for k in ENV_ARG_KEYS})
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    nt = nthreads or oracle.max_threads()
+    kw = dict(precision=32, dims=dims, obs_size=obs_size, traj_size=traj_size, nthreads=nt)
+    rng = np.random.default_rng(0)
+
+    def run(B, nsteps, nwarm):
+        qpos, qvel, start = initial_draws(fclip, ENVS_PER_GPU, 0, B)
+        s, _ = oracle.reset(blob, task, qpos, qvel, start, **kw)
+        first = {k: v.copy() for k, v in s.items()}
+        per_step = []
+        for it in range(nwarm + nsteps):
+            a = rng.uniform(-1, 1, size=(B, 30))
+            t0 = time.perf_counter()
+            s, o = oracle.step(blob, task, s, a, **kw)
+            d = o["done"] > 0  # AutoReset: restore the first pipeline state where done (info keeps running, Q7)
+            for k in ("qpos", "qvel", "act", "qacc_warmstart", "xpos", "xquat", "subtree_com", "qfrc_actuator"):
+                s[k][d] = first[k][d]
+            if it >= nwarm:
+                per_step.append(time.perf_counter() - t0)
+        return float(np.sum(per_step)), float(np.mean(per_step))
+
+    if sample_envs is None:
+        t_pilot, _ = run(8 * nt, 1, 1)
+        rate = 8 * nt / max(t_pilot, 1e-6)
+        nsteps = steps or 4
+        sample_envs = int(min(ENVS_PER_GPU, max(8 * nt, rate * seconds_target / nsteps)))
+    nsteps = steps or 4
+    total, mean = run(sample_envs, nsteps, warmup)
+    return dict(value=sample_envs * nsteps / total, ms_per_step=1e3 * mean, cores=nt, envs=sample_envs, steps=nsteps,
+                sample="%d envs x %d env steps of the bench workload (fp32 oracle, OpenMP over envs)" % (sample_envs, nsteps))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    r = cpu_oracle_rate(seconds_target=10.0, steps=max(1, min(args.steps, 8)), warmup=max(1, min(args.warmup, 2)))
+    line = {"impl": "reference", "metric": "rodent imitation env-steps/s", "value": r["value"], "unit": "env-steps/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "rodent imitation env step (rodent.xml, transform_snips_groom.p clip), CPU path, "
+                                   "bounded sample of the 4096-env workload", "envs_per_step": r["envs"]},
+            "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "the reference's own arithmetic lives in mujoco-mjx/brax/jax, none installable here (SURVEY 8c): this arm "
+                    "times the repo's CPU restatement (oracle port), not the reference's JAX-CPU path"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    sh = pkg("sharding")
+    rank, local_rank, world = sh.env_info()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus must equal WORLD_SIZE under torchrun")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node %d bench.py --gpus %d ..." % (args.gpus, args.gpus))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sh.init_process_group("nccl")
+    rod, mb, model, clip = build_workload()
+    envs = pkg("envs")
+    env = envs.RodentTracking(reference_clip=clip, model=model, device=str(dev), **rod.RODENT_ENV_ARGS)
+    eng = env.engine
+    B = args.envs_per_gpu
+    total = B * world
+    lo, hi = sh.shard_range(total, rank, world)
+    qpos, qvel, start = initial_draws(env._ref_traj, total, lo, hi)
+    K, W = args.steps, args.warmup
+
+    s0 = env.reset_from(qpos, qvel, start)
+    first = dict(s0.pipeline_state)
+    first_obs = s0.obs
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)  # Philox counter RNG on the device, pre-generated so RNG cost is outside the timed region
+    actions = torch.rand(W + K, B, env.action_size, generator=gen, device=dev) * 2 - 1
+
+    def fresh_state():
+        st = {k: v.clone() for k, v in first.items()}
+        st["cur_frame"] = s0.info["cur_frame"].clone()
+        st["sub_clip_frame"] = s0.info["sub_clip_frame"].clone()
+        return st
+
+    # ---- device-resident loop -----------------------------------------------------------------------------------
+    a_st, b_st, out = fresh_state(), eng.alloc_state(B), eng.alloc_outputs(B)
+    stats_acc = torch.zeros(4, dtype=torch.float64, device=dev)
+
+    def one_step(i):
+        nonlocal a_st, b_st
+        eng.step_autoreset(a_st, actions[i], b_st, out, first, first_obs)
+        a_st, b_st = b_st, a_st
+
+    for i in range(W):
+        one_step(i)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launches
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(W, W + K):
+        one_step(i)
+        stats_acc += out["stats"].sum(0)  # solver counters for the executed-FLOP model (tiny reduction, on stream)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.finish()
+    launches = eng.launches - launches0
+    done_frac = float(out["done"].mean())
+
+    # ---- kernel-only timing (no stats reduction in between) for the roofline -------------------------------------
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nk = min(K, 20)
+    k0.record()
+    for i in range(W, W + nk):
+        one_step(i)
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1) / nk
+
+    # ---- end to end through the public API with host buffers ------------------------------------------------------
+    host_actions = torch.empty(K, B, env.action_size, dtype=torch.float32).pin_memory()
+    host_actions.copy_(actions[W:W + K].cpu())
+    h_obs = torch.empty(B, eng.obs_size).pin_memory()
+    h_traj = torch.empty(B, eng.traj_size).pin_memory()
+    h_rew = torch.empty(B).pin_memory()
+    h_done = torch.empty(B).pin_memory()
+    state = s0
+    d_act = torch.empty(B, env.action_size, device=dev)
+    for i in range(min(W, 3)):
+        d_act.copy_(host_actions[i], non_blocking=True)
+        state = env.step(state, d_act)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(K):
+        d_act.copy_(host_actions[i], non_blocking=True)
+        state = env.step(state, d_act)
+        h_obs.copy_(state.obs, non_blocking=True)
+        h_traj.copy_(state.info["traj"], non_blocking=True)
+        h_rew.copy_(state.reward, non_blocking=True)
+        h_done.copy_(state.done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the host consumer needs this step's result before the next action
+    t1.record()
+    torch.cuda.synchronize()
+    e2e_ms_total = t0.elapsed_time(t1)
+    h2d = B * env.action_size * 4
+    d2h = B * (eng.obs_size + eng.traj_size + 2) * 4
+
+    # ---- FP32 probe ---------------------------------------------------------------------------------------------------
+    blocks, iters = 148 * 16, 20000
+    scratch = torch.empty(blocks * 256, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng.lib.vnl_ffma_probe(blocks, 200, scratch.data_ptr(), stream)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    eng.lib.vnl_ffma_probe(blocks, iters, scratch.data_ptr(), stream)
+    p1.record()
+    torch.cuda.synchronize()
+    ffma_tflops = blocks * 256 * iters * 32 / (p0.elapsed_time(p1) * 1e-3) / 1e12
+
+    # ---- max over ranks ---------------------------------------------------------------------------------------------
+    red = sh.reduce_scalars(dict(ms=ms_total, e2e=e2e_ms_total, kern=kernel_ms), op="max", device=dev)
+    sums = sh.reduce_scalars(dict(launches=float(launches)), op="sum", device=dev)
+    if rank != 0:
+        return
+    ms_total, e2e_ms_total, kernel_ms = red["ms"], red["e2e"], red["kern"]
+    value = total * K / (ms_total * 1e-3)
+    e2e_value = total * K / (e2e_ms_total * 1e-3)
+
+    dims = eng.dims
+    depth = mb.read_field(env.model_blob, "VNL_F_DOF_DEPTH", np.int32).astype(np.float64)
+    st = (stats_acc / (K * B)).cpu().numpy()  # per env step: solver iters, ls iters, active contacts, active limits
+    nfr = eng.n_frames
+    I = st[0] / nfr
+    L = st[1] / max(st[0], 1e-9)
+    flops = algorithmic_flops(dims, depth, nfr, I, L)
+    flops_static = algorithmic_flops(dims, depth, nfr, dims["iterations"], dims["ls_iterations"])
+    nbytes = algorithmic_bytes(dims, eng.obs_size, eng.traj_size, len(env._body_idxs))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    ach_gbs = B * nbytes / (kernel_ms * 1e-3) / 1e9
+    ach_tf = B * flops / (kernel_ms * 1e-3) / 1e12
+    line = {
+        "metric": "rodent imitation env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p), "
+                               "%d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "
+                               "reference's info-not-reset quirk" % B,
+                   "envs_per_gpu": B, "global_envs": total, "parallelism": "env shards, dp%d, no data-path collective" % world,
+                   "l2": "not flushed: the whole batch state (%.0f MB) is L2-resident; numbers are L2-warm as in the rollout loop"
+                         % (B * nbytes / 1e6), "done_fraction": done_frac},
+        "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms_total / K},
+        "gpu_launches": int(sums["launches"]),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                     "traffic": None, "peak_source": hbm_src, "bytes_per_env_step": nbytes, "kernel_ms": kernel_ms,
+                     "note": "this path is FP32-latency bound, not HBM bound (intensity ~%d flop/B); see roofline_fp32" % (flops / nbytes)},
+        "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": ach_tf / ffma_tflops,
+                          "peak_source": "FFMA microkernel measured in this run (nominal 74.4)", "flops_per_env_step": flops,
+                          "flops_per_env_step_static_max": flops_static,
+                          "executed": {"solver_iters_per_substep": I, "ls_iters_per_solver_iter": L,
+                                       "active_contacts_per_substep": st[2] / nfr, "active_limits_per_substep": st[3] / nfr}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_rate(seconds_target=12.0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=12)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -224,6 +224,14 @@ typedef struct VnlOutputs {
 int vnl_step(const void* model, const void* task, int B, const VnlState* in, const float* action,
              const VnlState* out, const VnlOutputs* outputs, void* stream);
 
+/* vnl_step followed by brax's AutoResetWrapper.step (brax/envs/wrappers/training.py, installed around the env at
+ * ppo_imitation/train.py:204-214), in the same launch: where the step's done flag is set, the state leaves written to
+ * `out` (qpos .. qfrc_actuator) and `outputs->obs` are replaced by `first` / `first_obs` (the cached reset state);
+ * info (cur_frame, sub_clip_frame, traj), reward, done and metrics are NOT restored. */
+int vnl_step_autoreset(const void* model, const void* task, int B, const VnlState* in, const float* action,
+                       const VnlState* out, const VnlOutputs* outputs, const VnlState* first, const float* first_obs,
+                       void* stream);
+
 /* Reset tail for B envs: qpos/qvel/cur_frame(start_frame) are read from `in` (act, ctrl and
  * qacc_warmstart are zero as in mjx.make_data), `out` receives the mjx.forward state, obs,
  * traj and info["termination_error"] (metrics[6]).  Replaces envs/rodent.py:148-176. */
@@ -258,6 +266,14 @@ int vnl_step_smem_bytes(const void* model_host);
  * size_t opaque_len)`), operand order documented in INTEGRATION.md. */
 void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len);
 void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+
+/* Measurement helper (bench.py): FFMA-saturating microkernel, flops = blocks * 256 * iters * 32.  `out` needs
+ * blocks * 256 floats (never written in practice).  Gives the FP32 roofline denominator of the device. */
+int vnl_ffma_probe(int blocks, int iters, float* out, void* stream);
+
+/* vnl_step with one CTA's per-phase clock64 accumulators written to prof[32] (developer hook, tools/gpu_prof.py). */
+int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action,
+                      const VnlState* out, const VnlOutputs* outputs, void* stream, long long* prof, int block);
 
 const char* vnl_version(void);
 

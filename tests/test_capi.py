@@ -1,0 +1,90 @@
+"""The C-ABI library loads and exports every symbol include/vnl_b200.h declares; host-side entry
+points (blob validation, sizing) behave.  No compute calls: this file runs without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, pkg
+
+libm = pkg("_lib")
+
+
+def _declared_functions():
+    txt = open(os.path.join(ROOT, "include", "vnl_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(vnl_[a-z_0-9]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(libm.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return libm.load_library()
+
+
+def test_header_and_binding_agree():
+    assert set(_declared_functions()) == set(libm.EXPORTS)
+
+
+def test_exports(lib):
+    for name in _declared_functions():
+        assert getattr(lib, name) is not None, name
+    assert b"sm_100a" in lib.vnl_version()
+
+
+def test_library_embeds_sm100a_code():
+    import subprocess
+    out = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-lelf", libm.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out
+
+
+def test_blob_validation(lib, rodent):
+    m, t = rodent["model_blob"], rodent["task_blob"]
+    assert lib.vnl_check_model(m.ctypes.data, m.nbytes) == 0
+    assert lib.vnl_check_task(t.ctypes.data, t.nbytes) == 0
+    assert lib.vnl_check_model(t.ctypes.data, t.nbytes) != 0  # wrong magic
+    assert lib.vnl_check_model(m.ctypes.data, m.nbytes - 4) != 0  # truncated
+    bad = m.copy(); bad[1] += 1
+    assert lib.vnl_check_model(bad.ctypes.data, bad.nbytes) != 0  # wrong version
+    bad = m.copy(); bad[pkg("model_blob").C["VNL_TABLE_OFF"]] = 2 ** 31
+    assert lib.vnl_check_model(bad.ctypes.data, bad.nbytes) != 0  # field out of range
+    assert lib.vnl_check_model(None, 0) != 0
+
+
+def test_sizes(lib, rodent, oracle_mod):
+    m = rodent["model_blob"]
+    smem = lib.vnl_step_smem_bytes(m.ctypes.data)
+    assert 0 < smem <= 227 * 1024
+    assert lib.vnl_dump_size(m.ctypes.data) == oracle_mod.lib().vnl_oracle_dump_size(m.ctypes.data_as(ctypes.c_void_p))
+
+
+def test_unregistered_blob_is_an_argument_error(lib):
+    st = libm.VnlState(); out = libm.VnlOutputs()
+    dummy = np.zeros(8, dtype=np.float32)
+    rc = lib.vnl_step(dummy.ctypes.data, dummy.ctypes.data, 4, ctypes.byref(st), dummy.ctypes.data, ctypes.byref(st),
+                      ctypes.byref(out), None)
+    assert rc < 0  # never launches: the model pointer was not registered
+    assert lib.vnl_step(None, None, 0, None, None, None, None, None) < 0
+    assert lib.vnl_unregister_blob(dummy.ctypes.data) != 0
+
+
+def test_engine_refuses_to_run_without_gpu(rodent):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        libm.Engine(rodent["model_blob"], rodent["task_blob"])
+
+
+def test_product_package_never_imports_the_oracle():
+    pk = os.path.join(ROOT, "vnl-brax-imitation_b200")
+    for dp, _, fs in os.walk(pk):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                for needle in ("import oracle", "from oracle", "libvnl_oracle", "vnl_oracle_"):
+                    assert needle not in src, (f, needle)

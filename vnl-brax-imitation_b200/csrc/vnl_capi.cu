@@ -84,6 +84,21 @@ int prepare(const void* model, const void* task, bool need_task, vnl::Params& p)
 
 }  // namespace
 
+__global__ void vnl_ffma_probe_kernel(int iters, float* out) {
+  float a[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) a[k] = 1.0f + 1e-3f * (float)(threadIdx.x + k);
+  const float m = 0.9999f, c = 1e-4f;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = fmaf(a[k], m, c);
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += a[k];
+  if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keeps the chains alive; practically never true
+}
+
 extern "C" {
 
 const char* vnl_version(void) { return "vnl_b200 0.1 (sm_100a)"; }
@@ -130,6 +145,20 @@ int vnl_step(const void* model, const void* task, int B, const VnlState* in, con
   Header ht;
   lookup(task, ht);
   p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  return (int)vnl::launch(0, p, (cudaStream_t)stream);
+}
+
+int vnl_step_autoreset(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+                       const VnlOutputs* outputs, const VnlState* first, const float* first_obs, void* stream) {
+  if (B <= 0 || !in || !out || !outputs || !action || !first || !first->qpos) return -1;
+  vnl::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc = prepare(model, task, true, p);
+  if (rc) return rc;
+  Header ht;
+  lookup(task, ht);
+  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.first = *first; p.first_obs = first_obs;
   return (int)vnl::launch(0, p, (cudaStream_t)stream);
 }
 
@@ -214,6 +243,14 @@ void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaq
   o.obs = (float*)buffers[23]; o.traj = (float*)buffers[24]; o.reward = (float*)buffers[25]; o.done = (float*)buffers[26];
   o.metrics = (float*)buffers[27]; o.stats = (int32_t*)buffers[28];
   vnl_reset(buffers[0], buffers[1], B, &in, &out, &o, stream);
+}
+
+// Measurement helper for bench.py: an FFMA-saturating microkernel (8 independent chains per thread) that gives the
+// FP32 CUDA-core roofline denominator on the device the benchmark runs on.  flops = blocks * 256 * iters * 16 * 2.
+int vnl_ffma_probe(int blocks, int iters, float* out, void* stream) {
+  if (blocks <= 0 || iters <= 0 || !out) return -1;
+  vnl_ffma_probe_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(iters, out);
+  return (int)cudaGetLastError();
 }
 
 }  // extern "C"

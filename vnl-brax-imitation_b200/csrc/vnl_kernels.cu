@@ -1262,8 +1262,27 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
       p.outputs.done[e] = done;
       float* mt = p.outputs.metrics + 7 * (size_t)e;
       mt[0] = rcom; mt[1] = rvl; mt[2] = rtr; mt[3] = rquat; mt[4] = ract; mt[5] = rapp; mt[6] = rtr;
+      ints[8] = done > 0.0f;
     }
     if (p.outputs.stats && tid < 4) p.outputs.stats[4 * e + tid] = stats[tid];
+    // brax AutoResetWrapper.step fused in: where done, the pipeline-state leaves and obs are replaced by the cached
+    // first ones; info (frames, traj), reward, done and metrics are kept.
+    if (p.first.qpos) {
+      __syncthreads();
+      if (ints[8]) {
+        const VnlState& f = p.first;
+        for (int i = tid; i < d.nq; i += nt) o.qpos[(size_t)e * d.nq + i] = f.qpos[(size_t)e * d.nq + i];
+        for (int i = tid; i < d.nv; i += nt) o.qvel[(size_t)e * d.nv + i] = f.qvel[(size_t)e * d.nv + i];
+        for (int i = tid; i < d.na; i += nt) o.act[(size_t)e * d.na + i] = f.act[(size_t)e * d.na + i];
+        for (int i = tid; i < d.nv; i += nt) o.qacc_warmstart[(size_t)e * d.nv + i] = f.qacc_warmstart[(size_t)e * d.nv + i];
+        for (int i = tid; i < d.nbody * 3; i += nt) o.xpos[(size_t)e * d.nbody * 3 + i] = f.xpos[(size_t)e * d.nbody * 3 + i];
+        for (int i = tid; i < d.nbody * 4; i += nt) o.xquat[(size_t)e * d.nbody * 4 + i] = f.xquat[(size_t)e * d.nbody * 4 + i];
+        for (int i = tid; i < d.nv; i += nt) o.qfrc_actuator[(size_t)e * d.nv + i] = f.qfrc_actuator[(size_t)e * d.nv + i];
+        if (tid < 3) o.subtree_com[(size_t)e * 3 + tid] = f.subtree_com[(size_t)e * 3 + tid];
+        if (p.first_obs)
+          for (int i = tid; i < obs_size; i += nt) p.outputs.obs[(size_t)e * obs_size + i] = p.first_obs[(size_t)e * obs_size + i];
+      }
+    }
   }
 }
 

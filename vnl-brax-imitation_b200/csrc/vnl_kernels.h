@@ -32,6 +32,8 @@ struct Params {
   Dims dims;
   int B, nsteps;
   VnlState in, out;
+  VnlState first;         // optional cached first state (AutoReset), first.qpos == nullptr when unused
+  const float* first_obs;
   const float* ctrl;
   VnlOutputs outputs;
   int32_t* stats;
