@@ -49,7 +49,7 @@ extern "C" {
  * ---------------------------------------------------------------------------------------- */
 #define VNL_MAGIC_MODEL 0x4d4c4e56u /* "VNLM" */
 #define VNL_MAGIC_TASK 0x544c4e56u  /* "VNLT" */
-#define VNL_BLOB_VERSION 4
+#define VNL_BLOB_VERSION 5
 #define VNL_TABLE_OFF 64
 #define VNL_MAX_FIELDS 96
 #define VNL_DATA_OFF (VNL_TABLE_OFF + 2 * VNL_MAX_FIELDS)
@@ -67,6 +67,7 @@ enum VnlModelHdr {
   VNL_MH_NM,          /* tree-sparse entries of the joint-space inertia */
   VNL_MH_NLEVEL,      /* body-tree depth (levels below the world body) */
   VNL_MH_MAXDEPTH,    /* longest dof ancestor chain */
+  VNL_MH_NROOT,       /* kinematic trees (bodies whose parent is the world) */
   /* floats (bit patterns) */
   VNL_MH_TIMESTEP = 32, VNL_MH_GRAVITY_X, VNL_MH_GRAVITY_Y, VNL_MH_GRAVITY_Z,
   VNL_MH_TOLERANCE, VNL_MH_LS_TOLERANCE, VNL_MH_IMPRATIO, VNL_MH_MEANINERTIA
@@ -152,7 +153,39 @@ enum VnlModelField {
   VNL_F_DESC_ENTRY,        /* i [nM-nv] sparse-entry index e with M_COL[e] == dof, M_ROW[e] = the descendant */
   VNL_F_DOFLEVEL_START,    /* i [maxdepth+2] CSR of dofs grouped by ancestor count */
   VNL_F_DOFLEVEL_DOF,      /* i [nv] */
+  VNL_F_DOF_ACTADR,        /* i [nv+1] CSR over the actuators driving each dof */
+  VNL_F_DOF_ACTLIST,       /* i [nu] */
+  VNL_F_KTAB,              /* packed u8 / u16 index tables the kernel stages in shared memory, see VnlKtab */
   VNL_F_MODEL_COUNT
+};
+
+/* VNL_F_KTAB: words [0 .. VNL_KT_COUNT) hold the BYTE offset of each table from the start of the field, word
+ * VNL_KT_COUNT the rows-per-lane R of VNL_KT_LANE_ROWS; every table is 4-byte aligned.  Built by model_blob.py. */
+enum VnlKtab {
+  VNL_KT_LVL_START = 0, /* u8  [nlevel+1] offsets into LVL_BP */
+  VNL_KT_LVL_BP,        /* u16 [nbody-1]  body | parent << 8, bodies sorted by tree level */
+  VNL_KT_PARENT,        /* u8  [nbody] */
+  VNL_KT_CHILD_ADR,     /* u8  [nbody+1] CSR over children */
+  VNL_KT_CHILD_LIST,    /* u8  [nbody-1] children of each body, descending id */
+  VNL_KT_BODY_DOFADR,   /* u8  [nbody] */
+  VNL_KT_BODY_DOFNUM,   /* u8  [nbody] number of dofs | 0x80 when the body's first joint is a free joint */
+  VNL_KT_BODY_TREE,     /* u8  [nbody] index of the body's kinematic tree */
+  VNL_KT_BODY_LASTDOF,  /* u8  [nbody] last dof of the body or of its nearest jointed ancestor, 0xFF if none */
+  VNL_KT_SUB_END,       /* u8  [nbody] bodies b .. end-1 are b's subtree */
+  VNL_KT_ROOTS,         /* u8  [nroot] root body of each tree */
+  VNL_KT_MROW,          /* u8  [nM] */
+  VNL_KT_MCOL,          /* u8  [nM] */
+  VNL_KT_DROW,          /* u8  [nM-nv] row (descendant dof) of each DENT entry */
+  VNL_KT_DOF_BODY,      /* u8  [nv] */
+  VNL_KT_LANE_ROWS,     /* u8  [32*R] dofs whose matrix rows each lane owns (load balanced), 0xFF = none */
+  VNL_KT_MADR,          /* u16 [nv+1] */
+  VNL_KT_DADR,          /* u16 [nv+1] */
+  VNL_KT_DENT,          /* u16 [nM-nv] */
+  VNL_KT_TRI,           /* u16 [maxdepth (maxdepth+1) / 2]  a | c << 8 with 1 <= a <= c, index c (c-1) / 2 + a - 1 */
+  VNL_KT_ANC_START,     /* u16 [nM] madr[mcol[e]]: row start of the entry's column dof */
+  VNL_KT_KITEM,         /* u16 [sum of dof depths] c | dof << 8, grouped by dof depth, descending c inside a group */
+  VNL_KT_KLVL,          /* u16 [maxdepth+2] offsets into KITEM by dof depth */
+  VNL_KT_COUNT
 };
 
 /* scalar header slots of a TASK blob (imitation task: clip + index tables) */
@@ -259,8 +292,9 @@ int vnl_check_task(const void* task_host, size_t nbytes);
 int vnl_register_blob(const void* blob_dev, const void* blob_host, size_t nbytes);
 int vnl_unregister_blob(const void* blob_dev);
 
-/* Dynamic shared memory one env's CTA needs for this model, and CTAs resident per SM. */
+/* Dynamic shared memory of one CTA for this model, and the number of envs (one warp each) a CTA holds. */
 int vnl_step_smem_bytes(const void* model_host);
+int vnl_envs_per_cta(const void* model_host);
 
 /* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
  * size_t opaque_len)`), operand order documented in INTEGRATION.md. */
@@ -271,7 +305,7 @@ void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaq
  * blocks * 256 floats (never written in practice).  Gives the FP32 roofline denominator of the device. */
 int vnl_ffma_probe(int blocks, int iters, float* out, void* stream);
 
-/* vnl_step with one CTA's per-phase clock64 accumulators written to prof[32] (developer hook, tools/gpu_prof.py). */
+/* vnl_step with one env's per-phase clock64 accumulators written to prof[32] (developer hook, tools/gpu_prof.py). */
 int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action,
                       const VnlState* out, const VnlOutputs* outputs, void* stream, long long* prof, int block);
 

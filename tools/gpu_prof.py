@@ -11,8 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 envs = importlib.import_module("vnl-brax-imitation_b200.envs")
 rod = importlib.import_module("vnl-brax-imitation_b200.envs.rodent")
-PHASES = ["fk", "com/cinert/cdof", "crb+cvel", "rne", "smooth/act", "M", "factor+K", "solve(smooth)", "constraints",
-          "warm select", "solver init", "linesearch", "update+beta", "(fwd tail)", "euler factor", "euler rest"]
+PHASES = ["fk", "com/cinert/cdof", "vel/acc down + crb/rne up", "smooth/act", "M", "factor+K", "solve(smooth)", "constraints",
+          "warm select", "solver init", "linesearch", "update+beta", "(fwd tail)", "euler factor", "euler rest", "load + task outputs"]
 
 
 def main():
@@ -36,15 +36,13 @@ def main():
     torch.cuda.synchronize()
     prof = torch.zeros(32, dtype=torch.int64, device="cuda")
     A, Bs, O = eng._state(st_a), eng._state(st_b), eng._outputs(out)
-    eng.lib.vnl_step_profiled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
-                                          ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
     rc = eng.lib.vnl_step_profiled(eng.model_dev.data_ptr(), eng.task_dev.data_ptr(), BB, ctypes.byref(A), a.data_ptr(),
                                    ctypes.byref(Bs), ctypes.byref(O), eng._stream(), prof.data_ptr(), BB // 2)
     torch.cuda.synchronize()
     assert rc == 0
     pr = prof.cpu().numpy()
     tot = pr.sum()
-    print("phase profile (CTA %d of %d), total %.0f kcycles" % (BB // 2, BB, tot / 1e3))
+    print("phase profile (env %d of %d, %d envs per CTA), total %.0f kcycles" % (BB // 2, BB, eng.envs_per_cta, tot / 1e3))
     for i, n in enumerate(PHASES):
         print("  %-16s %9.1f kcyc %5.1f%%" % (n, pr[i] / 1e3, 100.0 * pr[i] / max(tot, 1)))
     print("  stats", out["stats"][BB // 2].tolist())

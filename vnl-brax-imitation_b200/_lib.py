@@ -29,7 +29,7 @@ class VnlOutputs(ctypes.Structure):
 
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
-           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset")
+           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta")
 
 
 def load_library() -> ctypes.CDLL:
@@ -41,6 +41,7 @@ def load_library() -> ctypes.CDLL:
     lib.vnl_dump_size.restype = ctypes.c_size_t
     lib.vnl_dump_size.argtypes = [ctypes.c_void_p]
     lib.vnl_step_smem_bytes.argtypes = [ctypes.c_void_p]
+    lib.vnl_envs_per_cta.argtypes = [ctypes.c_void_p]
     lib.vnl_check_model.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_check_task.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_register_blob.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -98,6 +99,7 @@ class Engine:
         self.dims = mb.read_dims(self.model_host)
         self.dump_size = int(self.lib.vnl_dump_size(self.model_host.ctypes.data))
         self.smem_bytes = int(self.lib.vnl_step_smem_bytes(self.model_host.ctypes.data))
+        self.envs_per_cta = int(self.lib.vnl_envs_per_cta(self.model_host.ctypes.data))
         if self.task_host is not None:
             self.obs_size = int(self.task_host[mb.C["VNL_TH_OBS_SIZE"]])
             self.traj_size = int(self.task_host[mb.C["VNL_TH_TRAJ_SIZE"]])

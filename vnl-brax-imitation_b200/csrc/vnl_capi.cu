@@ -16,7 +16,7 @@
 
 namespace {
 
-struct Header { uint32_t w[VNL_TABLE_OFF]; };
+struct Header { uint32_t w[VNL_DATA_OFF]; };  // scalar header + field table
 std::mutex g_mu;
 std::unordered_map<const void*, Header> g_headers;  // device blob pointer -> host copy of its scalar header
 
@@ -33,7 +33,8 @@ void fill_dims(const uint32_t* w, vnl::Dims& d) {
   d.nbody = vnl_hdr_i(w, VNL_MH_NBODY); d.njnt = vnl_hdr_i(w, VNL_MH_NJNT); d.ngeom = vnl_hdr_i(w, VNL_MH_NGEOM);
   d.npair = vnl_hdr_i(w, VNL_MH_NPAIR); d.ncon = vnl_hdr_i(w, VNL_MH_NCON); d.nlimit = vnl_hdr_i(w, VNL_MH_NLIMIT);
   d.nefc = vnl_hdr_i(w, VNL_MH_NEFC); d.nM = vnl_hdr_i(w, VNL_MH_NM); d.nlevel = vnl_hdr_i(w, VNL_MH_NLEVEL);
-  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.solver = vnl_hdr_i(w, VNL_MH_SOLVER); d.iterations = vnl_hdr_i(w, VNL_MH_ITERATIONS);
+  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.nroot = vnl_hdr_i(w, VNL_MH_NROOT); d.ktab_words = (int)w[VNL_TABLE_OFF + 2 * VNL_F_KTAB + 1];
+  d.solver = vnl_hdr_i(w, VNL_MH_SOLVER); d.iterations = vnl_hdr_i(w, VNL_MH_ITERATIONS);
   d.ls_iterations = vnl_hdr_i(w, VNL_MH_LS_ITERATIONS); d.eulerdamp = vnl_hdr_i(w, VNL_MH_EULERDAMP);
   d.timestep = vnl_hdr_f(w, VNL_MH_TIMESTEP); d.gx = vnl_hdr_f(w, VNL_MH_GRAVITY_X); d.gy = vnl_hdr_f(w, VNL_MH_GRAVITY_Y);
   d.gz = vnl_hdr_f(w, VNL_MH_GRAVITY_Z); d.tolerance = vnl_hdr_f(w, VNL_MH_TOLERANCE); d.ls_tolerance = vnl_hdr_f(w, VNL_MH_LS_TOLERANCE);
@@ -126,7 +127,13 @@ int vnl_unregister_blob(const void* blob_dev) {
 int vnl_step_smem_bytes(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);
-  return vnl::smem_bytes(d);
+  return vnl::launch_info(d, 1 << 20).smem_bytes;
+}
+
+int vnl_envs_per_cta(const void* model_host) {
+  vnl::Dims d;
+  fill_dims((const uint32_t*)model_host, d);
+  return vnl::launch_info(d, 1 << 20).warps_per_cta;
 }
 
 size_t vnl_dump_size(const void* model_host) {
@@ -173,7 +180,7 @@ int vnl_step_profiled(const void* model, const void* task, int B, const VnlState
   Header ht;
   lookup(task, ht);
   p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
-  p.prof = prof; p.prof_block = block;
+  p.prof = prof; p.prof_env = block;
   return (int)vnl::launch(0, p, (cudaStream_t)stream);
 }
 

@@ -1,28 +1,29 @@
 // vnl_kernels.cu -- fused MJX-style physics + imitation reward/obs/termination step for sm_100a.
 //
-// One CTA per environment.  The whole env step -- n_frames x (forward dynamics, constraint
-// solve, semi-implicit Euler) and the clip-indexed reward / observation / trajectory window /
-// termination -- runs in ONE launch with the per-env working set resident in shared memory;
-// HBM is touched only for the state in / state + observations out (about 8 KB per env step).
+// ONE WARP PER ENVIRONMENT.  The whole env step -- n_frames x (forward dynamics, constraint solve, semi-implicit
+// Euler) and the clip-indexed reward / observation / trajectory window / termination -- runs in one launch with the
+// env's working set (~28 KB for the rodent) resident in shared memory; HBM is touched only for the state in and the
+// state + observations out (~8.7 KB per env step).  A CTA holds as many envs (warps) as shared memory allows plus one
+// copy of the packed index tables (VNL_F_KTAB); warps never synchronise with each other after the table load, so
+// there is no __syncthreads in the physics: lanes cooperate through shuffles and __syncwarp only.
 //
 // Formulation (differs from the dense one XLA executes for the reference, same mathematics):
-//   * joint-space inertia kept tree-sparse (MuJoCo qM layout), factorised as L^T D L without
-//     fill-in; the unit-triangular factor is inverted once per factorisation (the inverse has
-//     the same ancestor sparsity), so every later M^-1 x is two parallel sparse mat-vecs
-//     instead of two serial triangular sweeps;
-//   * the constraint Jacobian is never materialised: limit rows are one-hot, contact rows are
-//     frame . (v_lin + w x r) of the contact's body, so J x and J^T f are sums over the
-//     ancestor chain of a handful of bodies; only ACTIVE rows (pos < 0) are kept -- inactive
-//     rows contribute exactly zero to every solver quantity in the reference formulation;
-//   * subtree sums (composite inertia, RNE backward pass) use the DFS-preorder body numbering:
-//     a subtree is a contiguous id range, so they are flat reductions, not level-by-level scans.
+//   * joint-space inertia kept tree-sparse (MuJoCo qM layout), factorised as L^T D L without fill-in; the
+//     unit-triangular factor is inverted once per factorisation (the inverse has the same ancestor sparsity), so every
+//     later M^-1 x is two parallel sparse mat-vecs instead of two serial triangular sweeps;
+//   * the constraint Jacobian is never materialised: limit rows are one-hot, contact rows are frame . (v_lin + w x r)
+//     of the contact's body, so J x and J^T f are sums over the ancestor chain of a handful of bodies; only ACTIVE
+//     rows (pos < 0) are kept -- inactive rows contribute exactly zero to every solver quantity in the reference;
+//   * kinematics composes per-body local joint transforms level by level; velocities / accelerations go down the
+//     tree in one pass, composite inertias and RNE forces come back up in one pass (16 floats per body).
 //
-// Reference semantics restated: mjx.forward / mjx.step as reached from envs/rodent.py:148,181
-// and RodentTracking.step / reset (envs/rodent.py:119-470) -- see oracle/vnl_oracle.cpp, the
-// CPU restatement these kernels are tested against.
+// Reference semantics restated: mjx.forward / mjx.step as reached from envs/rodent.py:148,181 and
+// RodentTracking.step / reset (envs/rodent.py:119-470) -- see oracle/vnl_oracle.cpp, the CPU restatement these
+// kernels are tested against.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/vnl_blob.h"
 #include "vnl_device.cuh"
@@ -30,252 +31,253 @@
 
 namespace vnl {
 
-#define PROF(c, i) do { if ((c).prof) { __syncthreads(); if (threadIdx.x == 0) { long long t_ = clock64(); (c).prof[i] += t_ - (c).t0; (c).t0 = t_; } } } while (0)
+#define LANE ((int)(threadIdx.x & 31))
+#define FULLMASK 0xffffffffu
 
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
 
-// Shared-memory layout (float offsets), identical on host and device.
 __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   int o = 0;
 #define A(name, n) L.name = o; o += align4(n)
   A(qpos, d.nq); A(qvel, d.nv); A(act, d.na); A(ctrl, d.nu); A(warm, d.nv);
-  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3);
-  A(rcom, d.nbody * 3);
-  A(cinert, d.nbody * 10); A(crb, d.nbody * 10); A(cdof, d.nv * 6); A(cdofdot, d.nv * 6); A(cvel, d.nbody * 6);
-  A(cacc, d.nbody * 6); A(cfrc, d.nbody * 6);
-  A(M, d.nM); A(Lf, d.nM); A(K, d.nM);
+  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6); A(cvel, d.nbody * 6); A(M, d.nM); A(rcom, d.nroot * 3);
+  const int ab = o;
+  A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16); A(cacc, (d.nbody > d.nv ? d.nbody : d.nv) * 6);
+  const int a_end = o;
+  o = ab;
+  A(K, d.nM); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc);
+  if (a_end > o) o = a_end;
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
   A(lim_dof, d.nlimit); A(lim_sign, d.nlimit); A(limrow_of_dof, d.nv);
   A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 9); A(cmu, d.ncon); A(cwrench, d.ncon * 6);
-  A(efcD, d.nefc); A(aref, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc);
-  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv);
-  A(tmpv, d.nv);
-  A(red, 2 * kMaxWarps * 12);
+  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv);
   A(ints, 16);
-  A(mcol8, (d.nM + 3) / 4); A(mrow8, (d.nM + 3) / 4); A(madr16, (d.nv + 2) / 2); A(dadr16, (d.nv + 2) / 2);
-  A(dent16, (d.nM - d.nv + 1) / 2); A(drow8, (d.nM - d.nv + 3) / 4); A(dls8, (d.maxdepth + 2 + 3) / 4); A(dld8, (d.nv + 3) / 4);
 #undef A
   L.total = o;
 }
 
-// CTA-uniform context.  It lives at the start of dynamic shared memory so that the big phases can be
-// real (non-inlined) functions: one copy of each in the instruction stream instead of one per call site.
-struct __align__(16) Ctx {
+// CTA-shared context (start of dynamic shared memory): dimensions, layout, field offsets and the staged index tables.
+struct __align__(16) Cta {
   Dims d;
   Lay L;
-  float* s;            // shared memory base of the float arrays
-  const uint32_t* mb;  // model blob (global)
+  const uint32_t* mb;
   uint32_t foff[VNL_F_MODEL_COUNT];
-  const uint8_t *mcol, *mrow, *drow, *dls, *dld;
-  const uint16_t *madr, *dadr, *dent;
+  const uint8_t *lvl_start, *parent, *child_adr, *child_list, *body_dofadr, *body_dofnum, *body_tree, *lastdof, *sub_end, *roots,
+      *mrow, *mcol, *drow, *dof_body, *lane_rows;
+  const uint16_t *lvl_bp, *madr, *dadr, *dent, *tri, *anc_start, *kitem, *klvl;
+  int R;
   long long* prof;
-  long long t0;
-  int nt, nw;
+  int prof_env;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
   __device__ __forceinline__ const float* ff(int f) const { return (const float*)(mb + foff[f]); }
 };
-constexpr int kCtxFloats = (int)((sizeof(Ctx) + 15) / 16 * 4);
-#define TID ((int)threadIdx.x)
-#define LANE ((int)(threadIdx.x & 31))
-#define WARP ((int)(threadIdx.x >> 5))
+constexpr int kCtaFloats = (int)((sizeof(Cta) + 15) / 16 * 4);
 
-// Sum N per-thread values over the CTA; every thread returns the same totals (fixed order ->
-// bit-reproducible).  One __syncthreads per call (scratch is double-buffered).
-template <int N>
-__device__ __forceinline__ void block_sum(Ctx& c, float (&v)[N]) {
-#pragma unroll
-  for (int n = 0; n < N; ++n) v[n] = warp_sum(v[n]);
-  float* buf = c.s + c.L.red;
-  if (LANE == 0) {
-#pragma unroll
-    for (int n = 0; n < N; ++n) buf[WARP * N + n] = v[n];
+struct Prof {
+  long long* p;
+  long long t0;
+  __device__ __forceinline__ void mark(int i) {
+    if (p) { __syncwarp(); if (LANE == 0) { long long t = clock64(); p[i] += t - t0; t0 = t; } }
   }
-  __syncthreads();
-  const int nw = c.nw;
-#pragma unroll
-  for (int n = 0; n < N; ++n) {
-    float t = 0.0f;
-#pragma unroll 1
-    for (int w = 0; w < nw; ++w) t += buf[w * N + n];
-    v[n] = t;
+};
+
+// ---------------------------------------------------------------------------------------------------------------------
+// sparse-inertia helpers (one warp)
+// ---------------------------------------------------------------------------------------------------------------------
+// out = M x   (tree-sparse M, rows hold [diag, ancestors...]); each lane owns the rows LANE_ROWS assigns to it
+__device__ __noinline__ void mul_m(const Cta& c, float* s, const float* x, float* out) {
+  const float* M = s + c.L.M;
+  for (int r = 0; r < c.R; ++r) {
+    const int i = c.lane_rows[r * 32 + LANE];
+    if (i != 0xFF) {
+      float a0 = 0.0f, a1 = 0.0f;
+      int a = c.madr[i];
+      const int ae = c.madr[i + 1];
+      for (; a + 1 < ae; a += 2) { a0 += M[a] * x[c.mcol[a]]; a1 += M[a + 1] * x[c.mcol[a + 1]]; }
+      if (a < ae) a0 += M[a] * x[c.mcol[a]];
+      int k = c.dadr[i];
+      const int ke = c.dadr[i + 1];
+      for (; k + 1 < ke; k += 2) { a0 += M[c.dent[k]] * x[c.drow[k]]; a1 += M[c.dent[k + 1]] * x[c.drow[k + 1]]; }
+      if (k < ke) a0 += M[c.dent[k]] * x[c.drow[k]];
+      out[i] = a0 + a1;
+    }
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
-// sparse-inertia helpers
-// ---------------------------------------------------------------------------------------------
-// out = M x   (tree-sparse M, rows hold [diag, ancestors...])
-__device__ __noinline__ void mul_m(Ctx& c, const float* x, float* out) {
-  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
-  const uint16_t* dadr = c.dadr; const uint16_t* dent = c.dent; const uint8_t* drow = c.drow;
-  const float* M = c.s + c.L.M;
-  for (int i = TID; i < c.d.nv; i += c.nt) {
-    float a0 = 0.0f, a1 = 0.0f;
-    int a = madr[i];
-    const int ae = madr[i + 1];
-    for (; a + 1 < ae; a += 2) { a0 += M[a] * x[mcol[a]]; a1 += M[a + 1] * x[mcol[a + 1]]; }
-    if (a < ae) a0 += M[a] * x[mcol[a]];
-    int k = dadr[i];
-    const int ke = dadr[i + 1];
-    for (; k + 1 < ke; k += 2) { a0 += M[dent[k]] * x[drow[k]]; a1 += M[dent[k + 1]] * x[drow[k + 1]]; }
-    if (k < ke) a0 += M[dent[k]] * x[drow[k]];
-    out[i] = a0 + a1;
-  }
-}
-
-// L^T D L factorisation of `src` (+ dt * damping on the diagonal when `damp`), then K = L^-1.
-// Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots of L.K.
-__device__ __noinline__ void factor(Ctx& c, const float* src, bool damp) {
-  const int nv = c.d.nv, nM = c.d.nM;
-  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol; const uint8_t* mrow = c.mrow;
-  float* Lf = c.s + c.L.Lf;
-  float* K = c.s + c.L.K;
+// L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
+// Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
+__device__ __noinline__ void factor(const Cta& c, float* s, bool damp) {
+  const int nv = c.d.nv, nM = c.d.nM, lane = LANE;
+  const float* M = s + c.L.M;
+  float* F = s + c.L.K;
   const float* damping = c.ff(VNL_F_DOF_DAMPING);
-  for (int e = TID; e < nM; e += c.nt) {
-    float v = src[e];
-    if (damp && mcol[e] == mrow[e]) v += c.d.timestep * damping[mrow[e]];
-    Lf[e] = v;
+  for (int e = lane; e < nM; e += 32) {
+    float v = M[e];
+    if (damp && c.mcol[e] == c.mrow[e]) v += c.d.timestep * damping[c.mrow[e]];
+    F[e] = v;
   }
-  __syncthreads();
-  // eliminate dofs from the leaves: for ancestors a >= 1 of k and entries cidx >= 0 of that ancestor's row
-  //   L[anc_a(k)][cidx] -= L[k][a] * L[k][a + cidx] / L[k][0]     (rows stay un-normalised until the end)
+  __syncwarp();
+  // eliminate dofs from the leaves: for 1 <= a <= cc <= dk:  F[anc_a(k)][cc - a] -= F[k][a] * F[k][cc] / F[k][0]
+  // (rows stay un-normalised until the end); the (a, cc) pairs of one k are spread over the lanes through TRI
   for (int k = nv - 1; k > 0; --k) {
-    const int base = madr[k], dk = madr[k + 1] - base - 1;  // dk = number of ancestors
+    const int base = c.madr[k], dk = c.madr[k + 1] - base - 1;
     if (dk > 0) {
-      const float inv = 1.0f / Lf[base];
-      for (int a = 1 + WARP; a <= dk; a += c.nw) {  // targets are distinct for distinct (a, cidx)
-        const int tb = madr[mcol[base + a]];
-        const float t = Lf[base + a] * inv;
-        for (int cidx = LANE; cidx <= dk - a; cidx += 32) Lf[tb + cidx] -= t * Lf[base + a + cidx];
+      const float inv = 1.0f / F[base];
+      const int np = (dk * (dk + 1)) >> 1;
+      for (int pi = lane; pi < np; pi += 32) {
+        const uint32_t t = c.tri[pi];
+        const int a = t & 255, cc = t >> 8;
+        const int tgt = c.anc_start[base + a] + cc - a;
+        F[tgt] -= (F[base + a] * inv) * F[base + cc];
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
-  // normalise rows: Lhat = L / diag; keep 1 / D in the diagonal slot of K
-  for (int e = TID; e < nM; e += c.nt) {
-    const int b0 = madr[mrow[e]];
-    if (e == b0) K[e] = 1.0f / Lf[e];
-    else Lf[e] = Lf[e] / Lf[b0];
+  // normalise rows: Lhat = L / diag, then 1 / D in the diagonal slots
+  for (int e = lane; e < nM; e += 32) {
+    const int b0 = c.madr[c.mrow[e]];
+    if (e != b0) F[e] = F[e] / F[b0];
   }
-  __syncthreads();
-  // K = Lhat^-1 by levels of dof depth (Lhat K = I): for a dof i with ancestors anc_1..anc_d,
-  //   K[i][c] = -( Lhat[i][c] + sum_{a=1}^{c-1} Lhat[i][a] * K[anc_a(i)][c - a] ),  K[.][0] = 1 implicit
-  const uint8_t* dls = c.dls; const uint8_t* dld = c.dld;
+  __syncwarp();
+  for (int i = lane; i < nv; i += 32) F[c.madr[i]] = 1.0f / F[c.madr[i]];
+  __syncwarp();
+  // K = Lhat^-1 in place by levels of dof depth:  K[i][cc] = -( Lhat[i][cc] + sum_{a<cc} Lhat[i][a] K[anc_a(i)][cc - a] ).
+  // Items of a level are sorted by descending cc, so a later pass never reads a slot an earlier pass overwrote.
   for (int dl = 1; dl <= c.d.maxdepth; ++dl) {
-    const int s0 = dls[dl], n = (dls[dl + 1] - s0) * dl;
-    for (int it = TID; it < n; it += c.nt) {
-      const int i = dld[s0 + it / dl], cc = 1 + it % dl, base = madr[i];
-      float a0 = Lf[base + cc], a1 = 0.0f;
-      int a = 1;
-      for (; a + 1 < cc; a += 2) {
-        a0 += Lf[base + a] * K[madr[mcol[base + a]] + cc - a];
-        a1 += Lf[base + a + 1] * K[madr[mcol[base + a + 1]] + cc - a - 1];
+    const int i0 = c.klvl[dl], i1 = c.klvl[dl + 1];
+    for (int it0 = i0; it0 < i1; it0 += 32) {
+      const int it = it0 + lane;
+      float val = 0.0f;
+      int dst = -1;
+      if (it < i1) {
+        const uint32_t w = c.kitem[it];
+        const int cc = w & 255, base = c.madr[w >> 8];
+        float a0 = F[base + cc], a1 = 0.0f;
+        int a = 1;
+        for (; a + 1 < cc; a += 2) {
+          a0 += F[base + a] * F[c.anc_start[base + a] + cc - a];
+          a1 += F[base + a + 1] * F[c.anc_start[base + a + 1] + cc - a - 1];
+        }
+        if (a < cc) a0 += F[base + a] * F[c.anc_start[base + a] + cc - a];
+        val = -(a0 + a1);
+        dst = base + cc;
       }
-      if (a < cc) a0 += Lf[base + a] * K[madr[mcol[base + a]] + cc - a];
-      K[base + cc] = -(a0 + a1);
+      __syncwarp();
+      if (dst >= 0) F[dst] = val;
+      __syncwarp();
     }
-    __syncthreads();
   }
 }
 
-// x <- M^-1 x   via  K (D^-1 (K^T x));  `tmp` is nv scratch.
-__device__ __noinline__ void solve_m(Ctx& c, const float* x, float* out, float* tmp) {
-  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
-  const uint16_t* dadr = c.dadr; const uint16_t* dent = c.dent; const uint8_t* drow = c.drow;
-  const float* K = c.s + c.L.K;
-  for (int j = TID; j < c.d.nv; j += c.nt) {
-    float a0 = x[j], a1 = 0.0f;
-    int k = dadr[j];
-    const int ke = dadr[j + 1];
-    for (; k + 1 < ke; k += 2) { a0 += K[dent[k]] * x[drow[k]]; a1 += K[dent[k + 1]] * x[drow[k + 1]]; }
-    if (k < ke) a0 += K[dent[k]] * x[drow[k]];
-    tmp[j] = (a0 + a1) * K[madr[j]];
+// out <- M^-1 x   via  K (D^-1 (K^T x));  `tmp` is nv scratch.
+__device__ __noinline__ void solve_m(const Cta& c, float* s, const float* x, float* out, float* tmp) {
+  const float* K = s + c.L.K;
+  for (int r = 0; r < c.R; ++r) {
+    const int j = c.lane_rows[r * 32 + LANE];
+    if (j != 0xFF) {
+      float a0 = x[j], a1 = 0.0f;
+      int k = c.dadr[j];
+      const int ke = c.dadr[j + 1];
+      for (; k + 1 < ke; k += 2) { a0 += K[c.dent[k]] * x[c.drow[k]]; a1 += K[c.dent[k + 1]] * x[c.drow[k + 1]]; }
+      if (k < ke) a0 += K[c.dent[k]] * x[c.drow[k]];
+      tmp[j] = (a0 + a1) * K[c.madr[j]];
+    }
   }
-  __syncthreads();
-  for (int i = TID; i < c.d.nv; i += c.nt) {
-    float a0 = tmp[i], a1 = 0.0f;
-    int a = madr[i] + 1;
-    const int ae = madr[i + 1];
-    for (; a + 1 < ae; a += 2) { a0 += K[a] * tmp[mcol[a]]; a1 += K[a + 1] * tmp[mcol[a + 1]]; }
-    if (a < ae) a0 += K[a] * tmp[mcol[a]];
-    out[i] = a0 + a1;
+  __syncwarp();
+  for (int r = 0; r < c.R; ++r) {
+    const int i = c.lane_rows[r * 32 + LANE];
+    if (i != 0xFF) {
+      float a0 = tmp[i], a1 = 0.0f;
+      int a = c.madr[i] + 1;
+      const int ae = c.madr[i + 1];
+      for (; a + 1 < ae; a += 2) { a0 += K[a] * tmp[c.mcol[a]]; a1 += K[a + 1] * tmp[c.mcol[a + 1]]; }
+      if (a < ae) a0 += K[a] * tmp[c.mcol[a]];
+      out[i] = a0 + a1;
+    }
   }
-  __syncthreads();
+  __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
 // constraint Jacobian products on the compact active set
-// ---------------------------------------------------------------------------------------------
-// out[row] = (J x)[row]
-__device__ __noinline__ void jmul(Ctx& c, const float* x, float* out) {
-  const int* ints = (const int*)(c.s + c.L.ints);
-  const int nl = ints[0], nc = ints[1];
-  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol;
-  const int* lastdof = c.fi(VNL_F_BODY_LASTDOF);
-  const float* cdof = c.s + c.L.cdof;
-  const int* cbody = (const int*)(c.s + c.L.cbody);
-  const int* lim_dof = (const int*)(c.s + c.L.lim_dof);
-  const float* lim_sign = c.s + c.L.lim_sign;
-  for (int k = WARP; k < nc; k += c.nw) {
-    const int dl = lastdof[cbody[k]];
-    float sacc[6] = {0, 0, 0, 0, 0, 0};
-    if (dl >= 0) {
-      for (int a = madr[dl] + LANE; a < madr[dl + 1]; a += 32) {
-        const int j = mcol[a];
-        const float xj = x[j];
+// ---------------------------------------------------------------------------------------------------------------------
+// out[row] = (J x)[row].  Contacts: groups of G lanes walk the ancestor chain of the contact's body.
+__device__ __noinline__ void jmul(const Cta& c, float* s, const float* x, float* out) {
+  const int* ints = (const int*)(s + c.L.ints);
+  const int nl = ints[0], nc = ints[1], lane = LANE;
+  const float* cdof = s + c.L.cdof;
+  const int* cbody = (const int*)(s + c.L.cbody);
+  const int* lim_dof = (const int*)(s + c.L.lim_dof);
+  const float* lim_sign = s + c.L.lim_sign;
+  for (int r = lane; r < nl; r += 32) out[r] = lim_sign[r] * x[lim_dof[r]];
+  if (nc > 0) {
+    int G = 32;
+    while (G > 1 && (32 / G) < nc) G >>= 1;
+    const int per = 32 / G, sub = lane & (G - 1);
+    for (int k0 = 0; k0 < nc; k0 += per) {
+      const int k = k0 + lane / G;
+      float sacc[6] = {0, 0, 0, 0, 0, 0};
+      if (k < nc) {
+        const int dl = c.lastdof[cbody[k]];
+        if (dl != 0xFF) {
+          const int ae = c.madr[dl + 1];
+          for (int a = c.madr[dl] + sub; a < ae; a += G) {
+            const int j = c.mcol[a];
+            const float xj = x[j];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) sacc[q] += cdof[j * 6 + q] * xj;
+            for (int q = 0; q < 6; ++q) sacc[q] += cdof[j * 6 + q] * xj;
+          }
+        }
+      }
+      for (int o = G >> 1; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sacc[q] += __shfl_xor_sync(FULLMASK, sacc[q], o);
+      }
+      if (k < nc && sub == 0) {
+        const float* fr = s + c.L.cframe + 9 * k;
+        const V3 vel = v3(sacc[3], sacc[4], sacc[5]) + cross(v3(sacc[0], sacc[1], sacc[2]), ld3(s + c.L.crel + 3 * k));
+        const float un = dot(ld3(fr), vel), u1 = dot(ld3(fr + 3), vel), u2 = dot(ld3(fr + 6), vel);
+        const float mu = s[c.L.cmu + k];
+        float* o4 = out + nl + 4 * k;
+        o4[0] = un + u1 * mu; o4[1] = un + u1 * -mu; o4[2] = un + u2 * mu; o4[3] = un + u2 * -mu;
       }
     }
-#pragma unroll
-    for (int q = 0; q < 6; ++q) sacc[q] = warp_sum(sacc[q]);
-    if (LANE < 4) {
-      const float* fr = c.s + c.L.cframe + 9 * k;
-      V3 vel = v3(sacc[3], sacc[4], sacc[5]) + cross(v3(sacc[0], sacc[1], sacc[2]), ld3(c.s + c.L.crel + 3 * k));
-      const float un = dot(ld3(fr), vel);
-      const float ut = dot(ld3(fr + 3 * (1 + (LANE >> 1))), vel);
-      const float mu = c.s[c.L.cmu + k];
-      out[nl + 4 * k + LANE] = un + ut * ((LANE & 1) ? -mu : mu);
-    }
   }
-  for (int r = TID; r < nl; r += c.nt) out[r] = lim_sign[r] * x[lim_dof[r]];
+  __syncwarp();
 }
 
-// qfrc_con = J^T f with f[row] = -D Jaref [Jaref < 0]; returns nothing, needs a sync after.
-__device__ __noinline__ void jtmul_force(Ctx& c, float* qfrc) {
-  const int* ints = (const int*)(c.s + c.L.ints);
-  const int nl = ints[0], nc = ints[1];
-  const float* D = c.s + c.L.efcD;
-  const float* Jaref = c.s + c.L.Jaref;
-  for (int k = TID; k < nc; k += c.nt) {
+// qfrc = J^T f with f[row] = -D Jaref [Jaref < 0]
+__device__ __noinline__ void jtmul_force(const Cta& c, float* s, float* qfrc) {
+  const int* ints = (const int*)(s + c.L.ints);
+  const int nl = ints[0], nc = ints[1], lane = LANE;
+  const float* D = s + c.L.efcD;
+  const float* Jaref = s + c.L.Jaref;
+  for (int k = lane; k < nc; k += 32) {
     float f[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float ja = Jaref[nl + 4 * k + q];
       f[q] = (ja < 0.0f) ? -D[nl + 4 * k + q] * ja : 0.0f;
     }
-    const float mu = c.s[c.L.cmu + k];
+    const float mu = s[c.L.cmu + k];
     const float fn = f[0] + f[1] + f[2] + f[3], f1 = mu * (f[0] - f[1]), f2 = mu * (f[2] - f[3]);
-    const float* fr = c.s + c.L.cframe + 9 * k;
-    V3 F = ld3(fr) * fn + ld3(fr + 3) * f1 + ld3(fr + 6) * f2;
-    V3 tq = cross(ld3(c.s + c.L.crel + 3 * k), F);
-    st3(c.s + c.L.cwrench + 6 * k, tq);
-    st3(c.s + c.L.cwrench + 6 * k + 3, F);
+    const float* fr = s + c.L.cframe + 9 * k;
+    const V3 F = ld3(fr) * fn + ld3(fr + 3) * f1 + ld3(fr + 6) * f2;
+    st3(s + c.L.cwrench + 6 * k, cross(ld3(s + c.L.crel + 3 * k), F));
+    st3(s + c.L.cwrench + 6 * k + 3, F);
   }
-  __syncthreads();
-  const int* dof_body = c.fi(VNL_F_DOF_BODYID);
-  const int* sub_end = c.fi(VNL_F_BODY_SUBTREE_END);
-  const int* cbody = (const int*)(c.s + c.L.cbody);
-  const int* limrow = (const int*)(c.s + c.L.limrow_of_dof);
-  const float* lim_sign = c.s + c.L.lim_sign;
-  for (int i = TID; i < c.d.nv; i += c.nt) {
-    const int b = dof_body[i], be = sub_end[b];
-    const float* cd = c.s + c.L.cdof + 6 * i;
+  __syncwarp();
+  const int* cbody = (const int*)(s + c.L.cbody);
+  const int* limrow = (const int*)(s + c.L.limrow_of_dof);
+  const float* lim_sign = s + c.L.lim_sign;
+  for (int i = lane; i < c.d.nv; i += 32) {
+    const int b = c.dof_body[i], be = c.sub_end[b];
+    const float* cd = s + c.L.cdof + 6 * i;
     float acc = 0.0f;
     for (int k = 0; k < nc; ++k) {
       const int cb = cbody[k];
-      if (cb >= b && cb < be) acc += dot6(cd, c.s + c.L.cwrench + 6 * k);
+      if (cb >= b && cb < be) acc += dot6(cd, s + c.L.cwrench + 6 * k);
     }
     const int r = limrow[i];
     if (r >= 0) {
@@ -284,9 +286,11 @@ __device__ __noinline__ void jtmul_force(Ctx& c, float* qfrc) {
     }
     qfrc[i] = acc;
   }
+  __syncwarp();
 }
 
-// constraint._kbi
+// constraint._kbi  (the impedance power is 1 or 2 on every reference model: no powf on those paths)
+__device__ __noinline__ float imp_pow(float x, float p) { return powf(x, p); }
 __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const float* solimp, float pos, float& k, float& b, float& imp) {
   const float timeconst = fmaxf(sr0, 2.0f * d.timestep), dampratio = sr1;
   const float dmin = fminf(fmaxf(solimp[0], VNL_MINIMP), VNL_MAXIMP), dmax = fminf(fmaxf(solimp[1], VNL_MINIMP), VNL_MAXIMP);
@@ -295,32 +299,61 @@ __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const f
   b = 2.0f / (dmax * timeconst);
   if (sr0 <= 0.0f) k = -sr0 / (dmax * dmax);
   if (sr1 <= 0.0f) b = -sr1 / dmax;
-  const float imp_x = fabsf(pos) / width;
-  const float imp_a = (1.0f / powf(mid, power - 1.0f)) * powf(imp_x, power);
-  const float imp_b = 1.0f - (1.0f / powf(1.0f - mid, power - 1.0f)) * powf(1.0f - imp_x, power);
-  const float imp_y = imp_x < mid ? imp_a : imp_b;
+  const float x = fabsf(pos) / width;
+  float imp_a, imp_b;
+  if (power == 1.0f) { imp_a = x; imp_b = 1.0f - (1.0f - x); }
+  else if (power == 2.0f) { imp_a = (1.0f / mid) * (x * x); imp_b = 1.0f - (1.0f / (1.0f - mid)) * ((1.0f - x) * (1.0f - x)); }
+  else { imp_a = (1.0f / imp_pow(mid, power - 1.0f)) * imp_pow(x, power); imp_b = 1.0f - (1.0f / imp_pow(1.0f - mid, power - 1.0f)) * imp_pow(1.0f - x, power); }
+  const float imp_y = x < mid ? imp_a : imp_b;
   imp = dmin + imp_y * (dmax - dmin);
   imp = fminf(fmaxf(imp, dmin), dmax);
-  if (imp_x > 1.0f) imp = dmax;
+  if (x > 1.0f) imp = dmax;
 }
 
-// ---------------------------------------------------------------------------------------------
-// mjx.forward for the env held in shared memory
-// ---------------------------------------------------------------------------------------------
+// solver state carried between _update_constraint calls
+struct Sol { float cost, prev_cost, gauss, gradnorm; };
+
+// solver._update_constraint + _update_gradient (CG: Mgrad = M^-1 grad)
+__device__ __noinline__ void update_constraint(const Cta& c, float* s, Sol& st) {
+  const Lay& L = c.L;
+  const int* ints = (const int*)(s + L.ints);
+  const int nrow = ints[0] + 4 * ints[1], lane = LANE, nv = c.d.nv;
+  float* qfrc_con = s + L.qfrc_con;
+  jtmul_force(c, s, qfrc_con);
+  float v0 = 0.0f, v1 = 0.0f, g = 0.0f;
+  for (int r = lane; r < nrow; r += 32) { const float ja = s[L.Jaref + r]; if (ja < 0.0f) v0 += s[L.efcD + r] * ja * ja; }
+  for (int i = lane; i < nv; i += 32) {
+    const float ma = s[L.Ma + i], qs = s[L.qfrc_smooth + i];
+    v1 += (ma - qs) * (s[L.qacc + i] - s[L.qacc_smooth + i]);
+    const float gi = ma - qs - qfrc_con[i];
+    s[L.grad + i] = gi;
+    g += gi * gi;
+  }
+  v0 = warp_sum(v0); v1 = warp_sum(v1); g = warp_sum(g);
+  st.gauss = 0.5f * v1;
+  st.prev_cost = st.cost;
+  st.cost = 0.5f * v0 + st.gauss;
+  st.gradnorm = sqrtf(g);
+  __syncwarp();
+  solve_m(c, s, s + L.grad, s + L.Mgrad, s + L.tmpv);
+}
+
 struct LSP { float alpha, cost, d0, d1; };
 
-__device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
+// ---------------------------------------------------------------------------------------------------------------------
+// mjx.forward for the env held in this warp's shared-memory slice
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool DUMP>
+__device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* dump, Prof& pf) {
   const Dims& d = c.d;
   const Lay& L = c.L;
-  float* s = c.s;
-  const int tid = TID, nt = c.nt;
+  const int lane = LANE;
   int* ints = (int*)(s + L.ints);
 
-  // ---- smooth.kinematics: level-synchronous walk down the body tree --------------------------
+  // ---- smooth.kinematics ------------------------------------------------------------------------------------------
+  // (1) per body, in parallel: the body's pose in its PARENT frame after its own joints (lq, lp) and each joint's
+  //     anchor / axis in the parent frame; (2) compose down the tree level by level; (3) joint frames to world.
   {
-    const int* lstart = c.fi(VNL_F_LEVEL_START);
-    const int* lbody = c.fi(VNL_F_LEVEL_BODY);
-    const int* parent = c.fi(VNL_F_BODY_PARENTID);
     const int* jntadr = c.fi(VNL_F_BODY_JNTADR);
     const int* jntnum = c.fi(VNL_F_BODY_JNTNUM);
     const int* jtype = c.fi(VNL_F_JNT_TYPE);
@@ -330,77 +363,99 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
     const float* jpos = c.ff(VNL_F_JNT_POS);
     const float* jaxis = c.ff(VNL_F_JNT_AXIS);
     const float* qpos0 = c.ff(VNL_F_QPOS0);
-    if (tid == 0) {
-      s[L.xpos] = s[L.xpos + 1] = s[L.xpos + 2] = 0.0f;
-      s[L.xquat] = 1.0f; s[L.xquat + 1] = s[L.xquat + 2] = s[L.xquat + 3] = 0.0f;
-    }
-    __syncthreads();
-    for (int lv = 0; lv < d.nlevel; ++lv) {
-      for (int k = lstart[lv] + tid; k < lstart[lv + 1]; k += nt) {
-        const int b = lbody[k], p = parent[b];
-        Q4 pq = ld4(s + L.xquat + 4 * p);
-        V3 pos = ld3(s + L.xpos + 3 * p) + rotate(ld3(bpos + 3 * b), pq);
-        Q4 quat = quat_mul(pq, ld4(bquat + 4 * b));
-        for (int jj = 0; jj < jntnum[b]; ++jj) {
-          const int j = jntadr[b] + jj, qa = jqadr[j];
-          if (jtype[j] == 0) {
-            pos = ld3(s + L.qpos + qa);
-            st3(s + L.xanchor + 3 * j, pos);
+    for (int b = lane; b < d.nbody; b += 32) {
+      Q4 lq; lq.w = 1.0f; lq.x = lq.y = lq.z = 0.0f;
+      V3 lp = v3(0.0f, 0.0f, 0.0f);
+      if (b > 0) {
+        lq = ld4(bquat + 4 * b);
+        lp = ld3(bpos + 3 * b);
+        const int ja = jntadr[b], jn = jntnum[b];
+        for (int jj = 0; jj < jn; ++jj) {
+          const int j = ja + jj, qa = jqadr[j];
+          if (jtype[j] == 0) {  // free joint (its body hangs off the world): pose straight from qpos, quat normalised + written back
+            lp = ld3(s + L.qpos + qa);
+            lq = quat_normalize(ld4(s + L.qpos + qa + 3));
+            st4(s + L.qpos + qa + 3, lq);
+            st3(s + L.xanchor + 3 * j, lp);
             st3(s + L.xaxis + 3 * j, v3(0.0f, 0.0f, 1.0f));
-            quat = quat_normalize(ld4(s + L.qpos + qa + 3));
-            st4(s + L.qpos + qa + 3, quat);
           } else {
-            V3 jp = ld3(jpos + 3 * j), ja = ld3(jaxis + 3 * j);
-            V3 anchor = rotate(jp, quat) + pos;
+            const V3 jp = ld3(jpos + 3 * j), jax = ld3(jaxis + 3 * j);
+            const V3 anchor = rotate(jp, lq) + lp;
             st3(s + L.xanchor + 3 * j, anchor);
-            st3(s + L.xaxis + 3 * j, rotate(ja, quat));
-            quat = quat_mul(quat, axis_angle_quat(ja, s[L.qpos + qa] - qpos0[qa]));
-            pos = anchor - rotate(jp, quat);
+            st3(s + L.xaxis + 3 * j, rotate(jax, lq));
+            lq = quat_mul(lq, axis_angle_quat(jax, s[L.qpos + qa] - qpos0[qa]));
+            lp = anchor - rotate(jp, lq);
           }
         }
-        st3(s + L.xpos + 3 * b, pos);
-        st4(s + L.xquat + 4 * b, quat);
       }
-      __syncthreads();
+      st4(s + L.xquat + 4 * b, lq);
+      st3(s + L.xpos + 3 * b, lp);
     }
+    __syncwarp();
+    int k0 = c.lvl_start[1];  // level 0 (children of the world) is already in world coordinates
+    for (int lv = 1; lv < d.nlevel; ++lv) {
+      const int k1 = c.lvl_start[lv + 1];
+      if (k0 + lane < k1) {
+        const uint32_t bp = c.lvl_bp[k0 + lane];
+        const int b = bp & 255, p = bp >> 8;
+        const Q4 pq = ld4(s + L.xquat + 4 * p);
+        const V3 pp = ld3(s + L.xpos + 3 * p);
+        const Q4 lq = ld4(s + L.xquat + 4 * b);
+        const V3 lp = ld3(s + L.xpos + 3 * b);
+        st4(s + L.xquat + 4 * b, quat_mul(pq, lq));
+        st3(s + L.xpos + 3 * b, pp + rotate(lp, pq));
+      }
+      k0 = k1;
+      __syncwarp();
+    }
+    const int* jbody = c.fi(VNL_F_JNT_BODYID);
+    for (int j = lane; j < d.njnt; j += 32) {
+      const int p = c.parent[jbody[j]];
+      if (p > 0) {
+        const Q4 pq = ld4(s + L.xquat + 4 * p);
+        st3(s + L.xanchor + 3 * j, ld3(s + L.xpos + 3 * p) + rotate(ld3(s + L.xanchor + 3 * j), pq));
+        st3(s + L.xaxis + 3 * j, rotate(ld3(s + L.xaxis + 3 * j), pq));
+      }
+    }
+    __syncwarp();
   }
-  PROF(c, 0);
-  // ---- smooth.com_pos: xipos, root COM, cinert, cdof ------------------------------------------
+  pf.mark(0);
+  // ---- smooth.com_pos: xipos, tree COM, cinert (t16[0..9]), cdof ------------------------------------------------------
+  const int* dof_jnt = c.fi(VNL_F_DOF_JNTID);
+  const int* jtype = c.fi(VNL_F_JNT_TYPE);
+  const int* jdofadr = c.fi(VNL_F_JNT_DOFADR);
   {
     const float* ipos = c.ff(VNL_F_BODY_IPOS);
-    for (int b = tid; b < d.nbody; b += nt)
-      st3(s + L.xipos + 3 * b, ld3(s + L.xpos + 3 * b) + rotate(ld3(ipos + 3 * b), ld4(s + L.xquat + 4 * b)));
-    __syncthreads();
-    const int* rootid = c.fi(VNL_F_BODY_ROOTID);
-    const int* sub_end = c.fi(VNL_F_BODY_SUBTREE_END);
     const float* mass = c.ff(VNL_F_BODY_MASS);
-    // one warp per kinematic tree: subtree COM of the root = mass-weighted mean over its id range
-    for (int b = 1 + WARP; b < d.nbody; b += c.nw) {
-      if (rootid[b] != b) continue;
-      float acc[4] = {0, 0, 0, 0};
-      for (int q = b + LANE; q < sub_end[b]; q += 32) {
+    for (int b = lane; b < d.nbody; b += 32)
+      st3(s + L.xipos + 3 * b, ld3(s + L.xpos + 3 * b) + rotate(ld3(ipos + 3 * b), ld4(s + L.xquat + 4 * b)));
+    __syncwarp();
+    for (int t = 0; t < d.nroot; ++t) {  // subtree COM of each tree root = mass-weighted mean over its id range
+      const int rb = c.roots[t], re = c.sub_end[rb];
+      float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+      for (int q = rb + lane; q < re; q += 32) {
         const float mq = mass[q];
-        acc[0] += s[L.xipos + 3 * q] * mq; acc[1] += s[L.xipos + 3 * q + 1] * mq; acc[2] += s[L.xipos + 3 * q + 2] * mq; acc[3] += mq;
+        a0 += s[L.xipos + 3 * q] * mq; a1 += s[L.xipos + 3 * q + 1] * mq; a2 += s[L.xipos + 3 * q + 2] * mq; a3 += mq;
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) acc[q] = warp_sum(acc[q]);
-      if (LANE < 3) {
-        const float a = LANE == 0 ? acc[0] : (LANE == 1 ? acc[1] : acc[2]);
-        s[L.rcom + 3 * b + LANE] = (acc[3] < VNL_MINVAL) ? s[L.xipos + 3 * b + LANE] : a / fmaxf(acc[3], VNL_MINVAL);
+      a0 = warp_sum(a0); a1 = warp_sum(a1); a2 = warp_sum(a2); a3 = warp_sum(a3);
+      if (lane < 3) {
+        const float a = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+        s[L.rcom + 3 * t + lane] = (a3 < VNL_MINVAL) ? s[L.xipos + 3 * rb + lane] : a / fmaxf(a3, VNL_MINVAL);
       }
     }
-    __syncthreads();
+    __syncwarp();
     const float* iquat = c.ff(VNL_F_BODY_IQUAT);
     const float* inertia = c.ff(VNL_F_BODY_INERTIA);
-    for (int b = tid; b < d.nbody; b += nt) {
-      float* ci = s + L.cinert + 10 * b;
+    for (int b = lane; b < d.nbody; b += 32) {
+      float* ci = s + L.t16 + 16 * b;
       if (b == 0) {
-        for (int q = 0; q < 10; ++q) ci[q] = 0.0f;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ci[q] = 0.0f;
         continue;
       }
       float R[9];
       quat_to_mat(quat_mul(ld4(s + L.xquat + 4 * b), ld4(iquat + 4 * b)), R);
-      V3 off = ld3(s + L.xipos + 3 * b) - ld3(s + L.rcom + 3 * rootid[b]);
+      const V3 off = ld3(s + L.xipos + 3 * b) - ld3(s + L.rcom + 3 * c.body_tree[b]);
       const float I0 = inertia[3 * b], I1 = inertia[3 * b + 1], I2 = inertia[3 * b + 2], ms = mass[b];
       const float oo = dot(off, off);
       const float o[3] = {off.x, off.y, off.z};
@@ -415,135 +470,137 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
       }
       ci[6] = off.x * ms; ci[7] = off.y * ms; ci[8] = off.z * ms; ci[9] = ms;
     }
-    const int* jtype = c.fi(VNL_F_JNT_TYPE);
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
-    const int* jdof = c.fi(VNL_F_JNT_DOFADR);
-    for (int j = tid; j < d.njnt; j += nt) {
-      const int b = jbody[j], da = jdof[j];
-      V3 off = ld3(s + L.rcom + 3 * rootid[b]) - ld3(s + L.xanchor + 3 * j);
+    for (int j = lane; j < d.njnt; j += 32) {
+      const int b = jbody[j], da = jdofadr[j];
+      const V3 off = ld3(s + L.rcom + 3 * c.body_tree[b]) - ld3(s + L.xanchor + 3 * j);
       if (jtype[j] == 0) {
         float R[9];
         quat_to_mat(ld4(s + L.xquat + 4 * b), R);
+#pragma unroll
         for (int a = 0; a < 3; ++a) {
           float* ct = s + L.cdof + 6 * (da + a);
+#pragma unroll
           for (int q = 0; q < 6; ++q) ct[q] = 0.0f;
           ct[3 + a] = 1.0f;
-          V3 ax = v3(R[a], R[3 + a], R[6 + a]);
+          const V3 ax = v3(R[a], R[3 + a], R[6 + a]);
           st3(s + L.cdof + 6 * (da + 3 + a), ax);
           st3(s + L.cdof + 6 * (da + 3 + a) + 3, cross(ax, off));
         }
       } else {
-        V3 ax = ld3(s + L.xaxis + 3 * j);
+        const V3 ax = ld3(s + L.xaxis + 3 * j);
         st3(s + L.cdof + 6 * da, ax);
         st3(s + L.cdof + 6 * da + 3, cross(ax, off));
       }
     }
-    __syncthreads();
+    __syncwarp();
+    if (DUMP) {
+      for (int i = lane; i < d.nbody * 3; i += 32) dump[d.dump_xipos + i] = s[L.xipos + i];
+      for (int i = lane; i < d.njnt * 3; i += 32) { dump[d.dump_xanchor + i] = s[L.xanchor + i]; dump[d.dump_xanchor + d.njnt * 3 + i] = s[L.xaxis + i]; }
+      for (int i = lane; i < d.nbody * 10; i += 32) dump[d.dump_cinert + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int t = lane; t < d.nroot; t += 32) st3(dump + d.dump_subtree_com + 3 * c.roots[t], ld3(s + L.rcom + 3 * t));
+    }
   }
-  PROF(c, 1);
-  // ---- composite inertia (flat subtree sums), cvel chains ----------------------------------------
-  const uint16_t* madr = c.madr; const uint8_t* mcol = c.mcol; const uint8_t* mrow = c.mrow;
-  const int* lastdof = c.fi(VNL_F_BODY_LASTDOF);
-  const int* sub_end = c.fi(VNL_F_BODY_SUBTREE_END);
-  const int* dof_body = c.fi(VNL_F_DOF_BODYID);
-  const int* dof_jnt = c.fi(VNL_F_DOF_JNTID);
-  const int* jtype = c.fi(VNL_F_JNT_TYPE);
-  const int* jdofadr = c.fi(VNL_F_JNT_DOFADR);
+  pf.mark(1);
+  // ---- smooth.com_vel + the forward half of smooth.rne: cvel, cacc down the tree (cdof_dot stays in registers) ---------
   {
-    for (int it = tid; it < d.nbody * 10; it += nt) {
-      const int b = it / 10, q = it - 10 * b;
-      float acc = 0.0f;
-      if (b > 0)
-        for (int k = b; k < sub_end[b]; ++k) acc += s[L.cinert + 10 * k + q];
-      s[L.crb + it] = acc;
+    if (lane < 6) {
+      s[L.cvel + lane] = 0.0f;
+      s[L.cacc + lane] = (lane == 3) ? -d.gx : ((lane == 4) ? -d.gy : ((lane == 5) ? -d.gz : 0.0f));
     }
-    // velocity of the chain BEFORE each dof (smooth.com_vel): ancestors only; the three rotational
-    // dofs of a free joint all see the velocity after its translational dofs.
-    for (int it = tid; it < d.nv * 6; it += nt) {
-      const int i = it / 6, q = it - 6 * i;
-      const int j = dof_jnt[i];
-      const bool freej = jtype[j] == 0;
-      const int fa = jdofadr[j];
-      float acc = 0.0f;
-      for (int a = madr[i + 1] - 1; a > madr[i]; --a) {  // root-most ancestor first
-        const int k = mcol[a];
-        if (freej && k >= fa + 3) continue;
-        acc += s[L.cdof + 6 * k + q] * s[L.qvel + k];
+    __syncwarp();
+    int k0 = 0;
+    for (int lv = 0; lv < d.nlevel; ++lv) {
+      const int k1 = c.lvl_start[lv + 1];
+      if (k0 + lane < k1) {
+        const uint32_t bp = c.lvl_bp[k0 + lane];
+        const int b = bp & 255, p = bp >> 8;
+        float cv[6], ca[6], cd[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { cv[q] = s[L.cvel + 6 * p + q]; ca[q] = s[L.cacc + 6 * p + q]; }
+        const int dn = c.body_dofnum[b];
+        int i = c.body_dofadr[b];
+        const int ie = i + (dn & 0x7f);
+        if (dn & 0x80) {  // free joint: translations first (cdof_dot = 0), the three rotations all see that velocity
+#pragma unroll
+          for (int a = 0; a < 3; ++a) {
+            const float qv = s[L.qvel + i + a];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cv[q] += s[L.cdof + 6 * (i + a) + q] * qv;
+          }
+          float cv0[6];
+#pragma unroll
+          for (int q = 0; q < 6; ++q) cv0[q] = cv[q];
+#pragma unroll
+          for (int a = 3; a < 6; ++a) {
+            const float qv = s[L.qvel + i + a];
+            motion_cross(cv0, s + L.cdof + 6 * (i + a), cd);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { ca[q] += cd[q] * qv; cv[q] += s[L.cdof + 6 * (i + a) + q] * qv; }
+          }
+          i += 6;
+        }
+        for (; i < ie; ++i) {
+          const float qv = s[L.qvel + i];
+          motion_cross(cv, s + L.cdof + 6 * i, cd);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) { ca[q] += cd[q] * qv; cv[q] += s[L.cdof + 6 * i + q] * qv; }
+        }
+#pragma unroll
+        for (int q = 0; q < 6; ++q) { s[L.cvel + 6 * b + q] = cv[q]; s[L.cacc + 6 * b + q] = ca[q]; }
       }
-      s[L.cdofdot + it] = acc;
+      k0 = k1;
+      __syncwarp();
     }
-    for (int it = tid; it < d.nbody * 6; it += nt) {
-      const int b = it / 6, q = it - 6 * b;
-      const int dl = lastdof[b];
-      float acc = 0.0f;
-      if (dl >= 0)
-        for (int a = madr[dl + 1] - 1; a >= madr[dl]; --a) { const int k = mcol[a]; acc += s[L.cdof + 6 * k + q] * s[L.qvel + k]; }
-      s[L.cvel + it] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < d.nv; i += nt) {  // cdof_dot = motion_cross(cvel_before, cdof); 0 for free translations
-      float* cd = s + L.cdofdot + 6 * i;
-      const int j = dof_jnt[i];
-      if (jtype[j] == 0 && i < jdofadr[j] + 3) {
-        for (int q = 0; q < 6; ++q) cd[q] = 0.0f;
-      } else {
-        float v[6], r[6];
-        for (int q = 0; q < 6; ++q) v[q] = cd[q];
-        motion_cross(v, s + L.cdof + 6 * i, r);
-        for (int q = 0; q < 6; ++q) cd[q] = r[q];
-      }
-    }
-    __syncthreads();
-  }
-  PROF(c, 2);
-  // ---- smooth.rne: cacc chains, local cfrc, subtree sums, qfrc_bias (kept in tmpv) -------------------
-  {
-    for (int it = tid; it < d.nbody * 6; it += nt) {
-      const int b = it / 6, q = it - 6 * b;
-      const int dl = lastdof[b];
-      float acc = (q == 3) ? -d.gx : ((q == 4) ? -d.gy : ((q == 5) ? -d.gz : 0.0f));
-      if (dl >= 0)
-        for (int a = madr[dl + 1] - 1; a >= madr[dl]; --a) { const int k = mcol[a]; acc += s[L.cdofdot + 6 * k + q] * s[L.qvel + k]; }
-      s[L.cacc + it] = acc;
-    }
-    __syncthreads();
-    for (int b = tid; b < d.nbody; b += nt) {
+    // local RNE force of each body: cfrc = I cacc + cvel x* (I cvel)   -> t16[10..15]
+    for (int b = lane; b < d.nbody; b += 32) {
       float f1[6], iv[6], f2[6];
-      inert_mul(s + L.cinert + 10 * b, s + L.cacc + 6 * b, f1);
-      inert_mul(s + L.cinert + 10 * b, s + L.cvel + 6 * b, iv);
+      inert_mul(s + L.t16 + 16 * b, s + L.cacc + 6 * b, f1);
+      inert_mul(s + L.t16 + 16 * b, s + L.cvel + 6 * b, iv);
       motion_cross_force(s + L.cvel + 6 * b, iv, f2);
-      for (int q = 0; q < 6; ++q) s[L.cfrc + 6 * b + q] = f1[q] + f2[q];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) s[L.t16 + 16 * b + 10 + q] = f1[q] + f2[q];
     }
-    __syncthreads();
-    for (int it = tid; it < d.nbody * 6; it += nt) {  // cacc <- subtree-summed cfrc
-      const int b = it / 6, q = it - 6 * b;
-      float acc = 0.0f;
-      for (int k = b; k < sub_end[b]; ++k) acc += s[L.cfrc + 6 * k + q];
-      s[L.cacc + it] = acc;
+    __syncwarp();
+    // one pass up the tree: composite inertia (crb, in place over cinert) and subtree-summed RNE force
+    for (int lv = d.nlevel - 2; lv >= 0; --lv) {
+      const int q0 = c.lvl_start[lv], n16 = (c.lvl_start[lv + 1] - q0) * 16;
+      for (int it = lane; it < n16; it += 32) {
+        const int b = c.lvl_bp[q0 + (it >> 4)] & 255, q = it & 15;
+        const int ce = c.child_adr[b + 1];
+        int ch = c.child_adr[b];
+        if (ch < ce) {
+          float acc = s[L.t16 + 16 * b + q];
+          for (; ch < ce; ++ch) acc += s[L.t16 + 16 * c.child_list[ch] + q];
+          s[L.t16 + 16 * b + q] = acc;
+        }
+      }
+      __syncwarp();
     }
-    __syncthreads();
+    if (DUMP) {
+      for (int i = lane; i < d.nbody * 10; i += 32) dump[d.dump_cinert + d.nbody * 10 + d.nv * 6 + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int i = lane; i < d.nbody * 6; i += 32) dump[d.dump_cvel + i] = s[L.cvel + i];
+    }
   }
-  PROF(c, 3);
-  // ---- qfrc_smooth = passive - bias + actuator; act_dot ---------------------------------------------
+  pf.mark(2);
+  // ---- qfrc_smooth = passive - bias + actuator; act_dot -----------------------------------------------------------------
   {
     const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
     const float* stiff = c.ff(VNL_F_JNT_STIFFNESS);
     const float* qspring = c.ff(VNL_F_QPOS_SPRING);
     const float* damping = c.ff(VNL_F_DOF_DAMPING);
-    for (int i = tid; i < d.nv; i += nt) s[L.qfrc_act + i] = 0.0f;
-    __syncthreads();
-    const int* adof = c.fi(VNL_F_ACT_DOFADR);
+    const int* actadr = c.fi(VNL_F_DOF_ACTADR);
+    const int* actlist = c.fi(VNL_F_DOF_ACTLIST);
     const int* aadr = c.fi(VNL_F_ACT_ACTADR);
     const int* flim = c.fi(VNL_F_ACT_FORCELIMITED);
     const float* gain = c.ff(VNL_F_ACT_GAIN);
     const float* gear = c.ff(VNL_F_ACT_GEAR);
     const float* frange = c.ff(VNL_F_ACT_FORCERANGE);
     const float* dynprm = c.ff(VNL_F_ACT_DYNPRM);
-    // one thread per dof gathers its actuators in actuator order (deterministic, no atomics)
-    for (int i = tid; i < d.nv; i += nt) {
+    for (int i = lane; i < d.nv; i += 32) {
       float acc = 0.0f;
-      for (int u = 0; u < d.nu; ++u) {
-        if (adof[u] != i) continue;
+      for (int t = actadr[i]; t < actadr[i + 1]; ++t) {  // actuators of this dof in actuator order (no atomics)
+        const int u = actlist[t];
         const float ctrl = s[L.ctrl + u];
         float ca = ctrl;
         const int aa = aadr[u];
@@ -556,7 +613,6 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
         acc += gear[u] * force;
       }
       s[L.qfrc_act + i] = acc;
-      // passive
       const int j = dof_jnt[i];
       float pas;
       if (jtype[j] == 0) {
@@ -566,40 +622,40 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
         pas = -stiff[j] * (s[L.qpos + jqadr[j]] - qspring[jqadr[j]]);
       }
       pas -= damping[i] * s[L.qvel + i];
-      const float bias = dot6(s + L.cdof + 6 * i, s + L.cacc + 6 * dof_body[i]);
+      const float bias = dot6(s + L.cdof + 6 * i, s + L.t16 + 16 * c.dof_body[i] + 10);
       s[L.qfrc_smooth + i] = pas - bias + acc;
-      if (dump) { dump[c.d.dump_passive + i] = pas; dump[c.d.dump_passive + d.nv + i] = bias; }
+      if (DUMP) { dump[d.dump_passive + i] = pas; dump[d.dump_passive + d.nv + i] = bias; }
     }
-    __syncthreads();
+    __syncwarp();
   }
-  PROF(c, 4);
-  // ---- joint-space inertia (tree sparse): M[i][a] = cdof[anc_a(i)] . (crb[body_i] cdof_i) -------
+  pf.mark(3);
+  // ---- joint-space inertia (tree sparse): M[i][a] = cdof[anc_a(i)] . (crb[body_i] cdof_i) --------------------------
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
-    float* fd = s + L.cdofdot;  // cdof_dot is dead from here on: reuse as crb * cdof
-    for (int i = tid; i < d.nv; i += nt) inert_mul(s + L.crb + 10 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
-    __syncthreads();
-    for (int e = tid; e < d.nM; e += nt) {
-      const int i = mrow[e], j = mcol[e];
+    float* fd = s + L.cacc;  // cacc is dead: reuse as crb * cdof
+    for (int i = lane; i < d.nv; i += 32) inert_mul(s + L.t16 + 16 * c.dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
+    __syncwarp();
+    for (int e = lane; e < d.nM; e += 32) {
+      const int i = c.mrow[e], j = c.mcol[e];
       float v = dot6(fd + 6 * i, s + L.cdof + 6 * j);
       if (i == j) v += armature[i];
       s[L.M + e] = v;
     }
-    __syncthreads();
+    __syncwarp();
   }
-  PROF(c, 5);
-  factor(c, s + L.M, false);
-  PROF(c, 6);
-  solve_m(c, s + L.qfrc_smooth, s + L.qacc_smooth, s + L.tmpv);
-  PROF(c, 7);
+  pf.mark(4);
+  factor(c, s, false);
+  pf.mark(5);
+  solve_m(c, s, s + L.qfrc_smooth, s + L.qacc_smooth, s + L.tmpv);
+  pf.mark(6);
 
-  // ---- collision + constraint rows, compacted to the active set -----------------------------------
+  // ---- collision + constraint rows, compacted to the active set ----------------------------------------------------------
+  float* arefv = s + L.Jv;  // aref lives in the Jv slot until the solver iterations start
   {
-    if (tid == 0) { ints[0] = 0; ints[1] = 0; }
-    for (int i = tid; i < d.nv; i += nt) ((int*)(s + L.limrow_of_dof))[i] = -1;
-    __syncthreads();
-    if (WARP == 0) {
-      // joint limits (constraint._instantiate_limit_slide_hinge)
+    if (lane == 0) { ints[0] = 0; ints[1] = 0; }
+    for (int i = lane; i < d.nv; i += 32) ((int*)(s + L.limrow_of_dof))[i] = -1;
+    __syncwarp();
+    {  // joint limits (constraint._instantiate_limit_slide_hinge)
       const int* ljnt = c.fi(VNL_F_LIMIT_JNT);
       const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
       const float* range = c.ff(VNL_F_JNT_RANGE);
@@ -609,7 +665,7 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
       const float* invw = c.ff(VNL_F_DOF_INVWEIGHT0);
       int base = 0;
       for (int r0 = 0; r0 < d.nlimit; r0 += 32) {
-        const int r = r0 + LANE;
+        const int r = r0 + lane;
         bool active = false;
         float pos = 0.0f, sign = 0.0f;
         int j = 0;
@@ -621,9 +677,9 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
           active = pos < 0.0f;
           sign = (dmin < dmax) ? 1.0f : -1.0f;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, active);
+        const unsigned m = __ballot_sync(FULLMASK, active);
         if (active) {
-          const int slot = base + __popc(m & ((1u << LANE) - 1u));
+          const int slot = base + __popc(m & ((1u << lane) - 1u));
           const int dof = jdofadr[j];
           ((int*)(s + L.lim_dof))[slot] = dof;
           s[L.lim_sign + slot] = sign;
@@ -632,16 +688,15 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
           kbi(d, solref[2 * j], solref[2 * j + 1], solimp + 5 * j, pos, k, b, imp);
           const float R = fmaxf(invw[dof] * (1.0f - imp) / imp, VNL_MINVAL);
           s[L.efcD + slot] = 1.0f / R;
-          s[L.aref + slot] = -b * (sign * s[L.qvel + dof]) - k * imp * pos;
-          if (dump) { dump[d.dump_efc + r] = pos; dump[d.dump_efc + d.nefc + r] = 1.0f / R; dump[d.dump_efc + 2 * d.nefc + r] = s[L.aref + slot]; }
+          arefv[slot] = -b * (sign * s[L.qvel + dof]) - k * imp * pos;
+          if (DUMP) { dump[d.dump_efc + r] = pos; dump[d.dump_efc + d.nefc + r] = 1.0f / R; dump[d.dump_efc + 2 * d.nefc + r] = arefv[slot]; }
         }
         base += __popc(m);
       }
-      if (LANE == 0) ints[0] = base;
+      if (lane == 0) ints[0] = base;
     }
-    __syncthreads();
-    if (WARP == 0) {
-      // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
+    __syncwarp();
+    {  // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
       const int nl = ints[0];
       const int* cpair = c.fi(VNL_F_CON_PAIR);
       const float* csign = c.ff(VNL_F_CON_SIGN);
@@ -649,7 +704,6 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
       const int* g1 = c.fi(VNL_F_PAIR_GEOM1);
       const int* g2 = c.fi(VNL_F_PAIR_GEOM2);
       const int* gbody = c.fi(VNL_F_GEOM_BODYID);
-      const int* rootid = c.fi(VNL_F_BODY_ROOTID);
       const float* gpos = c.ff(VNL_F_GEOM_POS);
       const float* gquat = c.ff(VNL_F_GEOM_QUAT);
       const float* gsize = c.ff(VNL_F_GEOM_SIZE);
@@ -660,7 +714,7 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
       const float* binvw = c.ff(VNL_F_BODY_INVWEIGHT0);
       int base = 0;
       for (int c0 = 0; c0 < d.ncon; c0 += 32) {
-        const int ci = c0 + LANE;
+        const int ci = c0 + lane;
         bool active = false;
         float dist = 0.0f;
         V3 cp = v3(0, 0, 0), n = v3(0, 0, 1), fb = v3(0, 1, 0);
@@ -669,8 +723,7 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
           p = cpair[ci];
           const int ga = g1[p], gb = g2[p];
           body = gbody[gb];
-          // plane is attached to the world body: world frame = local frame
-          float Pm[9], Gm[9];
+          float Pm[9], Gm[9];  // the plane is attached to the world body: world frame = local frame
           quat_to_mat(ld4(gquat + 4 * ga), Pm);
           n = v3(Pm[2], Pm[5], Pm[8]);
           const V3 ppos = ld3(gpos + 3 * ga);
@@ -683,20 +736,20 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
             dist = dot(gp - ppos, n) - sz[0];
             cp = gp - n * (sz[0] + 0.5f * dist);
           } else if (ty == 3) {  // plane_capsule end
-            V3 axis = v3(Gm[2], Gm[5], Gm[8]);
+            const V3 axis = v3(Gm[2], Gm[5], Gm[8]);
             V3 b = axis - n * dot(n, axis);
             const float bn = normalize3(b);
             if (bn < 0.5f) b = (-0.5f < n.y && n.y < 0.5f) ? v3(0, 1, 0) : v3(0, 0, 1);
             fb = b;
-            V3 sp = gp + axis * (csign[ci] * sz[1]);
+            const V3 sp = gp + axis * (csign[ci] * sz[1]);
             dist = dot(sp - ppos, n) - sz[0];
             cp = sp - n * (sz[0] + 0.5f * dist);
           } else {  // plane_ellipsoid
-            V3 ln = v3(Gm[0] * n.x + Gm[3] * n.y + Gm[6] * n.z, Gm[1] * n.x + Gm[4] * n.y + Gm[7] * n.z, Gm[2] * n.x + Gm[5] * n.y + Gm[8] * n.z);
+            const V3 ln = v3(Gm[0] * n.x + Gm[3] * n.y + Gm[6] * n.z, Gm[1] * n.x + Gm[4] * n.y + Gm[7] * n.z, Gm[2] * n.x + Gm[5] * n.y + Gm[8] * n.z);
             V3 sup = v3(ln.x * sz[0], ln.y * sz[1], ln.z * sz[2]);
             normalize3(sup);
             sup = v3(-sup.x * sz[0], -sup.y * sz[1], -sup.z * sz[2]);
-            V3 pt = gp + v3(Gm[0] * sup.x + Gm[1] * sup.y + Gm[2] * sup.z, Gm[3] * sup.x + Gm[4] * sup.y + Gm[5] * sup.z, Gm[6] * sup.x + Gm[7] * sup.y + Gm[8] * sup.z);
+            const V3 pt = gp + v3(Gm[0] * sup.x + Gm[1] * sup.y + Gm[2] * sup.z, Gm[3] * sup.x + Gm[4] * sup.y + Gm[5] * sup.z, Gm[6] * sup.x + Gm[7] * sup.y + Gm[8] * sup.z);
             dist = dot(n, pt - ppos);
             cp = pt - n * (dist * 0.5f);
           }
@@ -709,7 +762,7 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
             normalize3(b);
             fb = b;
           }
-          if (dump) {
+          if (DUMP) {
             dump[d.dump_con + ci] = dist;
             st3(dump + d.dump_con + d.ncon + 3 * ci, cp);
             st3(dump + d.dump_con + 4 * d.ncon + 9 * ci, n); st3(dump + d.dump_con + 4 * d.ncon + 9 * ci + 3, fb);
@@ -718,11 +771,11 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
           dist -= pmargin[p];
           active = dist < 0.0f;
         }
-        const unsigned m = __ballot_sync(0xffffffffu, active);
+        const unsigned m = __ballot_sync(FULLMASK, active);
         if (active) {
-          const int k = base + __popc(m & ((1u << LANE) - 1u));
+          const int k = base + __popc(m & ((1u << lane) - 1u));
           ((int*)(s + L.cbody))[k] = body;
-          const V3 rel = cp - ld3(s + L.rcom + 3 * rootid[body]);
+          const V3 rel = cp - ld3(s + L.rcom + 3 * c.body_tree[body]);
           st3(s + L.crel + 3 * k, rel);
           const V3 t2 = cross(n, fb);
           st3(s + L.cframe + 9 * k, n); st3(s + L.cframe + 9 * k + 3, fb); st3(s + L.cframe + 9 * k + 6, t2);
@@ -740,161 +793,147 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
           const float ref = -kk * imp * dist;
           const int r = nl + 4 * k;
           s[L.efcD + r] = s[L.efcD + r + 1] = s[L.efcD + r + 2] = s[L.efcD + r + 3] = 1.0f / R;
-          s[L.aref + r] = -bb * (un + mu * u1) + ref;
-          s[L.aref + r + 1] = -bb * (un - mu * u1) + ref;
-          s[L.aref + r + 2] = -bb * (un + mu * u2) + ref;
-          s[L.aref + r + 3] = -bb * (un - mu * u2) + ref;
-          if (dump) {
+          arefv[r] = -bb * (un + mu * u1) + ref;
+          arefv[r + 1] = -bb * (un - mu * u1) + ref;
+          arefv[r + 2] = -bb * (un + mu * u2) + ref;
+          arefv[r + 3] = -bb * (un - mu * u2) + ref;
+          if (DUMP) {
             const int rr = d.nlimit + 4 * ci;
             for (int q = 0; q < 4; ++q) {
               dump[d.dump_efc + rr + q] = dist; dump[d.dump_efc + d.nefc + rr + q] = 1.0f / R;
-              dump[d.dump_efc + 2 * d.nefc + rr + q] = s[L.aref + r + q];
+              dump[d.dump_efc + 2 * d.nefc + rr + q] = arefv[r + q];
             }
           }
         }
         base += __popc(m);
       }
-      if (LANE == 0) ints[1] = base;
+      if (lane == 0) ints[1] = base;
     }
-    __syncthreads();
+    __syncwarp();
   }
-  PROF(c, 8);
+  pf.mark(7);
   const int nl = ints[0], nc = ints[1], nrow = nl + 4 * nc;
-  if (stats && tid == 0) { stats[2] += nc; stats[3] += nl; }
+  if (lane == 0) { stats[2] += nc; stats[3] += nl; }
 
-  // ---- solver.solve (CG with the MJX line search) ----------------------------------------------------
+  // ---- solver.solve (CG with the MJX line search) ------------------------------------------------------------------------
   float* qacc = s + L.qacc;
   float* Ma = s + L.Ma;
   float* Jaref = s + L.Jaref;
   float* Jv = s + L.Jv;
-  float* efcD = s + L.efcD;
+  const float* efcD = s + L.efcD;
   float* grad = s + L.grad;
   float* Mgrad = s + L.Mgrad;
   float* search = s + L.search;
   float* Mv = s + L.Mv;
-  float* qfrc_con = s + L.qfrc_con;
   const float* qfrc_smooth = s + L.qfrc_smooth;
   const float* qacc_smooth = s + L.qacc_smooth;
   int niter = 0, lsiter = 0;
   {
-    // cost of a candidate: 0.5 sum D Jaref^2 [Jaref<0] + 0.5 (Ma - qfrc_smooth).(qacc - qacc_smooth)
+    // candidate cost: 0.5 sum D Jaref^2 [Jaref<0] + 0.5 (Ma - qfrc_smooth).(qacc - qacc_smooth)
     float cost_w, cost_s;
     {
-      mul_m(c, s + L.warm, Ma);
-      jmul(c, s + L.warm, Jaref);
-      __syncthreads();
-      float v[2] = {0.0f, 0.0f};
-      for (int r = tid; r < nrow; r += nt) { const float ja = Jaref[r] - s[L.aref + r]; if (ja < 0.0f) v[0] += efcD[r] * ja * ja; }
-      for (int i = tid; i < d.nv; i += nt) v[1] += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
-      block_sum<2>(c, v);
-      cost_w = 0.5f * v[0] + 0.5f * v[1];
-      __syncthreads();
-      mul_m(c, qacc_smooth, Ma);
-      jmul(c, qacc_smooth, Jaref);
-      __syncthreads();
-      float w[2] = {0.0f, 0.0f};
-      for (int r = tid; r < nrow; r += nt) { const float ja = Jaref[r] - s[L.aref + r]; if (ja < 0.0f) w[0] += efcD[r] * ja * ja; }
-      for (int i = tid; i < d.nv; i += nt) w[1] += (Ma[i] - qfrc_smooth[i]) * (qacc_smooth[i] - qacc_smooth[i]);
-      block_sum<2>(c, w);
-      cost_s = 0.5f * w[0] + 0.5f * w[1];
-      __syncthreads();
+      mul_m(c, s, s + L.warm, Ma);
+      jmul(c, s, s + L.warm, Jaref);
+      float v0 = 0.0f, v1 = 0.0f;
+      for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) v0 += efcD[r] * ja * ja; }
+      for (int i = lane; i < d.nv; i += 32) v1 += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
+      v0 = warp_sum(v0); v1 = warp_sum(v1);
+      cost_w = 0.5f * v0 + 0.5f * v1;
+      __syncwarp();
+      mul_m(c, s, qacc_smooth, Ma);
+      jmul(c, s, qacc_smooth, Jaref);
+      float w0 = 0.0f, w1 = 0.0f;
+      for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) w0 += efcD[r] * ja * ja; }
+      for (int i = lane; i < d.nv; i += 32) w1 += (Ma[i] - qfrc_smooth[i]) * (qacc_smooth[i] - qacc_smooth[i]);
+      w0 = warp_sum(w0); w1 = warp_sum(w1);
+      cost_s = 0.5f * w0 + 0.5f * w1;
+      __syncwarp();
     }
-    PROF(c, 9);
-    const bool use_warm = cost_w < cost_s;
-    if (use_warm) {
-      for (int i = tid; i < d.nv; i += nt) qacc[i] = s[L.warm + i];
-      __syncthreads();
-      mul_m(c, qacc, Ma);
-      jmul(c, qacc, Jaref);
+    if (cost_w < cost_s) {
+      for (int i = lane; i < d.nv; i += 32) qacc[i] = s[L.warm + i];
+      __syncwarp();
+      mul_m(c, s, qacc, Ma);
+      jmul(c, s, qacc, Jaref);
     } else {
-      for (int i = tid; i < d.nv; i += nt) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
+      for (int i = lane; i < d.nv; i += 32) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
     }
-    __syncthreads();
-    for (int r = tid; r < nrow; r += nt) Jaref[r] -= s[L.aref + r];
-    __syncthreads();
+    __syncwarp();
+    for (int r = lane; r < nrow; r += 32) Jaref[r] -= arefv[r];
+    __syncwarp();
+    pf.mark(8);
     const float scale = d.meaninertia * (float)max(1, d.nv);
-    float cost = INFINITY, prev_cost = 0.0f, gauss = 0.0f, gradnorm = 0.0f;
-    // _update_constraint + _update_gradient
-    auto update = [&]() {
-      jtmul_force(c, qfrc_con);
-      float v[2] = {0.0f, 0.0f};
-      for (int r = tid; r < nrow; r += nt) { const float ja = Jaref[r]; if (ja < 0.0f) v[0] += efcD[r] * ja * ja; }
-      for (int i = tid; i < d.nv; i += nt) v[1] += (Ma[i] - qfrc_smooth[i]) * (qacc[i] - qacc_smooth[i]);
-      block_sum<2>(c, v);  // also orders qfrc_con writes before the reads below
-      gauss = 0.5f * v[1];
-      prev_cost = cost;
-      cost = 0.5f * v[0] + gauss;
-      float g[1] = {0.0f};
-      for (int i = tid; i < d.nv; i += nt) { const float gi = Ma[i] - qfrc_smooth[i] - qfrc_con[i]; grad[i] = gi; g[0] += gi * gi; }
-      block_sum<1>(c, g);
-      gradnorm = sqrtf(g[0]);
-      solve_m(c, grad, Mgrad, s + L.tmpv);
-    };
-    update();
-    PROF(c, 10);
-    for (int i = tid; i < d.nv; i += nt) search[i] = -Mgrad[i];
-    __syncthreads();
+    Sol st;
+    st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
+    update_constraint(c, s, st);
+    for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
+    __syncwarp();
+    pf.mark(9);
     while (true) {
-      const float improvement = (prev_cost - cost) / scale;
-      const float gradient = gradnorm / scale;
+      const float improvement = (st.prev_cost - st.cost) / scale;
+      const float gradient = st.gradnorm / scale;
       bool done = niter >= d.iterations;
       if (d.iterations != 1) { done |= improvement < d.tolerance; done |= gradient < d.tolerance; }
       if (done) break;
       // ---- _linesearch ----
-      mul_m(c, search, Mv);
-      jmul(c, search, Jv);
-      __syncthreads();
-      float qg[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      for (int i = tid; i < d.nv; i += nt) {
+      mul_m(c, s, search, Mv);
+      jmul(c, s, search, Jv);
+      float q0s = 0.0f, q1s = 0.0f, q2s = 0.0f, q3s = 0.0f;
+      for (int i = lane; i < d.nv; i += 32) {
         const float si = search[i];
-        qg[0] += si * si; qg[1] += si * Ma[i]; qg[2] += si * qfrc_smooth[i]; qg[3] += si * Mv[i];
+        q0s += si * si; q1s += si * Ma[i]; q2s += si * qfrc_smooth[i]; q3s += si * Mv[i];
       }
-      block_sum<4>(c, qg);
-      const float gtol = d.tolerance * d.ls_tolerance * (sqrtf(qg[0]) * scale);
-      const float g0 = gauss, g1 = qg[1] - qg[2], g2 = 0.5f * qg[3];
-      auto points = [&](int n, const float* alpha, LSP* out) {
-        float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        for (int r = tid; r < nrow; r += nt) {
-          const float x = Jaref[r], jv = Jv[r], D = efcD[r];
-          const float q0 = 0.5f * x * x * D, q1 = jv * x * D, q2 = 0.5f * jv * jv * D;
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            if (k < n && x + alpha[k] * jv < 0.0f) { acc[3 * k] += q0; acc[3 * k + 1] += q1; acc[3 * k + 2] += q2; }
-        }
-        block_sum<9>(c, acc);
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-          if (k < n) {
-            const float q0 = acc[3 * k] + g0, q1 = acc[3 * k + 1] + g1, q2 = acc[3 * k + 2] + g2, a = alpha[k];
-            out[k].alpha = a;
-            out[k].cost = a * a * q2 + a * q1 + q0;
-            out[k].d0 = 2.0f * a * q2 + q1;
-            out[k].d1 = 2.0f * q2 + (q2 == 0.0f ? VNL_MINVAL : 0.0f);
-          }
-      };
-      LSP p0, lo, hi, tmp3[3];
-      float al[3] = {0.0f, 0.0f, 0.0f};
-      points(1, al, tmp3);
-      p0 = tmp3[0];
-      al[0] = p0.alpha - p0.d0 / p0.d1;
-      points(1, al, tmp3);
-      lo = tmp3[0];
-      const bool lesser = lo.d0 < p0.d0;
-      hi = lesser ? p0 : lo;
-      lo = lesser ? lo : p0;
+      q0s = warp_sum(q0s); q1s = warp_sum(q1s); q2s = warp_sum(q2s); q3s = warp_sum(q3s);
+      const float gtol = d.tolerance * d.ls_tolerance * (sqrtf(q0s) * scale);
+      const float g0 = st.gauss, g1 = q1s - q2s, g2 = 0.5f * q3s;
+      // One evaluation site for all line-search points: phase 0 evaluates alpha = 0, phase 1 the Newton step from
+      // it, later phases the three candidates (lo_next, hi_next, mid) of one bracketing round.
+      LSP p0, lo, hi;
+      p0.alpha = p0.cost = p0.d0 = p0.d1 = 0.0f;
+      lo = p0; hi = p0;
       bool swap = true;
       int it = 0;
-      while (true) {
-        bool ldone = it >= d.ls_iterations;
-        ldone |= !swap;
-        ldone |= (lo.d0 < 0.0f) && (lo.d0 > -gtol);
-        ldone |= (hi.d0 > 0.0f) && (hi.d0 < gtol);
-        if (ldone) break;
-        al[0] = lo.alpha - lo.d0 / lo.d1;
-        al[1] = hi.alpha - hi.d0 / hi.d1;
-        al[2] = 0.5f * (lo.alpha + hi.alpha);
-        points(3, al, tmp3);
-        const LSP lo_next = tmp3[0], hi_next = tmp3[1], mid = tmp3[2];
+      for (int phase = 0;; ++phase) {
+        float al0, al1, al2;
+        if (phase == 0) { al0 = al1 = al2 = 0.0f; }
+        else if (phase == 1) { al0 = al1 = al2 = p0.alpha - p0.d0 / p0.d1; }
+        else {
+          bool ldone = it >= d.ls_iterations;
+          ldone |= !swap;
+          ldone |= (lo.d0 < 0.0f) && (lo.d0 > -gtol);
+          ldone |= (hi.d0 > 0.0f) && (hi.d0 < gtol);
+          if (ldone) break;
+          al0 = lo.alpha - lo.d0 / lo.d1;
+          al1 = hi.alpha - hi.d0 / hi.d1;
+          al2 = 0.5f * (lo.alpha + hi.alpha);
+        }
+        float acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int r = lane; r < nrow; r += 32) {
+          const float x = Jaref[r], jv = Jv[r], D = efcD[r];
+          const float q0 = 0.5f * x * x * D, q1 = jv * x * D, q2 = 0.5f * jv * jv * D;
+          if (x + al0 * jv < 0.0f) { acc[0] += q0; acc[1] += q1; acc[2] += q2; }
+          if (x + al1 * jv < 0.0f) { acc[3] += q0; acc[4] += q1; acc[5] += q2; }
+          if (x + al2 * jv < 0.0f) { acc[6] += q0; acc[7] += q1; acc[8] += q2; }
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) acc[q] = warp_sum(acc[q]);
+        LSP pt[3];
+        const float als[3] = {al0, al1, al2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float q0 = acc[3 * k] + g0, q1 = acc[3 * k + 1] + g1, q2 = acc[3 * k + 2] + g2, a = als[k];
+          pt[k].alpha = a;
+          pt[k].cost = a * a * q2 + a * q1 + q0;
+          pt[k].d0 = 2.0f * a * q2 + q1;
+          pt[k].d1 = 2.0f * q2 + (q2 == 0.0f ? VNL_MINVAL : 0.0f);
+        }
+        if (phase == 0) { p0 = pt[0]; continue; }
+        if (phase == 1) {
+          const bool lesser = pt[0].d0 < p0.d0;
+          hi = lesser ? p0 : pt[0];
+          lo = lesser ? pt[0] : p0;
+          continue;
+        }
+        const LSP lo_next = pt[0], hi_next = pt[1], mid = pt[2];
         const bool s1 = (lo.d0 > 0.0f) || (lo.d0 < lo_next.d0);
         if (s1) lo = lo_next;
         const bool s2 = (mid.d0 < 0.0f) && (lo.d0 < mid.d0);
@@ -911,76 +950,76 @@ __device__ __noinline__ void forward(Ctx& c, int* stats, float* dump) {
         ++it;
       }
       lsiter += it;
-      PROF(c, 11);
+      pf.mark(10);
       const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       const float ia = improved ? alpha : 0.0f * alpha;
-      for (int i = tid; i < d.nv; i += nt) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; }
-      for (int r = tid; r < nrow; r += nt) Jaref[r] += Jv[r] * ia;
-      // previous grad . Mgrad before they are overwritten
-      float pg[1] = {0.0f};
-      for (int i = tid; i < d.nv; i += nt) { pg[0] += grad[i] * Mgrad[i]; Mv[i] = Mgrad[i]; }  // Mv <- previous Mgrad
-      block_sum<1>(c, pg);
-      update();
-      if (d.solver == 2) {
-        for (int i = tid; i < d.nv; i += nt) search[i] = -Mgrad[i];
-      } else {  // Polak-Ribiere
-        float nb[1] = {0.0f};
-        for (int i = tid; i < d.nv; i += nt) nb[0] += grad[i] * (Mgrad[i] - Mv[i]);
-        block_sum<1>(c, nb);
-        const float beta = fmaxf(0.0f, nb[0] / fmaxf(VNL_MINVAL, pg[0]));
-        for (int i = tid; i < d.nv; i += nt) search[i] = -Mgrad[i] + beta * search[i];
+      float pg = 0.0f;  // previous grad . Mgrad before they are overwritten
+      for (int i = lane; i < d.nv; i += 32) {
+        qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia;
+        pg += grad[i] * Mgrad[i]; Mv[i] = Mgrad[i];  // Mv <- previous Mgrad
       }
-      __syncthreads();
-      PROF(c, 12);
+      for (int r = lane; r < nrow; r += 32) Jaref[r] += Jv[r] * ia;
+      pg = warp_sum(pg);
+      __syncwarp();
+      update_constraint(c, s, st);
+      if (d.solver == 2) {
+        for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
+      } else {  // Polak-Ribiere
+        float nb = 0.0f;
+        for (int i = lane; i < d.nv; i += 32) nb += grad[i] * (Mgrad[i] - Mv[i]);
+        nb = warp_sum(nb);
+        const float beta = fmaxf(0.0f, nb / fmaxf(VNL_MINVAL, pg));
+        for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i] + beta * search[i];
+      }
+      __syncwarp();
+      pf.mark(11);
       ++niter;
     }
   }
-  if (stats && tid == 0) { stats[0] += niter; stats[1] += lsiter; }
-  // qacc_warmstart <- qacc
-  for (int i = tid; i < d.nv; i += nt) s[L.warm + i] = qacc[i];
-  __syncthreads();
+  if (lane == 0) { stats[0] += niter; stats[1] += lsiter; }
+  for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = qacc[i];  // qacc_warmstart <- qacc
+  __syncwarp();
 }
 
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
 // forward.euler (implicit joint damping when enabled) + _advance
-// ---------------------------------------------------------------------------------------------
-__device__ __noinline__ void euler(Ctx& c) {
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __noinline__ void euler(const Cta& c, float* s, Prof& pf) {
   const Dims& d = c.d;
   const Lay& L = c.L;
-  float* s = c.s;
-  const int tid = TID, nt = c.nt;
+  const int lane = LANE;
   const float dt = d.timestep;
   float* qacc = s + L.qacc;
-  PROF(c, 13);
+  pf.mark(12);
   if (d.eulerdamp) {
-    factor(c, s + L.M, true);
-    PROF(c, 14);
-    for (int i = tid; i < d.nv; i += nt) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
-    __syncthreads();
-    solve_m(c, s + L.grad, s + L.Mgrad, s + L.tmpv);
+    factor(c, s, true);
+    pf.mark(13);
+    for (int i = lane; i < d.nv; i += 32) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
+    __syncwarp();
+    solve_m(c, s, s + L.grad, s + L.Mgrad, s + L.tmpv);
     qacc = s + L.Mgrad;
   }
-  for (int a = tid; a < d.na; a += nt) s[L.act + a] += s[L.act_dot + a] * dt;
-  for (int i = tid; i < d.nv; i += nt) s[L.qvel + i] += qacc[i] * dt;
-  __syncthreads();
+  for (int a = lane; a < d.na; a += 32) s[L.act + a] += s[L.act_dot + a] * dt;
+  for (int i = lane; i < d.nv; i += 32) s[L.qvel + i] += qacc[i] * dt;
+  __syncwarp();
   const int* jtype = c.fi(VNL_F_JNT_TYPE);
   const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
   const int* jdofadr = c.fi(VNL_F_JNT_DOFADR);
-  for (int j = tid; j < d.njnt; j += nt) {
+  for (int j = lane; j < d.njnt; j += 32) {
     const int qa = jqadr[j], da = jdofadr[j];
     if (jtype[j] == 0) {
       for (int k = 0; k < 3; ++k) s[L.qpos + qa + k] += s[L.qvel + da + k] * dt;
       V3 w = ld3(s + L.qvel + da + 3);
       const float norm = normalize3(w);
-      Q4 q = quat_normalize(quat_mul(ld4(s + L.qpos + qa + 3), axis_angle_quat(w, dt * norm)));
+      const Q4 q = quat_normalize(quat_mul(ld4(s + L.qpos + qa + 3), axis_angle_quat(w, dt * norm)));
       st4(s + L.qpos + qa + 3, q);
     } else {
       s[L.qpos + qa] += s[L.qvel + da] * dt;
     }
   }
-  __syncthreads();
-  PROF(c, 15);
+  __syncwarp();
+  pf.mark(14);
 }
 
 __device__ __forceinline__ float nan_to_num(float v) {
@@ -989,75 +1028,42 @@ __device__ __forceinline__ float nan_to_num(float v) {
   return v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// kernel: MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
-// ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------------------------------
+// one env, one warp.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
+// ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
-  extern __shared__ __align__(16) float smem[];
-  const int e = blockIdx.x;
-  if (e >= p.B) return;
-  Ctx& c = *reinterpret_cast<Ctx*>(smem);
-  float* s = smem + kCtxFloats;
-  const int tid = TID, nt = blockDim.x;
-  if (tid == 0) {
-    c.s = s;
-    c.mb = p.model;
-    c.nt = blockDim.x; c.nw = blockDim.x >> 5;
-    c.prof = (p.prof && blockIdx.x == p.prof_block) ? p.prof : nullptr;
-    c.t0 = clock64();
-    c.d = p.dims;
-    make_layout(c.d, c.L);
-    const Lay& L0 = c.L;
-    c.mcol = (const uint8_t*)(s + L0.mcol8); c.mrow = (const uint8_t*)(s + L0.mrow8); c.drow = (const uint8_t*)(s + L0.drow8);
-    c.dls = (const uint8_t*)(s + L0.dls8); c.dld = (const uint8_t*)(s + L0.dld8);
-    c.madr = (const uint16_t*)(s + L0.madr16); c.dadr = (const uint16_t*)(s + L0.dadr16); c.dent = (const uint16_t*)(s + L0.dent16);
-  }
-  for (int f = tid; f < VNL_F_MODEL_COUNT; f += nt) c.foff[f] = p.model[VNL_TABLE_OFF + 2 * f];
-  __syncthreads();
+__device__ __forceinline__ void env_run(const Cta& c, float* s, const Params& p, int e) {
   const Dims& d = c.d;
   const Lay& L = c.L;
-  {
-    uint8_t* mcol8 = (uint8_t*)(s + L.mcol8); uint8_t* mrow8 = (uint8_t*)(s + L.mrow8); uint8_t* drow8 = (uint8_t*)(s + L.drow8);
-    uint8_t* dls8 = (uint8_t*)(s + L.dls8); uint8_t* dld8 = (uint8_t*)(s + L.dld8);
-    uint16_t* madr16 = (uint16_t*)(s + L.madr16); uint16_t* dadr16 = (uint16_t*)(s + L.dadr16); uint16_t* dent16 = (uint16_t*)(s + L.dent16);
-    const int* g_mcol = vnl_field_i(p.model, VNL_F_M_COL); const int* g_mrow = vnl_field_i(p.model, VNL_F_M_ROW);
-    const int* g_madr = vnl_field_i(p.model, VNL_F_DOF_MADR); const int* g_dadr = vnl_field_i(p.model, VNL_F_DESC_ADR);
-    const int* g_dent = vnl_field_i(p.model, VNL_F_DESC_ENTRY);
-    const int* g_dls = vnl_field_i(p.model, VNL_F_DOFLEVEL_START); const int* g_dld = vnl_field_i(p.model, VNL_F_DOFLEVEL_DOF);
-    for (int i = tid; i < d.nM; i += nt) { mcol8[i] = (uint8_t)g_mcol[i]; mrow8[i] = (uint8_t)g_mrow[i]; }
-    for (int i = tid; i <= d.nv; i += nt) { madr16[i] = (uint16_t)g_madr[i]; dadr16[i] = (uint16_t)g_dadr[i]; }
-    for (int i = tid; i < d.nM - d.nv; i += nt) { const int en = g_dent[i]; dent16[i] = (uint16_t)en; drow8[i] = (uint8_t)g_mrow[en]; }
-    for (int i = tid; i < d.maxdepth + 2; i += nt) dls8[i] = (uint8_t)g_dls[i];
-    for (int i = tid; i < d.nv; i += nt) dld8[i] = (uint8_t)g_dld[i];
-  }
+  const int lane = LANE;
+  Prof pf;
+  pf.p = (c.prof && e == c.prof_env) ? c.prof : nullptr;
+  pf.t0 = clock64();
   int* ints = (int*)(s + L.ints);
-  if (tid < 16) ints[tid] = 0;
+  if (lane < 16) ints[lane] = 0;
 
-  // ---- load state ------------------------------------------------------------------------
-  for (int i = tid; i < d.nq; i += nt) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
-  for (int i = tid; i < d.nv; i += nt) s[L.qvel + i] = p.in.qvel[(size_t)e * d.nv + i];
+  // ---- load state -------------------------------------------------------------------------------------------------------
+  for (int i = lane; i < d.nq; i += 32) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
+  for (int i = lane; i < d.nv; i += 32) s[L.qvel + i] = p.in.qvel[(size_t)e * d.nv + i];
   if (MODE == 1) {
-    for (int i = tid; i < d.na; i += nt) s[L.act + i] = 0.0f;
-    for (int i = tid; i < d.nv; i += nt) s[L.warm + i] = 0.0f;
-    for (int i = tid; i < d.nu; i += nt) s[L.ctrl + i] = 0.0f;
+    for (int i = lane; i < d.na; i += 32) s[L.act + i] = 0.0f;
+    for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = 0.0f;
+    for (int i = lane; i < d.nu; i += 32) s[L.ctrl + i] = 0.0f;
   } else {
-    for (int i = tid; i < d.na; i += nt) s[L.act + i] = p.in.act ? p.in.act[(size_t)e * d.na + i] : 0.0f;
-    for (int i = tid; i < d.nv; i += nt) s[L.warm + i] = p.in.qacc_warmstart ? p.in.qacc_warmstart[(size_t)e * d.nv + i] : 0.0f;
-  }
-  __syncthreads();
-  if (MODE != 1) {
+    for (int i = lane; i < d.na; i += 32) s[L.act + i] = p.in.act ? p.in.act[(size_t)e * d.na + i] : 0.0f;
+    for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = p.in.qacc_warmstart ? p.in.qacc_warmstart[(size_t)e * d.nv + i] : 0.0f;
     const int* climited = c.fi(VNL_F_ACT_CTRLLIMITED);
     const float* crange = c.ff(VNL_F_ACT_CTRLRANGE);
-    for (int u = tid; u < d.nu; u += nt) {
+    for (int u = lane; u < d.nu; u += 32) {
       float v = p.ctrl ? p.ctrl[(size_t)e * d.nu + u] : 0.0f;
       if (climited[u]) v = fminf(fmaxf(v, crange[2 * u]), crange[2 * u + 1]);
       s[L.ctrl + u] = v;
     }
   }
+  __syncwarp();
   const uint32_t* tb = p.task;
-  // termination error of the PREVIOUS state and frame (envs/rodent.py:241-264, quirks Q2 / Q9):
-  // depends only on inputs, so evaluate it before the physics overwrites them.
+  // termination error of the PREVIOUS state and frame (envs/rodent.py:241-264, quirks Q2 / Q9): depends only on
+  // inputs, so evaluate it before the physics overwrites them.
   float rtrunk = 0.0f;
   int frame_old = 0;
   if (MODE == 0) {
@@ -1068,77 +1074,72 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
     const float* rb = vnl_field_f(tb, VNL_T_BODY_POSITIONS) + (size_t)f * ntrack * 3;
     const int* bidx = vnl_field_i(tb, VNL_T_BODY_IDXS);
     const float* xold = p.in.xpos + (size_t)e * d.nbody * 3;
-    float v[4] = {0, 0, 0, 0};
-    for (int j = tid; j < nj; j += nt) v[0] += fabsf(rj[j] - s[L.qpos + 7 + j]);
-    for (int b = tid; b < ntrack; b += nt)
-      for (int k = 0; k < 3; ++k) v[1 + k] += fabsf(rb[3 * b + k] - xold[3 * bidx[b] + k]);
-    block_sum<4>(c, v);
-    const float eb = fmaxf(v[1], fmaxf(v[2], v[3]));
-    const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v[0];
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;
+    for (int j = lane; j < nj; j += 32) v0 += fabsf(rj[j] - s[L.qpos + 7 + j]);
+    for (int b = lane; b < ntrack; b += 32) {
+      v1 += fabsf(rb[3 * b] - xold[3 * bidx[b]]);
+      v2 += fabsf(rb[3 * b + 1] - xold[3 * bidx[b] + 1]);
+      v3_ += fabsf(rb[3 * b + 2] - xold[3 * bidx[b] + 2]);
+    }
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
+    const float eb = fmaxf(v1, fmaxf(v2, v3_));
+    const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v0;
     rtrunk = 1.0f - err / vnl_hdr_f(tb, VNL_TH_TERM_THRESHOLD);
   }
-  __syncthreads();
 
   int* stats = ints + 4;  // [4..7]
   float* dump = (MODE == 3) ? p.dump + (size_t)e * d.dump_total : nullptr;
   const int nsteps = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
   for (int st = 0; st < nsteps; ++st) {
-    forward(c, stats, dump);
+    forward<MODE == 3>(c, s, stats, dump, pf);
     if (MODE == 1 || MODE == 3) break;
-    euler(c);
+    euler(c, s, pf);
   }
 
   if (MODE == 3) {
     // stage dump (layout = oracle.dump_layout); arrays this formulation never materialises stay NaN
-    auto put = [&](int off, const float* src, int n) { for (int i = tid; i < n; i += nt) dump[off + i] = src[i]; };
+    auto put = [&](int off, const float* src, int n) { for (int i = lane; i < n; i += 32) dump[off + i] = src[i]; };
     put(d.dump_xpos, s + L.xpos, d.nbody * 3);
     put(d.dump_xpos + d.nbody * 3, s + L.xquat, d.nbody * 4);
-    put(d.dump_xipos, s + L.xipos, d.nbody * 3);
-    put(d.dump_xanchor, s + L.xanchor, d.njnt * 3);
-    put(d.dump_xanchor + d.njnt * 3, s + L.xaxis, d.njnt * 3);
-    put(d.dump_cinert, s + L.cinert, d.nbody * 10);
     put(d.dump_cinert + d.nbody * 10, s + L.cdof, d.nv * 6);
-    put(d.dump_cinert + d.nbody * 10 + d.nv * 6, s + L.crb, d.nbody * 10);
-    const int* rootid = c.fi(VNL_F_BODY_ROOTID);
-    for (int b = tid; b < d.nbody; b += nt)
-      if (b > 0 && rootid[b] == b) st3(dump + d.dump_subtree_com + 3 * b, ld3(s + L.rcom + 3 * b));
-    const uint8_t* mrow = c.mrow; const uint8_t* mcol = c.mcol;
-    for (int i = tid; i < d.nv * d.nv; i += nt) dump[d.dump_qM + i] = 0.0f;
-    __syncthreads();
-    for (int q = tid; q < d.nM; q += nt) {
-      dump[d.dump_qM + mrow[q] * d.nv + mcol[q]] = s[L.M + q];
-      dump[d.dump_qM + mcol[q] * d.nv + mrow[q]] = s[L.M + q];
+    for (int i = lane; i < d.nv * d.nv; i += 32) dump[d.dump_qM + i] = 0.0f;
+    __syncwarp();
+    for (int q = lane; q < d.nM; q += 32) {
+      dump[d.dump_qM + c.mrow[q] * d.nv + c.mcol[q]] = s[L.M + q];
+      dump[d.dump_qM + c.mcol[q] * d.nv + c.mrow[q]] = s[L.M + q];
     }
-    put(d.dump_cvel, s + L.cvel, d.nbody * 6);
     put(d.dump_passive + 2 * d.nv, s + L.qfrc_act, d.nv);
     put(d.dump_passive + 3 * d.nv, s + L.act_dot, d.na);
     put(d.dump_passive + 3 * d.nv + d.na, s + L.qfrc_smooth, d.nv);
     put(d.dump_passive + 4 * d.nv + d.na, s + L.qacc_smooth, d.nv);
     put(d.dump_qacc, s + L.qacc, d.nv);
     put(d.dump_qacc + d.nv, s + L.qfrc_con, d.nv);
-    if (tid < 4) dump[d.dump_total - 4 + tid] = (float)stats[tid];
+    if (lane < 4) dump[d.dump_total - 4 + lane] = (float)stats[lane];
+    __syncwarp();
     return;
   }
 
-  // ---- write state -------------------------------------------------------------------------
+  // ---- write state ------------------------------------------------------------------------------------------------------
   const VnlState& o = p.out;
-  for (int i = tid; i < d.nq; i += nt) o.qpos[(size_t)e * d.nq + i] = s[L.qpos + i];
-  for (int i = tid; i < d.nv; i += nt) o.qvel[(size_t)e * d.nv + i] = s[L.qvel + i];
-  for (int i = tid; i < d.na; i += nt) o.act[(size_t)e * d.na + i] = s[L.act + i];
-  for (int i = tid; i < d.nv; i += nt) o.qacc_warmstart[(size_t)e * d.nv + i] = s[L.warm + i];
-  for (int i = tid; i < d.nbody * 3; i += nt) o.xpos[(size_t)e * d.nbody * 3 + i] = s[L.xpos + i];
-  for (int i = tid; i < d.nbody * 4; i += nt) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
-  for (int i = tid; i < d.nv; i += nt) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
+  for (int i = lane; i < d.nq; i += 32) o.qpos[(size_t)e * d.nq + i] = s[L.qpos + i];
+  for (int i = lane; i < d.nv; i += 32) o.qvel[(size_t)e * d.nv + i] = s[L.qvel + i];
+  for (int i = lane; i < d.na; i += 32) o.act[(size_t)e * d.na + i] = s[L.act + i];
+  for (int i = lane; i < d.nv; i += 32) o.qacc_warmstart[(size_t)e * d.nv + i] = s[L.warm + i];
+  for (int i = lane; i < d.nbody * 3; i += 32) o.xpos[(size_t)e * d.nbody * 3 + i] = s[L.xpos + i];
+  for (int i = lane; i < d.nbody * 4; i += 32) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
+  for (int i = lane; i < d.nv; i += 32) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
   const int torso = (MODE == 2) ? 1 : vnl_hdr_i(tb, VNL_TH_TORSO_BODY);
-  if (tid < 3) o.subtree_com[(size_t)e * 3 + tid] = s[L.rcom + 3 * torso + tid];
+  const float* rcom = s + L.rcom + 3 * c.body_tree[torso];  // subtree_com[torso]: torso is the root of its tree
+  if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = rcom[lane];
   if (MODE == 2) {
-    if (p.stats && tid < 4) p.stats[4 * e + tid] = stats[tid];
+    if (p.stats && lane < 4) p.stats[4 * e + lane] = stats[lane];
+    __syncwarp();
     return;
   }
 
-  // ---- task outputs: obs, traj, reward, done (envs/rodent.py:178-239 / 149-176) -----------------------
+  // ---- task outputs: obs, traj, reward, done (envs/rodent.py:178-239 / 149-176) ---------------------------------------
   const int T = vnl_hdr_i(tb, VNL_TH_CLIP_LEN), ref_len = vnl_hdr_i(tb, VNL_TH_REF_LEN), ntrack = vnl_hdr_i(tb, VNL_TH_NTRACK);
-  const int njidx = vnl_hdr_i(tb, VNL_TH_NJIDX), napp = vnl_hdr_i(tb, VNL_TH_NAPP), nee = vnl_hdr_i(tb, VNL_TH_NEE);
+  const int njidx = vnl_hdr_i(tb, VNL_TH_NJIDX), napp = vnl_hdr_i(tb, VNL_TH_NAPP);
   const int obs_size = vnl_hdr_i(tb, VNL_TH_OBS_SIZE), traj_size = vnl_hdr_i(tb, VNL_TH_TRAJ_SIZE), nj = d.nq - 7;
   const int* bidx = vnl_field_i(tb, VNL_T_BODY_IDXS);
   const int* eeidx = vnl_field_i(tb, VNL_T_EE_IDX);
@@ -1151,10 +1152,10 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
   int cur_frame, sub_clip_frame;
   if (MODE == 0) { cur_frame = frame_old + 1; sub_clip_frame = p.in.sub_clip_frame[e] + 1; }
   else { cur_frame = p.in.cur_frame[e]; sub_clip_frame = 0; }
-  if (tid == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; }
+  if (lane == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; }
   {
     float* obs = p.outputs.obs + (size_t)e * obs_size;
-    for (int i = tid; i < obs_size; i += nt) {
+    for (int i = lane; i < obs_size; i += 32) {
       float v;
       if (i < d.nq) v = s[L.qpos + i];
       else if (i < d.nq + d.nv) v = s[L.qvel + i - d.nq];
@@ -1167,7 +1168,7 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
     const int ws = min(max(cur_frame + 1, 0), T - ref_len);
     float* traj = p.outputs.traj + (size_t)e * traj_size;
     const int n_app = ref_len * napp * 3, n_bod = ref_len * ntrack * 3, n_root = ref_len * 3;
-    for (int i = tid; i < traj_size; i += nt) {
+    for (int i = lane; i < traj_size; i += 32) {
       float v;
       if (i < n_app) {
         const int w = i / (napp * 3), r = i - w * napp * 3;
@@ -1194,20 +1195,24 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
   if (MODE == 1) {
     // info["termination_error"] of the fresh state (rodent.py:169)
     const int f = min(max(cur_frame, 0), T - 1);
-    float v[4] = {0, 0, 0, 0};
-    for (int j = tid; j < nj; j += nt) v[0] += fabsf(rjoints[(size_t)f * nj + j] - s[L.qpos + 7 + j]);
-    for (int b = tid; b < ntrack; b += nt)
-      for (int k = 0; k < 3; ++k) v[1 + k] += fabsf(rbody[((size_t)f * ntrack + b) * 3 + k] - s[L.xpos + 3 * bidx[b] + k]);
-    block_sum<4>(c, v);
-    const float eb = fmaxf(v[1], fmaxf(v[2], v[3]));
-    const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v[0];
-    if (tid == 0) {
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;
+    for (int j = lane; j < nj; j += 32) v0 += fabsf(rjoints[(size_t)f * nj + j] - s[L.qpos + 7 + j]);
+    for (int b = lane; b < ntrack; b += 32) {
+      const float* rb = rbody + ((size_t)f * ntrack + b) * 3;
+      const float* xp = s + L.xpos + 3 * bidx[b];
+      v1 += fabsf(rb[0] - xp[0]); v2 += fabsf(rb[1] - xp[1]); v3_ += fabsf(rb[2] - xp[2]);
+    }
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
+    const float eb = fmaxf(v1, fmaxf(v2, v3_));
+    const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v0;
+    if (lane == 0) {
       p.outputs.reward[e] = 0.0f; p.outputs.done[e] = 0.0f;
       float* mt = p.outputs.metrics + 7 * (size_t)e;
       for (int k = 0; k < 6; ++k) mt[k] = 0.0f;
       mt[6] = 1.0f - err / vnl_hdr_f(tb, VNL_TH_TERM_THRESHOLD);
     }
-    if (p.outputs.stats && tid < 4) p.outputs.stats[4 * e + tid] = stats[tid];
+    if (p.outputs.stats && lane < 4) p.outputs.stats[4 * e + lane] = stats[lane];
+    __syncwarp();
     return;
   }
   // _calculate_reward (rodent.py:266-316): every reference lookup uses the OLD cur_frame
@@ -1216,74 +1221,105 @@ __global__ void __launch_bounds__(kThreads, 4) vnl_env_kernel(Params p) {
     const float* rvel = vnl_field_f(tb, VNL_T_VELOCITY) + (size_t)f * 3;
     const float* rang = vnl_field_f(tb, VNL_T_ANGULAR_VELOCITY) + (size_t)f * 3;
     const float* rjv = vnl_field_f(tb, VNL_T_JOINTS_VELOCITY) + (size_t)f * (d.nv - 6);
-    float v[4] = {0, 0, 0, 0};  // |qvel - ref|^2, sum qfrc_actuator^2, |app - ref|^2, nan count
-    for (int i = tid; i < d.nv; i += nt) {
+    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;  // |qvel - ref|^2, sum qfrc_actuator^2, |app - ref|^2, nan count
+    for (int i = lane; i < d.nv; i += 32) {
       const float ref = i < 3 ? rvel[i] : (i < 6 ? rang[i - 3] : rjv[i - 6]);
       const float df = s[L.qvel + i] - ref;
-      v[0] += df * df;
+      v0 += df * df;
       const float qa = s[L.qfrc_act + i];
-      v[1] += qa * qa;
-      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(qa)) v[3] += 1.0f;
+      v1 += qa * qa;
+      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(qa)) v3_ += 1.0f;
     }
-    for (int i = tid; i < napp * 3; i += nt) {
+    for (int i = lane; i < napp * 3; i += 32) {
       const int a = i / 3, k = i % 3;
       const float df = s[L.xpos + 3 * appidx[a] + k] - rbody[((size_t)f * ntrack + apprefidx[a]) * 3 + k];
-      v[2] += df * df;
+      v2 += df * df;
     }
-    for (int i = tid; i < d.nq; i += nt) if (isnan(s[L.qpos + i])) v[3] += 1.0f;
-    for (int i = tid; i < d.nbody * 3; i += nt) if (isnan(s[L.xpos + i])) v[3] += 1.0f;
-    for (int i = tid; i < d.na; i += nt) if (isnan(s[L.act + i])) v[3] += 1.0f;
-    block_sum<4>(c, v);
-    if (tid == 0) {
-      const int cri = vnl_hdr_i(tb, VNL_TH_COM_REF_IDX);
-      V3 dc = ld3(s + L.rcom + 3 * torso) - ld3(rbody + ((size_t)f * ntrack + cri) * 3);
-      float rcom = expf(-100.0f * sqrtf(dot(dc, dc)));
-      float rvl = expf(-0.1f * sqrtf(v[0]));
-      Q4 qc = quat_normalize(ld4(s + L.qpos + 3));
-      Q4 qr = quat_normalize(ld4(vnl_field_f(tb, VNL_T_QUATERNION) + (size_t)f * 4));
-      const float dq = qc.w * qr.w + qc.x * qr.x + qc.y * qr.y + qc.z * qr.z;
-      const float dist = fminf(1.0f, 2.0f * dq * dq - 1.0f);
-      float rquat = expf(-2.0f * fabsf(0.5f * acosf(dist)));
-      float ract = -0.015f * (v[1] / (float)d.nv);
-      float rapp = expf(-400.0f * sqrtf(v[2]));
-      const float z = s[L.qpos + 2];
-      float healthy = z < vnl_hdr_f(tb, VNL_TH_HEALTHY_LO) ? 0.0f : 1.0f;
-      if (z > vnl_hdr_f(tb, VNL_TH_HEALTHY_HI)) healthy = 0.0f;
-      rcom *= 0.01f; rvl *= 0.01f; rapp *= 0.01f;
-      float rtr = rtrunk * 0.01f;
-      rquat *= 0.01f; ract *= 0.0001f;
-      const float total = rcom + rvl + rtr + rquat + ract + rapp;
-      const float sub_healthy = sub_clip_frame < vnl_hdr_i(tb, VNL_TH_SUB_CLIP_LEN) ? 1.0f : 0.0f;
-      float done = rtr < 0.0f ? 1.0f : 0.0f;
-      done = fmaxf(1.0f - healthy, done);
-      done = fmaxf(1.0f - sub_healthy, done);
-      if (v[3] > 0.0f) done = 1.0f;
+    for (int i = lane; i < d.nq; i += 32) if (isnan(s[L.qpos + i])) v3_ += 1.0f;
+    for (int i = lane; i < d.nbody * 3; i += 32) if (isnan(s[L.xpos + i])) v3_ += 1.0f;
+    for (int i = lane; i < d.na; i += 32) if (isnan(s[L.act + i])) v3_ += 1.0f;
+    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
+    const int cri = vnl_hdr_i(tb, VNL_TH_COM_REF_IDX);
+    const V3 dc = ld3(rcom) - ld3(rbody + ((size_t)f * ntrack + cri) * 3);
+    float r_com = expf(-100.0f * sqrtf(dot(dc, dc)));
+    float rvl = expf(-0.1f * sqrtf(v0));
+    const Q4 qc = quat_normalize(ld4(s + L.qpos + 3));
+    const Q4 qr = quat_normalize(ld4(vnl_field_f(tb, VNL_T_QUATERNION) + (size_t)f * 4));
+    const float dq = qc.w * qr.w + qc.x * qr.x + qc.y * qr.y + qc.z * qr.z;
+    const float dist = fminf(1.0f, 2.0f * dq * dq - 1.0f);
+    float rquat = expf(-2.0f * fabsf(0.5f * acosf(dist)));
+    float ract = -0.015f * (v1 / (float)d.nv);
+    float rapp = expf(-400.0f * sqrtf(v2));
+    const float z = s[L.qpos + 2];
+    float healthy = z < vnl_hdr_f(tb, VNL_TH_HEALTHY_LO) ? 0.0f : 1.0f;
+    if (z > vnl_hdr_f(tb, VNL_TH_HEALTHY_HI)) healthy = 0.0f;
+    r_com *= 0.01f; rvl *= 0.01f; rapp *= 0.01f;
+    const float rtr = rtrunk * 0.01f;
+    rquat *= 0.01f; ract *= 0.0001f;
+    const float total = r_com + rvl + rtr + rquat + ract + rapp;
+    const float sub_healthy = sub_clip_frame < vnl_hdr_i(tb, VNL_TH_SUB_CLIP_LEN) ? 1.0f : 0.0f;
+    float done = rtr < 0.0f ? 1.0f : 0.0f;
+    done = fmaxf(1.0f - healthy, done);
+    done = fmaxf(1.0f - sub_healthy, done);
+    if (v3_ > 0.0f) done = 1.0f;
+    if (lane == 0) {
       p.outputs.reward[e] = nan_to_num(total);
       p.outputs.done[e] = done;
       float* mt = p.outputs.metrics + 7 * (size_t)e;
-      mt[0] = rcom; mt[1] = rvl; mt[2] = rtr; mt[3] = rquat; mt[4] = ract; mt[5] = rapp; mt[6] = rtr;
-      ints[8] = done > 0.0f;
+      mt[0] = r_com; mt[1] = rvl; mt[2] = rtr; mt[3] = rquat; mt[4] = ract; mt[5] = rapp; mt[6] = rtr;
     }
-    if (p.outputs.stats && tid < 4) p.outputs.stats[4 * e + tid] = stats[tid];
+    if (p.outputs.stats && lane < 4) p.outputs.stats[4 * e + lane] = stats[lane];
     // brax AutoResetWrapper.step fused in: where done, the pipeline-state leaves and obs are replaced by the cached
     // first ones; info (frames, traj), reward, done and metrics are kept.
-    if (p.first.qpos) {
-      __syncthreads();
-      if (ints[8]) {
-        const VnlState& f = p.first;
-        for (int i = tid; i < d.nq; i += nt) o.qpos[(size_t)e * d.nq + i] = f.qpos[(size_t)e * d.nq + i];
-        for (int i = tid; i < d.nv; i += nt) o.qvel[(size_t)e * d.nv + i] = f.qvel[(size_t)e * d.nv + i];
-        for (int i = tid; i < d.na; i += nt) o.act[(size_t)e * d.na + i] = f.act[(size_t)e * d.na + i];
-        for (int i = tid; i < d.nv; i += nt) o.qacc_warmstart[(size_t)e * d.nv + i] = f.qacc_warmstart[(size_t)e * d.nv + i];
-        for (int i = tid; i < d.nbody * 3; i += nt) o.xpos[(size_t)e * d.nbody * 3 + i] = f.xpos[(size_t)e * d.nbody * 3 + i];
-        for (int i = tid; i < d.nbody * 4; i += nt) o.xquat[(size_t)e * d.nbody * 4 + i] = f.xquat[(size_t)e * d.nbody * 4 + i];
-        for (int i = tid; i < d.nv; i += nt) o.qfrc_actuator[(size_t)e * d.nv + i] = f.qfrc_actuator[(size_t)e * d.nv + i];
-        if (tid < 3) o.subtree_com[(size_t)e * 3 + tid] = f.subtree_com[(size_t)e * 3 + tid];
-        if (p.first_obs)
-          for (int i = tid; i < obs_size; i += nt) p.outputs.obs[(size_t)e * obs_size + i] = p.first_obs[(size_t)e * obs_size + i];
-      }
+    if (p.first.qpos && done > 0.0f) {
+      const VnlState& f1 = p.first;
+      for (int i = lane; i < d.nq; i += 32) o.qpos[(size_t)e * d.nq + i] = f1.qpos[(size_t)e * d.nq + i];
+      for (int i = lane; i < d.nv; i += 32) o.qvel[(size_t)e * d.nv + i] = f1.qvel[(size_t)e * d.nv + i];
+      for (int i = lane; i < d.na; i += 32) o.act[(size_t)e * d.na + i] = f1.act[(size_t)e * d.na + i];
+      for (int i = lane; i < d.nv; i += 32) o.qacc_warmstart[(size_t)e * d.nv + i] = f1.qacc_warmstart[(size_t)e * d.nv + i];
+      for (int i = lane; i < d.nbody * 3; i += 32) o.xpos[(size_t)e * d.nbody * 3 + i] = f1.xpos[(size_t)e * d.nbody * 3 + i];
+      for (int i = lane; i < d.nbody * 4; i += 32) o.xquat[(size_t)e * d.nbody * 4 + i] = f1.xquat[(size_t)e * d.nbody * 4 + i];
+      for (int i = lane; i < d.nv; i += 32) o.qfrc_actuator[(size_t)e * d.nv + i] = f1.qfrc_actuator[(size_t)e * d.nv + i];
+      if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = f1.subtree_com[(size_t)e * 3 + lane];
+      if (p.first_obs)
+        for (int i = lane; i < obs_size; i += 32) p.outputs.obs[(size_t)e * obs_size + i] = p.first_obs[(size_t)e * obs_size + i];
     }
   }
+  __syncwarp();
+  pf.mark(15);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
+  extern __shared__ __align__(16) float smem[];
+  Cta& c = *reinterpret_cast<Cta*>(smem);
+  uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kCtaFloats);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const uint32_t* g_ktab = (const uint32_t*)vnl_field_i(p.model, VNL_F_KTAB);
+  for (int i = tid; i < p.dims.ktab_words; i += nt) ktab[i] = g_ktab[i];
+  for (int f = tid; f < VNL_F_MODEL_COUNT; f += nt) c.foff[f] = p.model[VNL_TABLE_OFF + 2 * f];
+  if (tid == 0) {
+    c.d = p.dims;
+    make_layout(c.d, c.L);
+    c.mb = p.model;
+    c.prof = p.prof; c.prof_env = p.prof_env;
+    const uint8_t* kb = (const uint8_t*)ktab;
+#define T8(name, id) c.name = kb + g_ktab[id]
+#define T16(name, id) c.name = (const uint16_t*)(kb + g_ktab[id])
+    T8(lvl_start, VNL_KT_LVL_START); T16(lvl_bp, VNL_KT_LVL_BP); T8(parent, VNL_KT_PARENT); T8(child_adr, VNL_KT_CHILD_ADR);
+    T8(child_list, VNL_KT_CHILD_LIST); T8(body_dofadr, VNL_KT_BODY_DOFADR); T8(body_dofnum, VNL_KT_BODY_DOFNUM);
+    T8(body_tree, VNL_KT_BODY_TREE); T8(lastdof, VNL_KT_BODY_LASTDOF); T8(sub_end, VNL_KT_SUB_END); T8(roots, VNL_KT_ROOTS);
+    T8(mrow, VNL_KT_MROW); T8(mcol, VNL_KT_MCOL); T8(drow, VNL_KT_DROW); T8(dof_body, VNL_KT_DOF_BODY); T8(lane_rows, VNL_KT_LANE_ROWS);
+    T16(madr, VNL_KT_MADR); T16(dadr, VNL_KT_DADR); T16(dent, VNL_KT_DENT); T16(tri, VNL_KT_TRI); T16(anc_start, VNL_KT_ANC_START);
+    T16(kitem, VNL_KT_KITEM); T16(klvl, VNL_KT_KLVL);
+#undef T8
+#undef T16
+    c.R = (int)g_ktab[VNL_KT_COUNT];
+  }
+  __syncthreads();
+  const int W = nt >> 5, warp = tid >> 5;
+  float* s = smem + kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
+  for (int e = blockIdx.x * W + warp; e < p.B; e += gridDim.x * W) env_run<MODE>(c, s, p, e);
 }
 
 template __global__ void vnl_env_kernel<0>(Params);
@@ -1291,23 +1327,40 @@ template __global__ void vnl_env_kernel<1>(Params);
 template __global__ void vnl_env_kernel<2>(Params);
 template __global__ void vnl_env_kernel<3>(Params);
 
-int smem_bytes(const Dims& d) {
+LaunchInfo launch_info(const Dims& d, int B) {
   Lay L;
   make_layout(d, L);
-  return (L.total + kCtxFloats) * (int)sizeof(float);
+  const int fixed = (kCtaFloats + align4(d.ktab_words)) * 4, per = L.total * 4;
+  int W = (227 * 1024 - fixed) / per;
+  if (W > kMaxWarps) W = kMaxWarps;
+  static int env_w = -1;
+  if (env_w < 0) { const char* ev = getenv("VNL_WARPS"); env_w = ev ? atoi(ev) : 0; }
+  if (env_w > 0 && env_w < W) W = env_w;
+  LaunchInfo li;
+  li.warps_per_cta = W;
+  li.smem_bytes = fixed + (W > 0 ? W : 1) * per;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  int resident = (227 * 1024) / (li.smem_bytes + 1024);
+  if (resident < 1) resident = 1;
+  const int max_threads_ctas = 2048 / ((W > 0 ? W : 1) * 32);
+  if (resident > max_threads_ctas) resident = max_threads_ctas;
+  const int need = W > 0 ? (B + W - 1) / W : 0;
+  li.ctas = need < sms * resident ? need : sms * resident;
+  return li;
 }
 
 cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
-  const int bytes = smem_bytes(p.dims);
+  const LaunchInfo li = launch_info(p.dims, p.B);
+  if (li.warps_per_cta < 1) return cudaErrorInvalidConfiguration;  // one env does not fit in shared memory
   void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
-  cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;
-  // leave the rest of the unified 228 KB array to L1: the model tables are re-read from it every substep
-  int ctas = 4;
-  while (ctas > 1 && ctas * (bytes + 1024) > 227 * 1024) --ctas;
-  int pct = (ctas * (bytes + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024);
-  cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, pct > 100 ? 100 : pct);
-  k<<<p.B, kThreads, bytes, stream>>>(p);
+  k<<<li.ctas, li.warps_per_cta * 32, li.smem_bytes, stream>>>(p);
   return cudaGetLastError();
 }
 

@@ -7,23 +7,27 @@
 
 namespace vnl {
 
-constexpr int kThreads = 128;  // one CTA per env
-constexpr int kMaxWarps = 8;
+constexpr int kMaxWarps = 8;   // envs (warps) per CTA upper bound
 
 struct Dims {
-  int nq, nv, nu, na, nbody, njnt, ngeom, npair, ncon, nlimit, nefc, nM, nlevel, maxdepth;
+  int nq, nv, nu, na, nbody, njnt, ngeom, npair, ncon, nlimit, nefc, nM, nlevel, maxdepth, nroot;
   int solver, iterations, ls_iterations, eulerdamp;
   float timestep, gx, gy, gz, tolerance, ls_tolerance, impratio, meaninertia;
+  int ktab_words;  // size of VNL_F_KTAB
   // stage-dump offsets (layout of oracle.dump_layout)
   int dump_xpos, dump_xipos, dump_xanchor, dump_subtree_com, dump_cinert, dump_qM, dump_cvel, dump_passive, dump_con,
       dump_efc, dump_qacc, dump_total;
 };
 
+// Per-env shared-memory layout (float offsets).  Region A (kinematic / inertial scratch) is dead once the joint-space
+// inertia is built and shares its storage with region B (inverse factor + constraint rows).
 struct Lay {
-  int qpos, qvel, act, ctrl, warm, xpos, xquat, xipos, xanchor, xaxis, rcom, cinert, crb, cdof, cdofdot, cvel, cacc, cfrc, M,
-      Lf, K, qfrc_smooth, qacc_smooth, qfrc_act, act_dot, lim_dof, lim_sign, limrow_of_dof, cbody, crel, cframe, cmu, cwrench,
-      efcD, aref, Jaref, Jv, qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, red, ints, mcol8, mrow8, madr16, dadr16,
-      dent16, drow8, dls8, dld8, total;
+  int qpos, qvel, act, ctrl, warm, xpos, xquat, cdof, cvel, M, rcom;
+  int xipos, xanchor, xaxis, t16, cacc;                                   // region A
+  int K, efcD, Jaref, Jv;                                                 // region B
+  int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
+  int lim_dof, lim_sign, limrow_of_dof, cbody, crel, cframe, cmu, cwrench;
+  int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, ints, total;
 };
 
 struct Params {
@@ -38,11 +42,13 @@ struct Params {
   VnlOutputs outputs;
   int32_t* stats;
   float* dump;
-  long long* prof;  // optional [32] per-phase clock64 accumulators of one CTA (developer hook)
-  int prof_block;
+  long long* prof;  // optional [32] per-phase clock64 accumulators of one env (developer hook)
+  int prof_env;
 };
 
-int smem_bytes(const Dims& d);
+struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };
+
+LaunchInfo launch_info(const Dims& d, int B);
 cudaError_t launch(int mode, const Params& p, cudaStream_t stream);
 
 }  // namespace vnl

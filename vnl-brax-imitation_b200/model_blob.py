@@ -137,7 +137,90 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
         raise NotImplementedError("planes must be attached to the world body")
     plane_mat = np.array([mjcf.quat_to_mat(A["geom_quat"][g]).reshape(9) for g in g1]).reshape(-1, 9)
     geom_mat = np.array([mjcf.quat_to_mat(A["geom_quat"][g]).reshape(9) for g in g2]).reshape(-1, 9)
-    return dict(level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
+    # ---- shared-memory index tables of the warp-per-env kernel (VNL_F_KTAB) -------------------------------------
+    if nb > 255 or nv > 255 or len(mcol) > 65535:
+        raise NotImplementedError("model too large for the packed kernel tables")
+    children = [[] for _ in range(nb)]
+    for b in range(nb - 1, 0, -1):
+        children[parent[b]].append(b)  # descending id: the order `crb[parent] += crb[b]` visits them
+    child_adr = [0]
+    for b in range(nb):
+        child_adr.append(child_adr[-1] + len(children[b]))
+    roots = [b for b in range(1, nb) if parent[b] == 0]
+    tree = np.zeros(nb, dtype=np.int64)
+    for b in range(1, nb):
+        tree[b] = roots.index(int(A["body_rootid"][b]))
+    dofnum_flag = np.array(A["body_dofnum"], dtype=np.int64).copy()
+    for b in range(1, nb):
+        if A["body_jntnum"][b] > 0 and A["jnt_type"][A["body_jntadr"][b]] == mjcf.JNT_FREE:
+            dofnum_flag[b] |= 0x80
+    load = [(madr[i + 1] - madr[i]) + (desc_adr[i + 1] - desc_adr[i]) for i in range(nv)]
+    lanes = [[] for _ in range(32)]
+    lane_load = [0] * 32
+    for i in sorted(range(nv), key=lambda i: -load[i]):
+        l = min(range(32), key=lambda l: (lane_load[l], len(lanes[l])))
+        lanes[l].append(i)
+        lane_load[l] += load[i] + 4
+    R = max(1, max(len(x) for x in lanes))
+    lane_rows = np.full((R, 32), 0xFF, dtype=np.int64)  # [r][lane]: coalesced across lanes
+    for l in range(32):
+        for r, i in enumerate(lanes[l]):
+            lane_rows[r, l] = i
+    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)]
+    kitem, klvl = [], [0, 0]
+    for dpt in range(1, maxd + 1):
+        items = [(c, i) for i in range(nv) if ddepth[i] == dpt for c in range(1, dpt + 1)]
+        items.sort(key=lambda t: (-t[0], t[1]))
+        kitem += [c | (i << 8) for c, i in items]
+        klvl.append(len(kitem))
+    u8 = lambda a: np.asarray(a, dtype=np.int64).astype(np.uint8)
+    u16 = lambda a: np.asarray(a, dtype=np.int64).astype(np.uint16)
+    lastdof_u8 = np.where(lastdof < 0, 0xFF, lastdof)
+    kt = [None] * C["VNL_KT_COUNT"]
+    kt[C["VNL_KT_LVL_START"]] = u8(level_start)
+    kt[C["VNL_KT_LVL_BP"]] = u16([b | (int(parent[b]) << 8) for b in order])
+    kt[C["VNL_KT_PARENT"]] = u8(parent)
+    kt[C["VNL_KT_CHILD_ADR"]] = u8(child_adr)
+    kt[C["VNL_KT_CHILD_LIST"]] = u8([ch for b in range(nb) for ch in children[b]])
+    kt[C["VNL_KT_BODY_DOFADR"]] = u8(np.maximum(A["body_dofadr"], 0))
+    kt[C["VNL_KT_BODY_DOFNUM"]] = u8(dofnum_flag)
+    kt[C["VNL_KT_BODY_TREE"]] = u8(tree)
+    kt[C["VNL_KT_BODY_LASTDOF"]] = u8(lastdof_u8)
+    kt[C["VNL_KT_SUB_END"]] = u8(sub_end)
+    kt[C["VNL_KT_ROOTS"]] = u8(roots)
+    kt[C["VNL_KT_MROW"]] = u8(mrow)
+    kt[C["VNL_KT_MCOL"]] = u8(mcol)
+    kt[C["VNL_KT_DROW"]] = u8([mrow[e] for e in desc_entry])
+    kt[C["VNL_KT_DOF_BODY"]] = u8(A["dof_bodyid"])
+    kt[C["VNL_KT_LANE_ROWS"]] = u8(lane_rows.reshape(-1))
+    kt[C["VNL_KT_MADR"]] = u16(madr)
+    kt[C["VNL_KT_DADR"]] = u16(desc_adr)
+    kt[C["VNL_KT_DENT"]] = u16(desc_entry)
+    kt[C["VNL_KT_TRI"]] = u16(tri)
+    kt[C["VNL_KT_ANC_START"]] = u16([madr[j] for j in mcol])
+    kt[C["VNL_KT_KITEM"]] = u16(kitem)
+    kt[C["VNL_KT_KLVL"]] = u16(klvl)
+    nkt = C["VNL_KT_COUNT"]
+    off = 4 * (nkt + 1)
+    dirw = np.zeros(nkt + 1, dtype=np.uint32)
+    blobs = []
+    for t, a in enumerate(kt):
+        raw = a.tobytes()
+        raw += b"\0" * ((-len(raw)) % 4)
+        dirw[t] = off
+        off += len(raw)
+        blobs.append(raw)
+    dirw[nkt] = R
+    ktab = np.frombuffer(dirw.tobytes() + b"".join(blobs), dtype=np.uint32).copy()
+    act_of_dof = [[] for _ in range(nv)]
+    for u, dadr in enumerate(A["actuator_dofadr"]):
+        act_of_dof[int(dadr)].append(u)
+    dof_actadr = [0]
+    for i in range(nv):
+        dof_actadr.append(dof_actadr[-1] + len(act_of_dof[i]))
+    return dict(ktab=ktab, nroot=len(roots), dof_actadr=np.array(dof_actadr),
+                dof_actlist=np.array([u for i in range(nv) for u in act_of_dof[i]], dtype=np.int64),
+                level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
                 m_col=np.array(mcol), dof_depth=np.array(ddepth), body_subtree_end=sub_end,
                 limit_jnt=np.array(limit_jnt, dtype=np.int64), con_pair=np.array(con_pair, dtype=np.int64),
                 con_sign=np.array(con_sign), geomc_body=A["geom_bodyid"][g2], geomc_pos=A["geom_pos"][g2],
@@ -192,6 +275,8 @@ _DERIVED_FIELDS = [
     ("VNL_F_M_ROW", "m_row", np.int32), ("VNL_F_BODY_LASTDOF", "body_lastdof", np.int32),
     ("VNL_F_DESC_ADR", "desc_adr", np.int32), ("VNL_F_DESC_ENTRY", "desc_entry", np.int32),
     ("VNL_F_DOFLEVEL_START", "doflevel_start", np.int32), ("VNL_F_DOFLEVEL_DOF", "doflevel_dof", np.int32),
+    ("VNL_F_DOF_ACTADR", "dof_actadr", np.int32), ("VNL_F_DOF_ACTLIST", "dof_actlist", np.int32),
+    ("VNL_F_KTAB", "ktab", np.uint32),
 ]
 
 
@@ -200,7 +285,7 @@ def model_dims(m: mjcf.Model) -> Dict[str, int]:
     ncon, nlimit = len(d["con_pair"]), len(d["limit_jnt"])
     return dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom,
                 npair=len(m.arrays["pair_geom1"]), ncon=ncon, nlimit=nlimit, nefc=nlimit + 4 * ncon,
-                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"])
+                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"])
 
 
 def build_model_blob(m: mjcf.Model) -> np.ndarray:
@@ -211,7 +296,7 @@ def build_model_blob(m: mjcf.Model) -> np.ndarray:
                       ("VNL_MH_NBODY", "nbody"), ("VNL_MH_NJNT", "njnt"), ("VNL_MH_NGEOM", "ngeom"),
                       ("VNL_MH_NPAIR", "npair"), ("VNL_MH_NCON", "ncon"), ("VNL_MH_NLIMIT", "nlimit"),
                       ("VNL_MH_NEFC", "nefc"), ("VNL_MH_NM", "nM"), ("VNL_MH_NLEVEL", "nlevel"),
-                      ("VNL_MH_MAXDEPTH", "maxdepth")]:
+                      ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot")]:
         w.set_i(slot, dims[key])
     w.set_i("VNL_MH_SOLVER", m.solver)
     w.set_i("VNL_MH_ITERATIONS", m.iterations)
@@ -237,7 +322,7 @@ def read_dims(blob: np.ndarray) -> Dict[str, int]:
     return dict(nq=g("VNL_MH_NQ"), nv=g("VNL_MH_NV"), nu=g("VNL_MH_NU"), na=g("VNL_MH_NA"),
                 nbody=g("VNL_MH_NBODY"), njnt=g("VNL_MH_NJNT"), ngeom=g("VNL_MH_NGEOM"), npair=g("VNL_MH_NPAIR"),
                 ncon=g("VNL_MH_NCON"), nlimit=g("VNL_MH_NLIMIT"), nefc=g("VNL_MH_NEFC"), nM=g("VNL_MH_NM"),
-                nlevel=g("VNL_MH_NLEVEL"), maxdepth=g("VNL_MH_MAXDEPTH"), solver=g("VNL_MH_SOLVER"),
+                nlevel=g("VNL_MH_NLEVEL"), maxdepth=g("VNL_MH_MAXDEPTH"), nroot=g("VNL_MH_NROOT"), solver=g("VNL_MH_SOLVER"),
                 iterations=g("VNL_MH_ITERATIONS"), ls_iterations=g("VNL_MH_LS_ITERATIONS"),
                 eulerdamp=g("VNL_MH_EULERDAMP"))
 
