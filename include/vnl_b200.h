@@ -68,6 +68,7 @@ enum VnlModelHdr {
   VNL_MH_NLEVEL,      /* body-tree depth (levels below the world body) */
   VNL_MH_MAXDEPTH,    /* longest dof ancestor chain */
   VNL_MH_NROOT,       /* kinematic trees (bodies whose parent is the world) */
+  VNL_MH_NDSLOT,      /* partial-sum slots of the descendant mat-vec program (= KTAB scalar VNL_KS_NDSLOT) */
   /* floats (bit patterns) */
   VNL_MH_TIMESTEP = 32, VNL_MH_GRAVITY_X, VNL_MH_GRAVITY_Y, VNL_MH_GRAVITY_Z,
   VNL_MH_TOLERANCE, VNL_MH_LS_TOLERANCE, VNL_MH_IMPRATIO, VNL_MH_MEANINERTIA
@@ -159,8 +160,8 @@ enum VnlModelField {
   VNL_F_MODEL_COUNT
 };
 
-/* VNL_F_KTAB: words [0 .. VNL_KT_COUNT) hold the BYTE offset of each table from the start of the field, word
- * VNL_KT_COUNT the rows-per-lane R of VNL_KT_LANE_ROWS; every table is 4-byte aligned.  Built by model_blob.py. */
+/* VNL_F_KTAB: words [0 .. VNL_KT_COUNT) hold the BYTE offset of each table from the start of the field, the next
+ * VNL_KT_NSCALAR words hold scalars (VnlKtabScalar); every table is 4-byte aligned.  Built by model_blob.py. */
 enum VnlKtab {
   VNL_KT_LVL_START = 0, /* u8  [nlevel+1] offsets into LVL_BP */
   VNL_KT_LVL_BP,        /* u16 [nbody-1]  body | parent << 8, bodies sorted by tree level */
@@ -175,18 +176,23 @@ enum VnlKtab {
   VNL_KT_ROOTS,         /* u8  [nroot] root body of each tree */
   VNL_KT_MROW,          /* u8  [nM] */
   VNL_KT_MCOL,          /* u8  [nM] */
-  VNL_KT_DROW,          /* u8  [nM-nv] row (descendant dof) of each DENT entry */
   VNL_KT_DOF_BODY,      /* u8  [nv] */
-  VNL_KT_LANE_ROWS,     /* u8  [32*R] dofs whose matrix rows each lane owns (load balanced), 0xFF = none */
+  VNL_KT_DPART_ADR,     /* u8  [nv+1] CSR: partial-sum slots of PROG_D that make up each dof's descendant sum */
   VNL_KT_MADR,          /* u16 [nv+1] */
-  VNL_KT_DADR,          /* u16 [nv+1] */
-  VNL_KT_DENT,          /* u16 [nM-nv] */
   VNL_KT_TRI,           /* u16 [maxdepth (maxdepth+1) / 2]  a | c << 8 with 1 <= a <= c, index c (c-1) / 2 + a - 1 */
   VNL_KT_ANC_START,     /* u16 [nM] madr[mcol[e]]: row start of the entry's column dof */
   VNL_KT_KITEM,         /* u16 [sum of dof depths] c | dof << 8, grouped by dof depth, descending c inside a group */
   VNL_KT_KLVL,          /* u16 [maxdepth+2] offsets into KITEM by dof depth */
+  /* Lane programs of the sparse mat-vecs with M and with the inverse factor K (same sparsity).  A program is
+   * [T][32] words, one term per lane per step: bits 0-13 entry * 4, bits 14-23 x index * 4, bits 24-31 the
+   * partial-sum slot to flush into after this term (0xFF = keep accumulating).  PROG_A: strict-ancestor terms
+   * (row i, entries madr[i]+1 ..), slot = dof.  PROG_D: descendant terms (column j), long columns split into chunks,
+   * slots listed by DPART_ADR.  Lanes are load balanced on the host; lists are padded with a zero term. */
+  VNL_KT_PROG_A,        /* u32 [TA*32] */
+  VNL_KT_PROG_D,        /* u32 [TD*32] */
   VNL_KT_COUNT
 };
+enum VnlKtabScalar { VNL_KS_TA = 0, VNL_KS_TD, VNL_KS_NDSLOT, VNL_KS_RESERVED, VNL_KT_NSCALAR };
 
 /* scalar header slots of a TASK blob (imitation task: clip + index tables) */
 enum VnlTaskHdr {

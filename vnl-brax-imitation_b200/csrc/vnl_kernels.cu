@@ -40,38 +40,49 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   int o = 0;
 #define A(name, n) L.name = o; o += align4(n)
   A(qpos, d.nq); A(qvel, d.nv); A(act, d.na); A(ctrl, d.nu); A(warm, d.nv);
-  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6); A(cvel, d.nbody * 6); A(M, d.nM); A(rcom, d.nroot * 3);
+  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6); A(cvel, d.nbody * 6); A(M, d.nM + 1); A(rcom, d.nroot * 3);
   const int ab = o;
   A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16); A(cacc, (d.nbody > d.nv ? d.nbody : d.nv) * 6);
   const int a_end = o;
   o = ab;
-  A(K, d.nM); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc);
+  A(K, d.nM + 1); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc);
   if (a_end > o) o = a_end;
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
   A(lim_dof, d.nlimit); A(lim_sign, d.nlimit); A(limrow_of_dof, d.nv);
   A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 9); A(cmu, d.ncon); A(cwrench, d.ncon * 6);
-  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv);
+  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.nv + d.ndslot);
   A(ints, 16);
 #undef A
   L.total = o;
 }
 
-// CTA-shared context (start of dynamic shared memory): dimensions, layout, field offsets and the staged index tables.
+// CTA-shared context (start of dynamic shared memory): dimensions, layout, field offsets and the BYTE offsets (from the
+// start of shared memory) of the staged index tables.  Everything in shared memory is addressed as smem + offset so
+// that the compiler emits 32-bit LDS / STS (a pointer stored in memory would come back generic).
 struct __align__(16) Cta {
   Dims d;
   Lay L;
   const uint32_t* mb;
   uint32_t foff[VNL_F_MODEL_COUNT];
-  const uint8_t *lvl_start, *parent, *child_adr, *child_list, *body_dofadr, *body_dofnum, *body_tree, *lastdof, *sub_end, *roots,
-      *mrow, *mcol, *drow, *dof_body, *lane_rows;
-  const uint16_t *lvl_bp, *madr, *dadr, *dent, *tri, *anc_start, *kitem, *klvl;
-  int R;
+  uint32_t o_lvl_start, o_lvl_bp, o_parent, o_child_adr, o_child_list, o_body_dofadr, o_body_dofnum, o_body_tree, o_lastdof, o_sub_end,
+      o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_madr, o_tri, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
+  int TA, TD, ndslot;
   long long* prof;
   int prof_env;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
   __device__ __forceinline__ const float* ff(int f) const { return (const float*)(mb + foff[f]); }
 };
 constexpr int kCtaFloats = (int)((sizeof(Cta) + 15) / 16 * 4);
+
+// Every device function re-derives its view of shared memory from the `smem` symbol: c = CTA context, s = this warp's
+// env slice (float offset `so`).
+#define VNL_SMEM                                                  \
+  extern __shared__ __align__(16) float smem[];                    \
+  const Cta& c = *reinterpret_cast<const Cta*>(smem);              \
+  float* const s = smem + so;
+#define TB8(name) (reinterpret_cast<const uint8_t*>(smem) + c.o_##name)
+#define TB16(name) reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(smem) + c.o_##name)
+#define TB32(name) reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(smem) + c.o_##name)
 
 struct Prof {
   long long* p;
@@ -82,119 +93,160 @@ struct Prof {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-// sparse-inertia helpers (one warp)
+// sparse-inertia helpers (one warp).  Vector arguments are float offsets into the env slice.
 // ---------------------------------------------------------------------------------------------------------------------
-// out = M x   (tree-sparse M, rows hold [diag, ancestors...]); each lane owns the rows LANE_ROWS assigns to it
-__device__ __noinline__ void mul_m(const Cta& c, float* s, const float* x, float* out) {
-  const float* M = s + c.L.M;
-  for (int r = 0; r < c.R; ++r) {
-    const int i = c.lane_rows[r * 32 + LANE];
-    if (i != 0xFF) {
-      float a0 = 0.0f, a1 = 0.0f;
-      int a = c.madr[i];
-      const int ae = c.madr[i + 1];
-      for (; a + 1 < ae; a += 2) { a0 += M[a] * x[c.mcol[a]]; a1 += M[a + 1] * x[c.mcol[a + 1]]; }
-      if (a < ae) a0 += M[a] * x[c.mcol[a]];
-      int k = c.dadr[i];
-      const int ke = c.dadr[i + 1];
-      for (; k + 1 < ke; k += 2) { a0 += M[c.dent[k]] * x[c.drow[k]]; a1 += M[c.dent[k + 1]] * x[c.drow[k + 1]]; }
-      if (k < ke) a0 += M[c.dent[k]] * x[c.drow[k]];
-      out[i] = a0 + a1;
-    }
+// One section of a lane program: part[slot] = sum over the lane's terms of V[entry] * x[index] (see VnlKtab).
+__device__ __forceinline__ void spmv_section(const uint32_t* prog, int T, const float* V, const float* x, float* part) {
+  const char* Vb = reinterpret_cast<const char*>(V);
+  const char* xb = reinterpret_cast<const char*>(x);
+  prog += LANE;
+  float acc = 0.0f;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    const uint32_t w = prog[t * 32];
+    acc += *reinterpret_cast<const float*>(Vb + (w & 0x3ffcu)) * *reinterpret_cast<const float*>(xb + ((w >> 14) & 0x3fcu));
+    if (w < 0xff000000u) { part[w >> 24] = acc; acc = 0.0f; }
+  }
+}
+
+// out = M x   (tree-sparse symmetric M: diagonal + strict-ancestor terms + descendant terms)
+__device__ __noinline__ void mul_m(int so, int xo, int outo) {
+  VNL_SMEM
+  const int nv = c.d.nv, lane = LANE;
+  float* const M = s + c.L.M;
+  const float* const x = s + xo;
+  float* const pa = s + c.L.part;
+  float* const pd = pa + nv;
+  if (lane == 0) M[c.d.nM] = 0.0f;  // the zero entry padded program terms point at
+  __syncwarp();
+  spmv_section(TB32(prog_a), c.TA, M, x, pa);
+  spmv_section(TB32(prog_d), c.TD, M, x, pd);
+  __syncwarp();
+  const uint16_t* const madr = TB16(madr);
+  const uint8_t* const dpa = TB8(dpart_adr);
+  float* const out = s + outo;
+  for (int i = lane; i < nv; i += 32) {
+    const int m0 = madr[i];
+    float acc = M[m0] * x[i];
+    if (madr[i + 1] - m0 > 1) acc += pa[i];
+    for (int q = dpa[i]; q < dpa[i + 1]; ++q) acc += pd[q];
+    out[i] = acc;
   }
   __syncwarp();
 }
 
 // L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
-__device__ __noinline__ void factor(const Cta& c, float* s, bool damp) {
-  const int nv = c.d.nv, nM = c.d.nM, lane = LANE;
-  const float* M = s + c.L.M;
-  float* F = s + c.L.K;
-  const float* damping = c.ff(VNL_F_DOF_DAMPING);
-  for (int e = lane; e < nM; e += 32) {
-    float v = M[e];
-    if (damp && c.mcol[e] == c.mrow[e]) v += c.d.timestep * damping[c.mrow[e]];
-    F[e] = v;
+__device__ __noinline__ void factor(int so, bool damp) {
+  VNL_SMEM
+  const int nv = c.d.nv, nM = c.d.nM, lane = LANE, maxdepth = c.d.maxdepth;
+  const float* const M = s + c.L.M;
+  float* const F = s + c.L.K;
+  const uint16_t* const madr = TB16(madr);
+  const uint16_t* const anc_start = TB16(anc_start);
+  const uint16_t* const tri = TB16(tri);
+  const uint8_t* const mrow = TB8(mrow);
+  const uint8_t* const mcol = TB8(mcol);
+  {
+    const float* damping = c.ff(VNL_F_DOF_DAMPING);
+    const float dt = c.d.timestep;
+    for (int e = lane; e < nM; e += 32) {
+      float v = M[e];
+      if (damp && mcol[e] == mrow[e]) v += dt * damping[mrow[e]];
+      F[e] = v;
+    }
+    if (lane == 0) F[nM] = 0.0f;
   }
   __syncwarp();
   // eliminate dofs from the leaves: for 1 <= a <= cc <= dk:  F[anc_a(k)][cc - a] -= F[k][a] * F[k][cc] / F[k][0]
   // (rows stay un-normalised until the end); the (a, cc) pairs of one k are spread over the lanes through TRI
   for (int k = nv - 1; k > 0; --k) {
-    const int base = c.madr[k], dk = c.madr[k + 1] - base - 1;
+    const int base = madr[k], dk = madr[k + 1] - base - 1;
     if (dk > 0) {
       const float inv = 1.0f / F[base];
       const int np = (dk * (dk + 1)) >> 1;
+      const float* const Fk = F + base;
+      const uint16_t* const ak = anc_start + base;
+#pragma unroll 2
       for (int pi = lane; pi < np; pi += 32) {
-        const uint32_t t = c.tri[pi];
+        const uint32_t t = tri[pi];
         const int a = t & 255, cc = t >> 8;
-        const int tgt = c.anc_start[base + a] + cc - a;
-        F[tgt] -= (F[base + a] * inv) * F[base + cc];
+        float* const tgt = F + (ak[a] + cc - a);
+        *tgt -= (Fk[a] * inv) * Fk[cc];
       }
     }
     __syncwarp();
   }
   // normalise rows: Lhat = L / diag, then 1 / D in the diagonal slots
   for (int e = lane; e < nM; e += 32) {
-    const int b0 = c.madr[c.mrow[e]];
+    const int b0 = madr[mrow[e]];
     if (e != b0) F[e] = F[e] / F[b0];
   }
   __syncwarp();
-  for (int i = lane; i < nv; i += 32) F[c.madr[i]] = 1.0f / F[c.madr[i]];
+  for (int i = lane; i < nv; i += 32) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
   __syncwarp();
   // K = Lhat^-1 in place by levels of dof depth:  K[i][cc] = -( Lhat[i][cc] + sum_{a<cc} Lhat[i][a] K[anc_a(i)][cc - a] ).
   // Items of a level are sorted by descending cc, so a later pass never reads a slot an earlier pass overwrote.
-  for (int dl = 1; dl <= c.d.maxdepth; ++dl) {
-    const int i0 = c.klvl[dl], i1 = c.klvl[dl + 1];
+  const uint16_t* const kitem = TB16(kitem);
+  const uint16_t* const klvl = TB16(klvl);
+  int i0 = klvl[1];
+  for (int dl = 1; dl <= maxdepth; ++dl) {
+    const int i1 = klvl[dl + 1];
     for (int it0 = i0; it0 < i1; it0 += 32) {
       const int it = it0 + lane;
       float val = 0.0f;
-      int dst = -1;
+      float* dst = nullptr;
       if (it < i1) {
-        const uint32_t w = c.kitem[it];
-        const int cc = w & 255, base = c.madr[w >> 8];
-        float a0 = F[base + cc], a1 = 0.0f;
+        const uint32_t w = kitem[it];
+        const int cc = w & 255, base = madr[w >> 8];
+        const float* const Fi = F + base;
+        const uint16_t* const ai = anc_start + base;
+        const float* const Fs = F + cc;  // K[anc_a][cc - a] = Fs[ai[a] - a]
+        float a0 = Fi[cc], a1 = 0.0f;
         int a = 1;
+#pragma unroll 2
         for (; a + 1 < cc; a += 2) {
-          a0 += F[base + a] * F[c.anc_start[base + a] + cc - a];
-          a1 += F[base + a + 1] * F[c.anc_start[base + a + 1] + cc - a - 1];
+          a0 += Fi[a] * Fs[ai[a] - a];
+          a1 += Fi[a + 1] * Fs[ai[a + 1] - a - 1];
         }
-        if (a < cc) a0 += F[base + a] * F[c.anc_start[base + a] + cc - a];
+        if (a < cc) a0 += Fi[a] * Fs[ai[a] - a];
         val = -(a0 + a1);
-        dst = base + cc;
+        dst = F + base + cc;
       }
       __syncwarp();
-      if (dst >= 0) F[dst] = val;
+      if (dst) *dst = val;
       __syncwarp();
     }
+    i0 = i1;
   }
 }
 
-// out <- M^-1 x   via  K (D^-1 (K^T x));  `tmp` is nv scratch.
-__device__ __noinline__ void solve_m(const Cta& c, float* s, const float* x, float* out, float* tmp) {
-  const float* K = s + c.L.K;
-  for (int r = 0; r < c.R; ++r) {
-    const int j = c.lane_rows[r * 32 + LANE];
-    if (j != 0xFF) {
-      float a0 = x[j], a1 = 0.0f;
-      int k = c.dadr[j];
-      const int ke = c.dadr[j + 1];
-      for (; k + 1 < ke; k += 2) { a0 += K[c.dent[k]] * x[c.drow[k]]; a1 += K[c.dent[k + 1]] * x[c.drow[k + 1]]; }
-      if (k < ke) a0 += K[c.dent[k]] * x[c.drow[k]];
-      tmp[j] = (a0 + a1) * K[c.madr[j]];
-    }
+// out <- M^-1 x   via  K (D^-1 (K^T x)).
+__device__ __noinline__ void solve_m(int so, int xo, int outo) {
+  VNL_SMEM
+  const int nv = c.d.nv, lane = LANE;
+  float* const K = s + c.L.K;
+  const float* const x = s + xo;
+  float* const pa = s + c.L.part;
+  float* const pd = pa + nv;
+  float* const tmp = s + c.L.tmpv;
+  const uint16_t* const madr = TB16(madr);
+  const uint8_t* const dpa = TB8(dpart_adr);
+  spmv_section(TB32(prog_d), c.TD, K, x, pd);   // K[nM] = 0 since factor()
+  __syncwarp();
+  for (int j = lane; j < nv; j += 32) {
+    float acc = x[j];
+    for (int q = dpa[j]; q < dpa[j + 1]; ++q) acc += pd[q];
+    tmp[j] = acc * K[madr[j]];
   }
   __syncwarp();
-  for (int r = 0; r < c.R; ++r) {
-    const int i = c.lane_rows[r * 32 + LANE];
-    if (i != 0xFF) {
-      float a0 = tmp[i], a1 = 0.0f;
-      int a = c.madr[i] + 1;
-      const int ae = c.madr[i + 1];
-      for (; a + 1 < ae; a += 2) { a0 += K[a] * tmp[c.mcol[a]]; a1 += K[a + 1] * tmp[c.mcol[a + 1]]; }
-      if (a < ae) a0 += K[a] * tmp[c.mcol[a]];
-      out[i] = a0 + a1;
-    }
+  spmv_section(TB32(prog_a), c.TA, K, tmp, pa);
+  __syncwarp();
+  float* const out = s + outo;
+  for (int i = lane; i < nv; i += 32) {
+    float acc = tmp[i];
+    if (madr[i + 1] - madr[i] > 1) acc += pa[i];
+    out[i] = acc;
   }
   __syncwarp();
 }
@@ -203,9 +255,15 @@ __device__ __noinline__ void solve_m(const Cta& c, float* s, const float* x, flo
 // constraint Jacobian products on the compact active set
 // ---------------------------------------------------------------------------------------------------------------------
 // out[row] = (J x)[row].  Contacts: groups of G lanes walk the ancestor chain of the contact's body.
-__device__ __noinline__ void jmul(const Cta& c, float* s, const float* x, float* out) {
+__device__ __noinline__ void jmul(int so, int xo, int outo) {
+  VNL_SMEM
   const int* ints = (const int*)(s + c.L.ints);
   const int nl = ints[0], nc = ints[1], lane = LANE;
+  const float* const x = s + xo;
+  float* const out = s + outo;
+  const uint16_t* const madr = TB16(madr);
+  const uint8_t* const mcol = TB8(mcol);
+  const uint8_t* const lastdof = TB8(lastdof);
   const float* cdof = s + c.L.cdof;
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* lim_dof = (const int*)(s + c.L.lim_dof);
@@ -219,11 +277,11 @@ __device__ __noinline__ void jmul(const Cta& c, float* s, const float* x, float*
       const int k = k0 + lane / G;
       float sacc[6] = {0, 0, 0, 0, 0, 0};
       if (k < nc) {
-        const int dl = c.lastdof[cbody[k]];
+        const int dl = lastdof[cbody[k]];
         if (dl != 0xFF) {
-          const int ae = c.madr[dl + 1];
-          for (int a = c.madr[dl] + sub; a < ae; a += G) {
-            const int j = c.mcol[a];
+          const int ae = madr[dl + 1];
+          for (int a = madr[dl] + sub; a < ae; a += G) {
+            const int j = mcol[a];
             const float xj = x[j];
 #pragma unroll
             for (int q = 0; q < 6; ++q) sacc[q] += cdof[j * 6 + q] * xj;
@@ -248,9 +306,13 @@ __device__ __noinline__ void jmul(const Cta& c, float* s, const float* x, float*
 }
 
 // qfrc = J^T f with f[row] = -D Jaref [Jaref < 0]
-__device__ __noinline__ void jtmul_force(const Cta& c, float* s, float* qfrc) {
+__device__ __noinline__ void jtmul_force(int so) {
+  VNL_SMEM
   const int* ints = (const int*)(s + c.L.ints);
-  const int nl = ints[0], nc = ints[1], lane = LANE;
+  const int nl = ints[0], nc = ints[1], lane = LANE, nv = c.d.nv;
+  float* const qfrc = s + c.L.qfrc_con;
+  const uint8_t* const dof_body = TB8(dof_body);
+  const uint8_t* const sub_end = TB8(sub_end);
   const float* D = s + c.L.efcD;
   const float* Jaref = s + c.L.Jaref;
   for (int k = lane; k < nc; k += 32) {
@@ -271,8 +333,8 @@ __device__ __noinline__ void jtmul_force(const Cta& c, float* s, float* qfrc) {
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* limrow = (const int*)(s + c.L.limrow_of_dof);
   const float* lim_sign = s + c.L.lim_sign;
-  for (int i = lane; i < c.d.nv; i += 32) {
-    const int b = c.dof_body[i], be = c.sub_end[b];
+  for (int i = lane; i < nv; i += 32) {
+    const int b = dof_body[i], be = sub_end[b];
     const float* cd = s + c.L.cdof + 6 * i;
     float acc = 0.0f;
     for (int k = 0; k < nc; ++k) {
@@ -314,12 +376,13 @@ __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const f
 struct Sol { float cost, prev_cost, gauss, gradnorm; };
 
 // solver._update_constraint + _update_gradient (CG: Mgrad = M^-1 grad)
-__device__ __noinline__ void update_constraint(const Cta& c, float* s, Sol& st) {
+__device__ __noinline__ void update_constraint(int so, Sol& st) {
+  VNL_SMEM
   const Lay& L = c.L;
   const int* ints = (const int*)(s + L.ints);
   const int nrow = ints[0] + 4 * ints[1], lane = LANE, nv = c.d.nv;
   float* qfrc_con = s + L.qfrc_con;
-  jtmul_force(c, s, qfrc_con);
+  jtmul_force(so);
   float v0 = 0.0f, v1 = 0.0f, g = 0.0f;
   for (int r = lane; r < nrow; r += 32) { const float ja = s[L.Jaref + r]; if (ja < 0.0f) v0 += s[L.efcD + r] * ja * ja; }
   for (int i = lane; i < nv; i += 32) {
@@ -335,7 +398,7 @@ __device__ __noinline__ void update_constraint(const Cta& c, float* s, Sol& st) 
   st.cost = 0.5f * v0 + st.gauss;
   st.gradnorm = sqrtf(g);
   __syncwarp();
-  solve_m(c, s, s + L.grad, s + L.Mgrad, s + L.tmpv);
+  solve_m(so, L.grad, L.Mgrad);
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -344,11 +407,17 @@ struct LSP { float alpha, cost, d0, d1; };
 // mjx.forward for the env held in this warp's shared-memory slice
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool DUMP>
-__device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* dump, Prof& pf) {
+__device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
+  VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
   const int lane = LANE;
   int* ints = (int*)(s + L.ints);
+  int* stats = ints + 4;
+  const uint8_t* const lvl_start = TB8(lvl_start);
+  const uint16_t* const lvl_bp = TB16(lvl_bp);
+  const uint8_t* const body_tree = TB8(body_tree);
+  const uint8_t* const dof_body = TB8(dof_body);
 
   // ---- smooth.kinematics ------------------------------------------------------------------------------------------
   // (1) per body, in parallel: the body's pose in its PARENT frame after its own joints (lq, lp) and each joint's
@@ -392,11 +461,11 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       st3(s + L.xpos + 3 * b, lp);
     }
     __syncwarp();
-    int k0 = c.lvl_start[1];  // level 0 (children of the world) is already in world coordinates
+    int k0 = lvl_start[1];  // level 0 (children of the world) is already in world coordinates
     for (int lv = 1; lv < d.nlevel; ++lv) {
-      const int k1 = c.lvl_start[lv + 1];
+      const int k1 = lvl_start[lv + 1];
       if (k0 + lane < k1) {
-        const uint32_t bp = c.lvl_bp[k0 + lane];
+        const uint32_t bp = lvl_bp[k0 + lane];
         const int b = bp & 255, p = bp >> 8;
         const Q4 pq = ld4(s + L.xquat + 4 * p);
         const V3 pp = ld3(s + L.xpos + 3 * p);
@@ -410,7 +479,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     }
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
     for (int j = lane; j < d.njnt; j += 32) {
-      const int p = c.parent[jbody[j]];
+      const int p = TB8(parent)[jbody[j]];
       if (p > 0) {
         const Q4 pq = ld4(s + L.xquat + 4 * p);
         st3(s + L.xanchor + 3 * j, ld3(s + L.xpos + 3 * p) + rotate(ld3(s + L.xanchor + 3 * j), pq));
@@ -431,7 +500,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       st3(s + L.xipos + 3 * b, ld3(s + L.xpos + 3 * b) + rotate(ld3(ipos + 3 * b), ld4(s + L.xquat + 4 * b)));
     __syncwarp();
     for (int t = 0; t < d.nroot; ++t) {  // subtree COM of each tree root = mass-weighted mean over its id range
-      const int rb = c.roots[t], re = c.sub_end[rb];
+      const int rb = TB8(roots)[t], re = TB8(sub_end)[rb];
       float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
       for (int q = rb + lane; q < re; q += 32) {
         const float mq = mass[q];
@@ -455,7 +524,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       }
       float R[9];
       quat_to_mat(quat_mul(ld4(s + L.xquat + 4 * b), ld4(iquat + 4 * b)), R);
-      const V3 off = ld3(s + L.xipos + 3 * b) - ld3(s + L.rcom + 3 * c.body_tree[b]);
+      const V3 off = ld3(s + L.xipos + 3 * b) - ld3(s + L.rcom + 3 * body_tree[b]);
       const float I0 = inertia[3 * b], I1 = inertia[3 * b + 1], I2 = inertia[3 * b + 2], ms = mass[b];
       const float oo = dot(off, off);
       const float o[3] = {off.x, off.y, off.z};
@@ -473,7 +542,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
     for (int j = lane; j < d.njnt; j += 32) {
       const int b = jbody[j], da = jdofadr[j];
-      const V3 off = ld3(s + L.rcom + 3 * c.body_tree[b]) - ld3(s + L.xanchor + 3 * j);
+      const V3 off = ld3(s + L.rcom + 3 * body_tree[b]) - ld3(s + L.xanchor + 3 * j);
       if (jtype[j] == 0) {
         float R[9];
         quat_to_mat(ld4(s + L.xquat + 4 * b), R);
@@ -498,7 +567,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       for (int i = lane; i < d.nbody * 3; i += 32) dump[d.dump_xipos + i] = s[L.xipos + i];
       for (int i = lane; i < d.njnt * 3; i += 32) { dump[d.dump_xanchor + i] = s[L.xanchor + i]; dump[d.dump_xanchor + d.njnt * 3 + i] = s[L.xaxis + i]; }
       for (int i = lane; i < d.nbody * 10; i += 32) dump[d.dump_cinert + i] = s[L.t16 + 16 * (i / 10) + i % 10];
-      for (int t = lane; t < d.nroot; t += 32) st3(dump + d.dump_subtree_com + 3 * c.roots[t], ld3(s + L.rcom + 3 * t));
+      for (int t = lane; t < d.nroot; t += 32) st3(dump + d.dump_subtree_com + 3 * TB8(roots)[t], ld3(s + L.rcom + 3 * t));
     }
   }
   pf.mark(1);
@@ -511,15 +580,15 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     __syncwarp();
     int k0 = 0;
     for (int lv = 0; lv < d.nlevel; ++lv) {
-      const int k1 = c.lvl_start[lv + 1];
+      const int k1 = lvl_start[lv + 1];
       if (k0 + lane < k1) {
-        const uint32_t bp = c.lvl_bp[k0 + lane];
+        const uint32_t bp = lvl_bp[k0 + lane];
         const int b = bp & 255, p = bp >> 8;
         float cv[6], ca[6], cd[6];
 #pragma unroll
         for (int q = 0; q < 6; ++q) { cv[q] = s[L.cvel + 6 * p + q]; ca[q] = s[L.cacc + 6 * p + q]; }
-        const int dn = c.body_dofnum[b];
-        int i = c.body_dofadr[b];
+        const int dn = TB8(body_dofnum)[b];
+        int i = TB8(body_dofadr)[b];
         const int ie = i + (dn & 0x7f);
         if (dn & 0x80) {  // free joint: translations first (cdof_dot = 0), the three rotations all see that velocity
 #pragma unroll
@@ -564,14 +633,14 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     __syncwarp();
     // one pass up the tree: composite inertia (crb, in place over cinert) and subtree-summed RNE force
     for (int lv = d.nlevel - 2; lv >= 0; --lv) {
-      const int q0 = c.lvl_start[lv], n16 = (c.lvl_start[lv + 1] - q0) * 16;
+      const int q0 = lvl_start[lv], n16 = (lvl_start[lv + 1] - q0) * 16;
       for (int it = lane; it < n16; it += 32) {
-        const int b = c.lvl_bp[q0 + (it >> 4)] & 255, q = it & 15;
-        const int ce = c.child_adr[b + 1];
-        int ch = c.child_adr[b];
+        const int b = lvl_bp[q0 + (it >> 4)] & 255, q = it & 15;
+        const int ce = TB8(child_adr)[b + 1];
+        int ch = TB8(child_adr)[b];
         if (ch < ce) {
           float acc = s[L.t16 + 16 * b + q];
-          for (; ch < ce; ++ch) acc += s[L.t16 + 16 * c.child_list[ch] + q];
+          for (; ch < ce; ++ch) acc += s[L.t16 + 16 * TB8(child_list)[ch] + q];
           s[L.t16 + 16 * b + q] = acc;
         }
       }
@@ -622,7 +691,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
         pas = -stiff[j] * (s[L.qpos + jqadr[j]] - qspring[jqadr[j]]);
       }
       pas -= damping[i] * s[L.qvel + i];
-      const float bias = dot6(s + L.cdof + 6 * i, s + L.t16 + 16 * c.dof_body[i] + 10);
+      const float bias = dot6(s + L.cdof + 6 * i, s + L.t16 + 16 * dof_body[i] + 10);
       s[L.qfrc_smooth + i] = pas - bias + acc;
       if (DUMP) { dump[d.dump_passive + i] = pas; dump[d.dump_passive + d.nv + i] = bias; }
     }
@@ -633,10 +702,10 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
     float* fd = s + L.cacc;  // cacc is dead: reuse as crb * cdof
-    for (int i = lane; i < d.nv; i += 32) inert_mul(s + L.t16 + 16 * c.dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
+    for (int i = lane; i < d.nv; i += 32) inert_mul(s + L.t16 + 16 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
     __syncwarp();
     for (int e = lane; e < d.nM; e += 32) {
-      const int i = c.mrow[e], j = c.mcol[e];
+      const int i = TB8(mrow)[e], j = TB8(mcol)[e];
       float v = dot6(fd + 6 * i, s + L.cdof + 6 * j);
       if (i == j) v += armature[i];
       s[L.M + e] = v;
@@ -644,9 +713,9 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     __syncwarp();
   }
   pf.mark(4);
-  factor(c, s, false);
+  factor(so, false);
   pf.mark(5);
-  solve_m(c, s, s + L.qfrc_smooth, s + L.qacc_smooth, s + L.tmpv);
+  solve_m(so, L.qfrc_smooth, L.qacc_smooth);
   pf.mark(6);
 
   // ---- collision + constraint rows, compacted to the active set ----------------------------------------------------------
@@ -775,7 +844,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
         if (active) {
           const int k = base + __popc(m & ((1u << lane) - 1u));
           ((int*)(s + L.cbody))[k] = body;
-          const V3 rel = cp - ld3(s + L.rcom + 3 * c.body_tree[body]);
+          const V3 rel = cp - ld3(s + L.rcom + 3 * body_tree[body]);
           st3(s + L.crel + 3 * k, rel);
           const V3 t2 = cross(n, fb);
           st3(s + L.cframe + 9 * k, n); st3(s + L.cframe + 9 * k + 3, fb); st3(s + L.cframe + 9 * k + 6, t2);
@@ -832,16 +901,16 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     // candidate cost: 0.5 sum D Jaref^2 [Jaref<0] + 0.5 (Ma - qfrc_smooth).(qacc - qacc_smooth)
     float cost_w, cost_s;
     {
-      mul_m(c, s, s + L.warm, Ma);
-      jmul(c, s, s + L.warm, Jaref);
+      mul_m(so, L.warm, L.Ma);
+      jmul(so, L.warm, L.Jaref);
       float v0 = 0.0f, v1 = 0.0f;
       for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) v0 += efcD[r] * ja * ja; }
       for (int i = lane; i < d.nv; i += 32) v1 += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
       v0 = warp_sum(v0); v1 = warp_sum(v1);
       cost_w = 0.5f * v0 + 0.5f * v1;
       __syncwarp();
-      mul_m(c, s, qacc_smooth, Ma);
-      jmul(c, s, qacc_smooth, Jaref);
+      mul_m(so, L.qacc_smooth, L.Ma);
+      jmul(so, L.qacc_smooth, L.Jaref);
       float w0 = 0.0f, w1 = 0.0f;
       for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) w0 += efcD[r] * ja * ja; }
       for (int i = lane; i < d.nv; i += 32) w1 += (Ma[i] - qfrc_smooth[i]) * (qacc_smooth[i] - qacc_smooth[i]);
@@ -852,8 +921,8 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     if (cost_w < cost_s) {
       for (int i = lane; i < d.nv; i += 32) qacc[i] = s[L.warm + i];
       __syncwarp();
-      mul_m(c, s, qacc, Ma);
-      jmul(c, s, qacc, Jaref);
+      mul_m(so, L.qacc, L.Ma);
+      jmul(so, L.qacc, L.Jaref);
     } else {
       for (int i = lane; i < d.nv; i += 32) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
     }
@@ -864,7 +933,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
-    update_constraint(c, s, st);
+    update_constraint(so, st);
     for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
     __syncwarp();
     pf.mark(9);
@@ -875,8 +944,8 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       if (d.iterations != 1) { done |= improvement < d.tolerance; done |= gradient < d.tolerance; }
       if (done) break;
       // ---- _linesearch ----
-      mul_m(c, s, search, Mv);
-      jmul(c, s, search, Jv);
+      mul_m(so, L.search, L.Mv);
+      jmul(so, L.search, L.Jv);
       float q0s = 0.0f, q1s = 0.0f, q2s = 0.0f, q3s = 0.0f;
       for (int i = lane; i < d.nv; i += 32) {
         const float si = search[i];
@@ -962,7 +1031,7 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
       for (int r = lane; r < nrow; r += 32) Jaref[r] += Jv[r] * ia;
       pg = warp_sum(pg);
       __syncwarp();
-      update_constraint(c, s, st);
+      update_constraint(so, st);
       if (d.solver == 2) {
         for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
       } else {  // Polak-Ribiere
@@ -985,7 +1054,8 @@ __device__ __noinline__ void forward(const Cta& c, float* s, int* stats, float* 
 // ---------------------------------------------------------------------------------------------------------------------
 // forward.euler (implicit joint damping when enabled) + _advance
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void euler(const Cta& c, float* s, Prof& pf) {
+__device__ __noinline__ void euler(int so, Prof& pf) {
+  VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
   const int lane = LANE;
@@ -993,11 +1063,11 @@ __device__ __noinline__ void euler(const Cta& c, float* s, Prof& pf) {
   float* qacc = s + L.qacc;
   pf.mark(12);
   if (d.eulerdamp) {
-    factor(c, s, true);
+    factor(so, true);
     pf.mark(13);
     for (int i = lane; i < d.nv; i += 32) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
     __syncwarp();
-    solve_m(c, s, s + L.grad, s + L.Mgrad, s + L.tmpv);
+    solve_m(so, L.grad, L.Mgrad);
     qacc = s + L.Mgrad;
   }
   for (int a = lane; a < d.na; a += 32) s[L.act + a] += s[L.act_dot + a] * dt;
@@ -1032,7 +1102,8 @@ __device__ __forceinline__ float nan_to_num(float v) {
 // one env, one warp.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void env_run(const Cta& c, float* s, const Params& p, int e) {
+__device__ __forceinline__ void env_run(int so, const Params& p, int e) {
+  VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
   const int lane = LANE;
@@ -1091,9 +1162,9 @@ __device__ __forceinline__ void env_run(const Cta& c, float* s, const Params& p,
   float* dump = (MODE == 3) ? p.dump + (size_t)e * d.dump_total : nullptr;
   const int nsteps = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
   for (int st = 0; st < nsteps; ++st) {
-    forward<MODE == 3>(c, s, stats, dump, pf);
+    forward<MODE == 3>(so, dump, pf);
     if (MODE == 1 || MODE == 3) break;
-    euler(c, s, pf);
+    euler(so, pf);
   }
 
   if (MODE == 3) {
@@ -1105,8 +1176,8 @@ __device__ __forceinline__ void env_run(const Cta& c, float* s, const Params& p,
     for (int i = lane; i < d.nv * d.nv; i += 32) dump[d.dump_qM + i] = 0.0f;
     __syncwarp();
     for (int q = lane; q < d.nM; q += 32) {
-      dump[d.dump_qM + c.mrow[q] * d.nv + c.mcol[q]] = s[L.M + q];
-      dump[d.dump_qM + c.mcol[q] * d.nv + c.mrow[q]] = s[L.M + q];
+      dump[d.dump_qM + TB8(mrow)[q] * d.nv + TB8(mcol)[q]] = s[L.M + q];
+      dump[d.dump_qM + TB8(mcol)[q] * d.nv + TB8(mrow)[q]] = s[L.M + q];
     }
     put(d.dump_passive + 2 * d.nv, s + L.qfrc_act, d.nv);
     put(d.dump_passive + 3 * d.nv, s + L.act_dot, d.na);
@@ -1129,7 +1200,7 @@ __device__ __forceinline__ void env_run(const Cta& c, float* s, const Params& p,
   for (int i = lane; i < d.nbody * 4; i += 32) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
   for (int i = lane; i < d.nv; i += 32) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
   const int torso = (MODE == 2) ? 1 : vnl_hdr_i(tb, VNL_TH_TORSO_BODY);
-  const float* rcom = s + L.rcom + 3 * c.body_tree[torso];  // subtree_com[torso]: torso is the root of its tree
+  const float* rcom = s + L.rcom + 3 * TB8(body_tree)[torso];  // subtree_com[torso]: torso is the root of its tree
   if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = rcom[lane];
   if (MODE == 2) {
     if (p.stats && lane < 4) p.stats[4 * e + lane] = stats[lane];
@@ -1303,23 +1374,22 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
     make_layout(c.d, c.L);
     c.mb = p.model;
     c.prof = p.prof; c.prof_env = p.prof_env;
-    const uint8_t* kb = (const uint8_t*)ktab;
-#define T8(name, id) c.name = kb + g_ktab[id]
-#define T16(name, id) c.name = (const uint16_t*)(kb + g_ktab[id])
-    T8(lvl_start, VNL_KT_LVL_START); T16(lvl_bp, VNL_KT_LVL_BP); T8(parent, VNL_KT_PARENT); T8(child_adr, VNL_KT_CHILD_ADR);
-    T8(child_list, VNL_KT_CHILD_LIST); T8(body_dofadr, VNL_KT_BODY_DOFADR); T8(body_dofnum, VNL_KT_BODY_DOFNUM);
-    T8(body_tree, VNL_KT_BODY_TREE); T8(lastdof, VNL_KT_BODY_LASTDOF); T8(sub_end, VNL_KT_SUB_END); T8(roots, VNL_KT_ROOTS);
-    T8(mrow, VNL_KT_MROW); T8(mcol, VNL_KT_MCOL); T8(drow, VNL_KT_DROW); T8(dof_body, VNL_KT_DOF_BODY); T8(lane_rows, VNL_KT_LANE_ROWS);
-    T16(madr, VNL_KT_MADR); T16(dadr, VNL_KT_DADR); T16(dent, VNL_KT_DENT); T16(tri, VNL_KT_TRI); T16(anc_start, VNL_KT_ANC_START);
-    T16(kitem, VNL_KT_KITEM); T16(klvl, VNL_KT_KLVL);
-#undef T8
-#undef T16
-    c.R = (int)g_ktab[VNL_KT_COUNT];
+    const uint32_t kb = (uint32_t)(kCtaFloats * 4);  // byte offset of the staged tables in shared memory
+#define TOFF(name, id) c.o_##name = kb + g_ktab[id]
+    TOFF(lvl_start, VNL_KT_LVL_START); TOFF(lvl_bp, VNL_KT_LVL_BP); TOFF(parent, VNL_KT_PARENT); TOFF(child_adr, VNL_KT_CHILD_ADR);
+    TOFF(child_list, VNL_KT_CHILD_LIST); TOFF(body_dofadr, VNL_KT_BODY_DOFADR); TOFF(body_dofnum, VNL_KT_BODY_DOFNUM);
+    TOFF(body_tree, VNL_KT_BODY_TREE); TOFF(lastdof, VNL_KT_BODY_LASTDOF); TOFF(sub_end, VNL_KT_SUB_END); TOFF(roots, VNL_KT_ROOTS);
+    TOFF(mrow, VNL_KT_MROW); TOFF(mcol, VNL_KT_MCOL); TOFF(dof_body, VNL_KT_DOF_BODY); TOFF(dpart_adr, VNL_KT_DPART_ADR);
+    TOFF(madr, VNL_KT_MADR); TOFF(tri, VNL_KT_TRI); TOFF(anc_start, VNL_KT_ANC_START); TOFF(kitem, VNL_KT_KITEM);
+    TOFF(klvl, VNL_KT_KLVL); TOFF(prog_a, VNL_KT_PROG_A); TOFF(prog_d, VNL_KT_PROG_D);
+#undef TOFF
+    c.TA = (int)g_ktab[VNL_KT_COUNT + VNL_KS_TA]; c.TD = (int)g_ktab[VNL_KT_COUNT + VNL_KS_TD];
+    c.ndslot = (int)g_ktab[VNL_KT_COUNT + VNL_KS_NDSLOT];
   }
   __syncthreads();
   const int W = nt >> 5, warp = tid >> 5;
-  float* s = smem + kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
-  for (int e = blockIdx.x * W + warp; e < p.B; e += gridDim.x * W) env_run<MODE>(c, s, p, e);
+  const int so = kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
+  for (int e = blockIdx.x * W + warp; e < p.B; e += gridDim.x * W) env_run<MODE>(so, p, e);
 }
 
 template __global__ void vnl_env_kernel<0>(Params);

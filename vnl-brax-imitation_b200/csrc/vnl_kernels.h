@@ -14,6 +14,7 @@ struct Dims {
   int solver, iterations, ls_iterations, eulerdamp;
   float timestep, gx, gy, gz, tolerance, ls_tolerance, impratio, meaninertia;
   int ktab_words;  // size of VNL_F_KTAB
+  int ndslot;      // partial-sum slots of the descendant mat-vec program (VNL_KS_NDSLOT)
   // stage-dump offsets (layout of oracle.dump_layout)
   int dump_xpos, dump_xipos, dump_xanchor, dump_subtree_com, dump_cinert, dump_qM, dump_cvel, dump_passive, dump_con,
       dump_efc, dump_qacc, dump_total;
@@ -27,7 +28,7 @@ struct Lay {
   int K, efcD, Jaref, Jv;                                                 // region B
   int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
   int lim_dof, lim_sign, limrow_of_dof, cbody, crel, cframe, cmu, cwrench;
-  int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, ints, total;
+  int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, part, ints, total;
 };
 
 struct Params {

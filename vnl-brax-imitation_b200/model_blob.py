@@ -154,18 +154,46 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     for b in range(1, nb):
         if A["body_jntnum"][b] > 0 and A["jnt_type"][A["body_jntadr"][b]] == mjcf.JNT_FREE:
             dofnum_flag[b] |= 0x80
-    load = [(madr[i + 1] - madr[i]) + (desc_adr[i + 1] - desc_adr[i]) for i in range(nv)]
-    lanes = [[] for _ in range(32)]
-    lane_load = [0] * 32
-    for i in sorted(range(nv), key=lambda i: -load[i]):
-        l = min(range(32), key=lambda l: (lane_load[l], len(lanes[l])))
-        lanes[l].append(i)
-        lane_load[l] += load[i] + 4
-    R = max(1, max(len(x) for x in lanes))
-    lane_rows = np.full((R, 32), 0xFF, dtype=np.int64)  # [r][lane]: coalesced across lanes
-    for l in range(32):
-        for r, i in enumerate(lanes[l]):
-            lane_rows[r, l] = i
+    # lane programs of the sparse mat-vecs (see VnlKtab in include/vnl_b200.h)
+    nM_ = len(mcol)
+    if 4 * (nM_ + 1) >= (1 << 14):
+        raise NotImplementedError("too many inertia entries for the packed mat-vec program")
+
+    def pack_program(rows):
+        """rows: list of (slot, [(entry, xindex), ...]) with non-empty term lists -> ([T*32] words, T)."""
+        lanes = [[] for _ in range(32)]
+        lane_load = [0] * 32
+        for slot, terms in sorted(rows, key=lambda r: -len(r[1])):
+            l = min(range(32), key=lambda l: lane_load[l])
+            lanes[l].append((slot, terms))
+            lane_load[l] += len(terms)
+        T = max(1, max(lane_load))
+        prog = np.zeros((T, 32), dtype=np.uint32)
+        pad = np.uint32((4 * nM_) | (0xFF << 24))  # entry nM is a zero slot, never flushed
+        prog[:, :] = pad
+        for l in range(32):
+            t = 0
+            for slot, terms in lanes[l]:
+                for k, (e, xi) in enumerate(terms):
+                    flush = slot if k == len(terms) - 1 else 0xFF
+                    prog[t, l] = np.uint32((4 * int(e)) | ((4 * int(xi)) << 14) | (int(flush) << 24))
+                    t += 1
+        return prog.reshape(-1), T
+
+    rows_a = [(i, [(madr[i] + a, mcol[madr[i] + a]) for a in range(1, madr[i + 1] - madr[i])]) for i in range(nv)]
+    rows_a = [r for r in rows_a if r[1]]
+    prog_a, TA = pack_program(rows_a)
+    CH = 24
+    rows_d, dpart_adr = [], [0]
+    for j in range(nv):
+        terms = [(e, mrow[e]) for e in desc[j]]
+        for k in range(0, len(terms), CH):
+            rows_d.append((len(rows_d), terms[k:k + CH]))
+        dpart_adr.append(len(rows_d))
+    if len(rows_d) > 254 or nv > 254:
+        raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
+    prog_d, TD = pack_program(rows_d) if rows_d else (np.zeros(32, dtype=np.uint32), 1)
+    ndslot = len(rows_d)
     tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)]
     kitem, klvl = [], [0, 0]
     for dpt in range(1, maxd + 1):
@@ -190,19 +218,18 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     kt[C["VNL_KT_ROOTS"]] = u8(roots)
     kt[C["VNL_KT_MROW"]] = u8(mrow)
     kt[C["VNL_KT_MCOL"]] = u8(mcol)
-    kt[C["VNL_KT_DROW"]] = u8([mrow[e] for e in desc_entry])
     kt[C["VNL_KT_DOF_BODY"]] = u8(A["dof_bodyid"])
-    kt[C["VNL_KT_LANE_ROWS"]] = u8(lane_rows.reshape(-1))
+    kt[C["VNL_KT_DPART_ADR"]] = u8(dpart_adr)
     kt[C["VNL_KT_MADR"]] = u16(madr)
-    kt[C["VNL_KT_DADR"]] = u16(desc_adr)
-    kt[C["VNL_KT_DENT"]] = u16(desc_entry)
     kt[C["VNL_KT_TRI"]] = u16(tri)
     kt[C["VNL_KT_ANC_START"]] = u16([madr[j] for j in mcol])
     kt[C["VNL_KT_KITEM"]] = u16(kitem)
     kt[C["VNL_KT_KLVL"]] = u16(klvl)
-    nkt = C["VNL_KT_COUNT"]
-    off = 4 * (nkt + 1)
-    dirw = np.zeros(nkt + 1, dtype=np.uint32)
+    kt[C["VNL_KT_PROG_A"]] = prog_a
+    kt[C["VNL_KT_PROG_D"]] = prog_d
+    nkt, nks = C["VNL_KT_COUNT"], C["VNL_KT_NSCALAR"]
+    off = 4 * (nkt + nks)
+    dirw = np.zeros(nkt + nks, dtype=np.uint32)
     blobs = []
     for t, a in enumerate(kt):
         raw = a.tobytes()
@@ -210,7 +237,9 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
         dirw[t] = off
         off += len(raw)
         blobs.append(raw)
-    dirw[nkt] = R
+    dirw[nkt + C["VNL_KS_TA"]] = TA
+    dirw[nkt + C["VNL_KS_TD"]] = TD
+    dirw[nkt + C["VNL_KS_NDSLOT"]] = ndslot
     ktab = np.frombuffer(dirw.tobytes() + b"".join(blobs), dtype=np.uint32).copy()
     act_of_dof = [[] for _ in range(nv)]
     for u, dadr in enumerate(A["actuator_dofadr"]):
@@ -218,7 +247,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     dof_actadr = [0]
     for i in range(nv):
         dof_actadr.append(dof_actadr[-1] + len(act_of_dof[i]))
-    return dict(ktab=ktab, nroot=len(roots), dof_actadr=np.array(dof_actadr),
+    return dict(ktab=ktab, nroot=len(roots), ndslot=ndslot, dof_actadr=np.array(dof_actadr),
                 dof_actlist=np.array([u for i in range(nv) for u in act_of_dof[i]], dtype=np.int64),
                 level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
                 m_col=np.array(mcol), dof_depth=np.array(ddepth), body_subtree_end=sub_end,
@@ -285,7 +314,7 @@ def model_dims(m: mjcf.Model) -> Dict[str, int]:
     ncon, nlimit = len(d["con_pair"]), len(d["limit_jnt"])
     return dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom,
                 npair=len(m.arrays["pair_geom1"]), ncon=ncon, nlimit=nlimit, nefc=nlimit + 4 * ncon,
-                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"])
+                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"], ndslot=d["ndslot"])
 
 
 def build_model_blob(m: mjcf.Model) -> np.ndarray:
@@ -296,7 +325,7 @@ def build_model_blob(m: mjcf.Model) -> np.ndarray:
                       ("VNL_MH_NBODY", "nbody"), ("VNL_MH_NJNT", "njnt"), ("VNL_MH_NGEOM", "ngeom"),
                       ("VNL_MH_NPAIR", "npair"), ("VNL_MH_NCON", "ncon"), ("VNL_MH_NLIMIT", "nlimit"),
                       ("VNL_MH_NEFC", "nefc"), ("VNL_MH_NM", "nM"), ("VNL_MH_NLEVEL", "nlevel"),
-                      ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot")]:
+                      ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot"), ("VNL_MH_NDSLOT", "ndslot")]:
         w.set_i(slot, dims[key])
     w.set_i("VNL_MH_SOLVER", m.solver)
     w.set_i("VNL_MH_ITERATIONS", m.iterations)
