@@ -66,7 +66,7 @@ struct __align__(16) Cta {
   uint32_t foff[VNL_F_MODEL_COUNT];
   uint32_t o_lvl_start, o_lvl_bp, o_parent, o_child_adr, o_child_list, o_body_dofadr, o_body_dofnum, o_body_tree, o_lastdof, o_sub_end,
       o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_madr, o_tri, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
-  int TA, TD, ndslot;
+  int TA, TD, ndslot, lockstep;
   long long* prof;
   int prof_env;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
@@ -96,7 +96,8 @@ struct Prof {
 // sparse-inertia helpers (one warp).  Vector arguments are float offsets into the env slice.
 // ---------------------------------------------------------------------------------------------------------------------
 // One section of a lane program: part[slot] = sum over the lane's terms of V[entry] * x[index] (see VnlKtab).
-__device__ __forceinline__ void spmv_section(const uint32_t* prog, int T, const float* V, const float* x, float* part) {
+__device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, int T, const float* __restrict__ V,
+                                             const float* __restrict__ x, float* __restrict__ part) {
   const char* Vb = reinterpret_cast<const char*>(V);
   const char* xb = reinterpret_cast<const char*>(x);
   prog += LANE;
@@ -137,7 +138,7 @@ __device__ __noinline__ void mul_m(int so, int xo, int outo) {
 
 // L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
-__device__ __noinline__ void factor(int so, bool damp) {
+__device__ __noinline__ void factor(int so, bool damp, Prof& pf) {
   VNL_SMEM
   const int nv = c.d.nv, nM = c.d.nM, lane = LANE, maxdepth = c.d.maxdepth;
   const float* const M = s + c.L.M;
@@ -163,20 +164,37 @@ __device__ __noinline__ void factor(int so, bool damp) {
   for (int k = nv - 1; k > 0; --k) {
     const int base = madr[k], dk = madr[k + 1] - base - 1;
     if (dk > 0) {
+      // row k is read-only during its own elimination: keep it in registers (lane l holds entries l and l + 32) and
+      // fetch the (a, cc) operands with shuffles, so the only memory dependence left is on the distinct targets
       const float inv = 1.0f / F[base];
       const int np = (dk * (dk + 1)) >> 1;
-      const float* const Fk = F + base;
+      const float r0 = (lane <= dk) ? F[base + lane] : 0.0f;
+      const float r1 = (lane + 32 <= dk) ? F[base + lane + 32] : 0.0f;
       const uint16_t* const ak = anc_start + base;
-#pragma unroll 2
-      for (int pi = lane; pi < np; pi += 32) {
-        const uint32_t t = tri[pi];
-        const int a = t & 255, cc = t >> 8;
-        float* const tgt = F + (ak[a] + cc - a);
-        *tgt -= (Fk[a] * inv) * Fk[cc];
+      for (int p0 = 0; p0 < np; p0 += 64) {
+        const int pa = p0 + lane, pb = pa + 32;
+        const uint32_t ta = tri[pa < np ? pa : 0], tb = tri[pb < np ? pb : 0];
+        const int aa = ta & 255, ca = ta >> 8, ab = tb & 255, cb = tb >> 8;
+        float va = __shfl_sync(FULLMASK, r0, aa), vca = __shfl_sync(FULLMASK, r0, ca);
+        float vb = __shfl_sync(FULLMASK, r0, ab), vcb = __shfl_sync(FULLMASK, r0, cb);
+        if (dk >= 32) {  // warp-uniform
+          const float wa = __shfl_sync(FULLMASK, r1, aa), wca = __shfl_sync(FULLMASK, r1, ca);
+          const float wb = __shfl_sync(FULLMASK, r1, ab), wcb = __shfl_sync(FULLMASK, r1, cb);
+          if (aa >= 32) va = wa;
+          if (ca >= 32) vca = wca;
+          if (ab >= 32) vb = wb;
+          if (cb >= 32) vcb = wcb;
+        }
+        float* const tga = F + (ak[aa] + ca - aa);
+        float* const tgb = F + (ak[ab] + cb - ab);
+        const float fa = (pa < np) ? *tga : 0.0f, fb = (pb < np) ? *tgb : 0.0f;
+        if (pa < np) *tga = fa - (va * inv) * vca;
+        if (pb < np) *tgb = fb - (vb * inv) * vcb;
       }
     }
     __syncwarp();
   }
+  pf.mark(16);
   // normalise rows: Lhat = L / diag, then 1 / D in the diagonal slots
   for (int e = lane; e < nM; e += 32) {
     const int b0 = madr[mrow[e]];
@@ -185,6 +203,7 @@ __device__ __noinline__ void factor(int so, bool damp) {
   __syncwarp();
   for (int i = lane; i < nv; i += 32) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
   __syncwarp();
+  pf.mark(17);
   // K = Lhat^-1 in place by levels of dof depth:  K[i][cc] = -( Lhat[i][cc] + sum_{a<cc} Lhat[i][a] K[anc_a(i)][cc - a] ).
   // Items of a level are sorted by descending cc, so a later pass never reads a slot an earlier pass overwrote.
   const uint16_t* const kitem = TB16(kitem);
@@ -202,15 +221,16 @@ __device__ __noinline__ void factor(int so, bool damp) {
         const float* const Fi = F + base;
         const uint16_t* const ai = anc_start + base;
         const float* const Fs = F + cc;  // K[anc_a][cc - a] = Fs[ai[a] - a]
-        float a0 = Fi[cc], a1 = 0.0f;
+        float a0 = Fi[cc], a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
         int a = 1;
-#pragma unroll 2
-        for (; a + 1 < cc; a += 2) {
+        for (; a + 3 < cc; a += 4) {
           a0 += Fi[a] * Fs[ai[a] - a];
           a1 += Fi[a + 1] * Fs[ai[a + 1] - a - 1];
+          a2 += Fi[a + 2] * Fs[ai[a + 2] - a - 2];
+          a3 += Fi[a + 3] * Fs[ai[a + 3] - a - 3];
         }
-        if (a < cc) a0 += Fi[a] * Fs[ai[a] - a];
-        val = -(a0 + a1);
+        for (; a < cc; ++a) a0 += Fi[a] * Fs[ai[a] - a];
+        val = -((a0 + a1) + (a2 + a3));
         dst = F + base + cc;
       }
       __syncwarp();
@@ -219,6 +239,7 @@ __device__ __noinline__ void factor(int so, bool damp) {
     }
     i0 = i1;
   }
+  pf.mark(18);
 }
 
 // out <- M^-1 x   via  K (D^-1 (K^T x)).
@@ -414,6 +435,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   const int lane = LANE;
   int* ints = (int*)(s + L.ints);
   int* stats = ints + 4;
+  const bool ls3 = c.lockstep >= 3;  // CTA-uniform: barriers at every phase boundary
   const uint8_t* const lvl_start = TB8(lvl_start);
   const uint16_t* const lvl_bp = TB16(lvl_bp);
   const uint8_t* const body_tree = TB8(body_tree);
@@ -489,6 +511,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     __syncwarp();
   }
   pf.mark(0);
+  if (ls3) __syncthreads();
   // ---- smooth.com_pos: xipos, tree COM, cinert (t16[0..9]), cdof ------------------------------------------------------
   const int* dof_jnt = c.fi(VNL_F_DOF_JNTID);
   const int* jtype = c.fi(VNL_F_JNT_TYPE);
@@ -571,6 +594,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     }
   }
   pf.mark(1);
+  if (ls3) __syncthreads();
   // ---- smooth.com_vel + the forward half of smooth.rne: cvel, cacc down the tree (cdof_dot stays in registers) ---------
   {
     if (lane < 6) {
@@ -652,6 +676,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     }
   }
   pf.mark(2);
+  if (ls3) __syncthreads();
   // ---- qfrc_smooth = passive - bias + actuator; act_dot -----------------------------------------------------------------
   {
     const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
@@ -698,6 +723,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     __syncwarp();
   }
   pf.mark(3);
+  if (ls3) __syncthreads();
   // ---- joint-space inertia (tree sparse): M[i][a] = cdof[anc_a(i)] . (crb[body_i] cdof_i) --------------------------
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
@@ -713,10 +739,13 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     __syncwarp();
   }
   pf.mark(4);
-  factor(so, false);
+  if (ls3) __syncthreads();
+  factor(so, false, pf);
   pf.mark(5);
+  if (ls3) __syncthreads();
   solve_m(so, L.qfrc_smooth, L.qacc_smooth);
   pf.mark(6);
+  if (ls3) __syncthreads();
 
   // ---- collision + constraint rows, compacted to the active set ----------------------------------------------------------
   float* arefv = s + L.Jv;  // aref lives in the Jv slot until the solver iterations start
@@ -881,6 +910,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     __syncwarp();
   }
   pf.mark(7);
+  if (ls3) __syncthreads();
   const int nl = ints[0], nc = ints[1], nrow = nl + 4 * nc;
   if (lane == 0) { stats[2] += nc; stats[3] += nl; }
 
@@ -930,6 +960,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     for (int r = lane; r < nrow; r += 32) Jaref[r] -= arefv[r];
     __syncwarp();
     pf.mark(8);
+    if (ls3) __syncthreads();
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
@@ -937,12 +968,15 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
     __syncwarp();
     pf.mark(9);
-    while (true) {
-      const float improvement = (st.prev_cost - st.cost) / scale;
-      const float gradient = st.gradnorm / scale;
-      bool done = niter >= d.iterations;
-      if (d.iterations != 1) { done |= improvement < d.tolerance; done |= gradient < d.tolerance; }
-      if (done) break;
+    bool done = false;
+    for (int itn = 0; itn < d.iterations; ++itn) {
+      if (ls3) __syncthreads();
+      if (!done && d.iterations != 1) {
+        const float improvement = (st.prev_cost - st.cost) / scale;
+        const float gradient = st.gradnorm / scale;
+        done = (improvement < d.tolerance) || (gradient < d.tolerance);
+      }
+      if (done) { if (ls3) continue; break; }
       // ---- _linesearch ----
       mul_m(so, L.search, L.Mv);
       jmul(so, L.search, L.Jv);
@@ -983,8 +1017,13 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
           if (x + al1 * jv < 0.0f) { acc[3] += q0; acc[4] += q1; acc[5] += q2; }
           if (x + al2 * jv < 0.0f) { acc[6] += q0; acc[7] += q1; acc[8] += q2; }
         }
+        if (phase < 2) {  // a single alpha: three sums
 #pragma unroll
-        for (int q = 0; q < 9; ++q) acc[q] = warp_sum(acc[q]);
+          for (int q = 0; q < 3; ++q) acc[q] = warp_sum(acc[q]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 9; ++q) acc[q] = warp_sum(acc[q]);
+        }
         LSP pt[3];
         const float als[3] = {al0, al1, al2};
 #pragma unroll
@@ -1063,7 +1102,7 @@ __device__ __noinline__ void euler(int so, Prof& pf) {
   float* qacc = s + L.qacc;
   pf.mark(12);
   if (d.eulerdamp) {
-    factor(so, true);
+    factor(so, true, pf);
     pf.mark(13);
     for (int i = lane; i < d.nv; i += 32) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
     __syncwarp();
@@ -1102,11 +1141,18 @@ __device__ __forceinline__ float nan_to_num(float v) {
 // one env, one warp.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
-__device__ __forceinline__ void env_run(int so, const Params& p, int e) {
+__device__ __forceinline__ void env_run(int so, const Params& p, int e, bool active) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
   const int lane = LANE;
+  if (!active) {  // a warp without an env in this round only keeps the CTA's phase barriers company
+    if (p.lockstep) {
+      const int ns = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
+      for (int st = 0; st < ns; ++st) { __syncthreads(); if (MODE == 1 || MODE == 3) break; if (p.lockstep > 1) __syncthreads(); }
+    }
+    return;
+  }
   Prof pf;
   pf.p = (c.prof && e == c.prof_env) ? c.prof : nullptr;
   pf.t0 = clock64();
@@ -1162,8 +1208,12 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e) {
   float* dump = (MODE == 3) ? p.dump + (size_t)e * d.dump_total : nullptr;
   const int nsteps = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
   for (int st = 0; st < nsteps; ++st) {
+    // Optional lockstep: the warps of a CTA start each substep together, so that they walk the (large) instruction
+    // footprint of a substep as one group instead of seven independent streams.
+    if (p.lockstep) __syncthreads();
     forward<MODE == 3>(so, dump, pf);
     if (MODE == 1 || MODE == 3) break;
+    if (p.lockstep > 1) __syncthreads();
     euler(so, pf);
   }
 
@@ -1373,7 +1423,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
     c.d = p.dims;
     make_layout(c.d, c.L);
     c.mb = p.model;
-    c.prof = p.prof; c.prof_env = p.prof_env;
+    c.prof = p.prof; c.prof_env = p.prof_env; c.lockstep = p.lockstep;
     const uint32_t kb = (uint32_t)(kCtaFloats * 4);  // byte offset of the staged tables in shared memory
 #define TOFF(name, id) c.o_##name = kb + g_ktab[id]
     TOFF(lvl_start, VNL_KT_LVL_START); TOFF(lvl_bp, VNL_KT_LVL_BP); TOFF(parent, VNL_KT_PARENT); TOFF(child_adr, VNL_KT_CHILD_ADR);
@@ -1389,7 +1439,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
   __syncthreads();
   const int W = nt >> 5, warp = tid >> 5;
   const int so = kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
-  for (int e = blockIdx.x * W + warp; e < p.B; e += gridDim.x * W) env_run<MODE>(so, p, e);
+  const int stride = gridDim.x * W, rounds = (p.B + stride - 1) / stride;
+  for (int r = 0; r < rounds; ++r) {
+    const int e = r * stride + blockIdx.x * W + warp;
+    env_run<MODE>(so, p, e, e < p.B);
+  }
 }
 
 template __global__ void vnl_env_kernel<0>(Params);
@@ -1430,7 +1484,11 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;
-  k<<<li.ctas, li.warps_per_cta * 32, li.smem_bytes, stream>>>(p);
+  static int lockstep = -1;
+  if (lockstep < 0) { const char* ev = getenv("VNL_LOCKSTEP"); lockstep = ev ? atoi(ev) : 1; }
+  Params q = p;
+  q.lockstep = lockstep;
+  k<<<li.ctas, li.warps_per_cta * 32, li.smem_bytes, stream>>>(q);
   return cudaGetLastError();
 }
 

@@ -45,6 +45,7 @@ struct Params {
   float* dump;
   long long* prof;  // optional [32] per-phase clock64 accumulators of one env (developer hook)
   int prof_env;
+  int lockstep;     // 0 = warps free-run, 1 = CTA barrier at every substep start, 2 = also before the integrator
 };
 
 struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };
