@@ -343,6 +343,13 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if int(tj.get("envs", 0)) == B:
+            traffic = float(tj["dram_bytes_per_launch"])
+    except Exception:
+        pass
     ach_gbs = B * nbytes / (kernel_ms * 1e-3) / 1e9
     ach_tf = B * flops / (kernel_ms * 1e-3) / 1e12
     line = {
@@ -360,7 +367,7 @@ def run_ours(args):
         "gpu_launches": int(sums["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "peak_source": hbm_src, "bytes_per_env_step": nbytes, "kernel_ms": kernel_ms,
+                     "traffic": traffic, "peak_source": hbm_src, "bytes_per_env_step": nbytes, "kernel_ms": kernel_ms,
                      "note": "this path is FP32-latency bound, not HBM bound (intensity ~%d flop/B); see roofline_fp32" % (flops / nbytes)},
         "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": ach_tf / ffma_tflops,
                           "peak_source": "FFMA microkernel measured in this run (nominal 74.4)", "flops_per_env_step": flops,
