@@ -144,7 +144,8 @@ def cpu_oracle_rate(seconds_target=12.0, nthreads=0, steps=None, sample_envs=Non
     task, fclip, idx, obs_size, traj_size = rod.rodent_task_tables(model, clip, **{k: rod.RODENT_ENV_ARGS[k] for k in ENV_ARG_KEYS})
     blob = mb.build_model_blob(model)
     dims = mb.read_dims(blob)
-    nt = nthreads or oracle.max_threads()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: size the pool from the cores this process may run on
+    nt = nthreads or len(os.sched_getaffinity(0))
     kw = dict(precision=32, dims=dims, obs_size=obs_size, traj_size=traj_size, nthreads=nt)
     rng = np.random.default_rng(0)
 
@@ -321,6 +322,13 @@ def run_ours(args):
     # ---- max over ranks ---------------------------------------------------------------------------------------------
     red = sh.reduce_scalars(dict(ms=ms_total, e2e=e2e_ms_total, kern=kernel_ms), op="max", device=dev)
     sums = sh.reduce_scalars(dict(launches=float(launches)), op="sum", device=dev)
+    rank_ms = [ms_total / K]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([ms_total / K], dtype=torch.float64, device=dev))
+        rank_ms = [float(g.item()) for g in gathered]
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     ms_total, e2e_ms_total, kernel_ms = red["ms"], red["e2e"], red["kern"]
@@ -354,7 +362,7 @@ def run_ours(args):
     ach_tf = B * flops / (kernel_ms * 1e-3) / 1e12
     line = {
         "metric": "rodent imitation env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": W, "ms_per_step": ms_total / K, "rank_ms_per_step": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p), "
                                "%d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "

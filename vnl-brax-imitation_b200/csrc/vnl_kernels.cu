@@ -160,36 +160,46 @@ __device__ __noinline__ void factor(int so, bool damp, Prof& pf) {
   }
   __syncwarp();
   // eliminate dofs from the leaves: for 1 <= a <= cc <= dk:  F[anc_a(k)][cc - a] -= F[k][a] * F[k][cc] / F[k][0]
-  // (rows stay un-normalised until the end); the (a, cc) pairs of one k are spread over the lanes through TRI
+  // (rows stay un-normalised until the end).  Row k is read-only during its own elimination: it sits in registers
+  // (lane l holds entries l and l + 32, plus the same scaled by 1 / pivot) and the (a, cc) operands of each update come
+  // from shuffles, so the only memory dependence left is on the distinct targets.  The (a, cc) pair list of every k is
+  // a prefix of the universal triangular table TRI (padded by 64 entries, so tails need no bounds select).
   for (int k = nv - 1; k > 0; --k) {
     const int base = madr[k], dk = madr[k + 1] - base - 1;
     if (dk > 0) {
-      // row k is read-only during its own elimination: keep it in registers (lane l holds entries l and l + 32) and
-      // fetch the (a, cc) operands with shuffles, so the only memory dependence left is on the distinct targets
       const float inv = 1.0f / F[base];
       const int np = (dk * (dk + 1)) >> 1;
       const float r0 = (lane <= dk) ? F[base + lane] : 0.0f;
-      const float r1 = (lane + 32 <= dk) ? F[base + lane + 32] : 0.0f;
+      const float u0 = r0 * inv;
       const uint16_t* const ak = anc_start + base;
-      for (int p0 = 0; p0 < np; p0 += 64) {
-        const int pa = p0 + lane, pb = pa + 32;
-        const uint32_t ta = tri[pa < np ? pa : 0], tb = tri[pb < np ? pb : 0];
-        const int aa = ta & 255, ca = ta >> 8, ab = tb & 255, cb = tb >> 8;
-        float va = __shfl_sync(FULLMASK, r0, aa), vca = __shfl_sync(FULLMASK, r0, ca);
-        float vb = __shfl_sync(FULLMASK, r0, ab), vcb = __shfl_sync(FULLMASK, r0, cb);
-        if (dk >= 32) {  // warp-uniform
-          const float wa = __shfl_sync(FULLMASK, r1, aa), wca = __shfl_sync(FULLMASK, r1, ca);
-          const float wb = __shfl_sync(FULLMASK, r1, ab), wcb = __shfl_sync(FULLMASK, r1, cb);
-          if (aa >= 32) va = wa;
-          if (ca >= 32) vca = wca;
-          if (ab >= 32) vb = wb;
-          if (cb >= 32) vcb = wcb;
+      if (dk < 32) {
+        for (int q0 = 0; q0 < np; q0 += 64) {  // warp-uniform trip count: every lane takes part in the shuffles
+          const int p0 = q0 + lane;
+          const uint32_t ta = tri[p0], tb = tri[p0 + 32];
+          const int aa = ta & 255, ca = ta >> 8, ab = tb & 255, cb = tb >> 8;
+          const float xa = __shfl_sync(FULLMASK, u0, aa), ya = __shfl_sync(FULLMASK, r0, ca);
+          const float xb = __shfl_sync(FULLMASK, u0, ab), yb = __shfl_sync(FULLMASK, r0, cb);
+          const bool oka = p0 < np, okb = p0 + 32 < np;
+          float* const tga = F + (oka ? ak[aa] + ca - aa : 0);
+          float* const tgb = F + (okb ? ak[ab] + cb - ab : 0);
+          const float fa = *tga, fb = *tgb;
+          if (oka) *tga = fa - xa * ya;
+          if (okb) *tgb = fb - xb * yb;
         }
-        float* const tga = F + (ak[aa] + ca - aa);
-        float* const tgb = F + (ak[ab] + cb - ab);
-        const float fa = (pa < np) ? *tga : 0.0f, fb = (pb < np) ? *tgb : 0.0f;
-        if (pa < np) *tga = fa - (va * inv) * vca;
-        if (pb < np) *tgb = fb - (vb * inv) * vcb;
+      } else {
+        const float r1 = (lane + 32 <= dk) ? F[base + lane + 32] : 0.0f;
+        const float u1 = r1 * inv;
+        for (int q0 = 0; q0 < np; q0 += 32) {
+          const int p0 = q0 + lane;
+          const uint32_t ta = tri[p0];
+          const int aa = ta & 255, ca = ta >> 8;
+          const float x0 = __shfl_sync(FULLMASK, u0, aa), x1 = __shfl_sync(FULLMASK, u1, aa);
+          const float y0 = __shfl_sync(FULLMASK, r0, ca), y1 = __shfl_sync(FULLMASK, r1, ca);
+          if (p0 < np) {
+            float* const tga = F + (ak[aa] + ca - aa);
+            *tga -= (aa >= 32 ? x1 : x0) * (ca >= 32 ? y1 : y0);
+          }
+        }
       }
     }
     __syncwarp();

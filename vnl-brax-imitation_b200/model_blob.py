@@ -194,7 +194,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
     prog_d, TD = pack_program(rows_d) if rows_d else (np.zeros(32, dtype=np.uint32), 1)
     ndslot = len(rows_d)
-    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)]
+    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)] + [1 | (1 << 8)] * 64  # padded tail
     kitem, klvl = [], [0, 0]
     for dpt in range(1, maxd + 1):
         items = [(c, i) for i in range(nv) if ddepth[i] == dpt for c in range(1, dpt + 1)]
