@@ -196,7 +196,7 @@ enum VnlKtabScalar { VNL_KS_TA = 0, VNL_KS_TD, VNL_KS_NDSLOT, VNL_KS_RESERVED, V
 
 /* scalar header slots of a TASK blob (imitation task: clip + index tables) */
 enum VnlTaskHdr {
-  VNL_TH_KIND = 4,        /* 0 = rodent (envs/rodent.py) */
+  VNL_TH_KIND = 4,        /* 0 = rodent (envs/rodent.py), 1 = humanoid (envs/humanoid.py); informative, the switches below decide */
   VNL_TH_CLIP_LEN,        /* frames in the clip tables (T) */
   VNL_TH_REF_LEN,         /* ref_traj_length (5) */
   VNL_TH_SUB_CLIP_LEN,    /* sub_clip_length (10) */
@@ -209,7 +209,15 @@ enum VnlTaskHdr {
   VNL_TH_TRAJ_SIZE,       /* 795 */
   VNL_TH_COM_REF_IDX,     /* column of the filtered body table used as COM reference (quirk Q4) */
   VNL_TH_TORSO_BODY,      /* body whose xmat defines the egocentric frame (1) */
-  VNL_TH_HEALTHY_LO = 32, VNL_TH_HEALTHY_HI, VNL_TH_TERM_THRESHOLD, VNL_TH_BODY_ERR_MULT
+  /* variant switches: rodent (envs/rodent.py) = all 0 except OBS_QFRC / USE_SUBCLIP; humanoid (envs/humanoid.py) see below */
+  VNL_TH_REWARD_OLD_STATE,/* 1: every reward term reads the PRE-step state (humanoid.py:275, `data_c = state.pipeline_state`) */
+  VNL_TH_TERM_MEAN,       /* 1: termination error = mean |.| over joints and over all body coordinates (humanoid.py:256-258);
+                             0: L1 sum over joints + max column abs-sum over tracked bodies (rodent.py:256-258) */
+  VNL_TH_USE_SUBCLIP,     /* 1: done when sub_clip_frame reaches sub_clip_length (rodent.py:207-215) */
+  VNL_TH_OBS_QFRC,        /* 1: obs carries qfrc_actuator and the end-effector positions (rodent.py:337-344) */
+  VNL_TH_COM_FROM_FIELD,  /* 1: COM reference = VNL_T_CENTER_OF_MASS (humanoid.py:279); 0: filtered body table column (quirk Q4) */
+  VNL_TH_HEALTHY_LO = 32, VNL_TH_HEALTHY_HI, VNL_TH_TERM_THRESHOLD, VNL_TH_BODY_ERR_MULT,
+  VNL_TH_DONE_RTRUNK      /* done when the UNSCALED rtrunk is below this (0 for the rodent, 0.5 for the humanoid: humanoid.py:199) */
 };
 
 enum VnlTaskField {
@@ -225,6 +233,7 @@ enum VnlTaskField {
   VNL_T_APP_IDX,          /* i [napp]    model body ids (rodent.py:71-76) */
   VNL_T_APP_REF_IDX,      /* i [napp]    app ids clamped into the filtered table (quirk Q5) */
   VNL_T_JOINT_COL,        /* i [njidx]   joint ids clamped into the nq-7 joint columns (quirk Q6) */
+  VNL_T_CENTER_OF_MASS,   /* f [T,3]     ReferenceClip.center_of_mass (old 13-field clip format, humanoid.py:279); zeros if absent */
   VNL_TASK_COUNT
 };
 

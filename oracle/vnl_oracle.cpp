@@ -805,8 +805,9 @@ template <class T> void step(const ModelView& m, Data<T>& d) { forward(m, d); eu
 struct TaskView {
   const uint32_t* w;
   int T_, ref_len, sub_clip_len, ntrack, njidx, napp, nee, nframes, obs_size, traj_size, com_ref_idx, torso;
-  float healthy_lo, healthy_hi, term_threshold, body_err_mult;
-  const float *position, *quaternion, *joints, *body_positions, *velocity, *angular_velocity, *joints_velocity;
+  int reward_old_state, term_mean, use_subclip, obs_qfrc, com_from_field;
+  float healthy_lo, healthy_hi, term_threshold, body_err_mult, done_rtrunk;
+  const float *position, *quaternion, *joints, *body_positions, *velocity, *angular_velocity, *joints_velocity, *center_of_mass;
   const int *body_idxs, *ee_idx, *app_idx, *app_ref_idx, *joint_col;
   explicit TaskView(const uint32_t* b) : w(b) {
     T_ = vnl_hdr_i(b, VNL_TH_CLIP_LEN); ref_len = vnl_hdr_i(b, VNL_TH_REF_LEN); sub_clip_len = vnl_hdr_i(b, VNL_TH_SUB_CLIP_LEN);
@@ -815,6 +816,10 @@ struct TaskView {
     com_ref_idx = vnl_hdr_i(b, VNL_TH_COM_REF_IDX); torso = vnl_hdr_i(b, VNL_TH_TORSO_BODY);
     healthy_lo = vnl_hdr_f(b, VNL_TH_HEALTHY_LO); healthy_hi = vnl_hdr_f(b, VNL_TH_HEALTHY_HI);
     term_threshold = vnl_hdr_f(b, VNL_TH_TERM_THRESHOLD); body_err_mult = vnl_hdr_f(b, VNL_TH_BODY_ERR_MULT);
+    reward_old_state = vnl_hdr_i(b, VNL_TH_REWARD_OLD_STATE); term_mean = vnl_hdr_i(b, VNL_TH_TERM_MEAN);
+    use_subclip = vnl_hdr_i(b, VNL_TH_USE_SUBCLIP); obs_qfrc = vnl_hdr_i(b, VNL_TH_OBS_QFRC);
+    com_from_field = vnl_hdr_i(b, VNL_TH_COM_FROM_FIELD); done_rtrunk = vnl_hdr_f(b, VNL_TH_DONE_RTRUNK);
+    center_of_mass = vnl_field_f(b, VNL_T_CENTER_OF_MASS);
     position = vnl_field_f(b, VNL_T_POSITION); quaternion = vnl_field_f(b, VNL_T_QUATERNION); joints = vnl_field_f(b, VNL_T_JOINTS);
     body_positions = vnl_field_f(b, VNL_T_BODY_POSITIONS); velocity = vnl_field_f(b, VNL_T_VELOCITY);
     angular_velocity = vnl_field_f(b, VNL_T_ANGULAR_VELOCITY); joints_velocity = vnl_field_f(b, VNL_T_JOINTS_VELOCITY);
@@ -833,6 +838,10 @@ template <class T> T termination(const ModelView& m, const TaskView& t, const T*
   for (int b = 0; b < t.ntrack; ++b)
     for (int k = 0; k < 3; ++k) col[k] += std::abs(T(t.body_positions[(f * t.ntrack + b) * 3 + k]) - xpos[3 * t.body_idxs[b] + k]);
   T eb = std::max(col[0], std::max(col[1], col[2]));
+  if (t.term_mean) {  // humanoid.py:256-258: jp.mean(jp.abs(.)) over the joints and over all body coordinates
+    ej = ej / T(nj);
+    eb = (col[0] + col[1] + col[2]) / T(3 * t.ntrack);
+  }
   T error = T(0.5) * T(t.body_err_mult) * eb + T(0.5) * ej;
   return T(1) - error / T(t.term_threshold);
 }
@@ -841,6 +850,7 @@ template <class T> void get_obs(const ModelView& m, const TaskView& t, const Dat
   int o = 0;
   for (int i = 0; i < m.nq; ++i) obs[o++] = d.qpos[i];
   for (int i = 0; i < m.nv; ++i) obs[o++] = d.qvel[i];
+  if (!t.obs_qfrc) return;  // humanoid.py:359-366: [qpos, qvel] only
   for (int i = 0; i < m.nv; ++i) obs[o++] = d.qfrc_actuator[i];
   for (int e = 0; e < t.nee; ++e)
     for (int k = 0; k < 3; ++k) obs[o++] = d.xpos[3 * t.ee_idx[e] + k];
@@ -903,8 +913,11 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
                                  const StateIO& out, const OutIO& o) {
   Data<T> d(m);
   load_state(m, in, e, d);
-  std::vector<T> qpos_old(d.qpos), xpos_old(m.nbody * 3);
+  std::vector<T> qpos_old(d.qpos), xpos_old(m.nbody * 3), qvel_old(d.qvel), qfrc_old(m.nv);
   for (int i = 0; i < m.nbody * 3; ++i) xpos_old[i] = T(in.xpos[e * m.nbody * 3 + i]);
+  for (int i = 0; i < m.nv; ++i) qfrc_old[i] = in.qfrc_actuator ? T(in.qfrc_actuator[e * m.nv + i]) : T(0);
+  T com_old[3] = {in.subtree_com ? T(in.subtree_com[e * 3]) : T(0), in.subtree_com ? T(in.subtree_com[e * 3 + 1]) : T(0),
+                  in.subtree_com ? T(in.subtree_com[e * 3 + 2]) : T(0)};
   for (int u = 0; u < m.nu; ++u) d.ctrl[u] = T(action[e * m.nu + u]);
   int stats[4] = {0, 0, 0, 0};
   for (int f = 0; f < t.nframes; ++f) {  // pipeline_step
@@ -918,36 +931,46 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   get_traj(m, t, d, cur_frame, traj.data());
   // _calculate_reward (rodent.py:266-316): every reference lookup uses the OLD cur_frame (Q3)
   int f = clampi(frame_old, 0, t.T_ - 1), nj = m.nq - 7;
+  // humanoid.py:275 evaluates every term on the PRE-step state (`data_c = state.pipeline_state`), the rodent on the new one
+  const bool old = t.reward_old_state != 0;
+  const T* r_qvel = old ? qvel_old.data() : d.qvel.data();
+  const T* r_qpos = old ? qpos_old.data() : d.qpos.data();
+  const T* r_qfrc = old ? qfrc_old.data() : d.qfrc_actuator.data();
+  const T* r_com = old ? com_old : d.subtree_com.data() + 3 * t.torso;
   T s = 0;
-  for (int k = 0; k < 3; ++k) { T df = d.subtree_com[3 * t.torso + k] - T(t.body_positions[(f * t.ntrack + t.com_ref_idx) * 3 + k]); s += df * df; }
+  for (int k = 0; k < 3; ++k) {
+    T cref = t.com_from_field ? T(t.center_of_mass[f * 3 + k]) : T(t.body_positions[(f * t.ntrack + t.com_ref_idx) * 3 + k]);
+    T df = r_com[k] - cref;
+    s += df * df;
+  }
   T rcom = std::exp(T(-100) * std::sqrt(s));
   s = 0;
   for (int i = 0; i < m.nv; ++i) {
     T ref = i < 3 ? T(t.velocity[f * 3 + i]) : (i < 6 ? T(t.angular_velocity[f * 3 + i - 3]) : T(t.joints_velocity[f * (m.nv - 6) + i - 6]));
-    T df = d.qvel[i] - ref;
+    T df = r_qvel[i] - ref;
     s += df * df;
   }
   T rvel = std::exp(T(-0.1) * std::sqrt(s));
   T rtrunk = termination(m, t, qpos_old.data(), xpos_old.data(), frame_old);  // OLD state, OLD frame (Q2)
-  T qc[4] = {d.qpos[3], d.qpos[4], d.qpos[5], d.qpos[6]};
+  T qc[4] = {r_qpos[3], r_qpos[4], r_qpos[5], r_qpos[6]};
   T qr[4] = {T(t.quaternion[4 * f]), T(t.quaternion[4 * f + 1]), T(t.quaternion[4 * f + 2]), T(t.quaternion[4 * f + 3])};
   normalize4(qc); normalize4(qr);  // _bounded_quat_dist (rodent.py:450-470)
   T dq = qc[0] * qr[0] + qc[1] * qr[1] + qc[2] * qr[2] + qc[3] * qr[3];
   T dist = std::min(T(1), T(2) * dq * dq - T(1));
   T rquat = std::exp(T(-2) * std::abs(T(0.5) * std::acos(dist)));
   s = 0;
-  for (int i = 0; i < m.nv; ++i) s += d.qfrc_actuator[i] * d.qfrc_actuator[i];
+  for (int i = 0; i < m.nv; ++i) s += r_qfrc[i] * r_qfrc[i];
   T ract = T(-0.015) * (s / T(m.nv));
   s = 0;
   for (int a = 0; a < t.napp; ++a)
     for (int k = 0; k < 3; ++k) { T df = d.xpos[3 * t.app_idx[a] + k] - T(t.body_positions[(f * t.ntrack + t.app_ref_idx[a]) * 3 + k]); s += df * df; }
-  T rapp = std::exp(T(-400) * std::sqrt(s));
-  T healthy = d.qpos[2] < T(t.healthy_lo) ? T(0) : T(1);
-  if (d.qpos[2] > T(t.healthy_hi)) healthy = 0;
+  T rapp = t.napp > 0 ? std::exp(T(-400) * std::sqrt(s)) : T(0);  // no appendage term in humanoid.py:200-205
+  T healthy = r_qpos[2] < T(t.healthy_lo) ? T(0) : T(1);
+  if (r_qpos[2] > T(t.healthy_hi)) healthy = 0;
+  T done = rtrunk < T(t.done_rtrunk) ? T(1) : T(0);  // rodent.py:213 (scaled rtrunk < 0) / humanoid.py:199 (rtrunk < 0.5 before scaling)
   rcom *= T(0.01); rvel *= T(0.01); rapp *= T(0.01); rtrunk *= T(0.01); rquat *= T(0.01); ract *= T(0.0001);  // rodent.py:193-199
   T total = rcom + rvel + rtrunk + rquat + ract + rapp;
-  T sub_healthy = sub_clip_frame < t.sub_clip_len ? T(1) : T(0);
-  T done = rtrunk < 0 ? T(1) : T(0);
+  T sub_healthy = (!t.use_subclip || sub_clip_frame < t.sub_clip_len) ? T(1) : T(0);
   done = std::max(T(1) - healthy, done);
   done = std::max(T(1) - sub_healthy, done);
   T reward = std::isnan(total) ? T(0) : total;  // jp.nan_to_num (inf -> large finite, as jnp does)

@@ -3,6 +3,7 @@
 
   vnl-brax-imitation_b200/data/rodent_model.npz  compiled rodent model (envs/rodent.py:39-63 recipe)
   vnl-brax-imitation_b200/data/rodent_clip.npz   process_clip() of clips/transform_snips_groom.p
+  vnl-brax-imitation_b200/data/humanoid_model.npz compiled humanoid model (envs/humanoid.py:40-54 recipe)
   tests/golden/rodent_clip_golden.npz            the old clip's own derived fields (known answers)
 """
 import importlib
@@ -31,7 +32,9 @@ def main(ref="/root/reference"):
                                                      "center_of_mass", "appendages", "velocity", "angular_velocity",
                                                      "joints_velocity")}
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "rodent_clip_golden.npz"), **gold)
-    print("model", model.nbody, model.nv, "clip", clip.position.shape, clip.body_positions.shape)
+    hum = mjcf.load_humanoid(os.path.join(ref, "assets", "humanoid.xml"))
+    mjcf.save_model(hum, os.path.join(data, "humanoid_model.npz"))
+    print("model", model.nbody, model.nv, "clip", clip.position.shape, clip.body_positions.shape, "humanoid", hum.nbody, hum.nv)
 
 
 if __name__ == "__main__":

@@ -60,6 +60,7 @@ class ReferenceClip:
     joints_velocity: Optional[np.ndarray] = None
     angular_velocity: Optional[np.ndarray] = None
     body_quaternions: Optional[np.ndarray] = None
+    center_of_mass: Optional[np.ndarray] = None  # old 13-field format only (mocap_preprocess.py:326-340); humanoid.py:279 reads it
 
     def replace(self, **kw):
         return replace(self, **kw)
@@ -139,9 +140,23 @@ def process_clip(stac_path: str, mjcf_path: str = "./assets/rodent.xml", scale_f
 
 
 def clip_to_npz_dict(clip: ReferenceClip) -> dict:
-    return {f.name: getattr(clip, f.name) for f in fields(clip)}
+    return {f.name: getattr(clip, f.name) for f in fields(clip) if getattr(clip, f.name) is not None}
 
 
 def clip_from_npz(path: str) -> ReferenceClip:
     z = np.load(path)
-    return ReferenceClip(**{f.name: z[f.name] for f in fields(ReferenceClip)})
+    return ReferenceClip(**{f.name: z[f.name] for f in fields(ReferenceClip) if f.name in z.files})
+
+
+def tiled_clip(model: mjcf.Model, qpos: np.ndarray, length: int = 256) -> ReferenceClip:
+    """Synthetic clip = one pose repeated `length` times with zero velocities, the way the reference's notebooks built
+    `ant_traj_still.p` (tile of the reset state, `notebooks/environments_explore.ipynb`) and the stand-in used here for the
+    absent `clips/humanoid_traj_stand.p`.  body_positions holds ALL bodies (humanoid.py:257 compares against data.xpos)."""
+    k = mjcf.kinematics(model, np.asarray(qpos, dtype=np.float64))
+    com = mjcf.subtree_com(model, k["xipos"])[1]
+    f32 = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float32), (length,) + np.shape(a)))
+    q = k["qpos"]
+    nv = model.nv
+    return ReferenceClip(position=f32(q[:3]), quaternion=f32(q[3:7]), joints=f32(q[7:]), body_positions=f32(k["xpos"]),
+                         velocity=f32(np.zeros(3)), joints_velocity=f32(np.zeros(nv - 6)), angular_velocity=f32(np.zeros(3)),
+                         body_quaternions=f32(k["xquat"]), center_of_mass=f32(com))

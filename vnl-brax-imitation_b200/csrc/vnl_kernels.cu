@@ -1147,6 +1147,44 @@ __device__ __forceinline__ float nan_to_num(float v) {
   return v;
 }
 
+// The reward terms that depend on (qvel, qpos, qfrc_actuator, subtree_com) of ONE state: the post-step state for the
+// rodent (rodent.py:266-316), the pre-step state for the humanoid (humanoid.py:264-311).  Warp-cooperative.
+struct RewardTerms { float rcom, rvel, rquat, ract, healthy; };
+__device__ __noinline__ RewardTerms reward_state_terms(const uint32_t* tb, int nv, int f, const float* qvel, const float* qpos,
+                                                       const float* qfrc, const float* com) {
+  const int lane = LANE;
+  const int ntrack = vnl_hdr_i(tb, VNL_TH_NTRACK);
+  const float* rvel = vnl_field_f(tb, VNL_T_VELOCITY) + (size_t)f * 3;
+  const float* rang = vnl_field_f(tb, VNL_T_ANGULAR_VELOCITY) + (size_t)f * 3;
+  const float* rjv = vnl_field_f(tb, VNL_T_JOINTS_VELOCITY) + (size_t)f * (nv - 6);
+  float v0 = 0.0f, v1 = 0.0f;
+  for (int i = lane; i < nv; i += 32) {
+    const float ref = i < 3 ? rvel[i] : (i < 6 ? rang[i - 3] : rjv[i - 6]);
+    const float df = qvel[i] - ref;
+    v0 += df * df;
+    const float qa = qfrc[i];
+    v1 += qa * qa;
+  }
+  v0 = warp_sum(v0); v1 = warp_sum(v1);
+  const float* cref = vnl_hdr_i(tb, VNL_TH_COM_FROM_FIELD)
+                          ? vnl_field_f(tb, VNL_T_CENTER_OF_MASS) + (size_t)f * 3
+                          : vnl_field_f(tb, VNL_T_BODY_POSITIONS) + ((size_t)f * ntrack + vnl_hdr_i(tb, VNL_TH_COM_REF_IDX)) * 3;
+  const V3 dc = ld3(com) - ld3(cref);
+  RewardTerms r;
+  r.rcom = expf(-100.0f * sqrtf(dot(dc, dc)));
+  r.rvel = expf(-0.1f * sqrtf(v0));
+  const Q4 qc = quat_normalize(ld4(qpos + 3));
+  const Q4 qr = quat_normalize(ld4(vnl_field_f(tb, VNL_T_QUATERNION) + (size_t)f * 4));
+  const float dq = qc.w * qr.w + qc.x * qr.x + qc.y * qr.y + qc.z * qr.z;
+  const float dist = fminf(1.0f, 2.0f * dq * dq - 1.0f);
+  r.rquat = expf(-2.0f * fabsf(0.5f * acosf(dist)));
+  r.ract = -0.015f * (v1 / (float)nv);
+  const float z = qpos[2];
+  r.healthy = z < vnl_hdr_f(tb, VNL_TH_HEALTHY_LO) ? 0.0f : 1.0f;
+  if (z > vnl_hdr_f(tb, VNL_TH_HEALTHY_HI)) r.healthy = 0.0f;
+  return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // one env, one warp.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1193,6 +1231,8 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   // inputs, so evaluate it before the physics overwrites them.
   float rtrunk = 0.0f;
   int frame_old = 0;
+  RewardTerms rt;
+  rt.rcom = rt.rvel = rt.rquat = rt.ract = rt.healthy = 0.0f;
   if (MODE == 0) {
     frame_old = p.in.cur_frame[e];
     const int T = vnl_hdr_i(tb, VNL_TH_CLIP_LEN), ntrack = vnl_hdr_i(tb, VNL_TH_NTRACK), nj = d.nq - 7;
@@ -1209,9 +1249,12 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       v3_ += fabsf(rb[3 * b + 2] - xold[3 * bidx[b] + 2]);
     }
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
-    const float eb = fmaxf(v1, fmaxf(v2, v3_));
+    float eb = fmaxf(v1, fmaxf(v2, v3_));
+    if (vnl_hdr_i(tb, VNL_TH_TERM_MEAN)) { v0 = v0 / (float)nj; eb = (v1 + v2 + v3_) / (float)(3 * ntrack); }  // humanoid.py:256-258
     const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v0;
     rtrunk = 1.0f - err / vnl_hdr_f(tb, VNL_TH_TERM_THRESHOLD);
+    if (vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE))  // humanoid.py:275: the whole reward reads the pre-step state
+      rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, p.in.qfrc_actuator + (size_t)e * d.nv, p.in.subtree_com + (size_t)e * 3);
   }
 
   int* stats = ints + 4;  // [4..7]
@@ -1286,7 +1329,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   if (lane == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; }
   {
     float* obs = p.outputs.obs + (size_t)e * obs_size;
-    for (int i = lane; i < obs_size; i += 32) {
+    for (int i = lane; i < obs_size; i += 32) {  // [qpos, qvel (, qfrc_actuator, xpos[end effectors])]
       float v;
       if (i < d.nq) v = s[L.qpos + i];
       else if (i < d.nq + d.nv) v = s[L.qvel + i - d.nq];
@@ -1334,7 +1377,8 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       v1 += fabsf(rb[0] - xp[0]); v2 += fabsf(rb[1] - xp[1]); v3_ += fabsf(rb[2] - xp[2]);
     }
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
-    const float eb = fmaxf(v1, fmaxf(v2, v3_));
+    float eb = fmaxf(v1, fmaxf(v2, v3_));
+    if (vnl_hdr_i(tb, VNL_TH_TERM_MEAN)) { v0 = v0 / (float)nj; eb = (v1 + v2 + v3_) / (float)(3 * ntrack); }
     const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v0;
     if (lane == 0) {
       p.outputs.reward[e] = 0.0f; p.outputs.done[e] = 0.0f;
@@ -1346,21 +1390,13 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     __syncwarp();
     return;
   }
-  // _calculate_reward (rodent.py:266-316): every reference lookup uses the OLD cur_frame
+  // _calculate_reward (rodent.py:266-316 / humanoid.py:264-311): every reference lookup uses the OLD cur_frame
   {
     const int f = min(max(frame_old, 0), T - 1);
-    const float* rvel = vnl_field_f(tb, VNL_T_VELOCITY) + (size_t)f * 3;
-    const float* rang = vnl_field_f(tb, VNL_T_ANGULAR_VELOCITY) + (size_t)f * 3;
-    const float* rjv = vnl_field_f(tb, VNL_T_JOINTS_VELOCITY) + (size_t)f * (d.nv - 6);
-    float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;  // |qvel - ref|^2, sum qfrc_actuator^2, |app - ref|^2, nan count
-    for (int i = lane; i < d.nv; i += 32) {
-      const float ref = i < 3 ? rvel[i] : (i < 6 ? rang[i - 3] : rjv[i - 6]);
-      const float df = s[L.qvel + i] - ref;
-      v0 += df * df;
-      const float qa = s[L.qfrc_act + i];
-      v1 += qa * qa;
-      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(qa)) v3_ += 1.0f;
-    }
+    if (!vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE)) rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, s + L.qfrc_act, rcom);
+    float v2 = 0.0f, v3_ = 0.0f;  // |app - ref|^2, nan count
+    for (int i = lane; i < d.nv; i += 32)
+      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(s[L.qfrc_act + i])) v3_ += 1.0f;
     for (int i = lane; i < napp * 3; i += 32) {
       const int a = i / 3, k = i % 3;
       const float df = s[L.xpos + 3 * appidx[a] + k] - rbody[((size_t)f * ntrack + apprefidx[a]) * 3 + k];
@@ -1369,28 +1405,16 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     for (int i = lane; i < d.nq; i += 32) if (isnan(s[L.qpos + i])) v3_ += 1.0f;
     for (int i = lane; i < d.nbody * 3; i += 32) if (isnan(s[L.xpos + i])) v3_ += 1.0f;
     for (int i = lane; i < d.na; i += 32) if (isnan(s[L.act + i])) v3_ += 1.0f;
-    v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
-    const int cri = vnl_hdr_i(tb, VNL_TH_COM_REF_IDX);
-    const V3 dc = ld3(rcom) - ld3(rbody + ((size_t)f * ntrack + cri) * 3);
-    float r_com = expf(-100.0f * sqrtf(dot(dc, dc)));
-    float rvl = expf(-0.1f * sqrtf(v0));
-    const Q4 qc = quat_normalize(ld4(s + L.qpos + 3));
-    const Q4 qr = quat_normalize(ld4(vnl_field_f(tb, VNL_T_QUATERNION) + (size_t)f * 4));
-    const float dq = qc.w * qr.w + qc.x * qr.x + qc.y * qr.y + qc.z * qr.z;
-    const float dist = fminf(1.0f, 2.0f * dq * dq - 1.0f);
-    float rquat = expf(-2.0f * fabsf(0.5f * acosf(dist)));
-    float ract = -0.015f * (v1 / (float)d.nv);
-    float rapp = expf(-400.0f * sqrtf(v2));
-    const float z = s[L.qpos + 2];
-    float healthy = z < vnl_hdr_f(tb, VNL_TH_HEALTHY_LO) ? 0.0f : 1.0f;
-    if (z > vnl_hdr_f(tb, VNL_TH_HEALTHY_HI)) healthy = 0.0f;
+    v2 = warp_sum(v2); v3_ = warp_sum(v3_);
+    float r_com = rt.rcom, rvl = rt.rvel, rquat = rt.rquat, ract = rt.ract;
+    float rapp = napp > 0 ? expf(-400.0f * sqrtf(v2)) : 0.0f;  // no appendage term in humanoid.py:200-205
+    float done = rtrunk < vnl_hdr_f(tb, VNL_TH_DONE_RTRUNK) ? 1.0f : 0.0f;  // rodent.py:213 / humanoid.py:199 (before scaling)
     r_com *= 0.01f; rvl *= 0.01f; rapp *= 0.01f;
     const float rtr = rtrunk * 0.01f;
     rquat *= 0.01f; ract *= 0.0001f;
     const float total = r_com + rvl + rtr + rquat + ract + rapp;
-    const float sub_healthy = sub_clip_frame < vnl_hdr_i(tb, VNL_TH_SUB_CLIP_LEN) ? 1.0f : 0.0f;
-    float done = rtr < 0.0f ? 1.0f : 0.0f;
-    done = fmaxf(1.0f - healthy, done);
+    const float sub_healthy = (!vnl_hdr_i(tb, VNL_TH_USE_SUBCLIP) || sub_clip_frame < vnl_hdr_i(tb, VNL_TH_SUB_CLIP_LEN)) ? 1.0f : 0.0f;
+    done = fmaxf(1.0f - rt.healthy, done);
     done = fmaxf(1.0f - sub_healthy, done);
     if (v3_ > 0.0f) done = 1.0f;
     if (lane == 0) {

@@ -1,8 +1,9 @@
 """Host-side mirrors of the reference task envs (`envs/rodent.py`, ...) over the CUDA engine."""
 from .base import State  # noqa: F401
+from .humanoid import HUMANOID_ENV_ARGS, HumanoidTracking, humanoid_task_tables  # noqa: F401
 from .rodent import RODENT_ENV_ARGS, RodentTracking, rodent_task_tables  # noqa: F401
 
-_REGISTRY = {"rodent": RodentTracking}
+_REGISTRY = {"rodent": RodentTracking, "humanoidtracking": HumanoidTracking}
 
 
 def register_environment(name, cls):  # `brax.envs.register_environment` (reference train.py:65-68)

@@ -371,14 +371,22 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
                     clip_length: int = 250, ref_traj_length: int = 5, sub_clip_length: int = 10,
                     healthy_z_range=(0.05, 0.5), termination_threshold: float = 5.0,
                     body_error_multiplier: float = 1.0, n_frames: int = 5, torso_body: int = 1,
-                    obs_size: int = 0, traj_size: int = 0) -> np.ndarray:
+                    obs_size: int = 0, traj_size: int = 0, kind: int = 0, reward_old_state: bool = False,
+                    term_mean: bool = False, use_subclip: bool = True, obs_qfrc: bool = True, com_from_field: bool = False,
+                    done_rtrunk: float = 0.0) -> np.ndarray:
     """Rodent imitation task tables.  `clip.body_positions` must already be filtered to
     `body_idxs` (`envs/rodent.py:114-115`).  The reference indexes that filtered table with
     MODEL body ids and relies on JAX clamping out-of-range gathers; the
     clamped indices are baked here so kernels only gather."""
     ntrack = len(body_idxs)
     w = _BlobWriter(C["VNL_MAGIC_TASK"], C["VNL_TASK_COUNT"])
-    w.set_i("VNL_TH_KIND", 0)
+    w.set_i("VNL_TH_KIND", kind)
+    w.set_i("VNL_TH_REWARD_OLD_STATE", int(reward_old_state))
+    w.set_i("VNL_TH_TERM_MEAN", int(term_mean))
+    w.set_i("VNL_TH_USE_SUBCLIP", int(use_subclip))
+    w.set_i("VNL_TH_OBS_QFRC", int(obs_qfrc))
+    w.set_i("VNL_TH_COM_FROM_FIELD", int(com_from_field))
+    w.set_f("VNL_TH_DONE_RTRUNK", done_rtrunk)
     w.set_i("VNL_TH_CLIP_LEN", clip.position.shape[0])
     w.set_i("VNL_TH_REF_LEN", ref_traj_length)
     w.set_i("VNL_TH_SUB_CLIP_LEN", sub_clip_length)
@@ -406,6 +414,8 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
     w.add("VNL_T_BODY_IDXS", body_idxs, np.int32)
     w.add("VNL_T_EE_IDX", end_eff_idx, np.int32)
     w.add("VNL_T_APP_IDX", app_idx, np.int32)
-    w.add("VNL_T_APP_REF_IDX", np.clip(np.asarray(app_idx), 0, ntrack - 1), np.int32)
-    w.add("VNL_T_JOINT_COL", np.clip(np.asarray(joint_idxs), 0, njoint_cols - 1), np.int32)
+    w.add("VNL_T_APP_REF_IDX", np.clip(np.asarray(app_idx, dtype=np.int64), 0, ntrack - 1), np.int32)
+    w.add("VNL_T_JOINT_COL", np.clip(np.asarray(joint_idxs, dtype=np.int64), 0, njoint_cols - 1), np.int32)
+    com = getattr(clip, "center_of_mass", None)
+    w.add("VNL_T_CENTER_OF_MASS", com if com is not None else np.zeros((clip.position.shape[0], 3)), np.float32)
     return w.finish()
