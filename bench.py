@@ -125,6 +125,37 @@ def build_workload():
     return rod, mb, model, clip
 
 
+WORKLOADS = {
+    # BASELINE.json configs[1] (the config the metric is quoted on) and configs[2]
+    "rodent": dict(envs=4096, nu=30, text="rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p)"),
+    "humanoid": dict(envs=8192, nu=21, text="CMU humanoid imitation env step+reward/obs (envs/humanoid.py, humanoid.xml, synthetic "
+                                            "standing clip: qpos0 tiled x256 -- the reference clip humanoid_traj_stand.p is absent)"),
+}
+
+
+def make_env(workload, device):
+    """(env, qpos, qvel, start) builder for the rank-local shard."""
+    envs = pkg("envs")
+    if workload == "humanoid":
+        hum = pkg("envs.humanoid")
+        model, clip = hum.packaged_humanoid()
+        return envs.HumanoidTracking(model=model, reference_clip=clip, device=device)
+    rod = pkg("envs.rodent")
+    model, clip = rod.packaged_rodent()
+    return envs.RodentTracking(reference_clip=clip, model=model, device=device, **rod.RODENT_ENV_ARGS)
+
+
+def workload_draws(workload, env, total, lo, hi):
+    if workload == "humanoid":  # HumanoidTracking.reset (humanoid.py:78-102): frame ~ randint(0, 250 - 150 - 5), no noise
+        rng = np.random.default_rng(0)
+        start = rng.integers(0, 95, size=total).astype(np.int32)[lo:hi]
+        rt = env._ref_traj
+        qpos = np.hstack([rt.position[start], rt.quaternion[start], rt.joints[start]]).astype(np.float32)
+        qvel = np.hstack([rt.velocity[start], rt.angular_velocity[start], rt.joints_velocity[start]]).astype(np.float32)
+        return qpos, qvel, start
+    return initial_draws(env._ref_traj, total, lo, hi)
+
+
 def initial_draws(fclip, total, lo, hi, seed=0):
     """RodentTracking.reset draws (envs/rodent.py:123-132) for global env ids [lo, hi) out of `total`."""
     rng = np.random.default_rng(seed)
@@ -210,14 +241,14 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         sh.init_process_group("nccl")
-    rod, mb, model, clip = build_workload()
-    envs = pkg("envs")
-    env = envs.RodentTracking(reference_clip=clip, model=model, device=str(dev), **rod.RODENT_ENV_ARGS)
+    mb = pkg("model_blob")
+    wl = WORKLOADS[args.workload]
+    env = make_env(args.workload, str(dev))
     eng = env.engine
-    B = args.envs_per_gpu
+    B = args.envs_per_gpu or wl["envs"]
     total = B * world
     lo, hi = sh.shard_range(total, rank, world)
-    qpos, qvel, start = initial_draws(env._ref_traj, total, lo, hi)
+    qpos, qvel, start = workload_draws(args.workload, env, total, lo, hi)
     K, W = args.steps, args.warmup
 
     s0 = env.reset_from(qpos, qvel, start)
@@ -343,7 +374,8 @@ def run_ours(args):
     L = st[1] / max(st[0], 1e-9)
     flops = algorithmic_flops(dims, depth, nfr, I, L)
     flops_static = algorithmic_flops(dims, depth, nfr, dims["iterations"], dims["ls_iterations"])
-    nbytes = algorithmic_bytes(dims, eng.obs_size, eng.traj_size, len(env._body_idxs))
+    ntrack = len(env._body_idxs) if hasattr(env, "_body_idxs") else dims["nbody"]
+    nbytes = algorithmic_bytes(dims, eng.obs_size, eng.traj_size, ntrack)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -354,19 +386,18 @@ def run_ours(args):
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        if int(tj.get("envs", 0)) == B:
+        if int(tj.get("envs", 0)) == B and args.workload == "rodent":
             traffic = float(tj["dram_bytes_per_launch"])
     except Exception:
         pass
     ach_gbs = B * nbytes / (kernel_ms * 1e-3) / 1e9
     ach_tf = B * flops / (kernel_ms * 1e-3) / 1e12
     line = {
-        "metric": "rodent imitation env-steps/s", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
+        "metric": "%s imitation env-steps/s" % args.workload, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "rank_ms_per_step": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p), "
-                               "%d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "
-                               "reference's info-not-reset quirk" % B,
+        "config": {"workload": "%s, %d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "
+                               "reference's info-not-reset quirk" % (wl["text"], B),
                    "envs_per_gpu": B, "global_envs": total, "parallelism": "env shards, dp%d, no data-path collective" % world,
                    "l2": "not flushed: the whole batch state (%.0f MB) is L2-resident; numbers are L2-warm as in the rollout loop"
                          % (B * nbytes / 1e6), "done_fraction": done_frac},
@@ -383,7 +414,7 @@ def run_ours(args):
                           "executed": {"solver_iters_per_substep": I, "ls_iters_per_solver_iter": L,
                                        "active_contacts_per_substep": st[2] / nfr, "active_limits_per_substep": st[3] / nfr}},
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and args.workload == "rodent":
         r = cpu_oracle_rate(seconds_target=12.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     else:
@@ -397,7 +428,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="default: the workload's BASELINE.json size")
+    ap.add_argument("--workload", default="rodent", choices=sorted(WORKLOADS), help="rodent = the config the metric is quoted on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

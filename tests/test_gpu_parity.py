@@ -359,3 +359,37 @@ def test_fused_autoreset_equals_wrapper_semantics(gpu_env, rodent):
     for k in ("traj", "reward", "done", "metrics"):
         assert torch.equal(oo2[k], oo1[k]), k
     assert torch.equal(o2["cur_frame"], o1["cur_frame"]) and torch.equal(o2["sub_clip_frame"], o1["sub_clip_frame"])
+
+
+def test_rodent_pair_physics_matches_oracle(oracle_mod):
+    """BASELINE configs[4] model: rodent_pair.xml (<replicate count=2>: 131 bodies, nv 146, 114 contacts, nefc 590, two
+    kinematic trees).  Physics only (the reference has no env for it): per-stage arrays and one pipeline step vs the oracle."""
+    import os
+    import torch
+    from conftest import ROOT
+    mj, mb, libm = pkg("mjcf"), pkg("model_blob"), pkg("_lib")
+    model = mj.load_model(os.path.join(ROOT, "vnl-brax-imitation_b200", "data", "rodent_pair_model.npz"))
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    assert (dims["nbody"], dims["nv"], dims["nu"], dims["ncon"], dims["nefc"], dims["nM"], dims["nroot"]) == (131, 146, 60, 114, 590, 2238, 2)
+    eng = libm.Engine(blob, None, device="cuda:0")
+    B = 6
+    rng = np.random.default_rng(20)
+    qpos = np.tile(model.arrays["qpos0"], (B, 1)).astype(np.float32)
+    qpos[:, 7:74] += (0.05 * rng.standard_normal((B, 67))).astype(np.float32)
+    qpos[:, 81:] += (0.05 * rng.standard_normal((B, 67))).astype(np.float32)
+    qpos[:, 2] -= 0.02; qpos[:, 76] -= 0.015  # press both animals into the floor: active contacts
+    qvel = (0.1 * rng.standard_normal((B, 146))).astype(np.float32)
+    ctrl = rng.uniform(-1, 1, size=(B, 60)).astype(np.float32)
+    st = dict(qpos=torch.tensor(qpos, device="cuda"), qvel=torch.tensor(qvel, device="cuda"))
+    g = oracle_mod.split_dump(dims, eng.forward_dump(st, torch.tensor(ctrl, device="cuda")).cpu().numpy().astype(np.float64))
+    ost = dict(qpos=qpos.astype(np.float64), qvel=qvel.astype(np.float64))
+    o32 = oracle_mod.forward_dump(blob, ost, ctrl.astype(np.float64), precision=32, dims=dims)
+    assert (o32["counters"][:, 2] > 0).all()
+    for name, tol in dict(xpos=3e-6, xquat=3e-6, cinert=3e-6, cdof=5e-6, crb=5e-6, qM=5e-6, cvel=5e-6, qfrc_bias=3e-5,
+                          qfrc_smooth=3e-5, qacc_smooth=2e-4, con_dist=5e-6, qacc=1e-2, qfrc_constraint=1e-2).items():
+        err = rel(g[name], o32[name])
+        assert np.isfinite(g[name]).all() and err < tol, (name, err)
+    assert np.array_equal(g["counters"][:, 2:4], o32["counters"][:, 2:4])
+    for t in (1, 66):  # subtree_com of both tree roots
+        assert rel(g["subtree_com"][:, t], o32["subtree_com"][:, t]) < 3e-6

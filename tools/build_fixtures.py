@@ -4,6 +4,7 @@
   vnl-brax-imitation_b200/data/rodent_model.npz  compiled rodent model (envs/rodent.py:39-63 recipe)
   vnl-brax-imitation_b200/data/rodent_clip.npz   process_clip() of clips/transform_snips_groom.p
   vnl-brax-imitation_b200/data/humanoid_model.npz compiled humanoid model (envs/humanoid.py:40-54 recipe)
+  vnl-brax-imitation_b200/data/rodent_pair_model.npz rodent_pair.xml (<replicate count=2>) with the rodent env recipe
   tests/golden/rodent_clip_golden.npz            the old clip's own derived fields (known answers)
 """
 import importlib
@@ -34,6 +35,8 @@ def main(ref="/root/reference"):
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "rodent_clip_golden.npz"), **gold)
     hum = mjcf.load_humanoid(os.path.join(ref, "assets", "humanoid.xml"))
     mjcf.save_model(hum, os.path.join(data, "humanoid_model.npz"))
+    pair = mjcf.load_rodent_pair(os.path.join(ref, "assets", "rodent_pair.xml"))
+    mjcf.save_model(pair, os.path.join(data, "rodent_pair_model.npz"))
     print("model", model.nbody, model.nv, "clip", clip.position.shape, clip.body_positions.shape, "humanoid", hum.nbody, hum.nv)
 
 

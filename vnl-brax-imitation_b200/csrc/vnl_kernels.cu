@@ -45,11 +45,11 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16); A(cacc, (d.nbody > d.nv ? d.nbody : d.nv) * 6);
   const int a_end = o;
   o = ab;
-  A(K, d.nM + 1); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc);
+  A(K, d.nM + 1); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
   if (a_end > o) o = a_end;
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
-  A(lim_dof, d.nlimit); A(lim_sign, d.nlimit); A(limrow_of_dof, d.nv);
-  A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 9); A(cmu, d.ncon); A(cwrench, d.ncon * 6);
+  A(lim_dof, d.nlimit); A(limrow_of_dof, d.nv);
+  A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
   A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.nv + d.ndslot);
   A(ints, 16);
 #undef A
@@ -298,8 +298,7 @@ __device__ __noinline__ void jmul(int so, int xo, int outo) {
   const float* cdof = s + c.L.cdof;
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* lim_dof = (const int*)(s + c.L.lim_dof);
-  const float* lim_sign = s + c.L.lim_sign;
-  for (int r = lane; r < nl; r += 32) out[r] = lim_sign[r] * x[lim_dof[r]];
+  for (int r = lane; r < nl; r += 32) { const int ld = lim_dof[r]; out[r] = ld < 0 ? -x[~ld] : x[ld]; }  // sign folded in: ~dof = upper limit
   if (nc > 0) {
     int G = 32;
     while (G > 1 && (32 / G) < nc) G >>= 1;
@@ -324,9 +323,10 @@ __device__ __noinline__ void jmul(int so, int xo, int outo) {
         for (int q = 0; q < 6; ++q) sacc[q] += __shfl_xor_sync(FULLMASK, sacc[q], o);
       }
       if (k < nc && sub == 0) {
-        const float* fr = s + c.L.cframe + 9 * k;
+        const float* fr = s + c.L.cframe + 6 * k;  // [n, b]; the second tangent is n x b
         const V3 vel = v3(sacc[3], sacc[4], sacc[5]) + cross(v3(sacc[0], sacc[1], sacc[2]), ld3(s + c.L.crel + 3 * k));
-        const float un = dot(ld3(fr), vel), u1 = dot(ld3(fr + 3), vel), u2 = dot(ld3(fr + 6), vel);
+        const V3 fn3 = ld3(fr), fb3 = ld3(fr + 3);
+        const float un = dot(fn3, vel), u1 = dot(fb3, vel), u2 = dot(cross(fn3, fb3), vel);
         const float mu = s[c.L.cmu + k];
         float* o4 = out + nl + 4 * k;
         o4[0] = un + u1 * mu; o4[1] = un + u1 * -mu; o4[2] = un + u2 * mu; o4[3] = un + u2 * -mu;
@@ -342,6 +342,7 @@ __device__ __noinline__ void jtmul_force(int so) {
   const int* ints = (const int*)(s + c.L.ints);
   const int nl = ints[0], nc = ints[1], lane = LANE, nv = c.d.nv;
   float* const qfrc = s + c.L.qfrc_con;
+  float* const cwrench = s + c.L.Jv;  // per-contact wrench scratch: Jv is dead whenever the constraint forces are mapped back
   const uint8_t* const dof_body = TB8(dof_body);
   const uint8_t* const sub_end = TB8(sub_end);
   const float* D = s + c.L.efcD;
@@ -355,27 +356,28 @@ __device__ __noinline__ void jtmul_force(int so) {
     }
     const float mu = s[c.L.cmu + k];
     const float fn = f[0] + f[1] + f[2] + f[3], f1 = mu * (f[0] - f[1]), f2 = mu * (f[2] - f[3]);
-    const float* fr = s + c.L.cframe + 9 * k;
-    const V3 F = ld3(fr) * fn + ld3(fr + 3) * f1 + ld3(fr + 6) * f2;
-    st3(s + c.L.cwrench + 6 * k, cross(ld3(s + c.L.crel + 3 * k), F));
-    st3(s + c.L.cwrench + 6 * k + 3, F);
+    const float* fr = s + c.L.cframe + 6 * k;
+    const V3 fn3 = ld3(fr), fb3 = ld3(fr + 3);
+    const V3 F = fn3 * fn + fb3 * f1 + cross(fn3, fb3) * f2;
+    st3(cwrench + 6 * k, cross(ld3(s + c.L.crel + 3 * k), F));
+    st3(cwrench + 6 * k + 3, F);
   }
   __syncwarp();
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* limrow = (const int*)(s + c.L.limrow_of_dof);
-  const float* lim_sign = s + c.L.lim_sign;
+  const int* lim_dof = (const int*)(s + c.L.lim_dof);
   for (int i = lane; i < nv; i += 32) {
     const int b = dof_body[i], be = sub_end[b];
     const float* cd = s + c.L.cdof + 6 * i;
     float acc = 0.0f;
     for (int k = 0; k < nc; ++k) {
       const int cb = cbody[k];
-      if (cb >= b && cb < be) acc += dot6(cd, s + c.L.cwrench + 6 * k);
+      if (cb >= b && cb < be) acc += dot6(cd, cwrench + 6 * k);
     }
     const int r = limrow[i];
     if (r >= 0) {
       const float ja = Jaref[r];
-      if (ja < 0.0f) acc += lim_sign[r] * (-D[r] * ja);
+      if (ja < 0.0f) acc += (lim_dof[r] < 0 ? -1.0f : 1.0f) * (-D[r] * ja);
     }
     qfrc[i] = acc;
   }
@@ -789,8 +791,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         if (active) {
           const int slot = base + __popc(m & ((1u << lane) - 1u));
           const int dof = jdofadr[j];
-          ((int*)(s + L.lim_dof))[slot] = dof;
-          s[L.lim_sign + slot] = sign;
+          ((int*)(s + L.lim_dof))[slot] = sign > 0.0f ? dof : ~dof;
           ((int*)(s + L.limrow_of_dof))[dof] = slot;
           float k, b, imp;
           kbi(d, solref[2 * j], solref[2 * j + 1], solimp + 5 * j, pos, k, b, imp);
@@ -886,7 +887,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
           const V3 rel = cp - ld3(s + L.rcom + 3 * body_tree[body]);
           st3(s + L.crel + 3 * k, rel);
           const V3 t2 = cross(n, fb);
-          st3(s + L.cframe + 9 * k, n); st3(s + L.cframe + 9 * k + 3, fb); st3(s + L.cframe + 9 * k + 6, t2);
+          st3(s + L.cframe + 6 * k, n); st3(s + L.cframe + 6 * k + 3, fb);
           const float mu = pfric[5 * p];
           s[L.cmu + k] = mu;
           float kk, bb, imp;
@@ -1489,27 +1490,38 @@ LaunchInfo launch_info(const Dims& d, int B) {
   Lay L;
   make_layout(d, L);
   const int fixed = (kCtaFloats + align4(d.ktab_words)) * 4, per = L.total * 4;
-  int W = (227 * 1024 - fixed) / per;
-  if (W > kMaxWarps) W = kMaxWarps;
+  int wmax = (227 * 1024 - fixed) / per;
+  if (wmax > kMaxWarps) wmax = kMaxWarps;
   static int env_w = -1;
   if (env_w < 0) { const char* ev = getenv("VNL_WARPS"); env_w = ev ? atoi(ev) : 0; }
-  if (env_w > 0 && env_w < W) W = env_w;
-  LaunchInfo li;
-  li.warps_per_cta = W;
-  li.smem_bytes = fixed + (W > 0 ? W : 1) * per;
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   }
-  int resident = (227 * 1024) / (li.smem_bytes + 1024);
-  if (resident < 1) resident = 1;
-  const int max_threads_ctas = 2048 / ((W > 0 ? W : 1) * 32);
-  if (resident > max_threads_ctas) resident = max_threads_ctas;
-  const int need = W > 0 ? (B + W - 1) / W : 0;
-  li.ctas = need < sms * resident ? need : sms * resident;
-  return li;
+  LaunchInfo best;
+  best.warps_per_cta = wmax; best.smem_bytes = fixed + (wmax > 0 ? wmax : 1) * per; best.ctas = 0;
+  if (wmax < 1) return best;
+  // The grid is persistent: every warp walks ceil(B / resident warps) envs.  More warps per SM only pay when they save a
+  // whole round (a warp sharing the SM with more neighbours runs each env slower), so take the fewest rounds and, on a
+  // tie, the fewest warps.
+  long best_rounds = -1;
+  for (int W = wmax; W >= 1 && W >= wmax - 2; --W) {
+    if (env_w > 0 && W != (env_w < wmax ? env_w : wmax)) continue;
+    const int smem = fixed + W * per;
+    int resident = (227 * 1024) / (smem + 1024);
+    if (resident < 1) resident = 1;
+    if (resident > 2048 / (W * 32)) resident = 2048 / (W * 32);
+    const int need = (B + W - 1) / W;
+    const int ctas = need < sms * resident ? need : sms * resident;
+    const long rounds = ((long)B + (long)ctas * W - 1) / ((long)ctas * W);
+    if (best_rounds < 0 || rounds <= best_rounds) {
+      best_rounds = rounds;
+      best.warps_per_cta = W; best.smem_bytes = smem; best.ctas = ctas;
+    }
+  }
+  return best;
 }
 
 cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {

@@ -27,7 +27,7 @@ struct Lay {
   int xipos, xanchor, xaxis, t16, cacc;                                   // region A
   int K, efcD, Jaref, Jv;                                                 // region B
   int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
-  int lim_dof, lim_sign, limrow_of_dof, cbody, crel, cframe, cmu, cwrench;
+  int lim_dof, limrow_of_dof, cbody, crel, cframe, cmu;
   int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, part, ints, total;
 };
 

@@ -145,6 +145,87 @@ def rescale_subtree(root: ET.Element, position_factor: float, size_factor: float
             rescale_subtree(child, position_factor, size_factor)
 
 
+def expand_replicate(root: ET.Element, degree: bool = True, eulerseq: str = "xyz") -> None:
+    """Expand `<replicate count offset euler sep>` (MuJoCo 3.1.2+, `assets/rodent_pair.xml:163`) in place.
+
+    Copy i (i = 0 .. count-1) of the enclosed subtree is placed in the frame (i * offset, euler applied i times) and
+    every `name` inside it gets the suffix `sep + i`.  Elements OUTSIDE the body tree that reference a replicated name
+    (actuators, sensors, contact pairs / excludes, tendon-free here) are replicated with the same suffix, which is what
+    gives rodent_pair nu = 60.  (The file is render-only in the reference -- `train.py:295-320` -- so there is no golden
+    for this interpretation; SURVEY assumption U7.)"""
+    import copy
+    wb = root.find("worldbody")
+    if wb is None:
+        return
+    suffixed: Dict[str, List[str]] = {}
+
+    def rename(el: ET.Element, suf: str, names: set) -> None:
+        for e in el.iter():
+            n = e.get("name")
+            if n is not None:
+                names.add(n)
+                e.set("name", n + suf)
+        for e in el.iter():  # references inside the copy (camera / light targets, ...)
+            for k in ("target", "body", "joint", "site", "geom"):
+                v = e.get(k)
+                if v is not None and v in names:
+                    e.set(k, v + suf)
+
+    def expand(parent: ET.Element) -> None:
+        for child in list(parent):
+            if child.tag == "replicate":
+                count = int(child.get("count", "1"))
+                sep = child.get("sep", "")
+                offset = _floats(child.get("offset")) if child.get("offset") else np.zeros(3)
+                step_q = _orientation({"euler": child.get("euler")}, degree, eulerseq) if child.get("euler") else np.array([1.0, 0, 0, 0])
+                idx = list(parent).index(child)
+                parent.remove(child)
+                q, pos = np.array([1.0, 0, 0, 0]), np.zeros(3)
+                for i in range(count):
+                    for sub in child:
+                        cp = copy.deepcopy(sub)
+                        names: set = set()
+                        suf = f"{sep}{i}"
+                        rename(cp, suf, names)
+                        for n in names:
+                            suffixed.setdefault(n, []).append(n + suf)
+                        if cp.tag in ("body", "geom", "site", "camera", "light", "frame"):
+                            lp = _floats(cp.get("pos")) if cp.get("pos") else np.zeros(3)
+                            lq = _orientation(cp.attrib, degree, eulerseq)
+                            for k in ("euler", "axisangle", "xyaxes", "zaxis"):
+                                cp.attrib.pop(k, None)
+                            cp.set("pos", _fmt(pos + rotate(lp, q)))
+                            cp.set("quat", _fmt(quat_mul(q, lq)))
+                        parent.insert(idx, cp)
+                        idx += 1
+                    pos = pos + rotate(offset, q)
+                    q = quat_mul(q, step_q)
+            else:
+                expand(child)
+
+    expand(wb)
+    if not suffixed:
+        return
+    for section in ("actuator", "sensor", "contact", "tendon", "equality"):
+        for sec in root.findall(section):
+            for el in list(sec):
+                refs = [k for k in ("joint", "site", "body", "body1", "body2", "geom", "geom1", "geom2", "objname", "tendon")
+                        if el.get(k) in suffixed]
+                if not refs:
+                    continue
+                ncopy = len(suffixed[el.get(refs[0])])
+                pos_in_sec = list(sec).index(el)
+                sec.remove(el)
+                for i in range(ncopy):
+                    cp = copy.deepcopy(el)
+                    for k in refs:
+                        cp.set(k, suffixed[el.get(k)][i])
+                    if cp.get("name") is not None:
+                        cp.set("name", suffixed[el.get(refs[0])][i].replace(el.get(refs[0]), cp.get("name"), 1)
+                               if False else cp.get("name") + suffixed[el.get(refs[0])][i][len(el.get(refs[0])):])
+                    sec.insert(pos_in_sec + i, cp)
+
+
 def torque_actuators(root: ET.Element) -> None:
     """`envs/rodent.py:41-45`: gainprm <- [forcerange[1]], drop biastype / biasprm."""
     for act in root.iter("general"):
@@ -331,6 +412,7 @@ def compile_model(root: ET.Element, *, name: str = "", solver: Optional[str] = N
     degree = comp.get("angle", "degree") == "degree"
     eulerseq = comp.get("eulerseq", "xyz")
     autolimits = comp.get("autolimits", "true") == "true"
+    expand_replicate(root, degree, eulerseq)
     defaults = _Defaults(root)
 
     m = Model(name=name or root.get("model", ""))
@@ -888,6 +970,21 @@ def load_rodent(mjcf_path: str, scale_factor: float = 0.9, solver: str = "cg", i
             root.remove(a)
     rescale_subtree(root, scale_factor, scale_factor)
     return compile_model(root, name="rodent", solver=solver, iterations=iterations, ls_iterations=ls_iterations)
+
+
+def load_rodent_pair(mjcf_path: str, scale_factor: float = 0.9, solver: str = "cg", iterations: int = 6,
+                     ls_iterations: int = 6) -> Model:
+    """`assets/rodent_pair.xml` (two replicated rodents; render-only overlay model in the reference, `train.py:295-320`)
+    compiled with the rodent env recipe (torque actuators, 0.9 rescale) for the physics-only throughput sweep of
+    BASELINE.json configs[4]."""
+    root = load_xml(mjcf_path)
+    comp = {}
+    for c in root.findall("compiler"):
+        comp.update(c.attrib)
+    expand_replicate(root, comp.get("angle", "degree") == "degree", comp.get("eulerseq", "xyz"))
+    torque_actuators(root)
+    rescale_subtree(root, scale_factor, scale_factor)
+    return compile_model(root, name="rodent_pair", solver=solver, iterations=iterations, ls_iterations=ls_iterations)
 
 
 def load_humanoid(mjcf_path: str, solver: str = "cg", iterations: int = 6, ls_iterations: int = 6) -> Model:
