@@ -96,18 +96,29 @@ struct Prof {
 // sparse-inertia helpers (one warp).  Vector arguments are float offsets into the env slice.
 // ---------------------------------------------------------------------------------------------------------------------
 // One section of a lane program: part[slot] = sum over the lane's terms of V[entry] * x[index] (see VnlKtab).
+// T is a multiple of 4 (host pads).  The four program words and their eight operands of a batch are loaded before any
+// partial sum is flushed, so the loads of a batch overlap instead of queueing behind the previous term's store.
 __device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, int T, const float* __restrict__ V,
                                              const float* __restrict__ x, float* __restrict__ part) {
   const char* Vb = reinterpret_cast<const char*>(V);
   const char* xb = reinterpret_cast<const char*>(x);
   prog += LANE;
   float acc = 0.0f;
-#pragma unroll 4
-  for (int t = 0; t < T; ++t) {
-    const uint32_t w = prog[t * 32];
-    acc += *reinterpret_cast<const float*>(Vb + (w & 0x3ffcu)) * *reinterpret_cast<const float*>(xb + ((w >> 14) & 0x3fcu));
-    if (w < 0xff000000u) { part[w >> 24] = acc; acc = 0.0f; }
+#define VNL_LDV(w) (*reinterpret_cast<const float*>(Vb + ((w) & 0x3ffcu)))
+#define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
+#define VNL_FLUSH(w) if ((w) < 0xff000000u) { part[(w) >> 24] = acc; acc = 0.0f; }
+  for (int t = 0; t < T; t += 4) {
+    const uint32_t w0 = prog[t * 32], w1 = prog[t * 32 + 32], w2 = prog[t * 32 + 64], w3 = prog[t * 32 + 96];
+    const float v0 = VNL_LDV(w0), x0 = VNL_LDX(w0), v1 = VNL_LDV(w1), x1 = VNL_LDX(w1);
+    const float v2 = VNL_LDV(w2), x2 = VNL_LDX(w2), v3 = VNL_LDV(w3), x3 = VNL_LDX(w3);
+    acc += v0 * x0; VNL_FLUSH(w0)
+    acc += v1 * x1; VNL_FLUSH(w1)
+    acc += v2 * x2; VNL_FLUSH(w2)
+    acc += v3 * x3; VNL_FLUSH(w3)
   }
+#undef VNL_LDV
+#undef VNL_LDX
+#undef VNL_FLUSH
 }
 
 // out = M x   (tree-sparse symmetric M: diagonal + strict-ancestor terms + descendant terms)
@@ -138,7 +149,7 @@ __device__ __noinline__ void mul_m(int so, int xo, int outo) {
 
 // L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
-__device__ __noinline__ void factor(int so, bool damp, Prof& pf) {
+__device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   VNL_SMEM
   const int nv = c.d.nv, nM = c.d.nM, lane = LANE, maxdepth = c.d.maxdepth;
   const float* const M = s + c.L.M;
@@ -214,6 +225,7 @@ __device__ __noinline__ void factor(int so, bool damp, Prof& pf) {
   for (int i = lane; i < nv; i += 32) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
   __syncwarp();
   pf.mark(17);
+  if (!invert) return;  // the caller solves by substitution (one right-hand side only)
   // K = Lhat^-1 in place by levels of dof depth:  K[i][cc] = -( Lhat[i][cc] + sum_{a<cc} Lhat[i][a] K[anc_a(i)][cc - a] ).
   // Items of a level are sorted by descending cc, so a later pass never reads a slot an earlier pass overwrote.
   const uint16_t* const kitem = TB16(kitem);
@@ -279,6 +291,41 @@ __device__ __noinline__ void solve_m(int so, int xo, int outo) {
     if (madr[i + 1] - madr[i] > 1) acc += pa[i];
     out[i] = acc;
   }
+  __syncwarp();
+}
+
+// out <- (L^T D L)^-1 x by substitution with the NON-inverted factor (Lhat off-diagonals, 1 / D in the diagonal slots):
+// used where a factorisation serves a single right-hand side (the implicit-damping solve of forward.euler), which
+// is cheaper than inverting the factor first.  mj_solveLD order: L^-T (dofs descending, scatter to the ancestors),
+// D^-1, L^-1 (dofs ascending, gather from the ancestors).
+__device__ __noinline__ void solve_ld(int so, int xo, int outo) {
+  VNL_SMEM
+  const int nv = c.d.nv, lane = LANE;
+  const float* const F = s + c.L.K;
+  const float* const x = s + xo;
+  float* const t = s + c.L.tmpv;
+  const uint16_t* const madr = TB16(madr);
+  const uint8_t* const mcol = TB8(mcol);
+  for (int i = lane; i < nv; i += 32) t[i] = x[i];
+  __syncwarp();
+  for (int i = nv - 1; i > 0; --i) {
+    const int base = madr[i], di = madr[i + 1] - base - 1;
+    const float ti = t[i];
+    for (int a = 1 + lane; a <= di; a += 32) t[mcol[base + a]] -= F[base + a] * ti;
+    __syncwarp();
+  }
+  for (int i = lane; i < nv; i += 32) t[i] *= F[madr[i]];
+  __syncwarp();
+  float* const out = s + outo;
+  for (int i = 1; i < nv; ++i) {
+    const int base = madr[i], di = madr[i + 1] - base - 1;
+    float acc = 0.0f;
+    for (int a = 1 + lane; a <= di; a += 32) acc += F[base + a] * t[mcol[base + a]];
+    acc = warp_sum(acc);
+    if (lane == 0) t[i] -= acc;
+    __syncwarp();
+  }
+  for (int i = lane; i < nv; i += 32) out[i] = t[i];
   __syncwarp();
 }
 
@@ -752,7 +799,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   }
   pf.mark(4);
   if (ls3) __syncthreads();
-  factor(so, false, pf);
+  factor(so, false, true, pf);
   pf.mark(5);
   if (ls3) __syncthreads();
   solve_m(so, L.qfrc_smooth, L.qacc_smooth);
@@ -1113,11 +1160,11 @@ __device__ __noinline__ void euler(int so, Prof& pf) {
   float* qacc = s + L.qacc;
   pf.mark(12);
   if (d.eulerdamp) {
-    factor(so, true, pf);
+    factor(so, true, false, pf);
     pf.mark(13);
     for (int i = lane; i < d.nv; i += 32) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
     __syncwarp();
-    solve_m(so, L.grad, L.Mgrad);
+    solve_ld(so, L.grad, L.Mgrad);
     qacc = s + L.Mgrad;
   }
   for (int a = lane; a < d.na; a += 32) s[L.act + a] += s[L.act_dot + a] * dt;

@@ -167,7 +167,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
             l = min(range(32), key=lambda l: lane_load[l])
             lanes[l].append((slot, terms))
             lane_load[l] += len(terms)
-        T = max(1, max(lane_load))
+        T = 4 * ((max(1, max(lane_load)) + 3) // 4)  # the kernel walks the program four terms at a time
         prog = np.zeros((T, 32), dtype=np.uint32)
         pad = np.uint32((4 * nM_) | (0xFF << 24))  # entry nM is a zero slot, never flushed
         prog[:, :] = pad
@@ -192,7 +192,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
         dpart_adr.append(len(rows_d))
     if len(rows_d) > 254 or nv > 254:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
-    prog_d, TD = pack_program(rows_d) if rows_d else (np.zeros(32, dtype=np.uint32), 1)
+    prog_d, TD = pack_program(rows_d) if rows_d else (np.full(128, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
     ndslot = len(rows_d)
     tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)] + [1 | (1 << 8)] * 64  # padded tail
     kitem, klvl = [], [0, 0]
