@@ -456,13 +456,15 @@ __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const f
 struct Sol { float cost, prev_cost, gauss, gradnorm; };
 
 // solver._update_constraint + _update_gradient (CG: Mgrad = M^-1 grad)
-__device__ __noinline__ void update_constraint(int so, Sol& st) {
+__device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
   VNL_SMEM
   const Lay& L = c.L;
   const int* ints = (const int*)(s + L.ints);
   const int nrow = ints[0] + 4 * ints[1], lane = LANE, nv = c.d.nv;
   float* qfrc_con = s + L.qfrc_con;
+  pf.mark(11);
   jtmul_force(so);
+  pf.mark(22);
   float v0 = 0.0f, v1 = 0.0f, g = 0.0f;
   for (int r = lane; r < nrow; r += 32) { const float ja = s[L.Jaref + r]; if (ja < 0.0f) v0 += s[L.efcD + r] * ja * ja; }
   for (int i = lane; i < nv; i += 32) {
@@ -478,7 +480,9 @@ __device__ __noinline__ void update_constraint(int so, Sol& st) {
   st.cost = 0.5f * v0 + st.gauss;
   st.gradnorm = sqrtf(g);
   __syncwarp();
+  pf.mark(23);
   solve_m(so, L.grad, L.Mgrad);
+  pf.mark(24);
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -1022,7 +1026,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
-    update_constraint(so, st);
+    update_constraint(so, st, pf);
     for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
     __syncwarp();
     pf.mark(9);
@@ -1037,7 +1041,9 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       if (done) { if (ls3) continue; break; }
       // ---- _linesearch ----
       mul_m(so, L.search, L.Mv);
+      pf.mark(19);
       jmul(so, L.search, L.Jv);
+      pf.mark(20);
       float q0s = 0.0f, q1s = 0.0f, q2s = 0.0f, q3s = 0.0f;
       for (int i = lane; i < d.nv; i += 32) {
         const float si = search[i];
@@ -1116,7 +1122,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         ++it;
       }
       lsiter += it;
-      pf.mark(10);
+      pf.mark(21);
       const bool improved = (lo.cost < p0.cost) || (hi.cost < p0.cost);
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       const float ia = improved ? alpha : 0.0f * alpha;
@@ -1128,7 +1134,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       for (int r = lane; r < nrow; r += 32) Jaref[r] += Jv[r] * ia;
       pg = warp_sum(pg);
       __syncwarp();
-      update_constraint(so, st);
+      update_constraint(so, st, pf);
       if (d.solver == 2) {
         for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
       } else {  // Polak-Ribiere
