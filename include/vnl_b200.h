@@ -49,7 +49,7 @@ extern "C" {
  * ---------------------------------------------------------------------------------------- */
 #define VNL_MAGIC_MODEL 0x4d4c4e56u /* "VNLM" */
 #define VNL_MAGIC_TASK 0x544c4e56u  /* "VNLT" */
-#define VNL_BLOB_VERSION 5
+#define VNL_BLOB_VERSION 6
 #define VNL_TABLE_OFF 64
 #define VNL_MAX_FIELDS 96
 #define VNL_DATA_OFF (VNL_TABLE_OFF + 2 * VNL_MAX_FIELDS)
@@ -69,6 +69,8 @@ enum VnlModelHdr {
   VNL_MH_MAXDEPTH,    /* longest dof ancestor chain */
   VNL_MH_NROOT,       /* kinematic trees (bodies whose parent is the world) */
   VNL_MH_NDSLOT,      /* partial-sum slots of the descendant mat-vec program (= KTAB scalar VNL_KS_NDSLOT) */
+  VNL_MH_ENV_WARPS,   /* warps cooperating on one env (1 or 2): the mat-vec lane programs have 32 * this many lanes */
+  VNL_MH_NASLOT,      /* partial-sum slots of the ancestor mat-vec program */
   /* floats (bit patterns) */
   VNL_MH_TIMESTEP = 32, VNL_MH_GRAVITY_X, VNL_MH_GRAVITY_Y, VNL_MH_GRAVITY_Z,
   VNL_MH_TOLERANCE, VNL_MH_LS_TOLERANCE, VNL_MH_IMPRATIO, VNL_MH_MEANINERTIA
@@ -178,18 +180,19 @@ enum VnlKtab {
   VNL_KT_MCOL,          /* u8  [nM] */
   VNL_KT_DOF_BODY,      /* u8  [nv] */
   VNL_KT_DPART_ADR,     /* u8  [nv+1] CSR: partial-sum slots of PROG_D that make up each dof's descendant sum */
+  VNL_KT_APART_ADR,     /* u8  [nv+1] CSR: partial-sum slots of PROG_A that make up each dof's strict-ancestor sum */
   VNL_KT_MADR,          /* u16 [nv+1] */
   VNL_KT_TRI,           /* u16 [maxdepth (maxdepth+1) / 2]  a | c << 8 with 1 <= a <= c, index c (c-1) / 2 + a - 1 */
   VNL_KT_ANC_START,     /* u16 [nM] madr[mcol[e]]: row start of the entry's column dof */
   VNL_KT_KITEM,         /* u16 [sum of dof depths] c | dof << 8, grouped by dof depth, descending c inside a group */
   VNL_KT_KLVL,          /* u16 [maxdepth+2] offsets into KITEM by dof depth */
   /* Lane programs of the sparse mat-vecs with M and with the inverse factor K (same sparsity).  A program is
-   * [T][32] words, one term per lane per step: bits 0-13 entry * 4, bits 14-23 x index * 4, bits 24-31 the
+   * [T][32 * env_warps] words, one term per lane per step: bits 0-13 entry * 4, bits 14-23 x index * 4, bits 24-31 the
    * partial-sum slot to flush into after this term (0xFF = keep accumulating).  PROG_A: strict-ancestor terms
-   * (row i, entries madr[i]+1 ..), slot = dof.  PROG_D: descendant terms (column j), long columns split into chunks,
-   * slots listed by DPART_ADR.  Lanes are load balanced on the host; lists are padded with a zero term. */
-  VNL_KT_PROG_A,        /* u32 [TA*32] */
-  VNL_KT_PROG_D,        /* u32 [TD*32] */
+   * (row i, entries madr[i]+1 ..), PROG_D: descendant terms (column j); long rows / columns are split into chunks,
+   * the chunks' slots are listed by APART_ADR / DPART_ADR.  Lanes are load balanced on the host; lists are padded with a zero term. */
+  VNL_KT_PROG_A,        /* u32 [TA*32*env_warps] */
+  VNL_KT_PROG_D,        /* u32 [TD*32*env_warps] */
   VNL_KT_COUNT
 };
 enum VnlKtabScalar { VNL_KS_TA = 0, VNL_KS_TD, VNL_KS_NDSLOT, VNL_KS_RESERVED, VNL_KT_NSCALAR };

@@ -33,7 +33,7 @@ void fill_dims(const uint32_t* w, vnl::Dims& d) {
   d.nbody = vnl_hdr_i(w, VNL_MH_NBODY); d.njnt = vnl_hdr_i(w, VNL_MH_NJNT); d.ngeom = vnl_hdr_i(w, VNL_MH_NGEOM);
   d.npair = vnl_hdr_i(w, VNL_MH_NPAIR); d.ncon = vnl_hdr_i(w, VNL_MH_NCON); d.nlimit = vnl_hdr_i(w, VNL_MH_NLIMIT);
   d.nefc = vnl_hdr_i(w, VNL_MH_NEFC); d.nM = vnl_hdr_i(w, VNL_MH_NM); d.nlevel = vnl_hdr_i(w, VNL_MH_NLEVEL);
-  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.nroot = vnl_hdr_i(w, VNL_MH_NROOT); d.ndslot = vnl_hdr_i(w, VNL_MH_NDSLOT); d.ktab_words = (int)w[VNL_TABLE_OFF + 2 * VNL_F_KTAB + 1];
+  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.nroot = vnl_hdr_i(w, VNL_MH_NROOT); d.ndslot = vnl_hdr_i(w, VNL_MH_NDSLOT); d.env_warps = vnl_hdr_i(w, VNL_MH_ENV_WARPS); d.naslot = vnl_hdr_i(w, VNL_MH_NASLOT); d.ktab_words = (int)w[VNL_TABLE_OFF + 2 * VNL_F_KTAB + 1];
   d.solver = vnl_hdr_i(w, VNL_MH_SOLVER); d.iterations = vnl_hdr_i(w, VNL_MH_ITERATIONS);
   d.ls_iterations = vnl_hdr_i(w, VNL_MH_LS_ITERATIONS); d.eulerdamp = vnl_hdr_i(w, VNL_MH_EULERDAMP);
   d.timestep = vnl_hdr_f(w, VNL_MH_TIMESTEP); d.gx = vnl_hdr_f(w, VNL_MH_GRAVITY_X); d.gy = vnl_hdr_f(w, VNL_MH_GRAVITY_Y);
@@ -127,13 +127,13 @@ int vnl_unregister_blob(const void* blob_dev) {
 int vnl_step_smem_bytes(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);
-  return vnl::launch_info(d, 1 << 20).smem_bytes;
+  return vnl::any_launch_info(d, 1 << 20).smem_bytes;
 }
 
 int vnl_envs_per_cta(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);
-  return vnl::launch_info(d, 1 << 20).warps_per_cta;
+  return vnl::any_launch_info(d, 1 << 20).warps_per_cta;
 }
 
 size_t vnl_dump_size(const void* model_host) {
@@ -152,7 +152,7 @@ int vnl_step(const void* model, const void* task, int B, const VnlState* in, con
   Header ht;
   lookup(task, ht);
   p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
-  return (int)vnl::launch(0, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
 int vnl_step_autoreset(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
@@ -166,7 +166,7 @@ int vnl_step_autoreset(const void* model, const void* task, int B, const VnlStat
   lookup(task, ht);
   p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   p.first = *first; p.first_obs = first_obs;
-  return (int)vnl::launch(0, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
 // Developer hook: vnl_step with per-phase clock64 accumulation for CTA `block` into prof[32].
@@ -181,7 +181,7 @@ int vnl_step_profiled(const void* model, const void* task, int B, const VnlState
   lookup(task, ht);
   p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   p.prof = prof; p.prof_env = block;
-  return (int)vnl::launch(0, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
 int vnl_reset(const void* model, const void* task, int B, const VnlState* in, const VnlState* out, const VnlOutputs* outputs,
@@ -192,7 +192,7 @@ int vnl_reset(const void* model, const void* task, int B, const VnlState* in, co
   int rc = prepare(model, task, true, p);
   if (rc) return rc;
   p.B = B; p.nsteps = 1; p.in = *in; p.out = *out; p.outputs = *outputs;
-  return (int)vnl::launch(1, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(1, p, (cudaStream_t)stream);
 }
 
 int vnl_pipeline_step(const void* model, int B, int nsteps, const VnlState* in, const float* ctrl, const VnlState* out,
@@ -203,7 +203,7 @@ int vnl_pipeline_step(const void* model, int B, int nsteps, const VnlState* in, 
   int rc = prepare(model, nullptr, false, p);
   if (rc) return rc;
   p.B = B; p.nsteps = nsteps; p.in = *in; p.out = *out; p.ctrl = ctrl; p.stats = stats;
-  return (int)vnl::launch(2, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(2, p, (cudaStream_t)stream);
 }
 
 int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* ctrl, float* dump, void* stream) {
@@ -215,7 +215,7 @@ int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* 
   p.B = B; p.nsteps = 1; p.in = *in; p.ctrl = ctrl; p.dump = dump;
   cudaError_t err = cudaMemsetAsync(dump, 0xFF, (size_t)B * p.dims.dump_total * sizeof(float), (cudaStream_t)stream);
   if (err != cudaSuccess) return (int)err;
-  return (int)vnl::launch(3, p, (cudaStream_t)stream);
+  return (int)vnl::any_launch(3, p, (cudaStream_t)stream);
 }
 
 // Legacy XLA custom calls.  `opaque` = two little-endian int32: B, then the operand layout version (1).

@@ -29,10 +29,42 @@
 #include "vnl_device.cuh"
 #include "vnl_kernels.h"
 
+#ifndef VNL_EW
+#define VNL_EW 1
+#endif
+#define VNL_CAT2(a, b) a##b
+#define VNL_CAT(a, b) VNL_CAT2(a, b)
+
 namespace vnl {
+namespace VNL_CAT(ew, VNL_EW) {  // one instantiation of everything below per env-group width (see Makefile)
+
+constexpr int kEnvWarps = VNL_EW;          // warps cooperating on one env
+constexpr int kEnvThreads = 32 * VNL_EW;   // = lanes of the mat-vec programs (VNL_MH_ENV_WARPS of the blob must agree)
 
 #define LANE ((int)(threadIdx.x & 31))
 #define FULLMASK 0xffffffffu
+// kEnvWarps warps (kEnvThreads threads) cooperate on one env.  ETID = thread index inside the env's group.  Wide loops
+// stride over kEnvThreads; reductions are done redundantly by every warp over all elements (identical results in each
+// warp, fixed order, no exchange); level-serial passes simply leave the extra lanes idle.
+#define ETID ((int)(threadIdx.x % kEnvThreads))
+#define EWARP ((int)((threadIdx.x >> 5) % kEnvWarps))
+#define ESLOT ((int)(threadIdx.x / kEnvThreads))
+
+// barrier over the threads of one env (named barrier 1 + slot; barrier 0 stays the CTA-wide lockstep barrier)
+__device__ __forceinline__ void env_sync() {
+  if (kEnvWarps == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + ESLOT), "n"(kEnvThreads) : "memory");
+}
+
+// Lockstep barrier over one GROUP of env slots (named barriers 9..15; `groups` <= 7).  The env slots of a CTA are split
+// into `groups` contiguous groups that each walk the substep in lockstep (shared instruction fetches) while the groups
+// drift against each other, so that one group's shared-memory-bound phases overlap another's latency-bound ones.
+__device__ __forceinline__ void group_sync(int groups) {
+  if (groups <= 1) { __syncthreads(); return; }
+  const int W = blockDim.x / kEnvThreads, g = ESLOT * groups / W;
+  const int first = (g * W + groups - 1) / groups, last = ((g + 1) * W + groups - 1) / groups;
+  asm volatile("bar.sync %0, %1;" ::"r"(9 + g), "r"((last - first) * kEnvThreads) : "memory");
+}
 
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
 
@@ -50,7 +82,7 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
   A(lim_dof, d.nlimit); A(limrow_of_dof, d.nv);
   A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
-  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.nv + d.ndslot);
+  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.naslot + d.ndslot);
   A(ints, 16);
 #undef A
   L.total = o;
@@ -65,7 +97,7 @@ struct __align__(16) Cta {
   const uint32_t* mb;
   uint32_t foff[VNL_F_MODEL_COUNT];
   uint32_t o_lvl_start, o_lvl_bp, o_parent, o_child_adr, o_child_list, o_body_dofadr, o_body_dofnum, o_body_tree, o_lastdof, o_sub_end,
-      o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_madr, o_tri, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
+      o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_apart_adr, o_madr, o_tri, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
   int TA, TD, ndslot, lockstep;
   long long* prof;
   int prof_env;
@@ -88,7 +120,7 @@ struct Prof {
   long long* p;
   long long t0;
   __device__ __forceinline__ void mark(int i) {
-    if (p) { __syncwarp(); if (LANE == 0) { long long t = clock64(); p[i] += t - t0; t0 = t; } }
+    if (p) { env_sync(); if (ETID == 0) { long long t = clock64(); p[i] += t - t0; t0 = t; } }
   }
 };
 
@@ -102,13 +134,13 @@ __device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, 
                                              const float* __restrict__ x, float* __restrict__ part) {
   const char* Vb = reinterpret_cast<const char*>(V);
   const char* xb = reinterpret_cast<const char*>(x);
-  prog += LANE;
+  prog += ETID;
   float acc = 0.0f;
 #define VNL_LDV(w) (*reinterpret_cast<const float*>(Vb + ((w) & 0x3ffcu)))
 #define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
 #define VNL_FLUSH(w) if ((w) < 0xff000000u) { part[(w) >> 24] = acc; acc = 0.0f; }
   for (int t = 0; t < T; t += 4) {
-    const uint32_t w0 = prog[t * 32], w1 = prog[t * 32 + 32], w2 = prog[t * 32 + 64], w3 = prog[t * 32 + 96];
+    const uint32_t w0 = prog[t * kEnvThreads], w1 = prog[(t + 1) * kEnvThreads], w2 = prog[(t + 2) * kEnvThreads], w3 = prog[(t + 3) * kEnvThreads];
     const float v0 = VNL_LDV(w0), x0 = VNL_LDX(w0), v1 = VNL_LDV(w1), x1 = VNL_LDX(w1);
     const float v2 = VNL_LDV(w2), x2 = VNL_LDX(w2), v3 = VNL_LDV(w3), x3 = VNL_LDX(w3);
     acc += v0 * x0; VNL_FLUSH(w0)
@@ -124,34 +156,34 @@ __device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, 
 // out = M x   (tree-sparse symmetric M: diagonal + strict-ancestor terms + descendant terms)
 __device__ __noinline__ void mul_m(int so, int xo, int outo) {
   VNL_SMEM
-  const int nv = c.d.nv, lane = LANE;
+  const int nv = c.d.nv, lane = LANE, tid = ETID;
   float* const M = s + c.L.M;
   const float* const x = s + xo;
   float* const pa = s + c.L.part;
-  float* const pd = pa + nv;
-  if (lane == 0) M[c.d.nM] = 0.0f;  // the zero entry padded program terms point at
-  __syncwarp();
+  float* const pd = pa + c.d.naslot;
+  if (tid == 0) M[c.d.nM] = 0.0f;  // the zero entry padded program terms point at
+  env_sync();
   spmv_section(TB32(prog_a), c.TA, M, x, pa);
   spmv_section(TB32(prog_d), c.TD, M, x, pd);
-  __syncwarp();
+  env_sync();
   const uint16_t* const madr = TB16(madr);
   const uint8_t* const dpa = TB8(dpart_adr);
+  const uint8_t* const apa = TB8(apart_adr);
   float* const out = s + outo;
-  for (int i = lane; i < nv; i += 32) {
-    const int m0 = madr[i];
-    float acc = M[m0] * x[i];
-    if (madr[i + 1] - m0 > 1) acc += pa[i];
+  for (int i = tid; i < nv; i += kEnvThreads) {
+    float acc = M[madr[i]] * x[i];
+    for (int q = apa[i]; q < apa[i + 1]; ++q) acc += pa[q];
     for (int q = dpa[i]; q < dpa[i + 1]; ++q) acc += pd[q];
     out[i] = acc;
   }
-  __syncwarp();
+  env_sync();
 }
 
 // L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
 __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   VNL_SMEM
-  const int nv = c.d.nv, nM = c.d.nM, lane = LANE, maxdepth = c.d.maxdepth;
+  const int nv = c.d.nv, nM = c.d.nM, lane = LANE, tid = ETID, maxdepth = c.d.maxdepth;
   const float* const M = s + c.L.M;
   float* const F = s + c.L.K;
   const uint16_t* const madr = TB16(madr);
@@ -162,14 +194,14 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   {
     const float* damping = c.ff(VNL_F_DOF_DAMPING);
     const float dt = c.d.timestep;
-    for (int e = lane; e < nM; e += 32) {
+    for (int e = tid; e < nM; e += kEnvThreads) {
       float v = M[e];
       if (damp && mcol[e] == mrow[e]) v += dt * damping[mrow[e]];
       F[e] = v;
     }
-    if (lane == 0) F[nM] = 0.0f;
+    if (tid == 0) F[nM] = 0.0f;
   }
-  __syncwarp();
+  env_sync();
   // eliminate dofs from the leaves: for 1 <= a <= cc <= dk:  F[anc_a(k)][cc - a] -= F[k][a] * F[k][cc] / F[k][0]
   // (rows stay un-normalised until the end).  Row k is read-only during its own elimination: it sits in registers
   // (lane l holds entries l and l + 32, plus the same scaled by 1 / pivot) and the (a, cc) operands of each update come
@@ -184,13 +216,13 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
       const float u0 = r0 * inv;
       const uint16_t* const ak = anc_start + base;
       if (dk < 32) {
-        for (int q0 = 0; q0 < np; q0 += 64) {  // warp-uniform trip count: every lane takes part in the shuffles
-          const int p0 = q0 + lane;
-          const uint32_t ta = tri[p0], tb = tri[p0 + 32];
+        for (int q0 = 0; q0 < np; q0 += 2 * kEnvThreads) {  // uniform trip count: every lane takes part in the shuffles
+          const int p0 = q0 + tid;
+          const uint32_t ta = tri[p0], tb = tri[p0 + kEnvThreads];
           const int aa = ta & 255, ca = ta >> 8, ab = tb & 255, cb = tb >> 8;
           const float xa = __shfl_sync(FULLMASK, u0, aa), ya = __shfl_sync(FULLMASK, r0, ca);
           const float xb = __shfl_sync(FULLMASK, u0, ab), yb = __shfl_sync(FULLMASK, r0, cb);
-          const bool oka = p0 < np, okb = p0 + 32 < np;
+          const bool oka = p0 < np, okb = p0 + kEnvThreads < np;
           float* const tga = F + (oka ? ak[aa] + ca - aa : 0);
           float* const tgb = F + (okb ? ak[ab] + cb - ab : 0);
           const float fa = *tga, fb = *tgb;
@@ -200,8 +232,8 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
       } else {
         const float r1 = (lane + 32 <= dk) ? F[base + lane + 32] : 0.0f;
         const float u1 = r1 * inv;
-        for (int q0 = 0; q0 < np; q0 += 32) {
-          const int p0 = q0 + lane;
+        for (int q0 = 0; q0 < np; q0 += kEnvThreads) {
+          const int p0 = q0 + tid;
           const uint32_t ta = tri[p0];
           const int aa = ta & 255, ca = ta >> 8;
           const float x0 = __shfl_sync(FULLMASK, u0, aa), x1 = __shfl_sync(FULLMASK, u1, aa);
@@ -213,17 +245,17 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
         }
       }
     }
-    __syncwarp();
+    env_sync();
   }
   pf.mark(16);
   // normalise rows: Lhat = L / diag, then 1 / D in the diagonal slots
-  for (int e = lane; e < nM; e += 32) {
+  for (int e = tid; e < nM; e += kEnvThreads) {
     const int b0 = madr[mrow[e]];
     if (e != b0) F[e] = F[e] / F[b0];
   }
-  __syncwarp();
-  for (int i = lane; i < nv; i += 32) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
-  __syncwarp();
+  env_sync();
+  for (int i = tid; i < nv; i += kEnvThreads) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
+  env_sync();
   pf.mark(17);
   if (!invert) return;  // the caller solves by substitution (one right-hand side only)
   // K = Lhat^-1 in place by levels of dof depth:  K[i][cc] = -( Lhat[i][cc] + sum_{a<cc} Lhat[i][a] K[anc_a(i)][cc - a] ).
@@ -233,8 +265,8 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   int i0 = klvl[1];
   for (int dl = 1; dl <= maxdepth; ++dl) {
     const int i1 = klvl[dl + 1];
-    for (int it0 = i0; it0 < i1; it0 += 32) {
-      const int it = it0 + lane;
+    for (int it0 = i0; it0 < i1; it0 += kEnvThreads) {
+      const int it = it0 + tid;
       float val = 0.0f;
       float* dst = nullptr;
       if (it < i1) {
@@ -255,9 +287,9 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
         val = -((a0 + a1) + (a2 + a3));
         dst = F + base + cc;
       }
-      __syncwarp();
+      env_sync();
       if (dst) *dst = val;
-      __syncwarp();
+      env_sync();
     }
     i0 = i1;
   }
@@ -267,31 +299,32 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
 // out <- M^-1 x   via  K (D^-1 (K^T x)).
 __device__ __noinline__ void solve_m(int so, int xo, int outo) {
   VNL_SMEM
-  const int nv = c.d.nv, lane = LANE;
+  const int nv = c.d.nv, lane = LANE, tid = ETID;
   float* const K = s + c.L.K;
   const float* const x = s + xo;
   float* const pa = s + c.L.part;
-  float* const pd = pa + nv;
+  float* const pd = pa + c.d.naslot;
   float* const tmp = s + c.L.tmpv;
   const uint16_t* const madr = TB16(madr);
   const uint8_t* const dpa = TB8(dpart_adr);
   spmv_section(TB32(prog_d), c.TD, K, x, pd);   // K[nM] = 0 since factor()
-  __syncwarp();
-  for (int j = lane; j < nv; j += 32) {
+  env_sync();
+  for (int j = tid; j < nv; j += kEnvThreads) {
     float acc = x[j];
     for (int q = dpa[j]; q < dpa[j + 1]; ++q) acc += pd[q];
     tmp[j] = acc * K[madr[j]];
   }
-  __syncwarp();
+  env_sync();
   spmv_section(TB32(prog_a), c.TA, K, tmp, pa);
-  __syncwarp();
+  env_sync();
   float* const out = s + outo;
-  for (int i = lane; i < nv; i += 32) {
+  const uint8_t* const apa = TB8(apart_adr);
+  for (int i = tid; i < nv; i += kEnvThreads) {
     float acc = tmp[i];
-    if (madr[i + 1] - madr[i] > 1) acc += pa[i];
+    for (int q = apa[i]; q < apa[i + 1]; ++q) acc += pa[q];
     out[i] = acc;
   }
-  __syncwarp();
+  env_sync();
 }
 
 // out <- (L^T D L)^-1 x by substitution with the NON-inverted factor (Lhat off-diagonals, 1 / D in the diagonal slots):
@@ -300,33 +333,33 @@ __device__ __noinline__ void solve_m(int so, int xo, int outo) {
 // D^-1, L^-1 (dofs ascending, gather from the ancestors).
 __device__ __noinline__ void solve_ld(int so, int xo, int outo) {
   VNL_SMEM
-  const int nv = c.d.nv, lane = LANE;
+  const int nv = c.d.nv, lane = LANE, tid = ETID;
   const float* const F = s + c.L.K;
   const float* const x = s + xo;
   float* const t = s + c.L.tmpv;
   const uint16_t* const madr = TB16(madr);
   const uint8_t* const mcol = TB8(mcol);
-  for (int i = lane; i < nv; i += 32) t[i] = x[i];
-  __syncwarp();
+  for (int i = tid; i < nv; i += kEnvThreads) t[i] = x[i];
+  env_sync();
   for (int i = nv - 1; i > 0; --i) {
     const int base = madr[i], di = madr[i + 1] - base - 1;
     const float ti = t[i];
-    for (int a = 1 + lane; a <= di; a += 32) t[mcol[base + a]] -= F[base + a] * ti;
-    __syncwarp();
+    for (int a = 1 + tid; a <= di; a += kEnvThreads) t[mcol[base + a]] -= F[base + a] * ti;
+    env_sync();
   }
-  for (int i = lane; i < nv; i += 32) t[i] *= F[madr[i]];
-  __syncwarp();
+  for (int i = tid; i < nv; i += kEnvThreads) t[i] *= F[madr[i]];
+  env_sync();
   float* const out = s + outo;
   for (int i = 1; i < nv; ++i) {
     const int base = madr[i], di = madr[i + 1] - base - 1;
     float acc = 0.0f;
     for (int a = 1 + lane; a <= di; a += 32) acc += F[base + a] * t[mcol[base + a]];
-    acc = warp_sum(acc);
-    if (lane == 0) t[i] -= acc;
-    __syncwarp();
+    acc = warp_sum(acc);  // every warp reduces the whole row: same value in each
+    if (tid == 0) t[i] -= acc;
+    env_sync();
   }
-  for (int i = lane; i < nv; i += 32) out[i] = t[i];
-  __syncwarp();
+  for (int i = tid; i < nv; i += kEnvThreads) out[i] = t[i];
+  env_sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -336,7 +369,7 @@ __device__ __noinline__ void solve_ld(int so, int xo, int outo) {
 __device__ __noinline__ void jmul(int so, int xo, int outo) {
   VNL_SMEM
   const int* ints = (const int*)(s + c.L.ints);
-  const int nl = ints[0], nc = ints[1], lane = LANE;
+  const int nl = ints[0], nc = ints[1], lane = LANE, tid = ETID;
   const float* const x = s + xo;
   float* const out = s + outo;
   const uint16_t* const madr = TB16(madr);
@@ -345,13 +378,13 @@ __device__ __noinline__ void jmul(int so, int xo, int outo) {
   const float* cdof = s + c.L.cdof;
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* lim_dof = (const int*)(s + c.L.lim_dof);
-  for (int r = lane; r < nl; r += 32) { const int ld = lim_dof[r]; out[r] = ld < 0 ? -x[~ld] : x[ld]; }  // sign folded in: ~dof = upper limit
+  for (int r = tid; r < nl; r += kEnvThreads) { const int ld = lim_dof[r]; out[r] = ld < 0 ? -x[~ld] : x[ld]; }  // sign folded in: ~dof = upper limit
   if (nc > 0) {
     int G = 32;
-    while (G > 1 && (32 / G) < nc) G >>= 1;
+    while (G > 1 && (32 / G) * kEnvWarps < nc) G >>= 1;
     const int per = 32 / G, sub = lane & (G - 1);
-    for (int k0 = 0; k0 < nc; k0 += per) {
-      const int k = k0 + lane / G;
+    for (int k0 = 0; k0 < nc; k0 += per * kEnvWarps) {  // contacts are dealt to the env's warps, `per` per warp per pass
+      const int k = k0 + EWARP * per + lane / G;
       float sacc[6] = {0, 0, 0, 0, 0, 0};
       if (k < nc) {
         const int dl = lastdof[cbody[k]];
@@ -380,21 +413,21 @@ __device__ __noinline__ void jmul(int so, int xo, int outo) {
       }
     }
   }
-  __syncwarp();
+  env_sync();
 }
 
 // qfrc = J^T f with f[row] = -D Jaref [Jaref < 0]
 __device__ __noinline__ void jtmul_force(int so) {
   VNL_SMEM
   const int* ints = (const int*)(s + c.L.ints);
-  const int nl = ints[0], nc = ints[1], lane = LANE, nv = c.d.nv;
+  const int nl = ints[0], nc = ints[1], lane = LANE, tid = ETID, nv = c.d.nv;
   float* const qfrc = s + c.L.qfrc_con;
   float* const cwrench = s + c.L.Jv;  // per-contact wrench scratch: Jv is dead whenever the constraint forces are mapped back
   const uint8_t* const dof_body = TB8(dof_body);
   const uint8_t* const sub_end = TB8(sub_end);
   const float* D = s + c.L.efcD;
   const float* Jaref = s + c.L.Jaref;
-  for (int k = lane; k < nc; k += 32) {
+  for (int k = tid; k < nc; k += kEnvThreads) {
     float f[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -409,11 +442,11 @@ __device__ __noinline__ void jtmul_force(int so) {
     st3(cwrench + 6 * k, cross(ld3(s + c.L.crel + 3 * k), F));
     st3(cwrench + 6 * k + 3, F);
   }
-  __syncwarp();
+  env_sync();
   const int* cbody = (const int*)(s + c.L.cbody);
   const int* limrow = (const int*)(s + c.L.limrow_of_dof);
   const int* lim_dof = (const int*)(s + c.L.lim_dof);
-  for (int i = lane; i < nv; i += 32) {
+  for (int i = tid; i < nv; i += kEnvThreads) {
     const int b = dof_body[i], be = sub_end[b];
     const float* cd = s + c.L.cdof + 6 * i;
     float acc = 0.0f;
@@ -428,7 +461,7 @@ __device__ __noinline__ void jtmul_force(int so) {
     }
     qfrc[i] = acc;
   }
-  __syncwarp();
+  env_sync();
 }
 
 // constraint._kbi  (the impedance power is 1 or 2 on every reference model: no powf on those paths)
@@ -460,12 +493,14 @@ __device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
   VNL_SMEM
   const Lay& L = c.L;
   const int* ints = (const int*)(s + L.ints);
-  const int nrow = ints[0] + 4 * ints[1], lane = LANE, nv = c.d.nv;
+  const int nrow = ints[0] + 4 * ints[1], lane = LANE, tid = ETID, nv = c.d.nv;
   float* qfrc_con = s + L.qfrc_con;
   pf.mark(11);
   jtmul_force(so);
   pf.mark(22);
   float v0 = 0.0f, v1 = 0.0f, g = 0.0f;
+  // reductions: every warp of the env sums ALL elements (same order, same result, no exchange); the grad stores of the
+  // warps carry identical values
   for (int r = lane; r < nrow; r += 32) { const float ja = s[L.Jaref + r]; if (ja < 0.0f) v0 += s[L.efcD + r] * ja * ja; }
   for (int i = lane; i < nv; i += 32) {
     const float ma = s[L.Ma + i], qs = s[L.qfrc_smooth + i];
@@ -479,7 +514,7 @@ __device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
   st.prev_cost = st.cost;
   st.cost = 0.5f * v0 + st.gauss;
   st.gradnorm = sqrtf(g);
-  __syncwarp();
+  env_sync();
   pf.mark(23);
   solve_m(so, L.grad, L.Mgrad);
   pf.mark(24);
@@ -495,7 +530,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
-  const int lane = LANE;
+  const int lane = LANE, tid = ETID;
   int* ints = (int*)(s + L.ints);
   int* stats = ints + 4;
   const bool ls3 = c.lockstep >= 3;  // CTA-uniform: barriers at every phase boundary
@@ -517,7 +552,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     const float* jpos = c.ff(VNL_F_JNT_POS);
     const float* jaxis = c.ff(VNL_F_JNT_AXIS);
     const float* qpos0 = c.ff(VNL_F_QPOS0);
-    for (int b = lane; b < d.nbody; b += 32) {
+    for (int b = tid; b < d.nbody; b += kEnvThreads) {
       Q4 lq; lq.w = 1.0f; lq.x = lq.y = lq.z = 0.0f;
       V3 lp = v3(0.0f, 0.0f, 0.0f);
       if (b > 0) {
@@ -545,12 +580,12 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       st4(s + L.xquat + 4 * b, lq);
       st3(s + L.xpos + 3 * b, lp);
     }
-    __syncwarp();
+    env_sync();
     int k0 = lvl_start[1];  // level 0 (children of the world) is already in world coordinates
     for (int lv = 1; lv < d.nlevel; ++lv) {
       const int k1 = lvl_start[lv + 1];
-      if (k0 + lane < k1) {
-        const uint32_t bp = lvl_bp[k0 + lane];
+      if (k0 + tid < k1) {
+        const uint32_t bp = lvl_bp[k0 + tid];
         const int b = bp & 255, p = bp >> 8;
         const Q4 pq = ld4(s + L.xquat + 4 * p);
         const V3 pp = ld3(s + L.xpos + 3 * p);
@@ -560,10 +595,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         st3(s + L.xpos + 3 * b, pp + rotate(lp, pq));
       }
       k0 = k1;
-      __syncwarp();
+      env_sync();
     }
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
-    for (int j = lane; j < d.njnt; j += 32) {
+    for (int j = tid; j < d.njnt; j += kEnvThreads) {
       const int p = TB8(parent)[jbody[j]];
       if (p > 0) {
         const Q4 pq = ld4(s + L.xquat + 4 * p);
@@ -571,7 +606,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         st3(s + L.xaxis + 3 * j, rotate(ld3(s + L.xaxis + 3 * j), pq));
       }
     }
-    __syncwarp();
+    env_sync();
   }
   pf.mark(0);
   if (ls3) __syncthreads();
@@ -582,9 +617,9 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   {
     const float* ipos = c.ff(VNL_F_BODY_IPOS);
     const float* mass = c.ff(VNL_F_BODY_MASS);
-    for (int b = lane; b < d.nbody; b += 32)
+    for (int b = tid; b < d.nbody; b += kEnvThreads)
       st3(s + L.xipos + 3 * b, ld3(s + L.xpos + 3 * b) + rotate(ld3(ipos + 3 * b), ld4(s + L.xquat + 4 * b)));
-    __syncwarp();
+    env_sync();
     for (int t = 0; t < d.nroot; ++t) {  // subtree COM of each tree root = mass-weighted mean over its id range
       const int rb = TB8(roots)[t], re = TB8(sub_end)[rb];
       float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
@@ -598,10 +633,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         s[L.rcom + 3 * t + lane] = (a3 < VNL_MINVAL) ? s[L.xipos + 3 * rb + lane] : a / fmaxf(a3, VNL_MINVAL);
       }
     }
-    __syncwarp();
+    env_sync();
     const float* iquat = c.ff(VNL_F_BODY_IQUAT);
     const float* inertia = c.ff(VNL_F_BODY_INERTIA);
-    for (int b = lane; b < d.nbody; b += 32) {
+    for (int b = tid; b < d.nbody; b += kEnvThreads) {
       float* ci = s + L.t16 + 16 * b;
       if (b == 0) {
 #pragma unroll
@@ -626,7 +661,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       ci[6] = off.x * ms; ci[7] = off.y * ms; ci[8] = off.z * ms; ci[9] = ms;
     }
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
-    for (int j = lane; j < d.njnt; j += 32) {
+    for (int j = tid; j < d.njnt; j += kEnvThreads) {
       const int b = jbody[j], da = jdofadr[j];
       const V3 off = ld3(s + L.rcom + 3 * body_tree[b]) - ld3(s + L.xanchor + 3 * j);
       if (jtype[j] == 0) {
@@ -648,12 +683,12 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         st3(s + L.cdof + 6 * da + 3, cross(ax, off));
       }
     }
-    __syncwarp();
+    env_sync();
     if (DUMP) {
-      for (int i = lane; i < d.nbody * 3; i += 32) dump[d.dump_xipos + i] = s[L.xipos + i];
-      for (int i = lane; i < d.njnt * 3; i += 32) { dump[d.dump_xanchor + i] = s[L.xanchor + i]; dump[d.dump_xanchor + d.njnt * 3 + i] = s[L.xaxis + i]; }
-      for (int i = lane; i < d.nbody * 10; i += 32) dump[d.dump_cinert + i] = s[L.t16 + 16 * (i / 10) + i % 10];
-      for (int t = lane; t < d.nroot; t += 32) st3(dump + d.dump_subtree_com + 3 * TB8(roots)[t], ld3(s + L.rcom + 3 * t));
+      for (int i = tid; i < d.nbody * 3; i += kEnvThreads) dump[d.dump_xipos + i] = s[L.xipos + i];
+      for (int i = tid; i < d.njnt * 3; i += kEnvThreads) { dump[d.dump_xanchor + i] = s[L.xanchor + i]; dump[d.dump_xanchor + d.njnt * 3 + i] = s[L.xaxis + i]; }
+      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int t = tid; t < d.nroot; t += kEnvThreads) st3(dump + d.dump_subtree_com + 3 * TB8(roots)[t], ld3(s + L.rcom + 3 * t));
     }
   }
   pf.mark(1);
@@ -664,12 +699,12 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       s[L.cvel + lane] = 0.0f;
       s[L.cacc + lane] = (lane == 3) ? -d.gx : ((lane == 4) ? -d.gy : ((lane == 5) ? -d.gz : 0.0f));
     }
-    __syncwarp();
+    env_sync();
     int k0 = 0;
     for (int lv = 0; lv < d.nlevel; ++lv) {
       const int k1 = lvl_start[lv + 1];
-      if (k0 + lane < k1) {
-        const uint32_t bp = lvl_bp[k0 + lane];
+      if (k0 + tid < k1) {
+        const uint32_t bp = lvl_bp[k0 + tid];
         const int b = bp & 255, p = bp >> 8;
         float cv[6], ca[6], cd[6];
 #pragma unroll
@@ -706,10 +741,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         for (int q = 0; q < 6; ++q) { s[L.cvel + 6 * b + q] = cv[q]; s[L.cacc + 6 * b + q] = ca[q]; }
       }
       k0 = k1;
-      __syncwarp();
+      env_sync();
     }
     // local RNE force of each body: cfrc = I cacc + cvel x* (I cvel)   -> t16[10..15]
-    for (int b = lane; b < d.nbody; b += 32) {
+    for (int b = tid; b < d.nbody; b += kEnvThreads) {
       float f1[6], iv[6], f2[6];
       inert_mul(s + L.t16 + 16 * b, s + L.cacc + 6 * b, f1);
       inert_mul(s + L.t16 + 16 * b, s + L.cvel + 6 * b, iv);
@@ -717,11 +752,11 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
 #pragma unroll
       for (int q = 0; q < 6; ++q) s[L.t16 + 16 * b + 10 + q] = f1[q] + f2[q];
     }
-    __syncwarp();
+    env_sync();
     // one pass up the tree: composite inertia (crb, in place over cinert) and subtree-summed RNE force
     for (int lv = d.nlevel - 2; lv >= 0; --lv) {
       const int q0 = lvl_start[lv], n16 = (lvl_start[lv + 1] - q0) * 16;
-      for (int it = lane; it < n16; it += 32) {
+      for (int it = tid; it < n16; it += kEnvThreads) {
         const int b = lvl_bp[q0 + (it >> 4)] & 255, q = it & 15;
         const int ce = TB8(child_adr)[b + 1];
         int ch = TB8(child_adr)[b];
@@ -731,11 +766,11 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
           s[L.t16 + 16 * b + q] = acc;
         }
       }
-      __syncwarp();
+      env_sync();
     }
     if (DUMP) {
-      for (int i = lane; i < d.nbody * 10; i += 32) dump[d.dump_cinert + d.nbody * 10 + d.nv * 6 + i] = s[L.t16 + 16 * (i / 10) + i % 10];
-      for (int i = lane; i < d.nbody * 6; i += 32) dump[d.dump_cvel + i] = s[L.cvel + i];
+      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + d.nbody * 10 + d.nv * 6 + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int i = tid; i < d.nbody * 6; i += kEnvThreads) dump[d.dump_cvel + i] = s[L.cvel + i];
     }
   }
   pf.mark(2);
@@ -754,7 +789,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     const float* gear = c.ff(VNL_F_ACT_GEAR);
     const float* frange = c.ff(VNL_F_ACT_FORCERANGE);
     const float* dynprm = c.ff(VNL_F_ACT_DYNPRM);
-    for (int i = lane; i < d.nv; i += 32) {
+    for (int i = tid; i < d.nv; i += kEnvThreads) {
       float acc = 0.0f;
       for (int t = actadr[i]; t < actadr[i + 1]; ++t) {  // actuators of this dof in actuator order (no atomics)
         const int u = actlist[t];
@@ -783,7 +818,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       s[L.qfrc_smooth + i] = pas - bias + acc;
       if (DUMP) { dump[d.dump_passive + i] = pas; dump[d.dump_passive + d.nv + i] = bias; }
     }
-    __syncwarp();
+    env_sync();
   }
   pf.mark(3);
   if (ls3) __syncthreads();
@@ -791,15 +826,15 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
     float* fd = s + L.cacc;  // cacc is dead: reuse as crb * cdof
-    for (int i = lane; i < d.nv; i += 32) inert_mul(s + L.t16 + 16 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
-    __syncwarp();
-    for (int e = lane; e < d.nM; e += 32) {
+    for (int i = tid; i < d.nv; i += kEnvThreads) inert_mul(s + L.t16 + 16 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
+    env_sync();
+    for (int e = tid; e < d.nM; e += kEnvThreads) {
       const int i = TB8(mrow)[e], j = TB8(mcol)[e];
       float v = dot6(fd + 6 * i, s + L.cdof + 6 * j);
       if (i == j) v += armature[i];
       s[L.M + e] = v;
     }
-    __syncwarp();
+    env_sync();
   }
   pf.mark(4);
   if (ls3) __syncthreads();
@@ -814,8 +849,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
   float* arefv = s + L.Jv;  // aref lives in the Jv slot until the solver iterations start
   {
     if (lane == 0) { ints[0] = 0; ints[1] = 0; }
-    for (int i = lane; i < d.nv; i += 32) ((int*)(s + L.limrow_of_dof))[i] = -1;
-    __syncwarp();
+    for (int i = tid; i < d.nv; i += kEnvThreads) ((int*)(s + L.limrow_of_dof))[i] = -1;
+    env_sync();
     {  // joint limits (constraint._instantiate_limit_slide_hinge)
       const int* ljnt = c.fi(VNL_F_LIMIT_JNT);
       const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
@@ -855,7 +890,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       }
       if (lane == 0) ints[0] = base;
     }
-    __syncwarp();
+    env_sync();
     {  // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
       const int nl = ints[0];
       const int* cpair = c.fi(VNL_F_CON_PAIR);
@@ -969,12 +1004,12 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       }
       if (lane == 0) ints[1] = base;
     }
-    __syncwarp();
+    env_sync();
   }
   pf.mark(7);
   if (ls3) __syncthreads();
   const int nl = ints[0], nc = ints[1], nrow = nl + 4 * nc;
-  if (lane == 0) { stats[2] += nc; stats[3] += nl; }
+  if (tid == 0) { stats[2] += nc; stats[3] += nl; }
 
   // ---- solver.solve (CG with the MJX line search) ------------------------------------------------------------------------
   float* qacc = s + L.qacc;
@@ -1000,7 +1035,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       for (int i = lane; i < d.nv; i += 32) v1 += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
       v0 = warp_sum(v0); v1 = warp_sum(v1);
       cost_w = 0.5f * v0 + 0.5f * v1;
-      __syncwarp();
+      env_sync();
       mul_m(so, L.qacc_smooth, L.Ma);
       jmul(so, L.qacc_smooth, L.Jaref);
       float w0 = 0.0f, w1 = 0.0f;
@@ -1008,27 +1043,27 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       for (int i = lane; i < d.nv; i += 32) w1 += (Ma[i] - qfrc_smooth[i]) * (qacc_smooth[i] - qacc_smooth[i]);
       w0 = warp_sum(w0); w1 = warp_sum(w1);
       cost_s = 0.5f * w0 + 0.5f * w1;
-      __syncwarp();
+      env_sync();
     }
     if (cost_w < cost_s) {
-      for (int i = lane; i < d.nv; i += 32) qacc[i] = s[L.warm + i];
-      __syncwarp();
+      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = s[L.warm + i];
+      env_sync();
       mul_m(so, L.qacc, L.Ma);
       jmul(so, L.qacc, L.Jaref);
     } else {
-      for (int i = lane; i < d.nv; i += 32) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
+      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
     }
-    __syncwarp();
-    for (int r = lane; r < nrow; r += 32) Jaref[r] -= arefv[r];
-    __syncwarp();
+    env_sync();
+    for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] -= arefv[r];
+    env_sync();
     pf.mark(8);
     if (ls3) __syncthreads();
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
     update_constraint(so, st, pf);
-    for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
-    __syncwarp();
+    for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
+    env_sync();
     pf.mark(9);
     bool done = false;
     for (int itn = 0; itn < d.iterations; ++itn) {
@@ -1127,31 +1162,29 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       const float ia = improved ? alpha : 0.0f * alpha;
       float pg = 0.0f;  // previous grad . Mgrad before they are overwritten
-      for (int i = lane; i < d.nv; i += 32) {
-        qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia;
-        pg += grad[i] * Mgrad[i]; Mv[i] = Mgrad[i];  // Mv <- previous Mgrad
-      }
-      for (int r = lane; r < nrow; r += 32) Jaref[r] += Jv[r] * ia;
+      for (int i = lane; i < d.nv; i += 32) pg += grad[i] * Mgrad[i];
       pg = warp_sum(pg);
-      __syncwarp();
+      for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; Mv[i] = Mgrad[i]; }  // Mv <- previous Mgrad
+      for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] += Jv[r] * ia;
+      env_sync();
       update_constraint(so, st, pf);
       if (d.solver == 2) {
-        for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i];
+        for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
       } else {  // Polak-Ribiere
         float nb = 0.0f;
         for (int i = lane; i < d.nv; i += 32) nb += grad[i] * (Mgrad[i] - Mv[i]);
         nb = warp_sum(nb);
         const float beta = fmaxf(0.0f, nb / fmaxf(VNL_MINVAL, pg));
-        for (int i = lane; i < d.nv; i += 32) search[i] = -Mgrad[i] + beta * search[i];
+        for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i] + beta * search[i];
       }
-      __syncwarp();
+      env_sync();
       pf.mark(11);
       ++niter;
     }
   }
-  if (lane == 0) { stats[0] += niter; stats[1] += lsiter; }
-  for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = qacc[i];  // qacc_warmstart <- qacc
-  __syncwarp();
+  if (tid == 0) { stats[0] += niter; stats[1] += lsiter; }
+  for (int i = tid; i < d.nv; i += kEnvThreads) s[L.warm + i] = qacc[i];  // qacc_warmstart <- qacc
+  env_sync();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1161,25 +1194,25 @@ __device__ __noinline__ void euler(int so, Prof& pf) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
-  const int lane = LANE;
+  const int lane = LANE, tid = ETID;
   const float dt = d.timestep;
   float* qacc = s + L.qacc;
   pf.mark(12);
   if (d.eulerdamp) {
     factor(so, true, false, pf);
     pf.mark(13);
-    for (int i = lane; i < d.nv; i += 32) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
-    __syncwarp();
+    for (int i = tid; i < d.nv; i += kEnvThreads) s[L.grad + i] = s[L.qfrc_smooth + i] + s[L.qfrc_con + i];
+    env_sync();
     solve_ld(so, L.grad, L.Mgrad);
     qacc = s + L.Mgrad;
   }
-  for (int a = lane; a < d.na; a += 32) s[L.act + a] += s[L.act_dot + a] * dt;
-  for (int i = lane; i < d.nv; i += 32) s[L.qvel + i] += qacc[i] * dt;
-  __syncwarp();
+  for (int a = tid; a < d.na; a += kEnvThreads) s[L.act + a] += s[L.act_dot + a] * dt;
+  for (int i = tid; i < d.nv; i += kEnvThreads) s[L.qvel + i] += qacc[i] * dt;
+  env_sync();
   const int* jtype = c.fi(VNL_F_JNT_TYPE);
   const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
   const int* jdofadr = c.fi(VNL_F_JNT_DOFADR);
-  for (int j = lane; j < d.njnt; j += 32) {
+  for (int j = tid; j < d.njnt; j += kEnvThreads) {
     const int qa = jqadr[j], da = jdofadr[j];
     if (jtype[j] == 0) {
       for (int k = 0; k < 3; ++k) s[L.qpos + qa + k] += s[L.qvel + da + k] * dt;
@@ -1191,7 +1224,7 @@ __device__ __noinline__ void euler(int so, Prof& pf) {
       s[L.qpos + qa] += s[L.qvel + da] * dt;
     }
   }
-  __syncwarp();
+  env_sync();
   pf.mark(14);
 }
 
@@ -1247,11 +1280,11 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
-  const int lane = LANE;
+  const int lane = LANE, tid = ETID;
   if (!active) {  // a warp without an env in this round only keeps the CTA's phase barriers company
     if (p.lockstep) {
       const int ns = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
-      for (int st = 0; st < ns; ++st) { __syncthreads(); if (MODE == 1 || MODE == 3) break; if (p.lockstep > 1) __syncthreads(); }
+      for (int st = 0; st < ns; ++st) { group_sync(p.lsgroups); if (MODE == 1 || MODE == 3) break; if (p.lockstep > 1) group_sync(p.lsgroups); }
     }
     return;
   }
@@ -1262,24 +1295,24 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   if (lane < 16) ints[lane] = 0;
 
   // ---- load state -------------------------------------------------------------------------------------------------------
-  for (int i = lane; i < d.nq; i += 32) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
-  for (int i = lane; i < d.nv; i += 32) s[L.qvel + i] = p.in.qvel[(size_t)e * d.nv + i];
+  for (int i = tid; i < d.nq; i += kEnvThreads) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
+  for (int i = tid; i < d.nv; i += kEnvThreads) s[L.qvel + i] = p.in.qvel[(size_t)e * d.nv + i];
   if (MODE == 1) {
-    for (int i = lane; i < d.na; i += 32) s[L.act + i] = 0.0f;
-    for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = 0.0f;
-    for (int i = lane; i < d.nu; i += 32) s[L.ctrl + i] = 0.0f;
+    for (int i = tid; i < d.na; i += kEnvThreads) s[L.act + i] = 0.0f;
+    for (int i = tid; i < d.nv; i += kEnvThreads) s[L.warm + i] = 0.0f;
+    for (int i = tid; i < d.nu; i += kEnvThreads) s[L.ctrl + i] = 0.0f;
   } else {
-    for (int i = lane; i < d.na; i += 32) s[L.act + i] = p.in.act ? p.in.act[(size_t)e * d.na + i] : 0.0f;
-    for (int i = lane; i < d.nv; i += 32) s[L.warm + i] = p.in.qacc_warmstart ? p.in.qacc_warmstart[(size_t)e * d.nv + i] : 0.0f;
+    for (int i = tid; i < d.na; i += kEnvThreads) s[L.act + i] = p.in.act ? p.in.act[(size_t)e * d.na + i] : 0.0f;
+    for (int i = tid; i < d.nv; i += kEnvThreads) s[L.warm + i] = p.in.qacc_warmstart ? p.in.qacc_warmstart[(size_t)e * d.nv + i] : 0.0f;
     const int* climited = c.fi(VNL_F_ACT_CTRLLIMITED);
     const float* crange = c.ff(VNL_F_ACT_CTRLRANGE);
-    for (int u = lane; u < d.nu; u += 32) {
+    for (int u = tid; u < d.nu; u += kEnvThreads) {
       float v = p.ctrl ? p.ctrl[(size_t)e * d.nu + u] : 0.0f;
       if (climited[u]) v = fminf(fmaxf(v, crange[2 * u]), crange[2 * u + 1]);
       s[L.ctrl + u] = v;
     }
   }
-  __syncwarp();
+  env_sync();
   const uint32_t* tb = p.task;
   // termination error of the PREVIOUS state and frame (envs/rodent.py:241-264, quirks Q2 / Q9): depends only on
   // inputs, so evaluate it before the physics overwrites them.
@@ -1317,22 +1350,22 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   for (int st = 0; st < nsteps; ++st) {
     // Optional lockstep: the warps of a CTA start each substep together, so that they walk the (large) instruction
     // footprint of a substep as one group instead of seven independent streams.
-    if (p.lockstep) __syncthreads();
+    if (p.lockstep) group_sync(p.lsgroups);
     forward<MODE == 3>(so, dump, pf);
     if (MODE == 1 || MODE == 3) break;
-    if (p.lockstep > 1) __syncthreads();
+    if (p.lockstep > 1) group_sync(p.lsgroups);
     euler(so, pf);
   }
 
   if (MODE == 3) {
     // stage dump (layout = oracle.dump_layout); arrays this formulation never materialises stay NaN
-    auto put = [&](int off, const float* src, int n) { for (int i = lane; i < n; i += 32) dump[off + i] = src[i]; };
+    auto put = [&](int off, const float* src, int n) { for (int i = tid; i < n; i += kEnvThreads) dump[off + i] = src[i]; };
     put(d.dump_xpos, s + L.xpos, d.nbody * 3);
     put(d.dump_xpos + d.nbody * 3, s + L.xquat, d.nbody * 4);
     put(d.dump_cinert + d.nbody * 10, s + L.cdof, d.nv * 6);
-    for (int i = lane; i < d.nv * d.nv; i += 32) dump[d.dump_qM + i] = 0.0f;
-    __syncwarp();
-    for (int q = lane; q < d.nM; q += 32) {
+    for (int i = tid; i < d.nv * d.nv; i += kEnvThreads) dump[d.dump_qM + i] = 0.0f;
+    env_sync();
+    for (int q = tid; q < d.nM; q += kEnvThreads) {
       dump[d.dump_qM + TB8(mrow)[q] * d.nv + TB8(mcol)[q]] = s[L.M + q];
       dump[d.dump_qM + TB8(mcol)[q] * d.nv + TB8(mrow)[q]] = s[L.M + q];
     }
@@ -1343,25 +1376,25 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     put(d.dump_qacc, s + L.qacc, d.nv);
     put(d.dump_qacc + d.nv, s + L.qfrc_con, d.nv);
     if (lane < 4) dump[d.dump_total - 4 + lane] = (float)stats[lane];
-    __syncwarp();
+    env_sync();
     return;
   }
 
   // ---- write state ------------------------------------------------------------------------------------------------------
   const VnlState& o = p.out;
-  for (int i = lane; i < d.nq; i += 32) o.qpos[(size_t)e * d.nq + i] = s[L.qpos + i];
-  for (int i = lane; i < d.nv; i += 32) o.qvel[(size_t)e * d.nv + i] = s[L.qvel + i];
-  for (int i = lane; i < d.na; i += 32) o.act[(size_t)e * d.na + i] = s[L.act + i];
-  for (int i = lane; i < d.nv; i += 32) o.qacc_warmstart[(size_t)e * d.nv + i] = s[L.warm + i];
-  for (int i = lane; i < d.nbody * 3; i += 32) o.xpos[(size_t)e * d.nbody * 3 + i] = s[L.xpos + i];
-  for (int i = lane; i < d.nbody * 4; i += 32) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
-  for (int i = lane; i < d.nv; i += 32) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
+  for (int i = tid; i < d.nq; i += kEnvThreads) o.qpos[(size_t)e * d.nq + i] = s[L.qpos + i];
+  for (int i = tid; i < d.nv; i += kEnvThreads) o.qvel[(size_t)e * d.nv + i] = s[L.qvel + i];
+  for (int i = tid; i < d.na; i += kEnvThreads) o.act[(size_t)e * d.na + i] = s[L.act + i];
+  for (int i = tid; i < d.nv; i += kEnvThreads) o.qacc_warmstart[(size_t)e * d.nv + i] = s[L.warm + i];
+  for (int i = tid; i < d.nbody * 3; i += kEnvThreads) o.xpos[(size_t)e * d.nbody * 3 + i] = s[L.xpos + i];
+  for (int i = tid; i < d.nbody * 4; i += kEnvThreads) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
+  for (int i = tid; i < d.nv; i += kEnvThreads) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
   const int torso = (MODE == 2) ? 1 : vnl_hdr_i(tb, VNL_TH_TORSO_BODY);
   const float* rcom = s + L.rcom + 3 * TB8(body_tree)[torso];  // subtree_com[torso]: torso is the root of its tree
   if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = rcom[lane];
   if (MODE == 2) {
     if (p.stats && lane < 4) p.stats[4 * e + lane] = stats[lane];
-    __syncwarp();
+    env_sync();
     return;
   }
 
@@ -1383,7 +1416,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   if (lane == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; }
   {
     float* obs = p.outputs.obs + (size_t)e * obs_size;
-    for (int i = lane; i < obs_size; i += 32) {  // [qpos, qvel (, qfrc_actuator, xpos[end effectors])]
+    for (int i = tid; i < obs_size; i += kEnvThreads) {  // [qpos, qvel (, qfrc_actuator, xpos[end effectors])]
       float v;
       if (i < d.nq) v = s[L.qpos + i];
       else if (i < d.nq + d.nv) v = s[L.qvel + i - d.nq];
@@ -1396,7 +1429,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     const int ws = min(max(cur_frame + 1, 0), T - ref_len);
     float* traj = p.outputs.traj + (size_t)e * traj_size;
     const int n_app = ref_len * napp * 3, n_bod = ref_len * ntrack * 3, n_root = ref_len * 3;
-    for (int i = lane; i < traj_size; i += 32) {
+    for (int i = tid; i < traj_size; i += kEnvThreads) {
       float v;
       if (i < n_app) {
         const int w = i / (napp * 3), r = i - w * napp * 3;
@@ -1441,7 +1474,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       mt[6] = 1.0f - err / vnl_hdr_f(tb, VNL_TH_TERM_THRESHOLD);
     }
     if (p.outputs.stats && lane < 4) p.outputs.stats[4 * e + lane] = stats[lane];
-    __syncwarp();
+    env_sync();
     return;
   }
   // _calculate_reward (rodent.py:266-316 / humanoid.py:264-311): every reference lookup uses the OLD cur_frame
@@ -1482,24 +1515,24 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     // first ones; info (frames, traj), reward, done and metrics are kept.
     if (p.first.qpos && done > 0.0f) {
       const VnlState& f1 = p.first;
-      for (int i = lane; i < d.nq; i += 32) o.qpos[(size_t)e * d.nq + i] = f1.qpos[(size_t)e * d.nq + i];
-      for (int i = lane; i < d.nv; i += 32) o.qvel[(size_t)e * d.nv + i] = f1.qvel[(size_t)e * d.nv + i];
-      for (int i = lane; i < d.na; i += 32) o.act[(size_t)e * d.na + i] = f1.act[(size_t)e * d.na + i];
-      for (int i = lane; i < d.nv; i += 32) o.qacc_warmstart[(size_t)e * d.nv + i] = f1.qacc_warmstart[(size_t)e * d.nv + i];
-      for (int i = lane; i < d.nbody * 3; i += 32) o.xpos[(size_t)e * d.nbody * 3 + i] = f1.xpos[(size_t)e * d.nbody * 3 + i];
-      for (int i = lane; i < d.nbody * 4; i += 32) o.xquat[(size_t)e * d.nbody * 4 + i] = f1.xquat[(size_t)e * d.nbody * 4 + i];
-      for (int i = lane; i < d.nv; i += 32) o.qfrc_actuator[(size_t)e * d.nv + i] = f1.qfrc_actuator[(size_t)e * d.nv + i];
+      for (int i = tid; i < d.nq; i += kEnvThreads) o.qpos[(size_t)e * d.nq + i] = f1.qpos[(size_t)e * d.nq + i];
+      for (int i = tid; i < d.nv; i += kEnvThreads) o.qvel[(size_t)e * d.nv + i] = f1.qvel[(size_t)e * d.nv + i];
+      for (int i = tid; i < d.na; i += kEnvThreads) o.act[(size_t)e * d.na + i] = f1.act[(size_t)e * d.na + i];
+      for (int i = tid; i < d.nv; i += kEnvThreads) o.qacc_warmstart[(size_t)e * d.nv + i] = f1.qacc_warmstart[(size_t)e * d.nv + i];
+      for (int i = tid; i < d.nbody * 3; i += kEnvThreads) o.xpos[(size_t)e * d.nbody * 3 + i] = f1.xpos[(size_t)e * d.nbody * 3 + i];
+      for (int i = tid; i < d.nbody * 4; i += kEnvThreads) o.xquat[(size_t)e * d.nbody * 4 + i] = f1.xquat[(size_t)e * d.nbody * 4 + i];
+      for (int i = tid; i < d.nv; i += kEnvThreads) o.qfrc_actuator[(size_t)e * d.nv + i] = f1.qfrc_actuator[(size_t)e * d.nv + i];
       if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = f1.subtree_com[(size_t)e * 3 + lane];
       if (p.first_obs)
-        for (int i = lane; i < obs_size; i += 32) p.outputs.obs[(size_t)e * obs_size + i] = p.first_obs[(size_t)e * obs_size + i];
+        for (int i = tid; i < obs_size; i += kEnvThreads) p.outputs.obs[(size_t)e * obs_size + i] = p.first_obs[(size_t)e * obs_size + i];
     }
   }
-  __syncwarp();
+  env_sync();
   pf.mark(15);
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
+__global__ void __launch_bounds__(kMaxEnvs * kEnvThreads, 1) vnl_env_kernel(Params p) {
   extern __shared__ __align__(16) float smem[];
   Cta& c = *reinterpret_cast<Cta*>(smem);
   uint32_t* ktab = reinterpret_cast<uint32_t*>(smem + kCtaFloats);
@@ -1517,7 +1550,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
     TOFF(lvl_start, VNL_KT_LVL_START); TOFF(lvl_bp, VNL_KT_LVL_BP); TOFF(parent, VNL_KT_PARENT); TOFF(child_adr, VNL_KT_CHILD_ADR);
     TOFF(child_list, VNL_KT_CHILD_LIST); TOFF(body_dofadr, VNL_KT_BODY_DOFADR); TOFF(body_dofnum, VNL_KT_BODY_DOFNUM);
     TOFF(body_tree, VNL_KT_BODY_TREE); TOFF(lastdof, VNL_KT_BODY_LASTDOF); TOFF(sub_end, VNL_KT_SUB_END); TOFF(roots, VNL_KT_ROOTS);
-    TOFF(mrow, VNL_KT_MROW); TOFF(mcol, VNL_KT_MCOL); TOFF(dof_body, VNL_KT_DOF_BODY); TOFF(dpart_adr, VNL_KT_DPART_ADR);
+    TOFF(mrow, VNL_KT_MROW); TOFF(mcol, VNL_KT_MCOL); TOFF(dof_body, VNL_KT_DOF_BODY); TOFF(dpart_adr, VNL_KT_DPART_ADR); TOFF(apart_adr, VNL_KT_APART_ADR);
     TOFF(madr, VNL_KT_MADR); TOFF(tri, VNL_KT_TRI); TOFF(anc_start, VNL_KT_ANC_START); TOFF(kitem, VNL_KT_KITEM);
     TOFF(klvl, VNL_KT_KLVL); TOFF(prog_a, VNL_KT_PROG_A); TOFF(prog_d, VNL_KT_PROG_D);
 #undef TOFF
@@ -1525,7 +1558,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) vnl_env_kernel(Params p) {
     c.ndslot = (int)g_ktab[VNL_KT_COUNT + VNL_KS_NDSLOT];
   }
   __syncthreads();
-  const int W = nt >> 5, warp = tid >> 5;
+  const int W = nt / kEnvThreads, warp = tid / kEnvThreads;  // env slots of this CTA, this thread's slot
   const int so = kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
   const int stride = gridDim.x * W, rounds = (p.B + stride - 1) / stride;
   for (int r = 0; r < rounds; ++r) {
@@ -1544,7 +1577,7 @@ LaunchInfo launch_info(const Dims& d, int B) {
   make_layout(d, L);
   const int fixed = (kCtaFloats + align4(d.ktab_words)) * 4, per = L.total * 4;
   int wmax = (227 * 1024 - fixed) / per;
-  if (wmax > kMaxWarps) wmax = kMaxWarps;
+  if (wmax > kMaxEnvs) wmax = kMaxEnvs;
   static int env_w = -1;
   if (env_w < 0) { const char* ev = getenv("VNL_WARPS"); env_w = ev ? atoi(ev) : 0; }
   static int sms = 0;
@@ -1565,7 +1598,7 @@ LaunchInfo launch_info(const Dims& d, int B) {
     const int smem = fixed + W * per;
     int resident = (227 * 1024) / (smem + 1024);
     if (resident < 1) resident = 1;
-    if (resident > 2048 / (W * 32)) resident = 2048 / (W * 32);
+    if (resident > 2048 / (W * kEnvThreads)) resident = 2048 / (W * kEnvThreads);
     const int need = (B + W - 1) / W;
     const int ctas = need < sms * resident ? need : sms * resident;
     const long rounds = ((long)B + (long)ctas * W - 1) / ((long)ctas * W);
@@ -1580,6 +1613,7 @@ LaunchInfo launch_info(const Dims& d, int B) {
 cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   const LaunchInfo li = launch_info(p.dims, p.B);
   if (li.warps_per_cta < 1) return cudaErrorInvalidConfiguration;  // one env does not fit in shared memory
+  if (p.dims.env_warps != kEnvWarps) return cudaErrorInvalidValue;   // the blob's lane programs are for another group width
   void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;
@@ -1587,8 +1621,13 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   if (lockstep < 0) { const char* ev = getenv("VNL_LOCKSTEP"); lockstep = ev ? atoi(ev) : 1; }
   Params q = p;
   q.lockstep = lockstep;
-  k<<<li.ctas, li.warps_per_cta * 32, li.smem_bytes, stream>>>(q);
+  static int lsgroups = -1;
+  if (lsgroups < 0) { const char* ev = getenv("VNL_LSGROUPS"); lsgroups = ev ? atoi(ev) : 1; }
+  q.lsgroups = lsgroups < 1 ? 1 : (lsgroups > li.warps_per_cta ? li.warps_per_cta : (lsgroups > 7 ? 7 : lsgroups));
+  if (q.lsgroups > 1 && lockstep >= 3) q.lockstep = 2;  // the per-phase barriers are CTA wide
+  k<<<li.ctas, li.warps_per_cta * kEnvThreads, li.smem_bytes, stream>>>(q);
   return cudaGetLastError();
 }
 
+}  // namespace ewN
 }  // namespace vnl

@@ -7,7 +7,7 @@
 
 namespace vnl {
 
-constexpr int kMaxWarps = 8;   // envs (warps) per CTA upper bound
+constexpr int kMaxEnvs = 8;   // envs per CTA upper bound (each env = 1 or 2 warps; named barriers 1..8 serve the groups)
 
 struct Dims {
   int nq, nv, nu, na, nbody, njnt, ngeom, npair, ncon, nlimit, nefc, nM, nlevel, maxdepth, nroot;
@@ -15,6 +15,8 @@ struct Dims {
   float timestep, gx, gy, gz, tolerance, ls_tolerance, impratio, meaninertia;
   int ktab_words;  // size of VNL_F_KTAB
   int ndslot;      // partial-sum slots of the descendant mat-vec program (VNL_KS_NDSLOT)
+  int naslot;      // partial-sum slots of the ancestor mat-vec program (VNL_MH_NASLOT)
+  int env_warps;   // warps cooperating on one env (VNL_MH_ENV_WARPS): lane count of the mat-vec programs / 32
   // stage-dump offsets (layout of oracle.dump_layout)
   int dump_xpos, dump_xipos, dump_xanchor, dump_subtree_com, dump_cinert, dump_qM, dump_cvel, dump_passive, dump_con,
       dump_efc, dump_qacc, dump_total;
@@ -45,12 +47,21 @@ struct Params {
   float* dump;
   long long* prof;  // optional [32] per-phase clock64 accumulators of one env (developer hook)
   int prof_env;
+  int lsgroups;     // lockstep groups per CTA (1 = the whole CTA)
   int lockstep;     // 0 = warps free-run, 1 = CTA barrier at every substep start, 2 = also before the integrator
 };
 
-struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };
+struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };  // warps_per_cta = env groups per CTA
 
-LaunchInfo launch_info(const Dims& d, int B);
-cudaError_t launch(int mode, const Params& p, cudaStream_t stream);
+// vnl_kernels.cu is compiled once per env-group width (-DVNL_EW=1, 2) into its own namespace.
+namespace ew1 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
+namespace ew2 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
+
+inline LaunchInfo any_launch_info(const Dims& d, int B) { return d.env_warps == 2 ? ew2::launch_info(d, B) : ew1::launch_info(d, B); }
+inline cudaError_t any_launch(int mode, const Params& p, cudaStream_t stream) {
+  if (p.dims.env_warps == 2) return ew2::launch(mode, p, stream);
+  if (p.dims.env_warps == 1) return ew1::launch(mode, p, stream);
+  return cudaErrorInvalidValue;
+}
 
 }  // namespace vnl

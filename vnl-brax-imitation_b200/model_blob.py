@@ -39,6 +39,7 @@ def _parse_header(path: str):
 
 
 C = _parse_header(_HEADER)
+DEFAULT_ENV_WARPS = 1
 
 
 class _BlobWriter:
@@ -73,7 +74,13 @@ class _BlobWriter:
         return np.concatenate([self.hdr] + self.chunks)
 
 
-def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
+def default_env_warps() -> int:
+    """Warps cooperating on one env in the kernel (1 or 2); `VNL_ENV_WARPS` overrides the default."""
+    ev = int(os.environ.get("VNL_ENV_WARPS", "0") or 0)
+    return ev if ev in (1, 2) else DEFAULT_ENV_WARPS
+
+
+def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
     """Host-precomputed index tables for the CUDA kernels (tree levels, sparse-inertia
     pattern, emitted-contact list, static geom frames)."""
     A = m.arrays
@@ -159,19 +166,22 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     if 4 * (nM_ + 1) >= (1 << 14):
         raise NotImplementedError("too many inertia entries for the packed mat-vec program")
 
+    env_warps = env_warps or default_env_warps()
+    NL = 32 * env_warps  # lanes of the mat-vec programs = threads cooperating on one env
+
     def pack_program(rows):
-        """rows: list of (slot, [(entry, xindex), ...]) with non-empty term lists -> ([T*32] words, T)."""
-        lanes = [[] for _ in range(32)]
-        lane_load = [0] * 32
+        """rows: list of (slot, [(entry, xindex), ...]) with non-empty term lists -> ([T*NL] words, T)."""
+        lanes = [[] for _ in range(NL)]
+        lane_load = [0] * NL
         for slot, terms in sorted(rows, key=lambda r: -len(r[1])):
-            l = min(range(32), key=lambda l: lane_load[l])
+            l = min(range(NL), key=lambda l: lane_load[l])
             lanes[l].append((slot, terms))
             lane_load[l] += len(terms)
         T = 4 * ((max(1, max(lane_load)) + 3) // 4)  # the kernel walks the program four terms at a time
-        prog = np.zeros((T, 32), dtype=np.uint32)
+        prog = np.zeros((T, NL), dtype=np.uint32)
         pad = np.uint32((4 * nM_) | (0xFF << 24))  # entry nM is a zero slot, never flushed
         prog[:, :] = pad
-        for l in range(32):
+        for l in range(NL):
             t = 0
             for slot, terms in lanes[l]:
                 for k, (e, xi) in enumerate(terms):
@@ -180,10 +190,19 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
                     t += 1
         return prog.reshape(-1), T
 
-    rows_a = [(i, [(madr[i] + a, mcol[madr[i] + a]) for a in range(1, madr[i + 1] - madr[i])]) for i in range(nv)]
-    rows_a = [r for r in rows_a if r[1]]
-    prog_a, TA = pack_program(rows_a)
-    CH = 24
+    # long rows / columns are cut into chunks so that the lanes can be balanced; one warp per env keeps whole rows
+    CH = 24 if env_warps == 1 else 12
+    CHA = 1 << 20 if env_warps == 1 else 12
+    rows_a, apart_adr = [], [0]
+    for i in range(nv):
+        terms = [(madr[i] + a, mcol[madr[i] + a]) for a in range(1, madr[i + 1] - madr[i])]
+        for k in range(0, len(terms), CHA):
+            rows_a.append((len(rows_a), terms[k:k + CHA]))
+        apart_adr.append(len(rows_a))
+    if len(rows_a) > 254:
+        raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
+    prog_a, TA = pack_program(rows_a) if rows_a else (np.full(4 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
+    naslot = len(rows_a)
     rows_d, dpart_adr = [], [0]
     for j in range(nv):
         terms = [(e, mrow[e]) for e in desc[j]]
@@ -192,9 +211,9 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
         dpart_adr.append(len(rows_d))
     if len(rows_d) > 254 or nv > 254:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
-    prog_d, TD = pack_program(rows_d) if rows_d else (np.full(128, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
+    prog_d, TD = pack_program(rows_d) if rows_d else (np.full(4 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
     ndslot = len(rows_d)
-    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)] + [1 | (1 << 8)] * 64  # padded tail
+    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)] + [1 | (1 << 8)] * 256  # padded tail (two pairs per thread past the end)
     kitem, klvl = [], [0, 0]
     for dpt in range(1, maxd + 1):
         items = [(c, i) for i in range(nv) if ddepth[i] == dpt for c in range(1, dpt + 1)]
@@ -220,6 +239,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     kt[C["VNL_KT_MCOL"]] = u8(mcol)
     kt[C["VNL_KT_DOF_BODY"]] = u8(A["dof_bodyid"])
     kt[C["VNL_KT_DPART_ADR"]] = u8(dpart_adr)
+    kt[C["VNL_KT_APART_ADR"]] = u8(apart_adr)
     kt[C["VNL_KT_MADR"]] = u16(madr)
     kt[C["VNL_KT_TRI"]] = u16(tri)
     kt[C["VNL_KT_ANC_START"]] = u16([madr[j] for j in mcol])
@@ -247,7 +267,7 @@ def derived_tables(m: mjcf.Model) -> Dict[str, np.ndarray]:
     dof_actadr = [0]
     for i in range(nv):
         dof_actadr.append(dof_actadr[-1] + len(act_of_dof[i]))
-    return dict(ktab=ktab, nroot=len(roots), ndslot=ndslot, dof_actadr=np.array(dof_actadr),
+    return dict(ktab=ktab, env_warps=env_warps, nroot=len(roots), ndslot=ndslot, naslot=naslot, dof_actadr=np.array(dof_actadr),
                 dof_actlist=np.array([u for i in range(nv) for u in act_of_dof[i]], dtype=np.int64),
                 level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
                 m_col=np.array(mcol), dof_depth=np.array(ddepth), body_subtree_end=sub_end,
@@ -309,24 +329,26 @@ _DERIVED_FIELDS = [
 ]
 
 
-def model_dims(m: mjcf.Model) -> Dict[str, int]:
-    d = derived_tables(m)
+def model_dims(m: mjcf.Model, d=None) -> Dict[str, int]:
+    d = d or derived_tables(m)
     ncon, nlimit = len(d["con_pair"]), len(d["limit_jnt"])
     return dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom,
                 npair=len(m.arrays["pair_geom1"]), ncon=ncon, nlimit=nlimit, nefc=nlimit + 4 * ncon,
-                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"], ndslot=d["ndslot"])
+                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"], ndslot=d["ndslot"], naslot=d["naslot"])
 
 
-def build_model_blob(m: mjcf.Model) -> np.ndarray:
-    d = derived_tables(m)
-    dims = model_dims(m)
+def build_model_blob(m: mjcf.Model, env_warps: int = 0) -> np.ndarray:
+    d = derived_tables(m, env_warps)
+    dims = model_dims(m, d)
     w = _BlobWriter(C["VNL_MAGIC_MODEL"], C["VNL_F_MODEL_COUNT"])
     for slot, key in [("VNL_MH_NQ", "nq"), ("VNL_MH_NV", "nv"), ("VNL_MH_NU", "nu"), ("VNL_MH_NA", "na"),
                       ("VNL_MH_NBODY", "nbody"), ("VNL_MH_NJNT", "njnt"), ("VNL_MH_NGEOM", "ngeom"),
                       ("VNL_MH_NPAIR", "npair"), ("VNL_MH_NCON", "ncon"), ("VNL_MH_NLIMIT", "nlimit"),
                       ("VNL_MH_NEFC", "nefc"), ("VNL_MH_NM", "nM"), ("VNL_MH_NLEVEL", "nlevel"),
-                      ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot"), ("VNL_MH_NDSLOT", "ndslot")]:
+                      ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot"), ("VNL_MH_NDSLOT", "ndslot"),
+                      ("VNL_MH_NASLOT", "naslot")]:
         w.set_i(slot, dims[key])
+    w.set_i("VNL_MH_ENV_WARPS", d["env_warps"])
     w.set_i("VNL_MH_SOLVER", m.solver)
     w.set_i("VNL_MH_ITERATIONS", m.iterations)
     w.set_i("VNL_MH_LS_ITERATIONS", m.ls_iterations)
@@ -353,7 +375,7 @@ def read_dims(blob: np.ndarray) -> Dict[str, int]:
                 ncon=g("VNL_MH_NCON"), nlimit=g("VNL_MH_NLIMIT"), nefc=g("VNL_MH_NEFC"), nM=g("VNL_MH_NM"),
                 nlevel=g("VNL_MH_NLEVEL"), maxdepth=g("VNL_MH_MAXDEPTH"), nroot=g("VNL_MH_NROOT"), solver=g("VNL_MH_SOLVER"),
                 iterations=g("VNL_MH_ITERATIONS"), ls_iterations=g("VNL_MH_LS_ITERATIONS"),
-                eulerdamp=g("VNL_MH_EULERDAMP"))
+                eulerdamp=g("VNL_MH_EULERDAMP"), env_warps=g("VNL_MH_ENV_WARPS"))
 
 
 def read_field(blob: np.ndarray, field: str, dtype) -> np.ndarray:
