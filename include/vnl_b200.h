@@ -182,7 +182,16 @@ enum VnlKtab {
   VNL_KT_DPART_ADR,     /* u8  [nv+1] CSR: partial-sum slots of PROG_D that make up each dof's descendant sum */
   VNL_KT_APART_ADR,     /* u8  [nv+1] CSR: partial-sum slots of PROG_A that make up each dof's strict-ancestor sum */
   VNL_KT_MADR,          /* u16 [nv+1] */
-  VNL_KT_TRI,           /* u16 [maxdepth (maxdepth+1) / 2]  a | c << 8 with 1 <= a <= c, index c (c-1) / 2 + a - 1 */
+  /* Level schedule of the L^T D L factorisation (left-looking) and of the L^-T sweep: rows (dofs) with descendants,
+   * grouped by dof HEIGHT (longest chain of descendants below the dof, leaves = 0) -- rows of one height are independent. */
+  VNL_KT_EROW,          /* u32 [2 nv] per row, by height, descending dof inside: madr | (row length - 1) << 13 |
+                         * lg2ceil(row length) << 19 | dof << 22; then DESC range begin | end << 16.  8-byte aligned. */
+  VNL_KT_ELVL,          /* u16 [nheight+2] first EROW row of heights 0.. | lg2ceil(most descendants of a row there) << 8 */
+  VNL_KT_DESC_ADR,      /* u16 [nv+1] CSR over the descendant lists */
+  VNL_KT_DESC_SRC,      /* u16 [sum of dof depths] entry madr[k] + a of descendant k (a = depth(k) - depth(row)), k descending */
+  VNL_KT_DESC_K,        /* u8  [sum of dof depths] the descendant dof k */
+  VNL_KT_DDOF,          /* u8  [dofs of depth >= 1] dofs grouped by depth (L^-1 sweep: gather from the ancestors) */
+  VNL_KT_DLVL,          /* u16 [maxdepth+1] first DDOF index of depths 1.. | lg2ceil(depth) << 8 */
   VNL_KT_ANC_START,     /* u16 [nM] madr[mcol[e]]: row start of the entry's column dof */
   VNL_KT_KITEM,         /* u16 [sum of dof depths] c | dof << 8, grouped by dof depth, descending c inside a group */
   VNL_KT_KLVL,          /* u16 [maxdepth+2] offsets into KITEM by dof depth */
@@ -195,7 +204,7 @@ enum VnlKtab {
   VNL_KT_PROG_D,        /* u32 [TD*32*env_warps] */
   VNL_KT_COUNT
 };
-enum VnlKtabScalar { VNL_KS_TA = 0, VNL_KS_TD, VNL_KS_NDSLOT, VNL_KS_RESERVED, VNL_KT_NSCALAR };
+enum VnlKtabScalar { VNL_KS_TA = 0, VNL_KS_TD, VNL_KS_NDSLOT, VNL_KS_NHEIGHT /* largest dof height */, VNL_KT_NSCALAR };
 
 /* scalar header slots of a TASK blob (imitation task: clip + index tables) */
 enum VnlTaskHdr {
@@ -313,6 +322,9 @@ int vnl_unregister_blob(const void* blob_dev);
 /* Dynamic shared memory of one CTA for this model, and the number of envs (one warp each) a CTA holds. */
 int vnl_step_smem_bytes(const void* model_host);
 int vnl_envs_per_cta(const void* model_host);
+/* Envs the persistent grid holds at once on the current device (CTAs x envs per CTA): a batch that is a multiple of
+ * this runs in whole rounds; host layers cut a step into chunks of this size to overlap result copies with compute. */
+int vnl_resident_envs(const void* model_host);
 
 /* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
  * size_t opaque_len)`), operand order documented in INTEGRATION.md. */

@@ -361,6 +361,33 @@ def test_fused_autoreset_equals_wrapper_semantics(gpu_env, rodent):
     assert torch.equal(o2["cur_frame"], o1["cur_frame"]) and torch.equal(o2["sub_clip_frame"], o1["sub_clip_frame"])
 
 
+def test_host_stepper_chunks_equal_one_launch(gpu_env, rodent):
+    """hostio.HostStepper (host buffers, chunked launches, D2H overlapped on a second stream) returns bit-identical
+    results to whole-batch vnl_step_autoreset launches; the chunking is invisible (envs are independent)."""
+    import torch
+    B, K = 300, 12
+    eng = gpu_env.engine
+    qpos, qvel, start = start_states(rodent, B, seed=21)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    acts = torch.tensor(np.random.default_rng(22).uniform(-1, 1, size=(K, B, 30)).astype(np.float32)).pin_memory()
+    stepper = pkg("hostio").HostStepper(gpu_env, s0, autoreset=True, chunk=128)  # 3 ragged chunks
+    assert [b - a for a, b in stepper.chunks] == [128, 128, 44]
+    first, first_obs = dict(s0.pipeline_state), s0.obs
+    st = {k: v.clone() for k, v in first.items()}
+    st["cur_frame"], st["sub_clip_frame"] = s0.info["cur_frame"].clone(), s0.info["sub_clip_frame"].clone()
+    nxt, out = eng.alloc_state(B), eng.alloc_outputs(B)
+    for i in range(K):  # crosses sub_clip_length = 10, so the AutoReset restore is exercised
+        host = stepper.step(acts[i])
+        eng.step_autoreset(st, acts[i].cuda(), nxt, out, first, first_obs)
+        torch.cuda.synchronize()
+        for k in ("obs", "traj", "reward", "done"):
+            assert torch.equal(host[k], out[k].cpu()), (i, k)
+        st, nxt = nxt, st
+    for k in STATE_KEYS + ("cur_frame", "sub_clip_frame"):
+        assert torch.equal(stepper.state[k], st[k]), k
+    assert float(host["done"].min()) == 1.0  # Q7: every env is past its sub-clip by now
+
+
 def test_rodent_pair_physics_matches_oracle(oracle_mod):
     """BASELINE configs[4] model: rodent_pair.xml (<replicate count=2>: 131 bodies, nv 146, 114 contacts, nefc 590, two
     kinematic trees).  Physics only (the reference has no env for it): per-stage arrays and one pipeline step vs the oracle."""

@@ -29,7 +29,8 @@ class VnlOutputs(ctypes.Structure):
 
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
-           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta")
+           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta",
+           "vnl_resident_envs")
 
 
 def load_library() -> ctypes.CDLL:
@@ -42,6 +43,7 @@ def load_library() -> ctypes.CDLL:
     lib.vnl_dump_size.argtypes = [ctypes.c_void_p]
     lib.vnl_step_smem_bytes.argtypes = [ctypes.c_void_p]
     lib.vnl_envs_per_cta.argtypes = [ctypes.c_void_p]
+    lib.vnl_resident_envs.argtypes = [ctypes.c_void_p]
     lib.vnl_check_model.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_check_task.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_register_blob.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -100,6 +102,8 @@ class Engine:
         self.dump_size = int(self.lib.vnl_dump_size(self.model_host.ctypes.data))
         self.smem_bytes = int(self.lib.vnl_step_smem_bytes(self.model_host.ctypes.data))
         self.envs_per_cta = int(self.lib.vnl_envs_per_cta(self.model_host.ctypes.data))
+        with torch.cuda.device(self.device):
+            self.resident_envs = int(self.lib.vnl_resident_envs(self.model_host.ctypes.data))
         if self.task_host is not None:
             self.obs_size = int(self.task_host[mb.C["VNL_TH_OBS_SIZE"]])
             self.traj_size = int(self.task_host[mb.C["VNL_TH_TRAJ_SIZE"]])

@@ -136,6 +136,13 @@ int vnl_envs_per_cta(const void* model_host) {
   return vnl::any_launch_info(d, 1 << 20).warps_per_cta;
 }
 
+int vnl_resident_envs(const void* model_host) {
+  vnl::Dims d;
+  fill_dims((const uint32_t*)model_host, d);
+  const vnl::LaunchInfo li = vnl::any_launch_info(d, 1 << 20);
+  return li.ctas * li.warps_per_cta;
+}
+
 size_t vnl_dump_size(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);

@@ -97,8 +97,8 @@ struct __align__(16) Cta {
   const uint32_t* mb;
   uint32_t foff[VNL_F_MODEL_COUNT];
   uint32_t o_lvl_start, o_lvl_bp, o_parent, o_child_adr, o_child_list, o_body_dofadr, o_body_dofnum, o_body_tree, o_lastdof, o_sub_end,
-      o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_apart_adr, o_madr, o_tri, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
-  int TA, TD, ndslot, lockstep;
+      o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_apart_adr, o_madr, o_erow, o_elvl, o_desc_adr, o_desc_src, o_desc_k, o_ddof, o_dlvl, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
+  int TA, TD, ndslot, nheight, lockstep;
   long long* prof;
   int prof_env;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
@@ -188,7 +188,6 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   float* const F = s + c.L.K;
   const uint16_t* const madr = TB16(madr);
   const uint16_t* const anc_start = TB16(anc_start);
-  const uint16_t* const tri = TB16(tri);
   const uint8_t* const mrow = TB8(mrow);
   const uint8_t* const mcol = TB8(mcol);
   {
@@ -202,59 +201,67 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
     if (tid == 0) F[nM] = 0.0f;
   }
   env_sync();
-  // eliminate dofs from the leaves: for 1 <= a <= cc <= dk:  F[anc_a(k)][cc - a] -= F[k][a] * F[k][cc] / F[k][0]
-  // (rows stay un-normalised until the end).  Row k is read-only during its own elimination: it sits in registers
-  // (lane l holds entries l and l + 32, plus the same scaled by 1 / pivot) and the (a, cc) operands of each update come
-  // from shuffles, so the only memory dependence left is on the distinct targets.  The (a, cc) pair list of every k is
-  // a prefix of the universal triangular table TRI (padded by 64 entries, so tails need no bounds select).
-  for (int k = nv - 1; k > 0; --k) {
-    const int base = madr[k], dk = madr[k + 1] - base - 1;
-    if (dk > 0) {
-      const float inv = 1.0f / F[base];
-      const int np = (dk * (dk + 1)) >> 1;
-      const float r0 = (lane <= dk) ? F[base + lane] : 0.0f;
-      const float u0 = r0 * inv;
-      const uint16_t* const ak = anc_start + base;
-      if (dk < 32) {
-        for (int q0 = 0; q0 < np; q0 += 2 * kEnvThreads) {  // uniform trip count: every lane takes part in the shuffles
-          const int p0 = q0 + tid;
-          const uint32_t ta = tri[p0], tb = tri[p0 + kEnvThreads];
-          const int aa = ta & 255, ca = ta >> 8, ab = tb & 255, cb = tb >> 8;
-          const float xa = __shfl_sync(FULLMASK, u0, aa), ya = __shfl_sync(FULLMASK, r0, ca);
-          const float xb = __shfl_sync(FULLMASK, u0, ab), yb = __shfl_sync(FULLMASK, r0, cb);
-          const bool oka = p0 < np, okb = p0 + kEnvThreads < np;
-          float* const tga = F + (oka ? ak[aa] + ca - aa : 0);
-          float* const tgb = F + (okb ? ak[ab] + cb - ab : 0);
-          const float fa = *tga, fb = *tgb;
-          if (oka) *tga = fa - xa * ya;
-          if (okb) *tgb = fb - xb * yb;
-        }
-      } else {
-        const float r1 = (lane + 32 <= dk) ? F[base + lane + 32] : 0.0f;
-        const float u1 = r1 * inv;
-        for (int q0 = 0; q0 < np; q0 += kEnvThreads) {
-          const int p0 = q0 + tid;
-          const uint32_t ta = tri[p0];
-          const int aa = ta & 255, ca = ta >> 8;
-          const float x0 = __shfl_sync(FULLMASK, u0, aa), x1 = __shfl_sync(FULLMASK, u1, aa);
-          const float y0 = __shfl_sync(FULLMASK, r0, ca), y1 = __shfl_sync(FULLMASK, r1, ca);
-          if (p0 < np) {
-            float* const tga = F + (ak[aa] + ca - aa);
-            *tga -= (aa >= 32 ? x1 : x0) * (ca >= 32 ? y1 : y0);
+  // Left-looking elimination by dof height, in Cholesky form.  A final row k holds C[k][a] = F[k][a] / sqrt(D_k)
+  // (a >= 1) and 1 / sqrt(D_k) in its diagonal slot, so that row j (entries c = 0 .. dj) receives from every descendant
+  // k at distance a just  F[j][c] -= C[k][a] * C[k][a + c].  Rows of one height are independent: one barrier per
+  // level.  Inside a row the lanes are (group g, column c): the groups share out the descendants and are summed by
+  // shuffles; the accumulation stays in registers, so no load ever waits on a store and the loop pipelines.
+  const uint2* const erow = reinterpret_cast<const uint2*>(TB32(erow));
+  const uint16_t* const elvl = TB16(elvl);
+  const uint16_t* const dsrc = TB16(desc_src);
+  {
+    int r0 = elvl[0] & 255;
+    for (int h = 0; h <= c.nheight; ++h) {
+      const int r1 = elvl[h + 1] & 255;
+      for (int r = r0 + EWARP; r < r1; r += kEnvWarps) {  // rows of the level are dealt to the env's warps
+        const uint2 w = erow[r];
+        const int base = w.x & 0x1fff, n = ((w.x >> 13) & 63) + 1, lg = (w.x >> 19) & 7;
+        const int d1 = w.y >> 16;
+        float* const Fb = F + base;
+        if (n <= 32) {
+          const int cc = lane & ((1 << lg) - 1), g = lane >> lg, G = 32 >> lg;
+          const bool own = (g == 0) && (cc < n);
+          const float* const Fc = F + (cc < n ? cc : 0);
+          float acc = own ? Fb[cc] : 0.0f, accb = 0.0f;
+          int t = (w.y & 0xffff) + g;
+          for (; t + 3 * G < d1; t += 4 * G) {
+            const int s0 = dsrc[t], s1 = dsrc[t + G], s2 = dsrc[t + 2 * G], s3 = dsrc[t + 3 * G];
+            const float u0 = F[s0], u1 = F[s1], u2 = F[s2], u3 = F[s3];
+            const float v0 = Fc[s0], v1 = Fc[s1], v2 = Fc[s2], v3 = Fc[s3];
+            acc = fmaf(-u0, v0, acc); accb = fmaf(-u1, v1, accb); acc = fmaf(-u2, v2, acc); accb = fmaf(-u3, v3, accb);
           }
+          for (; t < d1; t += G) { const int s0 = dsrc[t]; acc = fmaf(-F[s0], Fc[s0], acc); }
+          acc += accb;
+          for (int o = 1 << lg; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+          const float rs = rsqrtf(__shfl_sync(FULLMASK, acc, 0));
+          if (own) Fb[cc] = cc == 0 ? rs : acc * rs;
+        } else {  // rows longer than a warp: lane owns columns lane and lane + 32 (few descendants down there)
+          const bool on2 = lane + 32 < n;
+          const int c1 = on2 ? lane + 32 : 0;
+          float acc = Fb[lane], acc2 = on2 ? Fb[c1] : 0.0f;
+          for (int t = w.y & 0xffff; t < d1; ++t) {
+            const int s0 = dsrc[t];
+            const float u = F[s0];
+            acc = fmaf(-u, F[s0 + lane], acc);
+            acc2 = fmaf(-u, F[s0 + c1], acc2);
+          }
+          const float rs = rsqrtf(__shfl_sync(FULLMASK, acc, 0));
+          Fb[lane] = lane == 0 ? rs : acc * rs;
+          if (on2) Fb[c1] = acc2 * rs;
         }
       }
+      r0 = r1;
+      env_sync();
     }
-    env_sync();
   }
   pf.mark(16);
-  // normalise rows: Lhat = L / diag, then 1 / D in the diagonal slots
+  // normalise rows: Lhat = C / sqrt(D), then 1 / D in the diagonal slots (they hold 1 / sqrt(D))
   for (int e = tid; e < nM; e += kEnvThreads) {
     const int b0 = madr[mrow[e]];
-    if (e != b0) F[e] = F[e] / F[b0];
+    if (e != b0) F[e] = F[e] * F[b0];
   }
   env_sync();
-  for (int i = tid; i < nv; i += kEnvThreads) { const int m0 = madr[i]; F[m0] = 1.0f / F[m0]; }
+  for (int i = tid; i < nv; i += kEnvThreads) { const int m0 = madr[i]; const float rs = F[m0]; F[m0] = rs * rs; }
   env_sync();
   pf.mark(17);
   if (!invert) return;  // the caller solves by substitution (one right-hand side only)
@@ -329,8 +336,9 @@ __device__ __noinline__ void solve_m(int so, int xo, int outo) {
 
 // out <- (L^T D L)^-1 x by substitution with the NON-inverted factor (Lhat off-diagonals, 1 / D in the diagonal slots):
 // used where a factorisation serves a single right-hand side (the implicit-damping solve of forward.euler), which
-// is cheaper than inverting the factor first.  mj_solveLD order: L^-T (dofs descending, scatter to the ancestors),
-// D^-1, L^-1 (dofs ascending, gather from the ancestors).
+// is cheaper than inverting the factor first.  mj_solveLD order: L^-T, D^-1, L^-1 -- both sweeps in gather form and
+// level scheduled: L^-T by dof height (t[j] -= sum over descendants k of Lhat[k][a] t[k]), L^-1 by dof depth
+// (t[i] -= sum over ancestors).  A level packs 32 >> lg rows per warp, each row on a 2^lg-lane segment.
 __device__ __noinline__ void solve_ld(int so, int xo, int outo) {
   VNL_SMEM
   const int nv = c.d.nv, lane = LANE, tid = ETID;
@@ -341,23 +349,60 @@ __device__ __noinline__ void solve_ld(int so, int xo, int outo) {
   const uint8_t* const mcol = TB8(mcol);
   for (int i = tid; i < nv; i += kEnvThreads) t[i] = x[i];
   env_sync();
-  for (int i = nv - 1; i > 0; --i) {
-    const int base = madr[i], di = madr[i + 1] - base - 1;
-    const float ti = t[i];
-    for (int a = 1 + tid; a <= di; a += kEnvThreads) t[mcol[base + a]] -= F[base + a] * ti;
-    env_sync();
+  {
+    const uint2* const erow = reinterpret_cast<const uint2*>(TB32(erow));
+    const uint16_t* const elvl = TB16(elvl);
+    const uint16_t* const dsrc = TB16(desc_src);
+    const uint8_t* const dkk = TB8(desc_k);
+    uint32_t lw = elvl[1];  // height 0 (leaves) has nothing to gather
+    for (int h = 1; h <= c.nheight; ++h) {
+      const uint32_t lw1 = elvl[h + 1];
+      const int r0 = lw & 255, r1 = lw1 & 255, lg = lw >> 8;
+      const int sl = lane & ((1 << lg) - 1), per = 32 >> lg, W = 1 << lg;
+      for (int rs = r0 + EWARP * per; rs < r1; rs += per * kEnvWarps) {
+        const int r = rs + (lane >> lg);
+        float acc = 0.0f;
+        int j = 0;
+        if (r < r1) {
+          const uint2 w = erow[r];
+          j = w.x >> 22;
+          const int d1 = w.y >> 16;
+          for (int q = (w.y & 0xffff) + sl; q < d1; q += W) acc += F[dsrc[q]] * t[dkk[q]];
+        }
+        for (int o = W >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+        if (r < r1 && sl == 0) t[j] -= acc;
+      }
+      lw = lw1;
+      env_sync();
+    }
   }
   for (int i = tid; i < nv; i += kEnvThreads) t[i] *= F[madr[i]];
   env_sync();
-  float* const out = s + outo;
-  for (int i = 1; i < nv; ++i) {
-    const int base = madr[i], di = madr[i + 1] - base - 1;
-    float acc = 0.0f;
-    for (int a = 1 + lane; a <= di; a += 32) acc += F[base + a] * t[mcol[base + a]];
-    acc = warp_sum(acc);  // every warp reduces the whole row: same value in each
-    if (tid == 0) t[i] -= acc;
-    env_sync();
+  {
+    const uint8_t* const ddof = TB8(ddof);
+    const uint16_t* const dlvl = TB16(dlvl);
+    uint32_t lw = dlvl[0];
+    for (int dl = 1; dl <= c.d.maxdepth; ++dl) {
+      const uint32_t lw1 = dlvl[dl];
+      const int r0 = lw & 255, r1 = lw1 & 255, lg = lw >> 8;
+      const int sl = lane & ((1 << lg) - 1), per = 32 >> lg, W = 1 << lg;
+      for (int rs = r0 + EWARP * per; rs < r1; rs += per * kEnvWarps) {
+        const int r = rs + (lane >> lg);
+        float acc = 0.0f;
+        int i = 0;
+        if (r < r1) {
+          i = ddof[r];
+          const int base = madr[i];
+          for (int a = 1 + sl; a <= dl; a += W) acc += F[base + a] * t[mcol[base + a]];
+        }
+        for (int o = W >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
+        if (r < r1 && sl == 0) t[i] -= acc;
+      }
+      lw = lw1;
+      env_sync();
+    }
   }
+  float* const out = s + outo;
   for (int i = tid; i < nv; i += kEnvThreads) out[i] = t[i];
   env_sync();
 }
@@ -1551,11 +1596,13 @@ __global__ void __launch_bounds__(kMaxEnvs * kEnvThreads, 1) vnl_env_kernel(Para
     TOFF(child_list, VNL_KT_CHILD_LIST); TOFF(body_dofadr, VNL_KT_BODY_DOFADR); TOFF(body_dofnum, VNL_KT_BODY_DOFNUM);
     TOFF(body_tree, VNL_KT_BODY_TREE); TOFF(lastdof, VNL_KT_BODY_LASTDOF); TOFF(sub_end, VNL_KT_SUB_END); TOFF(roots, VNL_KT_ROOTS);
     TOFF(mrow, VNL_KT_MROW); TOFF(mcol, VNL_KT_MCOL); TOFF(dof_body, VNL_KT_DOF_BODY); TOFF(dpart_adr, VNL_KT_DPART_ADR); TOFF(apart_adr, VNL_KT_APART_ADR);
-    TOFF(madr, VNL_KT_MADR); TOFF(tri, VNL_KT_TRI); TOFF(anc_start, VNL_KT_ANC_START); TOFF(kitem, VNL_KT_KITEM);
+    TOFF(madr, VNL_KT_MADR); TOFF(erow, VNL_KT_EROW); TOFF(elvl, VNL_KT_ELVL); TOFF(desc_adr, VNL_KT_DESC_ADR); TOFF(desc_src, VNL_KT_DESC_SRC);
+    TOFF(desc_k, VNL_KT_DESC_K); TOFF(ddof, VNL_KT_DDOF); TOFF(dlvl, VNL_KT_DLVL); TOFF(anc_start, VNL_KT_ANC_START); TOFF(kitem, VNL_KT_KITEM);
     TOFF(klvl, VNL_KT_KLVL); TOFF(prog_a, VNL_KT_PROG_A); TOFF(prog_d, VNL_KT_PROG_D);
 #undef TOFF
     c.TA = (int)g_ktab[VNL_KT_COUNT + VNL_KS_TA]; c.TD = (int)g_ktab[VNL_KT_COUNT + VNL_KS_TD];
     c.ndslot = (int)g_ktab[VNL_KT_COUNT + VNL_KS_NDSLOT];
+    c.nheight = (int)g_ktab[VNL_KT_COUNT + VNL_KS_NHEIGHT];
   }
   __syncthreads();
   const int W = nt / kEnvThreads, warp = tid / kEnvThreads;  // env slots of this CTA, this thread's slot
@@ -1593,7 +1640,7 @@ LaunchInfo launch_info(const Dims& d, int B) {
   // whole round (a warp sharing the SM with more neighbours runs each env slower), so take the fewest rounds and, on a
   // tie, the fewest warps.
   long best_rounds = -1;
-  for (int W = wmax; W >= 1 && W >= wmax - 2; --W) {
+  for (int W = wmax; W >= 1 && (env_w > 0 || W >= wmax - 2); --W) {
     if (env_w > 0 && W != (env_w < wmax ? env_w : wmax)) continue;
     const int smem = fixed + W * per;
     int resident = (227 * 1024) / (smem + 1024);

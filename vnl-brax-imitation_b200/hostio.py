@@ -1,0 +1,72 @@
+"""Stepping an env whose consumer lives on the HOST (numpy policy, logger, another framework).
+
+`HostStepper.step(host_action)` is the host-buffer form of `env.step`: actions come from pinned host memory, obs /
+traj / reward / done land in pinned host memory, and the call returns when they are there.  The batch is cut into
+chunks of `Engine.resident_envs` (one full wave of the persistent grid each); the device-to-host copy of chunk k runs
+on a second stream while chunk k + 1 computes, so only the last chunk's copy is exposed.  The episode handling is
+brax's AutoResetWrapper as installed by the reference (`ppo_imitation/train.py:204-214`), fused into the launch
+(`vnl_step_autoreset`); the device state ping-pongs between two preallocated buffers, nothing is allocated per step.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+from ._lib import STATE_F, STATE_I
+
+HOST_FIELDS = ("obs", "traj", "reward", "done")
+
+
+class HostStepper:
+    def __init__(self, env, state0, autoreset: bool = True, chunk: int = 0):
+        import torch
+
+        self.torch, self.env, self.eng = torch, env, env.engine
+        eng = self.eng
+        ps = state0.pipeline_state
+        self.B = B = ps["qpos"].shape[0]
+        self.first = {k: ps[k].clone() for k in STATE_F}
+        self.first_obs = state0.obs.clone()
+        self.autoreset = autoreset
+        cur = {k: ps[k].clone() for k in STATE_F}
+        cur["cur_frame"] = state0.info["cur_frame"].clone()
+        cur["sub_clip_frame"] = state0.info["sub_clip_frame"].clone()
+        self.bufs = [cur, eng.alloc_state(B)]
+        self.out = eng.alloc_outputs(B)
+        self.d_action = torch.empty(B, env.action_size, dtype=torch.float32, device=eng.device)
+        self.host = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in HOST_FIELDS}
+        self.copy_stream = torch.cuda.Stream(device=eng.device)
+        C = int(chunk) if chunk > 0 else max(1, min(B, eng.resident_envs))
+        self.chunks = [(a, min(a + C, B)) for a in range(0, B, C)]
+        self.events = [torch.cuda.Event() for _ in self.chunks]
+        cut = lambda d, a, b: {k: v[a:b] for k, v in d.items() if v is not None}
+        # contiguous leading-dim views of every buffer, cut once
+        self.views = [dict(bufs=[cut(self.bufs[0], a, b), cut(self.bufs[1], a, b)], out=cut(self.out, a, b),
+                           first=cut(self.first, a, b), first_obs=self.first_obs[a:b], action=self.d_action[a:b],
+                           host={k: self.host[k][a:b] for k in HOST_FIELDS}) for a, b in self.chunks]
+        self.flip = 0
+        self.h2d_bytes = self.d_action.numel() * 4
+        self.d2h_bytes = sum(self.host[k].numel() * 4 for k in HOST_FIELDS)
+
+    @property
+    def state(self) -> Dict:
+        """The current device state (pipeline-state leaves + frame counters)."""
+        return self.bufs[self.flip]
+
+    def step(self, host_action) -> Dict:
+        torch, eng = self.torch, self.eng
+        main = torch.cuda.current_stream(eng.device)
+        self.d_action.copy_(host_action, non_blocking=True)
+        src, dst = self.flip, 1 - self.flip
+        for v, ev in zip(self.views, self.events):
+            if self.autoreset:
+                eng.step_autoreset(v["bufs"][src], v["action"], v["bufs"][dst], v["out"], v["first"], v["first_obs"])
+            else:
+                eng.step(v["bufs"][src], v["action"], v["bufs"][dst], v["out"])
+            ev.record(main)
+            with torch.cuda.stream(self.copy_stream):
+                self.copy_stream.wait_event(ev)
+                for k in HOST_FIELDS:
+                    v["host"][k].copy_(v["out"][k], non_blocking=True)
+        self.flip = dst
+        self.copy_stream.synchronize()  # the host consumer needs this step's result before it can pick the next action
+        return self.host

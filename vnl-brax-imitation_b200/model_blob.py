@@ -213,7 +213,39 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
     prog_d, TD = pack_program(rows_d) if rows_d else (np.full(4 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
     ndslot = len(rows_d)
-    tri = [(a | (c << 8)) for c in range(1, maxd + 1) for a in range(1, c + 1)] + [1 | (1 << 8)] * 256  # padded tail (two pairs per thread past the end)
+    # Level schedules of the factorisation and of the triangular solves (see VnlKtab): rows by dof HEIGHT (leaves = 0),
+    # each row with the list of its descendant dofs; dofs by DEPTH for the gather-from-ancestors sweep.
+    lg2c = lambda n: 0 if n <= 1 else min(5, int(np.ceil(np.log2(n))))
+    dpar = [int(mcol[madr[i] + 1]) if ddepth[i] > 0 else -1 for i in range(nv)]
+    desc_of = [[] for _ in range(nv)]
+    height = [0] * nv
+    for k in range(nv - 1, -1, -1):
+        j, a = dpar[k], 1
+        while j >= 0:
+            desc_of[j].append((k, a))  # k descending inside each list: the order a right-looking elimination visits
+            j, a = dpar[j], a + 1
+        if dpar[k] >= 0:
+            height[dpar[k]] = max(height[dpar[k]], height[k] + 1)
+    maxh = max(height) if nv else 0
+    erow, elvl, desc_adr, desc_src, desc_k = [], [], [0], [], []
+    for j in range(nv):
+        for k, a in desc_of[j]:
+            desc_src.append(madr[k] + a)
+            desc_k.append(k)
+        desc_adr.append(len(desc_src))
+    if nM_ >= (1 << 13) or len(desc_src) >= (1 << 16):
+        raise NotImplementedError("model too large for the packed factorisation schedule")
+    for h in range(0, maxh + 1):
+        rows = sorted([j for j in range(nv) if height[j] == h], reverse=True)
+        elvl.append(len(erow) // 2 | (lg2c(max(len(desc_of[j]) for j in rows)) << 8))
+        for j in rows:  # two words per row: entry base | (row length - 1) << 13 | lg2ceil(row length) << 19 | dof << 22; desc range
+            erow += [madr[j] | (int(ddepth[j]) << 13) | (lg2c(ddepth[j] + 1) << 19) | (j << 22), desc_adr[j] | (desc_adr[j + 1] << 16)]
+    elvl.append(len(erow) // 2)
+    ddof, dlvl = [], []
+    for dpt in range(1, maxd + 1):
+        dlvl.append(len(ddof) | (lg2c(dpt) << 8))
+        ddof += [i for i in range(nv) if ddepth[i] == dpt]
+    dlvl.append(len(ddof))
     kitem, klvl = [], [0, 0]
     for dpt in range(1, maxd + 1):
         items = [(c, i) for i in range(nv) if ddepth[i] == dpt for c in range(1, dpt + 1)]
@@ -241,25 +273,33 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
     kt[C["VNL_KT_DPART_ADR"]] = u8(dpart_adr)
     kt[C["VNL_KT_APART_ADR"]] = u8(apart_adr)
     kt[C["VNL_KT_MADR"]] = u16(madr)
-    kt[C["VNL_KT_TRI"]] = u16(tri)
+    kt[C["VNL_KT_EROW"]] = np.asarray(erow, dtype=np.int64).astype(np.uint32)
+    kt[C["VNL_KT_ELVL"]] = u16(elvl)
+    kt[C["VNL_KT_DESC_ADR"]] = u16(desc_adr)
+    kt[C["VNL_KT_DESC_SRC"]] = u16(desc_src)
+    kt[C["VNL_KT_DESC_K"]] = u8(desc_k)
+    kt[C["VNL_KT_DDOF"]] = u8(ddof)
+    kt[C["VNL_KT_DLVL"]] = u16(dlvl)
     kt[C["VNL_KT_ANC_START"]] = u16([madr[j] for j in mcol])
     kt[C["VNL_KT_KITEM"]] = u16(kitem)
     kt[C["VNL_KT_KLVL"]] = u16(klvl)
     kt[C["VNL_KT_PROG_A"]] = prog_a
     kt[C["VNL_KT_PROG_D"]] = prog_d
     nkt, nks = C["VNL_KT_COUNT"], C["VNL_KT_NSCALAR"]
-    off = 4 * (nkt + nks)
-    dirw = np.zeros(nkt + nks, dtype=np.uint32)
+    ndir = (nkt + nks + 1) // 2 * 2  # directory padded to an even word count: tables start 8-byte aligned
+    off = 4 * ndir
+    dirw = np.zeros(ndir, dtype=np.uint32)
     blobs = []
     for t, a in enumerate(kt):
         raw = a.tobytes()
-        raw += b"\0" * ((-len(raw)) % 4)
+        raw += b"\0" * ((-len(raw)) % 8)  # every table 8-byte aligned (EROW is read as 64-bit words)
         dirw[t] = off
         off += len(raw)
         blobs.append(raw)
     dirw[nkt + C["VNL_KS_TA"]] = TA
     dirw[nkt + C["VNL_KS_TD"]] = TD
     dirw[nkt + C["VNL_KS_NDSLOT"]] = ndslot
+    dirw[nkt + C["VNL_KS_NHEIGHT"]] = maxh
     ktab = np.frombuffer(dirw.tobytes() + b"".join(blobs), dtype=np.uint32).copy()
     act_of_dof = [[] for _ in range(nv)]
     for u, dadr in enumerate(A["actuator_dofadr"]):
