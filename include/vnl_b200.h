@@ -71,6 +71,8 @@ enum VnlModelHdr {
   VNL_MH_NDSLOT,      /* partial-sum slots of the descendant mat-vec program (= KTAB scalar VNL_KS_NDSLOT) */
   VNL_MH_ENV_WARPS,   /* warps cooperating on one env (1 or 2): the mat-vec lane programs have 32 * this many lanes */
   VNL_MH_NASLOT,      /* partial-sum slots of the ancestor mat-vec program */
+  VNL_MH_TA,          /* steps of the ancestor / descendant mat-vec programs (= KTAB scalars VNL_KS_TA / VNL_KS_TD) */
+  VNL_MH_TD,
   /* floats (bit patterns) */
   VNL_MH_TIMESTEP = 32, VNL_MH_GRAVITY_X, VNL_MH_GRAVITY_Y, VNL_MH_GRAVITY_Z,
   VNL_MH_TOLERANCE, VNL_MH_LS_TOLERANCE, VNL_MH_IMPRATIO, VNL_MH_MEANINERTIA
@@ -325,6 +327,13 @@ int vnl_envs_per_cta(const void* model_host);
 /* Envs the persistent grid holds at once on the current device (CTAs x envs per CTA): a batch that is a multiple of
  * this runs in whole rounds; host layers cut a step into chunks of this size to overlap result copies with compute. */
 int vnl_resident_envs(const void* model_host);
+
+/* Device workspace of the step kernels: the joint-space inertia of every RESIDENT env lives in global memory (L2),
+ * laid out in the order the mat-vec lane programs consume it, which is what lets ten rodent envs share an SM.
+ * The caller allocates vnl_workspace_bytes() bytes on the device once and binds them to the (registered) model blob;
+ * one workspace serves one stream at a time.  Every step / reset / pipeline call fails with -20 without it. */
+size_t vnl_workspace_bytes(const void* model_host);
+int vnl_set_workspace(const void* model_dev, void* workspace_dev, size_t nbytes);
 
 /* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
  * size_t opaque_len)`), operand order documented in INTEGRATION.md. */

@@ -30,7 +30,7 @@ class VnlOutputs(ctypes.Structure):
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
            "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta",
-           "vnl_resident_envs")
+           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace")
 
 
 def load_library() -> ctypes.CDLL:
@@ -44,6 +44,9 @@ def load_library() -> ctypes.CDLL:
     lib.vnl_step_smem_bytes.argtypes = [ctypes.c_void_p]
     lib.vnl_envs_per_cta.argtypes = [ctypes.c_void_p]
     lib.vnl_resident_envs.argtypes = [ctypes.c_void_p]
+    lib.vnl_workspace_bytes.restype = ctypes.c_size_t
+    lib.vnl_workspace_bytes.argtypes = [ctypes.c_void_p]
+    lib.vnl_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_check_model.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_check_task.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     lib.vnl_register_blob.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
@@ -104,6 +107,12 @@ class Engine:
         self.envs_per_cta = int(self.lib.vnl_envs_per_cta(self.model_host.ctypes.data))
         with torch.cuda.device(self.device):
             self.resident_envs = int(self.lib.vnl_resident_envs(self.model_host.ctypes.data))
+            nbytes = int(self.lib.vnl_workspace_bytes(self.model_host.ctypes.data))
+        # inertia workspace of the resident envs (L2-resident scratch the kernels address by CTA / env slot)
+        self.workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=self.device)
+        rc = self.lib.vnl_set_workspace(self.model_dev.data_ptr(), self.workspace.data_ptr(), self.workspace.numel() * 4)
+        if rc:
+            raise RuntimeError(f"vnl_set_workspace failed ({rc})")
         if self.task_host is not None:
             self.obs_size = int(self.task_host[mb.C["VNL_TH_OBS_SIZE"]])
             self.traj_size = int(self.task_host[mb.C["VNL_TH_TRAJ_SIZE"]])

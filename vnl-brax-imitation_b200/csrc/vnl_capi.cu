@@ -19,6 +19,8 @@ namespace {
 struct Header { uint32_t w[VNL_DATA_OFF]; };  // scalar header + field table
 std::mutex g_mu;
 std::unordered_map<const void*, Header> g_headers;  // device blob pointer -> host copy of its scalar header
+struct Work { float* p; size_t bytes; };
+std::unordered_map<const void*, Work> g_work;        // device model blob pointer -> bound inertia workspace
 
 bool lookup(const void* dev, Header& h) {
   std::lock_guard<std::mutex> lk(g_mu);
@@ -33,7 +35,7 @@ void fill_dims(const uint32_t* w, vnl::Dims& d) {
   d.nbody = vnl_hdr_i(w, VNL_MH_NBODY); d.njnt = vnl_hdr_i(w, VNL_MH_NJNT); d.ngeom = vnl_hdr_i(w, VNL_MH_NGEOM);
   d.npair = vnl_hdr_i(w, VNL_MH_NPAIR); d.ncon = vnl_hdr_i(w, VNL_MH_NCON); d.nlimit = vnl_hdr_i(w, VNL_MH_NLIMIT);
   d.nefc = vnl_hdr_i(w, VNL_MH_NEFC); d.nM = vnl_hdr_i(w, VNL_MH_NM); d.nlevel = vnl_hdr_i(w, VNL_MH_NLEVEL);
-  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.nroot = vnl_hdr_i(w, VNL_MH_NROOT); d.ndslot = vnl_hdr_i(w, VNL_MH_NDSLOT); d.env_warps = vnl_hdr_i(w, VNL_MH_ENV_WARPS); d.naslot = vnl_hdr_i(w, VNL_MH_NASLOT); d.ktab_words = (int)w[VNL_TABLE_OFF + 2 * VNL_F_KTAB + 1];
+  d.maxdepth = vnl_hdr_i(w, VNL_MH_MAXDEPTH); d.nroot = vnl_hdr_i(w, VNL_MH_NROOT); d.ndslot = vnl_hdr_i(w, VNL_MH_NDSLOT); d.env_warps = vnl_hdr_i(w, VNL_MH_ENV_WARPS); d.naslot = vnl_hdr_i(w, VNL_MH_NASLOT); d.TA = vnl_hdr_i(w, VNL_MH_TA); d.TD = vnl_hdr_i(w, VNL_MH_TD); d.ktab_words = (int)w[VNL_TABLE_OFF + 2 * VNL_F_KTAB + 1];
   d.solver = vnl_hdr_i(w, VNL_MH_SOLVER); d.iterations = vnl_hdr_i(w, VNL_MH_ITERATIONS);
   d.ls_iterations = vnl_hdr_i(w, VNL_MH_LS_ITERATIONS); d.eulerdamp = vnl_hdr_i(w, VNL_MH_EULERDAMP);
   d.timestep = vnl_hdr_f(w, VNL_MH_TIMESTEP); d.gx = vnl_hdr_f(w, VNL_MH_GRAVITY_X); d.gy = vnl_hdr_f(w, VNL_MH_GRAVITY_Y);
@@ -73,6 +75,15 @@ int prepare(const void* model, const void* task, bool need_task, vnl::Params& p)
   if (!model || !lookup(model, hm)) return -10;
   if (hm.w[0] != VNL_MAGIC_MODEL) return -11;
   fill_dims(hm.w, p.dims);
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_work.find(model);
+    if (it == g_work.end()) return -20;
+    const vnl::LaunchInfo li = vnl::any_launch_info(p.dims, 1 << 20);
+    p.work_stride = vnl::work_stride(p.dims);
+    if ((size_t)li.ctas * li.warps_per_cta * p.work_stride * sizeof(float) > it->second.bytes) return -21;
+    p.work = it->second.p;
+  }
   p.model = (const uint32_t*)model;
   p.task = (const uint32_t*)task;
   if (need_task) {
@@ -121,7 +132,23 @@ int vnl_register_blob(const void* blob_dev, const void* blob_host, size_t nbytes
 
 int vnl_unregister_blob(const void* blob_dev) {
   std::lock_guard<std::mutex> lk(g_mu);
+  g_work.erase(blob_dev);
   return g_headers.erase(blob_dev) ? 0 : -1;
+}
+
+size_t vnl_workspace_bytes(const void* model_host) {
+  vnl::Dims d;
+  fill_dims((const uint32_t*)model_host, d);
+  const vnl::LaunchInfo li = vnl::any_launch_info(d, 1 << 20);
+  return (size_t)li.ctas * li.warps_per_cta * vnl::work_stride(d) * sizeof(float);
+}
+
+int vnl_set_workspace(const void* model_dev, void* workspace_dev, size_t nbytes) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!model_dev || g_headers.find(model_dev) == g_headers.end()) return -1;
+  if (!workspace_dev) { g_work.erase(model_dev); return 0; }
+  g_work[model_dev] = Work{(float*)workspace_dev, nbytes};
+  return 0;
 }
 
 int vnl_step_smem_bytes(const void* model_host) {

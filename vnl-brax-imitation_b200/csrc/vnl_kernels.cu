@@ -25,6 +25,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "../../include/vnl_blob.h"
 #include "vnl_device.cuh"
 #include "vnl_kernels.h"
@@ -40,6 +42,9 @@ namespace VNL_CAT(ew, VNL_EW) {  // one instantiation of everything below per en
 
 constexpr int kEnvWarps = VNL_EW;          // warps cooperating on one env
 constexpr int kEnvThreads = 32 * VNL_EW;   // = lanes of the mat-vec programs (VNL_MH_ENV_WARPS of the blob must agree)
+// envs per CTA upper bound: one-warp groups are bounded by shared memory (10 rodents), two-warp groups by the register
+// file (16 warps x 128 registers) and by the named barriers (1 .. 8 for the groups)
+constexpr int kMaxEnvs = VNL_EW == 1 ? 12 : 8;
 
 #define LANE ((int)(threadIdx.x & 31))
 #define FULLMASK 0xffffffffu
@@ -72,17 +77,23 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   int o = 0;
 #define A(name, n) L.name = o; o += align4(n)
   A(qpos, d.nq); A(qvel, d.nv); A(act, d.na); A(ctrl, d.nu); A(warm, d.nv);
-  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6); A(cvel, d.nbody * 6); A(M, d.nM + 1); A(rcom, d.nroot * 3);
+  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6);
+  // cvel is dead once the contact rows are built (its last reader); Jaref and the limit list are born after that
+  { const int need = align4(d.nefc) + align4(d.nlimit); A(cvel, d.nbody * 6 > need ? d.nbody * 6 : need); }
+  L.Jaref = L.cvel; L.lim_dof = L.cvel + align4(d.nefc);
+  A(Mdiag, d.nv); A(rcom, d.nroot * 3);
   const int ab = o;
-  A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16); A(cacc, (d.nbody > d.nv ? d.nbody : d.nv) * 6);
+  A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16);
   const int a_end = o;
   o = ab;
-  A(K, d.nM + 1); A(efcD, d.nefc); A(Jaref, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
+  A(K, d.nM + 1); A(efcD, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
   if (a_end > o) o = a_end;
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
-  A(lim_dof, d.nlimit); A(limrow_of_dof, d.nv);
+  A(limrow_of_dof, d.nv);
   A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
   A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.naslot + d.ndslot);
+  L.cacc = L.qacc;  // spatial accelerations / crb * cdof live where the solver vectors will be (dead until the solve)
+  if (o - L.qacc < (d.nbody > d.nv ? d.nbody : d.nv) * 6) o = L.qacc + align4((d.nbody > d.nv ? d.nbody : d.nv) * 6);
   A(ints, 16);
 #undef A
   L.total = o;
@@ -98,7 +109,8 @@ struct __align__(16) Cta {
   uint32_t foff[VNL_F_MODEL_COUNT];
   uint32_t o_lvl_start, o_lvl_bp, o_parent, o_child_adr, o_child_list, o_body_dofadr, o_body_dofnum, o_body_tree, o_lastdof, o_sub_end,
       o_roots, o_mrow, o_mcol, o_dof_body, o_dpart_adr, o_apart_adr, o_madr, o_erow, o_elvl, o_desc_adr, o_desc_src, o_desc_k, o_ddof, o_dlvl, o_anc_start, o_kitem, o_klvl, o_prog_a, o_prog_d;
-  int TA, TD, ndslot, nheight, lockstep;
+  int TA, TD, ndslot, nheight, lockstep, work_stride;
+  float* work;
   long long* prof;
   int prof_env;
   __device__ __forceinline__ const int* fi(int f) const { return (const int*)(mb + foff[f]); }
@@ -153,25 +165,99 @@ __device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, 
 #undef VNL_FLUSH
 }
 
+// The joint-space inertia M lives in GLOBAL memory (L2), one copy per mat-vec program, in the order the program's lanes
+// consume it: word (t, lane) of the copy is the V operand of program word (t, lane).  Every thread only ever reads the
+// words it wrote itself, so no fence is needed.  Loads / stores bypass L1 (.cg).
+__device__ __forceinline__ float* slot_work(const Cta& c) {
+  return c.work + (size_t)(blockIdx.x * (blockDim.x / kEnvThreads) + ESLOT) * (size_t)c.work_stride;
+}
+__device__ __forceinline__ void spill_section(const uint32_t* __restrict__ prog, int T, const float* __restrict__ V, float* __restrict__ g) {
+  const char* Vb = reinterpret_cast<const char*>(V);
+  prog += ETID; g += ETID;
+  for (int t = 0; t < T; t += 4) {
+    const uint32_t w0 = prog[t * kEnvThreads], w1 = prog[(t + 1) * kEnvThreads], w2 = prog[(t + 2) * kEnvThreads], w3 = prog[(t + 3) * kEnvThreads];
+    const float v0 = *reinterpret_cast<const float*>(Vb + (w0 & 0x3ffcu)), v1 = *reinterpret_cast<const float*>(Vb + (w1 & 0x3ffcu));
+    const float v2 = *reinterpret_cast<const float*>(Vb + (w2 & 0x3ffcu)), v3 = *reinterpret_cast<const float*>(Vb + (w3 & 0x3ffcu));
+    __stcg(g + t * kEnvThreads, v0); __stcg(g + (t + 1) * kEnvThreads, v1);
+    __stcg(g + (t + 2) * kEnvThreads, v2); __stcg(g + (t + 3) * kEnvThreads, v3);
+  }
+}
+// the inverse of spill_section for the ancestor program (it covers every off-diagonal entry exactly once; padding
+// words point at the zero slot `pad` and are skipped)
+__device__ __forceinline__ void restore_section(const uint32_t* __restrict__ prog, int T, float* __restrict__ V, const float* __restrict__ g, uint32_t pad) {
+  char* Vb = reinterpret_cast<char*>(V);
+  prog += ETID; g += ETID;
+  for (int t = 0; t < T; t += 4) {
+    const uint32_t w0 = prog[t * kEnvThreads] & 0x3ffcu, w1 = prog[(t + 1) * kEnvThreads] & 0x3ffcu;
+    const uint32_t w2 = prog[(t + 2) * kEnvThreads] & 0x3ffcu, w3 = prog[(t + 3) * kEnvThreads] & 0x3ffcu;
+    const float v0 = __ldcg(g + t * kEnvThreads), v1 = __ldcg(g + (t + 1) * kEnvThreads);
+    const float v2 = __ldcg(g + (t + 2) * kEnvThreads), v3 = __ldcg(g + (t + 3) * kEnvThreads);
+    if (w0 != pad) *reinterpret_cast<float*>(Vb + w0) = v0;
+    if (w1 != pad) *reinterpret_cast<float*>(Vb + w1) = v1;
+    if (w2 != pad) *reinterpret_cast<float*>(Vb + w2) = v2;
+    if (w3 != pad) *reinterpret_cast<float*>(Vb + w3) = v3;
+  }
+}
+// spmv_section with the V operands streamed from the workspace copy: eight terms per batch, three batches of V words in
+// flight (L2 latency is several batches long).  Walks the ancestor and the descendant program back to back -- they and
+// their workspace copies are contiguous -- so the stream never drains in between (T = TA + TD, a multiple of 8).  The
+// flush slots of the descendant program are offset by `dslot0`.
+__device__ __forceinline__ void spmv_stream_g(const uint32_t* __restrict__ prog, int T, int TA, const float* __restrict__ g,
+                                              const float* __restrict__ x, float* __restrict__ part, int dslot0) {
+  const char* xb = reinterpret_cast<const char*>(x);
+  prog += ETID; g += ETID;
+  float acc = 0.0f;
+  float q0[8], q1[8], q2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    q0[k] = __ldcg(g + k * kEnvThreads);
+    q1[k] = 8 < T ? __ldcg(g + (8 + k) * kEnvThreads) : 0.0f;
+    q2[k] = 16 < T ? __ldcg(g + (16 + k) * kEnvThreads) : 0.0f;
+  }
+#define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
+#define VNL_BATCH(q, t0)                                                                          \
+  if ((t0) < T) {                                                                                 \
+    float v[8], xv[8];                                                                            \
+    uint32_t w[8];                                                                                \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) { v[k] = q[k]; w[k] = pp[k * kEnvThreads]; }    \
+    if ((t0) + 24 < T) {                                                                          \
+      _Pragma("unroll") for (int k = 0; k < 8; ++k) q[k] = __ldcg(gq + k * kEnvThreads);          \
+    }                                                                                             \
+    pp += 8 * kEnvThreads; gq += 8 * kEnvThreads;                                                 \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) xv[k] = VNL_LDX(w[k]);                          \
+    float* const pt = (t0) >= TA ? part + dslot0 : part;                                          \
+    _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                               \
+      acc += v[k] * xv[k];                                                                        \
+      if (w[k] < 0xff000000u) { pt[w[k] >> 24] = acc; acc = 0.0f; }                               \
+    }                                                                                             \
+  }
+  const uint32_t* pp = prog;                    // running pointers: every access is base + immediate
+  const float* gq = g + 24 * kEnvThreads;
+  for (int t = 0; t < T; t += 24) {
+    VNL_BATCH(q0, t)
+    VNL_BATCH(q1, t + 8)
+    VNL_BATCH(q2, t + 16)
+  }
+#undef VNL_BATCH
+#undef VNL_LDX
+}
+
 // out = M x   (tree-sparse symmetric M: diagonal + strict-ancestor terms + descendant terms)
 __device__ __noinline__ void mul_m(int so, int xo, int outo) {
   VNL_SMEM
   const int nv = c.d.nv, lane = LANE, tid = ETID;
-  float* const M = s + c.L.M;
+  const float* const Mdiag = s + c.L.Mdiag;
   const float* const x = s + xo;
   float* const pa = s + c.L.part;
   float* const pd = pa + c.d.naslot;
-  if (tid == 0) M[c.d.nM] = 0.0f;  // the zero entry padded program terms point at
+  const float* const wk = slot_work(c);
+  spmv_stream_g(TB32(prog_a), c.TA + c.TD, c.TA, wk, x, pa, c.d.naslot);  // PROG_D follows PROG_A in the staged tables
   env_sync();
-  spmv_section(TB32(prog_a), c.TA, M, x, pa);
-  spmv_section(TB32(prog_d), c.TD, M, x, pd);
-  env_sync();
-  const uint16_t* const madr = TB16(madr);
   const uint8_t* const dpa = TB8(dpart_adr);
   const uint8_t* const apa = TB8(apart_adr);
   float* const out = s + outo;
   for (int i = tid; i < nv; i += kEnvThreads) {
-    float acc = M[madr[i]] * x[i];
+    float acc = Mdiag[i] * x[i];
     for (int q = apa[i]; q < apa[i + 1]; ++q) acc += pa[q];
     for (int q = dpa[i]; q < dpa[i + 1]; ++q) acc += pd[q];
     out[i] = acc;
@@ -179,28 +265,25 @@ __device__ __noinline__ void mul_m(int so, int xo, int outo) {
   env_sync();
 }
 
-// L^T D L factorisation of M (+ dt * damping on the diagonal when `damp`) into the K region, then K = L^-1 in place.
+// L^T D L factorisation in place in the K region, then K = L^-1 in place.  `damp` = false: the region already holds M
+// (forward() builds it there); `damp` = true: M + dt * damping is first put back from the workspace copy and Mdiag.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
 __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   VNL_SMEM
   const int nv = c.d.nv, nM = c.d.nM, lane = LANE, tid = ETID, maxdepth = c.d.maxdepth;
-  const float* const M = s + c.L.M;
   float* const F = s + c.L.K;
   const uint16_t* const madr = TB16(madr);
   const uint16_t* const anc_start = TB16(anc_start);
   const uint8_t* const mrow = TB8(mrow);
   const uint8_t* const mcol = TB8(mcol);
-  {
+  if (damp) {
     const float* damping = c.ff(VNL_F_DOF_DAMPING);
     const float dt = c.d.timestep;
-    for (int e = tid; e < nM; e += kEnvThreads) {
-      float v = M[e];
-      if (damp && mcol[e] == mrow[e]) v += dt * damping[mrow[e]];
-      F[e] = v;
-    }
+    restore_section(TB32(prog_a), c.TA, F, slot_work(c), 4u * (uint32_t)nM);
+    for (int i = tid; i < nv; i += kEnvThreads) F[madr[i]] = s[c.L.Mdiag + i] + dt * damping[i];
     if (tid == 0) F[nM] = 0.0f;
+    env_sync();
   }
-  env_sync();
   // Left-looking elimination by dof height, in Cholesky form.  A final row k holds C[k][a] = F[k][a] / sqrt(D_k)
   // (a >= 1) and 1 / sqrt(D_k) in its diagonal slot, so that row j (entries c = 0 .. dj) receives from every descendant
   // k at distance a just  F[j][c] -= C[k][a] * C[k][a + c].  Rows of one height are independent: one barrier per
@@ -873,13 +956,29 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     float* fd = s + L.cacc;  // cacc is dead: reuse as crb * cdof
     for (int i = tid; i < d.nv; i += kEnvThreads) inert_mul(s + L.t16 + 16 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
     env_sync();
+    float* const F = s + L.K;  // built straight into the factorisation's workspace (region A's head is dead by now)
     for (int e = tid; e < d.nM; e += kEnvThreads) {
       const int i = TB8(mrow)[e], j = TB8(mcol)[e];
       float v = dot6(fd + 6 * i, s + L.cdof + 6 * j);
-      if (i == j) v += armature[i];
-      s[L.M + e] = v;
+      if (i == j) { v += armature[i]; s[L.Mdiag + i] = v; }
+      F[e] = v;
     }
+    if (tid == 0) F[d.nM] = 0.0f;  // the zero entry padded program terms point at
     env_sync();
+    if (DUMP) {
+      for (int i = tid; i < d.nv * d.nv; i += kEnvThreads) dump[d.dump_qM + i] = 0.0f;
+      env_sync();
+      for (int q = tid; q < d.nM; q += kEnvThreads) {
+        dump[d.dump_qM + TB8(mrow)[q] * d.nv + TB8(mcol)[q]] = F[q];
+        dump[d.dump_qM + TB8(mcol)[q] * d.nv + TB8(mrow)[q]] = F[q];
+      }
+    }
+    {  // program-ordered copies of M for the solver's mat-vecs and for the integrator's second factorisation
+      float* const wk = slot_work(c);
+      spill_section(TB32(prog_a), c.TA, F, wk);
+      spill_section(TB32(prog_d), c.TD, F, wk + c.TA * kEnvThreads);
+    }
+    if (kEnvWarps > 1) env_sync();  // the factorisation rewrites F: every warp of the env must be done copying
   }
   pf.mark(4);
   if (ls3) __syncthreads();
@@ -896,7 +995,11 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
     if (lane == 0) { ints[0] = 0; ints[1] = 0; }
     for (int i = tid; i < d.nv; i += kEnvThreads) ((int*)(s + L.limrow_of_dof))[i] = -1;
     env_sync();
-    {  // joint limits (constraint._instantiate_limit_slide_hinge)
+    // joint limits (constraint._instantiate_limit_slide_hinge).  Their rows come first, but the list itself is written
+    // AFTER the contact rows: it shares storage with cvel, whose last reader is the contact block -- so the limits are
+    // counted first (WRITE = false), the contacts instantiated, then the limit rows filled in.
+    auto limit_rows = [&](auto write_tag) {
+      constexpr bool WRITE = decltype(write_tag)::value;
       const int* ljnt = c.fi(VNL_F_LIMIT_JNT);
       const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
       const float* range = c.ff(VNL_F_JNT_RANGE);
@@ -919,7 +1022,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
           sign = (dmin < dmax) ? 1.0f : -1.0f;
         }
         const unsigned m = __ballot_sync(FULLMASK, active);
-        if (active) {
+        if (WRITE && active) {
           const int slot = base + __popc(m & ((1u << lane) - 1u));
           const int dof = jdofadr[j];
           ((int*)(s + L.lim_dof))[slot] = sign > 0.0f ? dof : ~dof;
@@ -933,8 +1036,9 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         }
         base += __popc(m);
       }
-      if (lane == 0) ints[0] = base;
-    }
+      if (!WRITE && lane == 0) ints[0] = base;
+    };
+    limit_rows(std::false_type{});
     env_sync();
     {  // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
       const int nl = ints[0];
@@ -1049,6 +1153,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       }
       if (lane == 0) ints[1] = base;
     }
+    env_sync();
+    limit_rows(std::true_type{});
     env_sync();
   }
   pf.mark(7);
@@ -1408,12 +1514,6 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     put(d.dump_xpos, s + L.xpos, d.nbody * 3);
     put(d.dump_xpos + d.nbody * 3, s + L.xquat, d.nbody * 4);
     put(d.dump_cinert + d.nbody * 10, s + L.cdof, d.nv * 6);
-    for (int i = tid; i < d.nv * d.nv; i += kEnvThreads) dump[d.dump_qM + i] = 0.0f;
-    env_sync();
-    for (int q = tid; q < d.nM; q += kEnvThreads) {
-      dump[d.dump_qM + TB8(mrow)[q] * d.nv + TB8(mcol)[q]] = s[L.M + q];
-      dump[d.dump_qM + TB8(mcol)[q] * d.nv + TB8(mrow)[q]] = s[L.M + q];
-    }
     put(d.dump_passive + 2 * d.nv, s + L.qfrc_act, d.nv);
     put(d.dump_passive + 3 * d.nv, s + L.act_dot, d.na);
     put(d.dump_passive + 3 * d.nv + d.na, s + L.qfrc_smooth, d.nv);
@@ -1590,6 +1690,7 @@ __global__ void __launch_bounds__(kMaxEnvs * kEnvThreads, 1) vnl_env_kernel(Para
     make_layout(c.d, c.L);
     c.mb = p.model;
     c.prof = p.prof; c.prof_env = p.prof_env; c.lockstep = p.lockstep;
+    c.work = p.work; c.work_stride = p.work_stride;
     const uint32_t kb = (uint32_t)(kCtaFloats * 4);  // byte offset of the staged tables in shared memory
 #define TOFF(name, id) c.o_##name = kb + g_ktab[id]
     TOFF(lvl_start, VNL_KT_LVL_START); TOFF(lvl_bp, VNL_KT_LVL_BP); TOFF(parent, VNL_KT_PARENT); TOFF(child_adr, VNL_KT_CHILD_ADR);

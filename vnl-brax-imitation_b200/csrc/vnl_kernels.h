@@ -7,7 +7,6 @@
 
 namespace vnl {
 
-constexpr int kMaxEnvs = 8;   // envs per CTA upper bound (each env = 1 or 2 warps; named barriers 1..8 serve the groups)
 
 struct Dims {
   int nq, nv, nu, na, nbody, njnt, ngeom, npair, ncon, nlimit, nefc, nM, nlevel, maxdepth, nroot;
@@ -15,6 +14,7 @@ struct Dims {
   float timestep, gx, gy, gz, tolerance, ls_tolerance, impratio, meaninertia;
   int ktab_words;  // size of VNL_F_KTAB
   int ndslot;      // partial-sum slots of the descendant mat-vec program (VNL_KS_NDSLOT)
+  int TA, TD;      // steps of the mat-vec lane programs (VNL_MH_TA / VNL_MH_TD)
   int naslot;      // partial-sum slots of the ancestor mat-vec program (VNL_MH_NASLOT)
   int env_warps;   // warps cooperating on one env (VNL_MH_ENV_WARPS): lane count of the mat-vec programs / 32
   // stage-dump offsets (layout of oracle.dump_layout)
@@ -26,10 +26,11 @@ struct Dims {
 // inertia is built and shares its storage with region B (inverse factor + constraint rows).
 struct Lay {
   int qpos, qvel, act, ctrl, warm, xpos, xquat, cdof, cvel, M, rcom;
-  int xipos, xanchor, xaxis, t16, cacc;                                   // region A
+  int xipos, xanchor, xaxis, t16;                                         // region A
+  int cacc;                                                               // aliases the solver vectors (dead until the solve)
   int K, efcD, Jaref, Jv;                                                 // region B
   int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
-  int lim_dof, limrow_of_dof, cbody, crel, cframe, cmu;
+  int lim_dof, limrow_of_dof, cbody, crel, cframe, cmu, Mdiag;
   int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, part, ints, total;
 };
 
@@ -47,11 +48,16 @@ struct Params {
   float* dump;
   long long* prof;  // optional [32] per-phase clock64 accumulators of one env (developer hook)
   int prof_env;
+  float* work;      // inertia workspace (vnl_set_workspace), work_stride floats per resident env
+  int work_stride;
   int lsgroups;     // lockstep groups per CTA (1 = the whole CTA)
   int lockstep;     // 0 = warps free-run, 1 = CTA barrier at every substep start, 2 = also before the integrator
 };
 
 struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };  // warps_per_cta = env groups per CTA
+
+// floats of inertia workspace per resident env: the A-order and the D-order copy of the off-diagonal entries
+inline int work_stride(const Dims& d) { return ((d.TA + d.TD) * 32 * d.env_warps + 31) & ~31; }
 
 // vnl_kernels.cu is compiled once per env-group width (-DVNL_EW=1, 2) into its own namespace.
 namespace ew1 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }

@@ -177,7 +177,7 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
             l = min(range(NL), key=lambda l: lane_load[l])
             lanes[l].append((slot, terms))
             lane_load[l] += len(terms)
-        T = 4 * ((max(1, max(lane_load)) + 3) // 4)  # the kernel walks the program four terms at a time
+        T = 8 * ((max(1, max(lane_load)) + 7) // 8)  # the kernel walks the program eight terms at a time
         prog = np.zeros((T, NL), dtype=np.uint32)
         pad = np.uint32((4 * nM_) | (0xFF << 24))  # entry nM is a zero slot, never flushed
         prog[:, :] = pad
@@ -201,7 +201,7 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
         apart_adr.append(len(rows_a))
     if len(rows_a) > 254:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
-    prog_a, TA = pack_program(rows_a) if rows_a else (np.full(4 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
+    prog_a, TA = pack_program(rows_a) if rows_a else (np.full(8 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 8)
     naslot = len(rows_a)
     rows_d, dpart_adr = [], [0]
     for j in range(nv):
@@ -211,7 +211,7 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
         dpart_adr.append(len(rows_d))
     if len(rows_d) > 254 or nv > 254:
         raise NotImplementedError("too many partial-sum slots for the packed mat-vec program")
-    prog_d, TD = pack_program(rows_d) if rows_d else (np.full(4 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 4)
+    prog_d, TD = pack_program(rows_d) if rows_d else (np.full(8 * NL, np.uint32((4 * nM_) | (0xFF << 24)), dtype=np.uint32), 8)
     ndslot = len(rows_d)
     # Level schedules of the factorisation and of the triangular solves (see VnlKtab): rows by dof HEIGHT (leaves = 0),
     # each row with the list of its descendant dofs; dofs by DEPTH for the gather-from-ancestors sweep.
@@ -296,6 +296,8 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
         dirw[t] = off
         off += len(raw)
         blobs.append(raw)
+    # the kernel streams PROG_A and PROG_D as one program
+    assert dirw[C["VNL_KT_PROG_D"]] == dirw[C["VNL_KT_PROG_A"]] + 4 * TA * NL
     dirw[nkt + C["VNL_KS_TA"]] = TA
     dirw[nkt + C["VNL_KS_TD"]] = TD
     dirw[nkt + C["VNL_KS_NDSLOT"]] = ndslot
@@ -307,7 +309,7 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
     dof_actadr = [0]
     for i in range(nv):
         dof_actadr.append(dof_actadr[-1] + len(act_of_dof[i]))
-    return dict(ktab=ktab, env_warps=env_warps, nroot=len(roots), ndslot=ndslot, naslot=naslot, dof_actadr=np.array(dof_actadr),
+    return dict(ktab=ktab, TA=TA, TD=TD, env_warps=env_warps, nroot=len(roots), ndslot=ndslot, naslot=naslot, dof_actadr=np.array(dof_actadr),
                 dof_actlist=np.array([u for i in range(nv) for u in act_of_dof[i]], dtype=np.int64),
                 level_start=np.array(level_start), level_body=np.array(order), dof_madr=np.array(madr),
                 m_col=np.array(mcol), dof_depth=np.array(ddepth), body_subtree_end=sub_end,
@@ -374,7 +376,7 @@ def model_dims(m: mjcf.Model, d=None) -> Dict[str, int]:
     ncon, nlimit = len(d["con_pair"]), len(d["limit_jnt"])
     return dict(nq=m.nq, nv=m.nv, nu=m.nu, na=m.na, nbody=m.nbody, njnt=m.njnt, ngeom=m.ngeom,
                 npair=len(m.arrays["pair_geom1"]), ncon=ncon, nlimit=nlimit, nefc=nlimit + 4 * ncon,
-                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"], ndslot=d["ndslot"], naslot=d["naslot"])
+                nM=len(d["m_col"]), nlevel=d["nlevel"], maxdepth=d["maxdepth"], nroot=d["nroot"], ndslot=d["ndslot"], naslot=d["naslot"], TA=d["TA"], TD=d["TD"])
 
 
 def build_model_blob(m: mjcf.Model, env_warps: int = 0) -> np.ndarray:
@@ -386,7 +388,7 @@ def build_model_blob(m: mjcf.Model, env_warps: int = 0) -> np.ndarray:
                       ("VNL_MH_NPAIR", "npair"), ("VNL_MH_NCON", "ncon"), ("VNL_MH_NLIMIT", "nlimit"),
                       ("VNL_MH_NEFC", "nefc"), ("VNL_MH_NM", "nM"), ("VNL_MH_NLEVEL", "nlevel"),
                       ("VNL_MH_MAXDEPTH", "maxdepth"), ("VNL_MH_NROOT", "nroot"), ("VNL_MH_NDSLOT", "ndslot"),
-                      ("VNL_MH_NASLOT", "naslot")]:
+                      ("VNL_MH_NASLOT", "naslot"), ("VNL_MH_TA", "TA"), ("VNL_MH_TD", "TD")]:
         w.set_i(slot, dims[key])
     w.set_i("VNL_MH_ENV_WARPS", d["env_warps"])
     w.set_i("VNL_MH_SOLVER", m.solver)
