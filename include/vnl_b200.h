@@ -230,7 +230,15 @@ enum VnlTaskHdr {
   VNL_TH_USE_SUBCLIP,     /* 1: done when sub_clip_frame reaches sub_clip_length (rodent.py:207-215) */
   VNL_TH_OBS_QFRC,        /* 1: obs carries qfrc_actuator and the end-effector positions (rodent.py:337-344) */
   VNL_TH_COM_FROM_FIELD,  /* 1: COM reference = VNL_T_CENTER_OF_MASS (humanoid.py:279); 0: filtered body table column (quirk Q4) */
+  VNL_TH_ROT_BODY,        /* body whose xmat rotates into the egocentric frame: 1 = torso (rodent.py:385), 0 = world for the ant
+                           * (ant.py:333 reads data.xmat[0], i.e. the identity) */
+  VNL_TH_TRAJ_OLD_FRAME,  /* 1: the step's reference window starts at OLD cur_frame + 1 (ant.py:182 hands state.info to _get_obs
+                           * before the increment); 0: at NEW cur_frame + 1 (rodent.py:188-190) */
+  VNL_TH_RACT_ACTION,     /* 1: ract = 0.01 * -0.015 * sum(action^2) / nu (ant.py:251); 0: -0.015 * mean(qfrc_actuator^2) */
+  VNL_TH_METRICS_RAW,     /* 1: metrics hold the UNWEIGHTED reward terms (ant.py:203-210); 0: the weighted ones (rodent.py:193-199) */
   VNL_TH_HEALTHY_LO = 32, VNL_TH_HEALTHY_HI, VNL_TH_TERM_THRESHOLD, VNL_TH_BODY_ERR_MULT,
+  VNL_TH_W_RCOM, VNL_TH_W_RVEL, VNL_TH_W_RTRUNK, VNL_TH_W_RQUAT, VNL_TH_W_RACT, VNL_TH_W_RAPP, /* reward weights:
+                           * rodent / humanoid 0.01 x4, 1e-4, 0.01 (rodent.py:193-199); ant 0.05 0.01 0.20 0.01 0.001 0 (ant.py:186-192) */
   VNL_TH_DONE_RTRUNK      /* done when the UNSCALED rtrunk is below this (0 for the rodent, 0.5 for the humanoid: humanoid.py:199) */
 };
 

@@ -805,8 +805,9 @@ template <class T> void step(const ModelView& m, Data<T>& d) { forward(m, d); eu
 struct TaskView {
   const uint32_t* w;
   int T_, ref_len, sub_clip_len, ntrack, njidx, napp, nee, nframes, obs_size, traj_size, com_ref_idx, torso;
-  int reward_old_state, term_mean, use_subclip, obs_qfrc, com_from_field;
+  int reward_old_state, term_mean, use_subclip, obs_qfrc, com_from_field, rot_body, traj_old_frame, ract_action, metrics_raw;
   float healthy_lo, healthy_hi, term_threshold, body_err_mult, done_rtrunk;
+  double w_rcom, w_rvel, w_rtrunk, w_rquat, w_ract, w_rapp;
   const float *position, *quaternion, *joints, *body_positions, *velocity, *angular_velocity, *joints_velocity, *center_of_mass;
   const int *body_idxs, *ee_idx, *app_idx, *app_ref_idx, *joint_col;
   explicit TaskView(const uint32_t* b) : w(b) {
@@ -819,6 +820,13 @@ struct TaskView {
     reward_old_state = vnl_hdr_i(b, VNL_TH_REWARD_OLD_STATE); term_mean = vnl_hdr_i(b, VNL_TH_TERM_MEAN);
     use_subclip = vnl_hdr_i(b, VNL_TH_USE_SUBCLIP); obs_qfrc = vnl_hdr_i(b, VNL_TH_OBS_QFRC);
     com_from_field = vnl_hdr_i(b, VNL_TH_COM_FROM_FIELD); done_rtrunk = vnl_hdr_f(b, VNL_TH_DONE_RTRUNK);
+    rot_body = vnl_hdr_i(b, VNL_TH_ROT_BODY); traj_old_frame = vnl_hdr_i(b, VNL_TH_TRAJ_OLD_FRAME);
+    ract_action = vnl_hdr_i(b, VNL_TH_RACT_ACTION); metrics_raw = vnl_hdr_i(b, VNL_TH_METRICS_RAW);
+    // the reward weights are short decimal literals in the reference (0.01, 0.20, 1e-4 ...); the blob holds them as
+    // fp32, so the fp64 build snaps them back to the literal (7 significant digits) instead of inheriting fp32 rounding
+    auto lit = [](float f) { if (f == 0.0f) return 0.0; double e = std::pow(10.0, 6 - std::floor(std::log10(std::fabs((double)f)))); return std::round((double)f * e) / e; };
+    w_rcom = lit(vnl_hdr_f(b, VNL_TH_W_RCOM)); w_rvel = lit(vnl_hdr_f(b, VNL_TH_W_RVEL)); w_rtrunk = lit(vnl_hdr_f(b, VNL_TH_W_RTRUNK));
+    w_rquat = lit(vnl_hdr_f(b, VNL_TH_W_RQUAT)); w_ract = lit(vnl_hdr_f(b, VNL_TH_W_RACT)); w_rapp = lit(vnl_hdr_f(b, VNL_TH_W_RAPP));
     center_of_mass = vnl_field_f(b, VNL_T_CENTER_OF_MASS);
     position = vnl_field_f(b, VNL_T_POSITION); quaternion = vnl_field_f(b, VNL_T_QUATERNION); joints = vnl_field_f(b, VNL_T_JOINTS);
     body_positions = vnl_field_f(b, VNL_T_BODY_POSITIONS); velocity = vnl_field_f(b, VNL_T_VELOCITY);
@@ -858,7 +866,7 @@ template <class T> void get_obs(const ModelView& m, const TaskView& t, const Dat
 // _get_traj (rodent.py:346-448); window start = clamp(cur_frame + 1, 0, T - ref_len) (dynamic_slice semantics)
 template <class T> void get_traj(const ModelView& m, const TaskView& t, const Data<T>& d, int cur_frame, T* traj) {
   int s = clampi(cur_frame + 1, 0, t.T_ - t.ref_len), nj = m.nq - 7, o = 0;
-  const T* R = d.xmat.data() + 9 * t.torso;
+  const T* R = d.xmat.data() + 9 * t.rot_body;  // rodent.py:385 xmat[1]; ant.py:333 xmat[0] (world: identity)
   for (int w = 0; w < t.ref_len; ++w)  // get_reference_appendages_pos: filtered[:, app_idx] clamped (Q5)
     for (int a = 0; a < t.napp; ++a)
       for (int k = 0; k < 3; ++k) traj[o++] = T(t.body_positions[((s + w) * t.ntrack + t.app_ref_idx[a]) * 3 + k]);
@@ -928,7 +936,7 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   int cur_frame = frame_old + 1, sub_clip_frame = in.sub_clip_frame[e] + 1;
   std::vector<T> obs(t.obs_size), traj(t.traj_size);
   get_obs(m, t, d, obs.data());
-  get_traj(m, t, d, cur_frame, traj.data());
+  get_traj(m, t, d, t.traj_old_frame ? frame_old : cur_frame, traj.data());  // ant.py:182: window from the OLD info
   // _calculate_reward (rodent.py:266-316): every reference lookup uses the OLD cur_frame (Q3)
   int f = clampi(frame_old, 0, t.T_ - 1), nj = m.nq - 7;
   // humanoid.py:275 evaluates every term on the PRE-step state (`data_c = state.pipeline_state`), the rodent on the new one
@@ -961,6 +969,11 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   s = 0;
   for (int i = 0; i < m.nv; ++i) s += r_qfrc[i] * r_qfrc[i];
   T ract = T(-0.015) * (s / T(m.nv));
+  if (t.ract_action) {  // ant.py:251
+    s = 0;
+    for (int u = 0; u < m.nu; ++u) s += T(action[e * m.nu + u]) * T(action[e * m.nu + u]);
+    ract = T(0.01) * T(-0.015) * s / T(m.nu);
+  }
   s = 0;
   for (int a = 0; a < t.napp; ++a)
     for (int k = 0; k < 3; ++k) { T df = d.xpos[3 * t.app_idx[a] + k] - T(t.body_positions[(f * t.ntrack + t.app_ref_idx[a]) * 3 + k]); s += df * df; }
@@ -968,7 +981,8 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   T healthy = r_qpos[2] < T(t.healthy_lo) ? T(0) : T(1);
   if (r_qpos[2] > T(t.healthy_hi)) healthy = 0;
   T done = rtrunk < T(t.done_rtrunk) ? T(1) : T(0);  // rodent.py:213 (scaled rtrunk < 0) / humanoid.py:199 (rtrunk < 0.5 before scaling)
-  rcom *= T(0.01); rvel *= T(0.01); rapp *= T(0.01); rtrunk *= T(0.01); rquat *= T(0.01); ract *= T(0.0001);  // rodent.py:193-199
+  const T raw[6] = {rcom, rvel, rtrunk, rquat, ract, rapp};
+  rcom *= T(t.w_rcom); rvel *= T(t.w_rvel); rapp *= T(t.w_rapp); rtrunk *= T(t.w_rtrunk); rquat *= T(t.w_rquat); ract *= T(t.w_ract);  // rodent.py:193-199 / ant.py:186-192
   T total = rcom + rvel + rtrunk + rquat + ract + rapp;
   T sub_healthy = (!t.use_subclip || sub_clip_frame < t.sub_clip_len) ? T(1) : T(0);
   done = std::max(T(1) - healthy, done);
@@ -988,6 +1002,7 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   o.reward[e] = reward; o.done[e] = done;
   double* mt = o.metrics + 7 * e;
   mt[0] = rcom; mt[1] = rvel; mt[2] = rtrunk; mt[3] = rquat; mt[4] = ract; mt[5] = rapp; mt[6] = rtrunk;
+  if (t.metrics_raw) { for (int k = 0; k < 6; ++k) mt[k] = raw[k]; mt[6] = raw[2]; }  // ant.py:203-210
   if (o.stats) for (int k = 0; k < 4; ++k) o.stats[4 * e + k] = stats[k];
 }
 

@@ -5,6 +5,7 @@
   vnl-brax-imitation_b200/data/rodent_clip.npz   process_clip() of clips/transform_snips_groom.p
   vnl-brax-imitation_b200/data/humanoid_model.npz compiled humanoid model (envs/humanoid.py:40-54 recipe)
   vnl-brax-imitation_b200/data/rodent_pair_model.npz rodent_pair.xml (<replicate count=2>) with the rodent env recipe
+  vnl-brax-imitation_b200/data/ant_model.npz     ant.xml, brax-style load (jointless bodies fused; envs/ant.py:40-52 recipe)
   tests/golden/rodent_clip_golden.npz            the old clip's own derived fields (known answers)
 """
 import importlib
@@ -37,6 +38,9 @@ def main(ref="/root/reference"):
     mjcf.save_model(hum, os.path.join(data, "humanoid_model.npz"))
     pair = mjcf.load_rodent_pair(os.path.join(ref, "assets", "rodent_pair.xml"))
     mjcf.save_model(pair, os.path.join(data, "rodent_pair_model.npz"))
+    ant = mjcf.load_ant(os.path.join(ref, "assets", "ant.xml"))
+    mjcf.save_model(ant, os.path.join(data, "ant_model.npz"))
+    print("ant", ant.nbody, ant.nv, ant.nu)
     print("model", model.nbody, model.nv, "clip", clip.position.shape, clip.body_positions.shape, "humanoid", hum.nbody, hum.nv)
 
 

@@ -92,6 +92,8 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(limrow_of_dof, d.nv);
   A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
   A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.naslot + d.ndslot);
+  L.Mn = L.H = L.jr = 0;
+  if (d.solver == 2) { A(Mn, d.nM); A(H, d.nv * d.nv); A(jr, 3 * d.nv); }  // Newton: natural-order M, dense Hessian, row scratch
   L.cacc = L.qacc;  // spatial accelerations / crb * cdof live where the solver vectors will be (dead until the solve)
   if (o - L.qacc < (d.nbody > d.nv ? d.nbody : d.nv) * 6) o = L.qacc + align4((d.nbody > d.nv ? d.nbody : d.nv) * 6);
   A(ints, 16);
@@ -613,6 +615,97 @@ __device__ __forceinline__ void kbi(const Dims& d, float sr0, float sr1, const f
   if (x > 1.0f) imp = dmax;
 }
 
+// solver._update_gradient for the Newton solver: Mgrad = H^-1 grad with H = M + J^T diag(D [Jaref < 0]) J, dense
+// (nv x nv) and Cholesky-factorised per call, as MJX does (opt.jacobian = dense on the reference path, envs/ant.py:50).
+// The rows of J are never stored: a limit row is one-hot, the four pyramid rows of a contact are a +- mu b, a +- mu t
+// with (a, b, t)_i = frame . (cdof_lin_i + cdof_ang_i x rel) on the dofs above the contact's body.
+__device__ __noinline__ void newton_mgrad(int so) {
+  VNL_SMEM
+  const Lay& L = c.L;
+  const int* ints = (const int*)(s + L.ints);
+  const int nl = ints[0], nc = ints[1], nv = c.d.nv, nM = c.d.nM, tid = ETID, lane = LANE;
+  float* const H = s + L.H;
+  float* const jr = s + L.jr;
+  const float* const D = s + L.efcD;
+  const float* const Jaref = s + L.Jaref;
+  const uint8_t* const mrow = TB8(mrow);
+  const uint8_t* const mcol = TB8(mcol);
+  for (int q = tid; q < nv * nv; q += kEnvThreads) H[q] = 0.0f;
+  env_sync();
+  for (int e = tid; e < nM; e += kEnvThreads) {
+    const int i = mrow[e], j = mcol[e];
+    const float v = s[L.Mn + e];
+    H[i * nv + j] = v; H[j * nv + i] = v;
+  }
+  env_sync();
+  const int* lim_dof = (const int*)(s + L.lim_dof);
+  for (int r = tid; r < nl; r += kEnvThreads)  // one row per limited joint: distinct dofs, no collisions
+    if (Jaref[r] < 0.0f) { const int ld = lim_dof[r], dof = ld < 0 ? ~ld : ld; H[dof * nv + dof] += D[r]; }
+  env_sync();
+  const int* cbody = (const int*)(s + L.cbody);
+  const uint8_t* const dof_body = TB8(dof_body);
+  const uint8_t* const sub_end = TB8(sub_end);
+  for (int k = 0; k < nc; ++k) {
+    const int cb = cbody[k], r = nl + 4 * k;
+    const float* fr = s + L.cframe + 6 * k;
+    const V3 fn3 = ld3(fr), fb3 = ld3(fr + 3), ft3 = cross(fn3, fb3), rel = ld3(s + L.crel + 3 * k);
+    for (int i = tid; i < nv; i += kEnvThreads) {
+      const int b = dof_body[i];
+      float a = 0.0f, bb = 0.0f, t = 0.0f;
+      if (cb >= b && cb < sub_end[b]) {
+        const float* cd = s + L.cdof + 6 * i;
+        const V3 p = ld3(cd + 3) + cross(ld3(cd), rel);
+        a = dot(fn3, p); bb = dot(fb3, p); t = dot(ft3, p);
+      }
+      jr[i] = a; jr[nv + i] = bb; jr[2 * nv + i] = t;
+    }
+    env_sync();
+    const float mu = s[L.cmu + k];
+    const float w0 = Jaref[r] < 0.0f ? D[r] : 0.0f, w1 = Jaref[r + 1] < 0.0f ? D[r + 1] : 0.0f;
+    const float w2 = Jaref[r + 2] < 0.0f ? D[r + 2] : 0.0f, w3 = Jaref[r + 3] < 0.0f ? D[r + 3] : 0.0f;
+    for (int q = tid; q < nv * nv; q += kEnvThreads) {
+      const int i = q / nv, j = q - i * nv;
+      const float ai = jr[i], bi = mu * jr[nv + i], ti = mu * jr[2 * nv + i];
+      const float aj = jr[j], bj = mu * jr[nv + j], tj = mu * jr[2 * nv + j];
+      H[q] += w0 * (ai + bi) * (aj + bj) + w1 * (ai - bi) * (aj - bj) + w2 * (ai + ti) * (aj + tj) + w3 * (ai - ti) * (aj - tj);
+    }
+    env_sync();
+  }
+  // in-place Cholesky H = L L^T (lower triangle), right-looking
+  for (int k = 0; k < nv; ++k) {
+    const float dk = sqrtf(H[k * nv + k]);
+    env_sync();
+    if (tid == 0) H[k * nv + k] = dk;
+    for (int i = k + 1 + tid; i < nv; i += kEnvThreads) H[i * nv + k] = H[i * nv + k] / dk;
+    env_sync();
+    const int m = nv - k - 1;
+    for (int q = tid; q < m * m; q += kEnvThreads) {
+      const int i = k + 1 + q / m, j = k + 1 + q % m;
+      if (j <= i) H[i * nv + j] -= H[i * nv + k] * H[j * nv + k];
+    }
+    env_sync();
+  }
+  // Mgrad = L^-T L^-1 grad
+  float* const y = s + L.Mgrad;
+  for (int i = tid; i < nv; i += kEnvThreads) y[i] = s[L.grad + i];
+  env_sync();
+  for (int k = 0; k < nv; ++k) {
+    const float yk = y[k] / H[k * nv + k];
+    env_sync();
+    if (tid == 0) y[k] = yk;
+    for (int i = k + 1 + tid; i < nv; i += kEnvThreads) y[i] -= H[i * nv + k] * yk;
+    env_sync();
+  }
+  for (int k = nv - 1; k >= 0; --k) {
+    const float yk = y[k] / H[k * nv + k];
+    env_sync();
+    if (tid == 0) y[k] = yk;
+    for (int i = tid; i < k; i += kEnvThreads) y[i] -= H[k * nv + i] * yk;
+    env_sync();
+  }
+  (void)lane;
+}
+
 // solver state carried between _update_constraint calls
 struct Sol { float cost, prev_cost, gauss, gradnorm; };
 
@@ -644,7 +737,8 @@ __device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
   st.gradnorm = sqrtf(g);
   env_sync();
   pf.mark(23);
-  solve_m(so, L.grad, L.Mgrad);
+  if (c.d.solver == 2) newton_mgrad(so);
+  else solve_m(so, L.grad, L.Mgrad);
   pf.mark(24);
 }
 
@@ -962,6 +1056,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       float v = dot6(fd + 6 * i, s + L.cdof + 6 * j);
       if (i == j) { v += armature[i]; s[L.Mdiag + i] = v; }
       F[e] = v;
+      if (d.solver == 2) s[L.Mn + e] = v;
     }
     if (tid == 0) F[d.nM] = 0.0f;  // the zero entry padded program terms point at
     env_sync();
@@ -1570,8 +1665,10 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       obs[i] = (MODE == 0) ? nan_to_num(v) : v;
     }
     float R[9];
-    quat_to_mat(ld4(s + L.xquat + 4 * torso), R);
-    const int ws = min(max(cur_frame + 1, 0), T - ref_len);
+    quat_to_mat(ld4(s + L.xquat + 4 * vnl_hdr_i(tb, VNL_TH_ROT_BODY)), R);  // rodent.py:385 xmat[1]; ant.py:333 xmat[0]
+    // window start: NEW cur_frame + 1 (rodent.py:188-190); the ant hands the not yet incremented info to _get_obs (ant.py:182)
+    const int wf = (MODE == 0 && vnl_hdr_i(tb, VNL_TH_TRAJ_OLD_FRAME)) ? frame_old : cur_frame;
+    const int ws = min(max(wf + 1, 0), T - ref_len);
     float* traj = p.outputs.traj + (size_t)e * traj_size;
     const int n_app = ref_len * napp * 3, n_bod = ref_len * ntrack * 3, n_root = ref_len * 3;
     for (int i = tid; i < traj_size; i += kEnvThreads) {
@@ -1639,11 +1736,18 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     for (int i = lane; i < d.na; i += 32) if (isnan(s[L.act + i])) v3_ += 1.0f;
     v2 = warp_sum(v2); v3_ = warp_sum(v3_);
     float r_com = rt.rcom, rvl = rt.rvel, rquat = rt.rquat, ract = rt.ract;
+    if (vnl_hdr_i(tb, VNL_TH_RACT_ACTION)) {  // ant.py:251: 0.01 * -0.015 * sum(action^2) / nu on the RAW action
+      float sa = 0.0f;
+      for (int u = lane; u < d.nu; u += 32) { const float au = p.ctrl[(size_t)e * d.nu + u]; sa += au * au; }
+      sa = warp_sum(sa);
+      ract = 0.01f * -0.015f * sa / (float)d.nu;
+    }
     float rapp = napp > 0 ? expf(-400.0f * sqrtf(v2)) : 0.0f;  // no appendage term in humanoid.py:200-205
     float done = rtrunk < vnl_hdr_f(tb, VNL_TH_DONE_RTRUNK) ? 1.0f : 0.0f;  // rodent.py:213 / humanoid.py:199 (before scaling)
-    r_com *= 0.01f; rvl *= 0.01f; rapp *= 0.01f;
-    const float rtr = rtrunk * 0.01f;
-    rquat *= 0.01f; ract *= 0.0001f;
+    const float raw0 = r_com, raw1 = rvl, raw3 = rquat, raw4 = ract, raw5 = rapp;
+    r_com *= vnl_hdr_f(tb, VNL_TH_W_RCOM); rvl *= vnl_hdr_f(tb, VNL_TH_W_RVEL); rapp *= vnl_hdr_f(tb, VNL_TH_W_RAPP);
+    const float rtr = rtrunk * vnl_hdr_f(tb, VNL_TH_W_RTRUNK);
+    rquat *= vnl_hdr_f(tb, VNL_TH_W_RQUAT); ract *= vnl_hdr_f(tb, VNL_TH_W_RACT);
     const float total = r_com + rvl + rtr + rquat + ract + rapp;
     const float sub_healthy = (!vnl_hdr_i(tb, VNL_TH_USE_SUBCLIP) || sub_clip_frame < vnl_hdr_i(tb, VNL_TH_SUB_CLIP_LEN)) ? 1.0f : 0.0f;
     done = fmaxf(1.0f - rt.healthy, done);
@@ -1654,6 +1758,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       p.outputs.done[e] = done;
       float* mt = p.outputs.metrics + 7 * (size_t)e;
       mt[0] = r_com; mt[1] = rvl; mt[2] = rtr; mt[3] = rquat; mt[4] = ract; mt[5] = rapp; mt[6] = rtr;
+      if (vnl_hdr_i(tb, VNL_TH_METRICS_RAW)) { mt[0] = raw0; mt[1] = raw1; mt[2] = rtrunk; mt[3] = raw3; mt[4] = raw4; mt[5] = raw5; mt[6] = rtrunk; }  // ant.py:203-210
     }
     if (p.outputs.stats && lane < 4) p.outputs.stats[4 * e + lane] = stats[lane];
     // brax AutoResetWrapper.step fused in: where done, the pipeline-state leaves and obs are replaced by the cached

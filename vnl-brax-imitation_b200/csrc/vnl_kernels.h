@@ -31,6 +31,7 @@ struct Lay {
   int K, efcD, Jaref, Jv;                                                 // region B
   int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
   int lim_dof, limrow_of_dof, cbody, crel, cframe, cmu, Mdiag;
+  int Mn, H, jr;                                                          // Newton solver only (dense Hessian)
   int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, part, ints, total;
 };
 

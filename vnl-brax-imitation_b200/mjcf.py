@@ -987,6 +987,58 @@ def load_rodent_pair(mjcf_path: str, scale_factor: float = 0.9, solver: str = "c
     return compile_model(root, name="rodent_pair", solver=solver, iterations=iterations, ls_iterations=ls_iterations)
 
 
+def fuse_jointless_bodies(root: ET.Element) -> None:
+    """brax `io.mjcf.load` fuses every body that has no joint into its parent before compiling (`_fuse_bodies`,
+    reached from `envs/ant.py:40`): the body's geoms / sites / cameras / child bodies move up, their `pos` (`fromto`) and
+    orientation composed with the fused body's frame, appended after the parent's remaining children.  ant.xml loses its
+    four `*_leg` bodies that way (nbody 14 -> 10)."""
+    comp = {}
+    for c in root.findall("compiler"):
+        comp.update(c.attrib)
+    degree = comp.get("angle", "degree") == "degree"
+    eulerseq = comp.get("eulerseq", "xyz")
+
+    def fuse(elem: ET.Element) -> None:
+        for child in list(elem):
+            fuse(child)
+            if child.tag != "body" or any(e.tag in ("joint", "freejoint") for e in child):
+                continue
+            cpos = _floats(child.get("pos")) if child.get("pos") else np.zeros(3)
+            cquat = _orientation(child.attrib, degree, eulerseq)
+            moved = not (np.allclose(cpos, 0.0) and np.allclose(cquat, [1.0, 0, 0, 0]))
+            for g in list(child):
+                if moved and g.tag in ("body", "geom", "site", "camera", "light"):
+                    if g.get("fromto") is not None:
+                        ft = _floats(g.get("fromto"))
+                        g.set("fromto", _fmt(np.concatenate([cpos + rotate(ft[:3], cquat), cpos + rotate(ft[3:], cquat)])))
+                    else:
+                        gpos = _floats(g.get("pos")) if g.get("pos") else np.zeros(3)
+                        gquat = _orientation(g.attrib, degree, eulerseq)
+                        for k in ("euler", "axisangle", "xyaxes", "zaxis"):
+                            g.attrib.pop(k, None)
+                        g.set("pos", _fmt(cpos + rotate(gpos, cquat)))
+                        g.set("quat", _fmt(quat_mul(cquat, gquat)))
+                elem.append(g)
+            elem.remove(child)
+
+    wb = root.find("worldbody")
+    if wb is not None:
+        fuse(wb)
+
+
+def load_ant(mjcf_path: str, solver: str = "newton", iterations: int = 1, ls_iterations: int = 4) -> Model:
+    """`AntTracking.__init__` (`envs/ant.py:40-52`): brax-style load (jointless bodies fused), solver overrides from
+    `configs/env_config.yaml:17-23`, eulerdamp disabled.  The `init_qpos` custom numeric (ant.xml:11) rides along as
+    `arrays["init_qpos"]`: the reference's still clip is that pose tiled."""
+    root = load_xml(mjcf_path)
+    fuse_jointless_bodies(root)
+    m = compile_model(root, name="ant", solver=solver, iterations=iterations, ls_iterations=ls_iterations, eulerdamp=False)
+    for num in root.iter("numeric"):
+        if num.get("name") == "init_qpos":
+            m.arrays["init_qpos"] = _floats(num.get("data"))
+    return m
+
+
 def load_humanoid(mjcf_path: str, solver: str = "cg", iterations: int = 6, ls_iterations: int = 6) -> Model:
     """`HumanoidTracking.__init__` (`envs/humanoid.py:40-54`): no rescale, eulerdamp disabled."""
     root = load_xml(mjcf_path)

@@ -437,7 +437,8 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
                     body_error_multiplier: float = 1.0, n_frames: int = 5, torso_body: int = 1,
                     obs_size: int = 0, traj_size: int = 0, kind: int = 0, reward_old_state: bool = False,
                     term_mean: bool = False, use_subclip: bool = True, obs_qfrc: bool = True, com_from_field: bool = False,
-                    done_rtrunk: float = 0.0) -> np.ndarray:
+                    done_rtrunk: float = 0.0, rot_body: int = -1, traj_old_frame: bool = False, ract_action: bool = False,
+                    metrics_raw: bool = False, weights=(0.01, 0.01, 0.01, 0.01, 0.0001, 0.01)) -> np.ndarray:
     """Rodent imitation task tables.  `clip.body_positions` must already be filtered to
     `body_idxs` (`envs/rodent.py:114-115`).  The reference indexes that filtered table with
     MODEL body ids and relies on JAX clamping out-of-range gathers; the
@@ -451,6 +452,12 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
     w.set_i("VNL_TH_OBS_QFRC", int(obs_qfrc))
     w.set_i("VNL_TH_COM_FROM_FIELD", int(com_from_field))
     w.set_f("VNL_TH_DONE_RTRUNK", done_rtrunk)
+    w.set_i("VNL_TH_ROT_BODY", torso_body if rot_body < 0 else rot_body)
+    w.set_i("VNL_TH_TRAJ_OLD_FRAME", int(traj_old_frame))
+    w.set_i("VNL_TH_RACT_ACTION", int(ract_action))
+    w.set_i("VNL_TH_METRICS_RAW", int(metrics_raw))
+    for slot, v in zip(("RCOM", "RVEL", "RTRUNK", "RQUAT", "RACT", "RAPP"), weights):
+        w.set_f("VNL_TH_W_" + slot, v)
     w.set_i("VNL_TH_CLIP_LEN", clip.position.shape[0])
     w.set_i("VNL_TH_REF_LEN", ref_traj_length)
     w.set_i("VNL_TH_SUB_CLIP_LEN", sub_clip_length)
