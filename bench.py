@@ -130,6 +130,9 @@ WORKLOADS = {
     "rodent": dict(envs=4096, nu=30, text="rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p)"),
     "humanoid": dict(envs=8192, nu=21, text="CMU humanoid imitation env step+reward/obs (envs/humanoid.py, humanoid.xml, synthetic "
                                             "standing clip: qpos0 tiled x256 -- the reference clip humanoid_traj_stand.p is absent)"),
+    # BASELINE.json configs[0]: the reference's own CPU-runnable plumbing case (a parity case; benched only on request)
+    "ant": dict(envs=256, nu=8, text="ant imitation env step+reward/obs (envs/ant.py, ant.xml brax-style fused, Newton 1x4, still clip: "
+                                     "init_qpos tiled -- the reference clip ant_traj_still.p is absent)"),
 }
 
 
@@ -140,6 +143,10 @@ def make_env(workload, device):
         hum = pkg("envs.humanoid")
         model, clip = hum.packaged_humanoid()
         return envs.HumanoidTracking(model=model, reference_clip=clip, device=device)
+    if workload == "ant":
+        antm = pkg("envs.ant")
+        model, clip = antm.packaged_ant()
+        return envs.AntTracking(model=model, reference_clip=clip, device=device)
     rod = pkg("envs.rodent")
     model, clip = rod.packaged_rodent()
     return envs.RodentTracking(reference_clip=clip, model=model, device=device, **rod.RODENT_ENV_ARGS)
@@ -149,6 +156,12 @@ def workload_draws(workload, env, total, lo, hi):
     if workload == "humanoid":  # HumanoidTracking.reset (humanoid.py:78-102): frame ~ randint(0, 250 - 150 - 5), no noise
         rng = np.random.default_rng(0)
         start = rng.integers(0, 95, size=total).astype(np.int32)[lo:hi]
+        rt = env._ref_traj
+        qpos = np.hstack([rt.position[start], rt.quaternion[start], rt.joints[start]]).astype(np.float32)
+        qvel = np.hstack([rt.velocity[start], rt.angular_velocity[start], rt.joints_velocity[start]]).astype(np.float32)
+        return qpos, qvel, start
+    if workload == "ant":  # AntTracking.reset (ant.py:76-103): start_frame = 0, no noise
+        start = np.zeros(total, dtype=np.int32)[lo:hi]
         rt = env._ref_traj
         qpos = np.hstack([rt.position[start], rt.quaternion[start], rt.joints[start]]).astype(np.float32)
         qvel = np.hstack([rt.velocity[start], rt.angular_velocity[start], rt.joints_velocity[start]]).astype(np.float32)
