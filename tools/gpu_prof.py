@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 envs = importlib.import_module("vnl-brax-imitation_b200.envs")
 rod = importlib.import_module("vnl-brax-imitation_b200.envs.rodent")
 PHASES = ["fk", "com/cinert/cdof", "vel/acc down + crb/rne up", "smooth/act", "M", "factor+K", "solve(smooth)", "constraints",
-          "warm select", "solver init", "linesearch", "update+beta", "(fwd tail)", "euler factor", "euler rest", "load + task outputs", "  factor: eliminate", "  factor: normalise", "  factor: invert", "  ls: mul_m", "  ls: jmul", "  ls: sums+points", "  upd: jtmul_force", "  upd: reductions", "  upd: solve_m"]
+          "warm select", "solver init", "linesearch", "update+beta", "(fwd tail)", "euler factor", "euler rest", "load + task outputs", "  factor: eliminate", "  factor: normalise", "  factor: invert", "  ls: mul_m", "  ls: jmul", "  ls: sums+points", "  upd: jtmul_force", "  upd: reductions", "  upd: solve_m", "  fk: local transforms", "  fk: compose levels", "  vel/acc down", "  local rne"]
 
 
 def main():

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvnl_b200.so")
+LIB_PATH = os.environ.get("VNL_B200_LIB") or os.path.join(_HERE, "libvnl_b200.so")  # override: developer A/B builds
 
 STATE_F = ("qpos", "qvel", "act", "qacc_warmstart", "xpos", "xquat", "subtree_com", "qfrc_actuator")
 STATE_I = ("cur_frame", "sub_clip_frame")

@@ -803,6 +803,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       st3(s + L.xpos + 3 * b, lp);
     }
     env_sync();
+    pf.mark(25);
     int k0 = lvl_start[1];  // level 0 (children of the world) is already in world coordinates
     for (int lv = 1; lv < d.nlevel; ++lv) {
       const int k1 = lvl_start[lv + 1];
@@ -819,6 +820,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       k0 = k1;
       env_sync();
     }
+    pf.mark(26);
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
     for (int j = tid; j < d.njnt; j += kEnvThreads) {
       const int p = TB8(parent)[jbody[j]];
@@ -965,6 +967,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       k0 = k1;
       env_sync();
     }
+    pf.mark(27);
     // local RNE force of each body: cfrc = I cacc + cvel x* (I cvel)   -> t16[10..15]
     for (int b = tid; b < d.nbody; b += kEnvThreads) {
       float f1[6], iv[6], f2[6];
@@ -975,6 +978,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       for (int q = 0; q < 6; ++q) s[L.t16 + 16 * b + 10 + q] = f1[q] + f2[q];
     }
     env_sync();
+    pf.mark(28);
     // one pass up the tree: composite inertia (crb, in place over cinert) and subtree-summed RNE force
     for (int lv = d.nlevel - 2; lv >= 0; --lv) {
       const int q0 = lvl_start[lv], n16 = (lvl_start[lv + 1] - q0) * 16;
@@ -1871,7 +1875,7 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;
   static int lockstep = -1;
-  if (lockstep < 0) { const char* ev = getenv("VNL_LOCKSTEP"); lockstep = ev ? atoi(ev) : 1; }
+  if (lockstep < 0) { const char* ev = getenv("VNL_LOCKSTEP"); lockstep = ev ? atoi(ev) : 3; }
   Params q = p;
   q.lockstep = lockstep;
   static int lsgroups = -1;

@@ -52,7 +52,7 @@ struct Params {
   float* work;      // inertia workspace (vnl_set_workspace), work_stride floats per resident env
   int work_stride;
   int lsgroups;     // lockstep groups per CTA (1 = the whole CTA)
-  int lockstep;     // 0 = warps free-run, 1 = CTA barrier at every substep start, 2 = also before the integrator
+  int lockstep;     // 0 = warps free-run, 1 = CTA barrier at every substep start, 2 = also before the integrator, 3 = at every phase boundary (default)
 };
 
 struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };  // warps_per_cta = env groups per CTA
