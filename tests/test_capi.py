@@ -72,6 +72,49 @@ def test_unregistered_blob_is_an_argument_error(lib):
     assert lib.vnl_unregister_blob(dummy.ctypes.data) != 0
 
 
+def test_workspace_is_required_and_sized(lib, rodent):
+    """The step entry points refuse to launch (-20 / -21, before any device access) until a big enough inertia
+    workspace is bound to the registered model blob; sizing follows the resident-env count and both lane-program lengths."""
+    mb = pkg("model_blob")
+    m, t = rodent["model_blob"], rodent["task_blob"]
+    lib.vnl_workspace_bytes.restype = ctypes.c_size_t
+    need = lib.vnl_workspace_bytes(m.ctypes.data)
+    d = mb.model_dims(rodent["model"])
+    per_env = ((d["TA"] + d["TD"]) * 32 + 31) // 32 * 32 * 4
+    assert need == lib.vnl_resident_envs(m.ctypes.data) * per_env and per_env == 10240
+    assert lib.vnl_resident_envs(m.ctypes.data) % lib.vnl_envs_per_cta(m.ctypes.data) == 0 and lib.vnl_envs_per_cta(m.ctypes.data) == 10
+    fake_model, fake_task, fake_work = 0x7000000000, 0x7100000000, 0x7200000000  # never dereferenced on these paths
+    assert lib.vnl_set_workspace(fake_model, fake_work, need) == -1              # unknown model blob
+    assert lib.vnl_register_blob(fake_model, m.ctypes.data, m.nbytes) == 0
+    assert lib.vnl_register_blob(fake_task, t.ctypes.data, t.nbytes) == 0
+    st = libm.VnlState(); out = libm.VnlOutputs()
+    dummy = np.zeros(8, dtype=np.float32)
+    call = lambda: lib.vnl_step(fake_model, fake_task, 4, ctypes.byref(st), dummy.ctypes.data, ctypes.byref(st), ctypes.byref(out), None)
+    assert call() == -20
+    assert lib.vnl_set_workspace(fake_model, fake_work, need - 4) == 0 and call() == -21
+    assert lib.vnl_set_workspace(fake_model, None, 0) == 0 and call() == -20   # unbound again
+    assert lib.vnl_unregister_blob(fake_model) == 0 and lib.vnl_unregister_blob(fake_task) == 0
+
+
+def test_two_warp_blob_has_wider_lane_programs(rodent):
+    mb = pkg("model_blob")
+    b1, b2 = mb.build_model_blob(rodent["model"], 1), mb.build_model_blob(rodent["model"], 2)
+    d1, d2 = mb.read_dims(b1), mb.read_dims(b2)
+    assert (d1["env_warps"], d2["env_warps"]) == (1, 2)
+    t1, t2 = mb.derived_tables(rodent["model"], 1), mb.derived_tables(rodent["model"], 2)
+    assert t2["TA"] < t1["TA"] and t2["TD"] < t1["TD"] and t1["TA"] % 8 == 0 and t2["TD"] % 8 == 0
+    # every off-diagonal inertia entry appears exactly once in each ancestor program, whatever the lane count
+    C = mb.C
+    for tb, nl in ((t1, 32), (t2, 64)):
+        kt = tb["ktab"]
+        off = kt[C["VNL_KT_PROG_A"]] // 4
+        prog = kt[off:off + tb["TA"] * nl]
+        ent = (prog & 0x3FFC) >> 2
+        nM = len(tb["m_col"])
+        real = ent[ent != nM]
+        assert len(real) == nM - rodent["model"].nv and len(set(real.tolist())) == len(real)
+
+
 def test_engine_refuses_to_run_without_gpu(rodent):
     import torch
     if torch.cuda.is_available():

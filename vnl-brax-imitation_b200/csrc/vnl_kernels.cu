@@ -1819,7 +1819,9 @@ __global__ void __launch_bounds__(kMaxEnvs * kEnvThreads, 1) vnl_env_kernel(Para
   const int so = kCtaFloats + align4(c.d.ktab_words) + warp * c.L.total;
   const int stride = gridDim.x * W, rounds = (p.B + stride - 1) / stride;
   for (int r = 0; r < rounds; ++r) {
-    const int e = r * stride + blockIdx.x * W + warp;
+    // slot-major env numbering: a partial last round thins out EVERY CTA (fewer co-resident envs each, all faster)
+    // instead of leaving whole SMs idle next to full ones
+    const int e = r * stride + warp * gridDim.x + blockIdx.x;
     env_run<MODE>(so, p, e, e < p.B);
   }
 }
