@@ -1,11 +1,15 @@
 // vnl_kernels.cu -- fused MJX-style physics + imitation reward/obs/termination step for sm_100a.
 //
-// ONE WARP PER ENVIRONMENT.  The whole env step -- n_frames x (forward dynamics, constraint solve, semi-implicit
-// Euler) and the clip-indexed reward / observation / trajectory window / termination -- runs in one launch with the
-// env's working set (~28 KB for the rodent) resident in shared memory; HBM is touched only for the state in and the
-// state + observations out (~8.7 KB per env step).  A CTA holds as many envs (warps) as shared memory allows plus one
-// copy of the packed index tables (VNL_F_KTAB); warps never synchronise with each other after the table load, so
-// there is no __syncthreads in the physics: lanes cooperate through shuffles and __syncwarp only.
+// ONE WARP PER ENVIRONMENT (optionally two: -DVNL_EW=2, a second instantiation in the same library).  The whole env
+// step -- n_frames x (forward dynamics, constraint solve, semi-implicit Euler) and the clip-indexed reward /
+// observation / trajectory window / termination -- runs in one launch with the env's working set (~20 KB for the
+// rodent) resident in shared memory; the joint-space inertia alone lives in an L2-resident global workspace, laid out
+// in the order the mat-vec lane programs consume it.  HBM is touched only for the state in and the state +
+// observations out (~8.7 KB per env step).  A CTA holds as many envs as shared memory allows (10 rodents) plus one
+// copy of the packed index tables (VNL_F_KTAB); the grid is persistent (one CTA per SM, envs dealt slot-major).
+// Inside an env the lanes cooperate through shuffles and __syncwarp only; the CTA-wide barriers are NOT data
+// dependencies: they keep the co-resident warps at the same phase of the substep so that they share instruction
+// fetches (the substep's ~200 KB of SASS dwarfs the instruction caches) -- see `lockstep`.
 //
 // Formulation (differs from the dense one XLA executes for the reference, same mathematics):
 //   * joint-space inertia kept tree-sparse (MuJoCo qM layout), factorised as L^T D L without fill-in; the
@@ -139,7 +143,7 @@ struct Prof {
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
-// sparse-inertia helpers (one warp).  Vector arguments are float offsets into the env slice.
+// sparse-inertia helpers (one env group).  Vector arguments are float offsets into the env slice.
 // ---------------------------------------------------------------------------------------------------------------------
 // One section of a lane program: part[slot] = sum over the lane's terms of V[entry] * x[index] (see VnlKtab).
 // T is a multiple of 4 (host pads).  The four program words and their eight operands of a batch are loaded before any
@@ -1523,7 +1527,7 @@ __device__ __noinline__ RewardTerms reward_state_terms(const uint32_t* tb, int n
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// one env, one warp.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
+// one env, one env group.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool active) {
