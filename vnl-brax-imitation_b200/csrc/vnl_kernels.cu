@@ -46,9 +46,10 @@ namespace VNL_CAT(ew, VNL_EW) {  // one instantiation of everything below per en
 
 constexpr int kEnvWarps = VNL_EW;          // warps cooperating on one env
 constexpr int kEnvThreads = 32 * VNL_EW;   // = lanes of the mat-vec programs (VNL_MH_ENV_WARPS of the blob must agree)
-// envs per CTA upper bound: one-warp groups are bounded by shared memory (10 rodents), two-warp groups by the register
+// envs per CTA upper bound: one-warp groups are bounded by shared memory (10 rodents) or by the register file (16 warps x 128
+// registers: humanoid, ant), two-warp groups by the register
 // file (16 warps x 128 registers) and by the named barriers (1 .. 8 for the groups)
-constexpr int kMaxEnvs = VNL_EW == 1 ? 12 : 8;
+constexpr int kMaxEnvs = VNL_EW == 1 ? 16 : 8;
 
 #define LANE ((int)(threadIdx.x & 31))
 #define FULLMASK 0xffffffffu
@@ -1862,6 +1863,8 @@ LaunchInfo launch_info(const Dims& d, int B) {
     int resident = (227 * 1024) / (smem + 1024);
     if (resident < 1) resident = 1;
     if (resident > 2048 / (W * kEnvThreads)) resident = 2048 / (W * kEnvThreads);
+    if (resident > 65536 / (W * kEnvThreads * 128)) resident = 65536 / (W * kEnvThreads * 128);  // register file (<= 128 / thread)
+    if (resident < 1) resident = 1;
     const int need = (B + W - 1) / W;
     const int ctas = need < sms * resident ? need : sms * resident;
     const long rounds = ((long)B + (long)ctas * W - 1) / ((long)ctas * W);
