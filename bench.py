@@ -407,7 +407,7 @@ def run_ours(args):
                          % (B * nbytes / 1e6), "done_fraction": done_frac},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms_total / K, "launches_per_step": e2e_chunks,
-                "api": "hostio.HostStepper.step (chunked vnl_step_autoreset, D2H of chunk k overlaps compute of chunk k+1)"},
+                "api": "hostio.HostStepper.step (vnl_step_autoreset in two launches cut at a wave boundary, D2H of the first overlaps compute of the last wave)"},
         "gpu_launches": int(sums["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,

@@ -1,9 +1,10 @@
 """Stepping an env whose consumer lives on the HOST (numpy policy, logger, another framework).
 
 `HostStepper.step(host_action)` is the host-buffer form of `env.step`: actions come from pinned host memory, obs /
-traj / reward / done land in pinned host memory, and the call returns when they are there.  The batch is cut into
-chunks of `Engine.resident_envs` (one full wave of the persistent grid each); the device-to-host copy of chunk k runs
-on a second stream while chunk k + 1 computes, so only the last chunk's copy is exposed.  The episode handling is
+traj / reward / done land in pinned host memory, and the call returns when they are there.  The batch is cut in two at
+a wave boundary of the persistent grid (`Engine.resident_envs`): the leading full waves, then the last wave; the
+device-to-host copy of the first chunk runs on a second stream while the last wave computes, so only the last wave's
+copy is exposed.  The episode handling is
 brax's AutoResetWrapper as installed by the reference (`ppo_imitation/train.py:204-214`), fused into the launch
 (`vnl_step_autoreset`); the device state ping-pongs between two preallocated buffers, nothing is allocated per step.
 """
@@ -35,8 +36,16 @@ class HostStepper:
         self.d_action = torch.empty(B, env.action_size, dtype=torch.float32, device=eng.device)
         self.host = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in HOST_FIELDS}
         self.copy_stream = torch.cuda.Stream(device=eng.device)
-        C = int(chunk) if chunk > 0 else max(1, min(B, eng.resident_envs))
-        self.chunks = [(a, min(a + C, B)) for a in range(0, B, C)]
+        if chunk > 0:
+            C = int(chunk)
+            self.chunks = [(a, min(a + C, B)) for a in range(0, B, C)]
+        else:
+            # two launches: all the full waves but the last in one (the persistent grid walks them back to back, no kernel
+            # boundary in between), then the last wave -- its compute hides the first chunk's copy, only its own copy
+            # (the smallest possible) is exposed
+            R = max(1, eng.resident_envs)
+            head = (B - 1) // R * R
+            self.chunks = [(0, head), (head, B)] if head > 0 else [(0, B)]
         self.events = [torch.cuda.Event() for _ in self.chunks]
         cut = lambda d, a, b: {k: v[a:b] for k, v in d.items() if v is not None}
         # contiguous leading-dim views of every buffer, cut once
