@@ -302,6 +302,23 @@ int vnl_step_autoreset(const void* model, const void* task, int B, const VnlStat
                        const VnlState* out, const VnlOutputs* outputs, const VnlState* first, const float* first_obs,
                        void* stream);
 
+/* Episode bookkeeping of brax's EpisodeWrapper + AutoResetWrapper (`envs.training.wrap`, reached from
+ * ppo_imitation/train.py:204-214 with action_repeat = 1, train.py:121): info["steps"] and info["truncation"]. */
+typedef struct VnlEpisode {
+  const float* steps_in;  /* [B] info["steps"] of the incoming state */
+  const float* done_in;   /* [B] done of the incoming state: AutoResetWrapper zeroes the counter of a finished episode */
+  float* steps_out;       /* [B] (may alias steps_in) */
+  float* truncation_out;  /* [B] info["truncation"] = 1 - done where the episode length is reached, else 0 */
+  float episode_length;   /* train_config.yaml:7 (150) */
+} VnlEpisode;
+
+/* vnl_step wrapped the way the reference trains (ppo_imitation/train.py:204-214): AutoResetWrapper(EpisodeWrapper(env)),
+ * action_repeat 1, all in the one launch.  steps = (done_in ? 0 : steps_in) + 1; where steps >= episode_length:
+ * truncation = 1 - done, done = 1; then the AutoReset restore of vnl_step_autoreset on that final done flag. */
+int vnl_step_training(const void* model, const void* task, int B, const VnlState* in, const float* action,
+                      const VnlState* out, const VnlOutputs* outputs, const VnlState* first, const float* first_obs,
+                      const VnlEpisode* episode, void* stream);
+
 /* Reset tail for B envs: qpos/qvel/cur_frame(start_frame) are read from `in` (act, ctrl and
  * qacc_warmstart are zero as in mjx.make_data), `out` receives the mjx.forward state, obs,
  * traj and info["termination_error"] (metrics[6]).  Replaces envs/rodent.py:148-176. */

@@ -361,6 +361,52 @@ def test_fused_autoreset_equals_wrapper_semantics(gpu_env, rodent):
     assert torch.equal(o2["cur_frame"], o1["cur_frame"]) and torch.equal(o2["sub_clip_frame"], o1["sub_clip_frame"])
 
 
+def test_fused_training_wrappers_equal_brax_semantics(gpu_env, rodent):
+    """vnl_step_training == AutoResetWrapper(EpisodeWrapper(env)).step of brax (envs/wrappers/training.py) as installed at
+    ppo_imitation/train.py:204-214 with action_repeat 1: the wrappers restated in torch around vnl_step, step by step."""
+    import torch
+    B, K, EP = 64, 16, 7.0  # episode_length 7 < sub_clip_length 10: truncation fires before the env's own done
+    eng = gpu_env.engine
+    qpos, qvel, start = start_states(rodent, B, seed=41)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    first, first_obs = dict(s0.pipeline_state), s0.obs
+    mk = lambda: dict({k: v.clone() for k, v in first.items()}, cur_frame=s0.info["cur_frame"].clone(),
+                      sub_clip_frame=s0.info["sub_clip_frame"].clone())
+    ref, fus = mk(), mk()
+    ref["qpos"][5::9, 2] = 0.6; fus["qpos"][5::9, 2] = 0.6  # a few envs start unhealthy: done on step 1, counter restarts
+    z = lambda: torch.zeros(B, device="cuda")
+    r_steps, r_done = z(), z()
+    f_steps, f_done, f_trunc = z(), z(), z()
+    rng = np.random.default_rng(42)
+    seen_trunc = seen_restart = False
+    for it in range(K):
+        a = torch.tensor(rng.uniform(-1, 1, size=(B, 30)).astype(np.float32), device="cuda")
+        # --- reference: AutoResetWrapper.step { steps = where(done, 0, steps); EpisodeWrapper.step { env.step } ; restore }
+        r_steps = torch.where(r_done > 0, torch.zeros_like(r_steps), r_steps)
+        nxt, out = eng.alloc_state(B), eng.alloc_outputs(B)
+        eng.step(ref, a, nxt, out)
+        r_steps = r_steps + 1
+        over = r_steps >= EP
+        trunc = torch.where(over, 1 - out["done"], torch.zeros_like(r_steps))
+        done = torch.where(over, torch.ones_like(r_steps), out["done"])
+        for k in STATE_KEYS:
+            nxt[k] = torch.where(done.reshape((B,) + (1,) * (nxt[k].dim() - 1)) > 0, first[k], nxt[k])
+        obs = torch.where(done[:, None] > 0, first_obs, out["obs"])
+        ref, r_done = nxt, done
+        # --- fused
+        fn, fo = eng.alloc_state(B), eng.alloc_outputs(B)
+        eng.step_training(fus, a, fn, fo, first, first_obs, f_steps, f_done, f_steps, f_trunc, EP)  # steps updated in place
+        torch.cuda.synchronize()
+        assert torch.equal(f_steps, r_steps) and torch.equal(f_trunc, trunc) and torch.equal(fo["done"], done), it
+        assert torch.equal(fo["obs"], obs) and torch.equal(fo["reward"], out["reward"]) and torch.equal(fo["traj"], out["traj"])
+        for k in STATE_KEYS + ("cur_frame", "sub_clip_frame"):
+            assert torch.equal(fn[k], ref[k]), (it, k)
+        fus, f_done = fn, fo["done"].clone()
+        seen_trunc = seen_trunc or bool((trunc > 0).any())
+        seen_restart = seen_restart or bool(((r_steps == 1) & (torch.tensor(it > 0, device="cuda"))).any())
+    assert float(r_steps.max()) <= EP and seen_trunc and seen_restart  # both wrapper paths were exercised
+
+
 def test_host_stepper_chunks_equal_one_launch(gpu_env, rodent):
     """hostio.HostStepper (host buffers, chunked launches, D2H overlapped on a second stream) returns bit-identical
     results to whole-batch vnl_step_autoreset launches; the chunking is invisible (envs are independent)."""

@@ -23,6 +23,11 @@ class VnlState(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in STATE_F + STATE_I]
 
 
+class VnlEpisode(ctypes.Structure):
+    _fields_ = [("steps_in", ctypes.c_void_p), ("done_in", ctypes.c_void_p), ("steps_out", ctypes.c_void_p),
+                ("truncation_out", ctypes.c_void_p), ("episode_length", ctypes.c_float)]
+
+
 class VnlOutputs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in OUT_F + ("stats",)]
 
@@ -30,7 +35,7 @@ class VnlOutputs(ctypes.Structure):
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
            "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta",
-           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace")
+           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace", "vnl_step_training")
 
 
 def load_library() -> ctypes.CDLL:
@@ -56,6 +61,9 @@ def load_library() -> ctypes.CDLL:
     lib.vnl_step_autoreset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
                                        ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.POINTER(VnlState),
                                        ctypes.c_void_p, ctypes.c_void_p]
+    lib.vnl_step_training.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
+                                      ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.POINTER(VnlState),
+                                      ctypes.c_void_p, ctypes.POINTER(VnlEpisode), ctypes.c_void_p]
     lib.vnl_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState),
                               ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p]
     lib.vnl_pipeline_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
@@ -191,6 +199,19 @@ class Engine:
         self._check(self.lib.vnl_step_autoreset(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                                 action.data_ptr(), ctypes.byref(b), ctypes.byref(o), ctypes.byref(f),
                                                 first_obs.data_ptr(), self._stream()), "vnl_step_autoreset")
+
+    def step_training(self, state: Dict, action, out_state: Dict, outputs: Dict, first: Dict, first_obs, steps, done_in,
+                      steps_out, truncation, episode_length: float):
+        """`vnl_step_training`: AutoResetWrapper(EpisodeWrapper(env)).step in one launch (action_repeat 1)."""
+        B = state["qpos"].shape[0]
+        a, b, o, f = self._state(state), self._state(out_state), self._outputs(outputs), self._state(first)
+        assert action.is_contiguous() and action.shape == (B, self.dims["nu"]) and first_obs.is_contiguous()
+        for t in (steps, done_in, steps_out, truncation):
+            assert t.is_contiguous() and t.shape == (B,) and t.element_size() == 4 and t.dtype.is_floating_point
+        ep = VnlEpisode(steps.data_ptr(), done_in.data_ptr(), steps_out.data_ptr(), truncation.data_ptr(), float(episode_length))
+        self._check(self.lib.vnl_step_training(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+                                               action.data_ptr(), ctypes.byref(b), ctypes.byref(o), ctypes.byref(f),
+                                               first_obs.data_ptr(), ctypes.byref(ep), self._stream()), "vnl_step_training")
 
     def reset(self, state: Dict, out_state: Dict, outputs: Dict):
         B = state["qpos"].shape[0]

@@ -203,6 +203,22 @@ int vnl_step_autoreset(const void* model, const void* task, int B, const VnlStat
   return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
+int vnl_step_training(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+                      const VnlOutputs* outputs, const VnlState* first, const float* first_obs, const VnlEpisode* episode,
+                      void* stream) {
+  if (B <= 0 || !in || !out || !outputs || !action || !first || !first->qpos || !episode) return -1;
+  if (!episode->steps_in || !episode->done_in || !episode->steps_out || !episode->truncation_out) return -1;
+  vnl::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc = prepare(model, task, true, p);
+  if (rc) return rc;
+  Header ht;
+  lookup(task, ht);
+  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.first = *first; p.first_obs = first_obs; p.episode = *episode;
+  return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
+}
+
 // Developer hook: vnl_step with per-phase clock64 accumulation for CTA `block` into prof[32].
 int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
                       const VnlOutputs* outputs, void* stream, long long* prof, int block) {

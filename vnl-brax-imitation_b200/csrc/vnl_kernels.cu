@@ -1762,6 +1762,13 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     done = fmaxf(1.0f - rt.healthy, done);
     done = fmaxf(1.0f - sub_healthy, done);
     if (v3_ > 0.0f) done = 1.0f;
+    if (p.episode.steps_out) {  // brax EpisodeWrapper.step inside AutoResetWrapper.step (envs/wrappers/training.py)
+      const float steps = (p.episode.done_in[e] > 0.0f ? 0.0f : p.episode.steps_in[e]) + 1.0f;
+      const bool over = steps >= p.episode.episode_length;
+      const float trunc = over ? 1.0f - done : 0.0f;
+      if (over) done = 1.0f;
+      if (lane == 0) { p.episode.steps_out[e] = steps; p.episode.truncation_out[e] = trunc; }
+    }
     if (lane == 0) {
       p.outputs.reward[e] = nan_to_num(total);
       p.outputs.done[e] = done;

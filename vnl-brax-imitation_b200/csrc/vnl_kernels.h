@@ -43,6 +43,7 @@ struct Params {
   VnlState in, out;
   VnlState first;         // optional cached first state (AutoReset), first.qpos == nullptr when unused
   const float* first_obs;
+  VnlEpisode episode;     // optional EpisodeWrapper bookkeeping, episode.steps_out == nullptr when unused
   const float* ctrl;
   VnlOutputs outputs;
   int32_t* stats;

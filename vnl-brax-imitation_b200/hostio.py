@@ -18,7 +18,10 @@ HOST_FIELDS = ("obs", "traj", "reward", "done")
 
 
 class HostStepper:
-    def __init__(self, env, state0, autoreset: bool = True, chunk: int = 0):
+    """`episode_length` > 0 adds brax's EpisodeWrapper inside the AutoReset (`envs.training.wrap`: info["steps"],
+    info["truncation"], done at the episode length), still one fused launch per chunk (`vnl_step_training`)."""
+
+    def __init__(self, env, state0, autoreset: bool = True, chunk: int = 0, episode_length: float = 0.0):
         import torch
 
         self.torch, self.env, self.eng = torch, env, env.engine
@@ -33,6 +36,12 @@ class HostStepper:
         cur["sub_clip_frame"] = state0.info["sub_clip_frame"].clone()
         self.bufs = [cur, eng.alloc_state(B)]
         self.out = eng.alloc_outputs(B)
+        self.episode_length = float(episode_length)
+        if self.episode_length > 0 and not autoreset:
+            raise ValueError("the episode counter is part of the AutoReset wrapping (envs.training.wrap)")
+        self.steps = torch.zeros(B, dtype=torch.float32, device=eng.device)
+        self.truncation = torch.zeros(B, dtype=torch.float32, device=eng.device)
+        self.prev_done = torch.zeros(B, dtype=torch.float32, device=eng.device)
         self.d_action = torch.empty(B, env.action_size, dtype=torch.float32, device=eng.device)
         self.host = {k: torch.empty_like(self.out[k], device="cpu").pin_memory() for k in HOST_FIELDS}
         self.copy_stream = torch.cuda.Stream(device=eng.device)
@@ -51,6 +60,7 @@ class HostStepper:
         # contiguous leading-dim views of every buffer, cut once
         self.views = [dict(bufs=[cut(self.bufs[0], a, b), cut(self.bufs[1], a, b)], out=cut(self.out, a, b),
                            first=cut(self.first, a, b), first_obs=self.first_obs[a:b], action=self.d_action[a:b],
+                           steps=self.steps[a:b], truncation=self.truncation[a:b], prev_done=self.prev_done[a:b],
                            host={k: self.host[k][a:b] for k in HOST_FIELDS}) for a, b in self.chunks]
         self.flip = 0
         self.h2d_bytes = self.d_action.numel() * 4
@@ -67,7 +77,11 @@ class HostStepper:
         self.d_action.copy_(host_action, non_blocking=True)
         src, dst = self.flip, 1 - self.flip
         for v, ev in zip(self.views, self.events):
-            if self.autoreset:
+            if self.episode_length > 0:
+                eng.step_training(v["bufs"][src], v["action"], v["bufs"][dst], v["out"], v["first"], v["first_obs"],
+                                  v["steps"], v["prev_done"], v["steps"], v["truncation"], self.episode_length)
+                v["prev_done"].copy_(v["out"]["done"])  # the next step's `state.done` (same stream, after the launch)
+            elif self.autoreset:
                 eng.step_autoreset(v["bufs"][src], v["action"], v["bufs"][dst], v["out"], v["first"], v["first_obs"])
             else:
                 eng.step(v["bufs"][src], v["action"], v["bufs"][dst], v["out"])
