@@ -432,6 +432,21 @@ def test_host_stepper_chunks_equal_one_launch(gpu_env, rodent):
     for k in STATE_KEYS + ("cur_frame", "sub_clip_frame"):
         assert torch.equal(stepper.state[k], st[k]), k
     assert float(host["done"].min()) == 1.0  # Q7: every env is past its sub-clip by now
+    # with the episode counter (vnl_step_training per chunk): same thing against whole-batch launches
+    ep = pkg("hostio").HostStepper(gpu_env, s0, autoreset=True, chunk=128, episode_length=5)
+    st = {k: v.clone() for k, v in first.items()}
+    st["cur_frame"], st["sub_clip_frame"] = s0.info["cur_frame"].clone(), s0.info["sub_clip_frame"].clone()
+    steps, done_prev, trunc = (torch.zeros(B, device="cuda") for _ in range(3))
+    for i in range(K):
+        host = ep.step(acts[i])
+        eng.step_training(st, acts[i].cuda(), nxt, out, first, first_obs, steps, done_prev, steps, trunc, 5.0)
+        torch.cuda.synchronize()
+        done_prev = out["done"].clone()
+        for k in ("obs", "traj", "reward", "done"):
+            assert torch.equal(host[k], out[k].cpu()), (i, k)
+        assert torch.equal(ep.steps, steps) and torch.equal(ep.truncation, trunc)
+        st, nxt = nxt, st
+    assert float(steps.max()) <= 5.0
 
 
 def test_two_warps_per_env_build_matches_one_warp(gpu_env, rodent):
