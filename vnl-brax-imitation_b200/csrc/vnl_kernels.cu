@@ -752,8 +752,11 @@ struct LSP { float alpha, cost, d0, d1; };
 // ---------------------------------------------------------------------------------------------------------------------
 // mjx.forward for the env held in this warp's shared-memory slice
 // ---------------------------------------------------------------------------------------------------------------------
+// `gx` != nullptr (the last substep of a call): xpos / xquat / qfrc_actuator of this forward pass are the ones the caller
+// sees; they are stored to the env's rows of the output state right where they are produced (gx -> xpos, gq -> xquat,
+// gf -> qfrc_actuator), because their shared-memory homes are recycled by the solver.
 template <bool DUMP>
-__device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
+__device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, float* gq, float* gf) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
@@ -826,6 +829,14 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
       env_sync();
     }
     pf.mark(26);
+    if (gx) {
+      for (int i = tid; i < d.nbody * 3; i += kEnvThreads) gx[i] = s[L.xpos + i];
+      for (int i = tid; i < d.nbody * 4; i += kEnvThreads) gq[i] = s[L.xquat + i];
+    }
+    if (DUMP) {
+      for (int i = tid; i < d.nbody * 3; i += kEnvThreads) dump[d.dump_xpos + i] = s[L.xpos + i];
+      for (int i = tid; i < d.nbody * 4; i += kEnvThreads) dump[d.dump_xpos + d.nbody * 3 + i] = s[L.xquat + i];
+    }
     const int* jbody = c.fi(VNL_F_JNT_BODYID);
     for (int j = tid; j < d.njnt; j += kEnvThreads) {
       const int p = TB8(parent)[jbody[j]];
@@ -1035,7 +1046,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf) {
         if (flim[u]) force = fminf(fmaxf(force, frange[2 * u]), frange[2 * u + 1]);
         acc += gear[u] * force;
       }
-      s[L.qfrc_act + i] = acc;
+      if (gf) gf[i] = acc;
+      if (DUMP) dump[d.dump_passive + 2 * d.nv + i] = acc;
       const int j = dof_jnt[i];
       float pas;
       if (jtype[j] == 0) {
@@ -1606,7 +1618,11 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     // Optional lockstep: the warps of a CTA start each substep together, so that they walk the (large) instruction
     // footprint of a substep as one group instead of seven independent streams.
     if (p.lockstep) group_sync(p.lsgroups);
-    forward<MODE == 3>(so, dump, pf);
+    {
+      const bool last = (MODE != 3) && (st == nsteps - 1);  // MODE 3 has no output state
+      forward<MODE == 3>(so, dump, pf, last ? p.out.xpos + (size_t)e * d.nbody * 3 : nullptr,
+                         last ? p.out.xquat + (size_t)e * d.nbody * 4 : nullptr, last ? p.out.qfrc_actuator + (size_t)e * d.nv : nullptr);
+    }
     if (MODE == 1 || MODE == 3) break;
     if (p.lockstep > 1) group_sync(p.lsgroups);
     euler(so, pf);
@@ -1615,10 +1631,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   if (MODE == 3) {
     // stage dump (layout = oracle.dump_layout); arrays this formulation never materialises stay NaN
     auto put = [&](int off, const float* src, int n) { for (int i = tid; i < n; i += kEnvThreads) dump[off + i] = src[i]; };
-    put(d.dump_xpos, s + L.xpos, d.nbody * 3);
-    put(d.dump_xpos + d.nbody * 3, s + L.xquat, d.nbody * 4);
     put(d.dump_cinert + d.nbody * 10, s + L.cdof, d.nv * 6);
-    put(d.dump_passive + 2 * d.nv, s + L.qfrc_act, d.nv);
     put(d.dump_passive + 3 * d.nv, s + L.act_dot, d.na);
     put(d.dump_passive + 3 * d.nv + d.na, s + L.qfrc_smooth, d.nv);
     put(d.dump_passive + 4 * d.nv + d.na, s + L.qacc_smooth, d.nv);
@@ -1635,9 +1648,11 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   for (int i = tid; i < d.nv; i += kEnvThreads) o.qvel[(size_t)e * d.nv + i] = s[L.qvel + i];
   for (int i = tid; i < d.na; i += kEnvThreads) o.act[(size_t)e * d.na + i] = s[L.act + i];
   for (int i = tid; i < d.nv; i += kEnvThreads) o.qacc_warmstart[(size_t)e * d.nv + i] = s[L.warm + i];
-  for (int i = tid; i < d.nbody * 3; i += kEnvThreads) o.xpos[(size_t)e * d.nbody * 3 + i] = s[L.xpos + i];
-  for (int i = tid; i < d.nbody * 4; i += kEnvThreads) o.xquat[(size_t)e * d.nbody * 4 + i] = s[L.xquat + i];
-  for (int i = tid; i < d.nv; i += kEnvThreads) o.qfrc_actuator[(size_t)e * d.nv + i] = s[L.qfrc_act + i];
+  // xpos / xquat / qfrc_actuator were stored by the last forward pass; the task code below reads them back (same warp,
+  // ordered by the env barriers in between)
+  const float* const gxp = o.xpos + (size_t)e * d.nbody * 3;
+  const float* const gxq = o.xquat + (size_t)e * d.nbody * 4;
+  const float* const gfa = o.qfrc_actuator + (size_t)e * d.nv;
   const int torso = (MODE == 2) ? 1 : vnl_hdr_i(tb, VNL_TH_TORSO_BODY);
   const float* rcom = s + L.rcom + 3 * TB8(body_tree)[torso];  // subtree_com[torso]: torso is the root of its tree
   if (lane < 3) o.subtree_com[(size_t)e * 3 + lane] = rcom[lane];
@@ -1669,12 +1684,12 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       float v;
       if (i < d.nq) v = s[L.qpos + i];
       else if (i < d.nq + d.nv) v = s[L.qvel + i - d.nq];
-      else if (i < d.nq + 2 * d.nv) v = s[L.qfrc_act + i - d.nq - d.nv];
-      else { const int k = i - d.nq - 2 * d.nv; v = s[L.xpos + 3 * eeidx[k / 3] + k % 3]; }
+      else if (i < d.nq + 2 * d.nv) v = gfa[i - d.nq - d.nv];
+      else { const int k = i - d.nq - 2 * d.nv; v = gxp[3 * eeidx[k / 3] + k % 3]; }
       obs[i] = (MODE == 0) ? nan_to_num(v) : v;
     }
     float R[9];
-    quat_to_mat(ld4(s + L.xquat + 4 * vnl_hdr_i(tb, VNL_TH_ROT_BODY)), R);  // rodent.py:385 xmat[1]; ant.py:333 xmat[0]
+    quat_to_mat(ld4(gxq + 4 * vnl_hdr_i(tb, VNL_TH_ROT_BODY)), R);  // rodent.py:385 xmat[1]; ant.py:333 xmat[0]
     // window start: NEW cur_frame + 1 (rodent.py:188-190); the ant hands the not yet incremented info to _get_obs (ant.py:182)
     const int wf = (MODE == 0 && vnl_hdr_i(tb, VNL_TH_TRAJ_OLD_FRAME)) ? frame_old : cur_frame;
     const int ws = min(max(wf + 1, 0), T - ref_len);
@@ -1688,11 +1703,11 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
       } else if (i < n_app + n_bod) {
         const int q = i - n_app, w = q / (ntrack * 3), r = q - w * ntrack * 3, b = r / 3, cl = r % 3;
         const float* rb = rbody + ((size_t)(ws + w) * ntrack + b) * 3;
-        const float* xp = s + L.xpos + 3 * bidx[b];
+        const float* xp = gxp + 3 * bidx[b];
         v = (rb[0] - xp[0]) * R[cl] + (rb[1] - xp[1]) * R[3 + cl] + (rb[2] - xp[2]) * R[6 + cl];
       } else if (i < n_app + 2 * n_bod) {
         const int q = i - n_app - n_bod, w = q / (ntrack * 3), r = q - w * ntrack * 3, b = r / 3, k = r % 3;
-        v = rbody[((size_t)(ws + w) * ntrack + b) * 3 + k] - s[L.xpos + 3 * bidx[b] + k];
+        v = rbody[((size_t)(ws + w) * ntrack + b) * 3 + k] - gxp[3 * bidx[b] + k];
       } else if (i < n_app + 2 * n_bod + n_root) {
         const int q = i - n_app - 2 * n_bod, w = q / 3, cl = q % 3;
         const float* rp = rpos + (size_t)(ws + w) * 3;
@@ -1711,7 +1726,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     for (int j = lane; j < nj; j += 32) v0 += fabsf(rjoints[(size_t)f * nj + j] - s[L.qpos + 7 + j]);
     for (int b = lane; b < ntrack; b += 32) {
       const float* rb = rbody + ((size_t)f * ntrack + b) * 3;
-      const float* xp = s + L.xpos + 3 * bidx[b];
+      const float* xp = gxp + 3 * bidx[b];
       v1 += fabsf(rb[0] - xp[0]); v2 += fabsf(rb[1] - xp[1]); v3_ += fabsf(rb[2] - xp[2]);
     }
     v0 = warp_sum(v0); v1 = warp_sum(v1); v2 = warp_sum(v2); v3_ = warp_sum(v3_);
@@ -1731,17 +1746,17 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   // _calculate_reward (rodent.py:266-316 / humanoid.py:264-311): every reference lookup uses the OLD cur_frame
   {
     const int f = min(max(frame_old, 0), T - 1);
-    if (!vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE)) rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, s + L.qfrc_act, rcom);
+    if (!vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE)) rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, gfa, rcom);
     float v2 = 0.0f, v3_ = 0.0f;  // |app - ref|^2, nan count
     for (int i = lane; i < d.nv; i += 32)
-      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(s[L.qfrc_act + i])) v3_ += 1.0f;
+      if (isnan(s[L.qvel + i]) || isnan(s[L.warm + i]) || isnan(gfa[i])) v3_ += 1.0f;
     for (int i = lane; i < napp * 3; i += 32) {
       const int a = i / 3, k = i % 3;
-      const float df = s[L.xpos + 3 * appidx[a] + k] - rbody[((size_t)f * ntrack + apprefidx[a]) * 3 + k];
+      const float df = gxp[3 * appidx[a] + k] - rbody[((size_t)f * ntrack + apprefidx[a]) * 3 + k];
       v2 += df * df;
     }
     for (int i = lane; i < d.nq; i += 32) if (isnan(s[L.qpos + i])) v3_ += 1.0f;
-    for (int i = lane; i < d.nbody * 3; i += 32) if (isnan(s[L.xpos + i])) v3_ += 1.0f;
+    for (int i = lane; i < d.nbody * 3; i += 32) if (isnan(gxp[i])) v3_ += 1.0f;
     for (int i = lane; i < d.na; i += 32) if (isnan(s[L.act + i])) v3_ += 1.0f;
     v2 = warp_sum(v2); v3_ = warp_sum(v3_);
     float r_com = rt.rcom, rvl = rt.rvel, rquat = rt.rquat, ract = rt.ract;
@@ -1779,6 +1794,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     if (p.outputs.stats && lane < 4) p.outputs.stats[4 * e + lane] = stats[lane];
     // brax AutoResetWrapper.step fused in: where done, the pipeline-state leaves and obs are replaced by the cached
     // first ones; info (frames, traj), reward, done and metrics are kept.
+    env_sync();  // every read of the stored xpos / xquat / qfrc_actuator rows above precedes the restore below
     if (p.first.qpos && done > 0.0f) {
       const VnlState& f1 = p.first;
       for (int i = tid; i < d.nq; i += kEnvThreads) o.qpos[(size_t)e * d.nq + i] = f1.qpos[(size_t)e * d.nq + i];
