@@ -80,9 +80,9 @@ def test_workspace_is_required_and_sized(lib, rodent):
     lib.vnl_workspace_bytes.restype = ctypes.c_size_t
     need = lib.vnl_workspace_bytes(m.ctypes.data)
     d = mb.model_dims(rodent["model"])
-    per_env = ((d["TA"] + d["TD"]) * 32 + 31) // 32 * 32 * 4
-    assert need == lib.vnl_resident_envs(m.ctypes.data) * per_env and per_env == 10240
-    assert lib.vnl_resident_envs(m.ctypes.data) % lib.vnl_envs_per_cta(m.ctypes.data) == 0 and lib.vnl_envs_per_cta(m.ctypes.data) == 10
+    per_env = (2 * (d["TA"] + d["TD"]) * 32 + 31) // 32 * 32 * 4  # M and K, one copy per lane program each
+    assert need == lib.vnl_resident_envs(m.ctypes.data) * per_env and per_env == 20480
+    assert lib.vnl_resident_envs(m.ctypes.data) % lib.vnl_envs_per_cta(m.ctypes.data) == 0 and lib.vnl_envs_per_cta(m.ctypes.data) == 14
     fake_model, fake_task, fake_work = 0x7000000000, 0x7100000000, 0x7200000000  # never dereferenced on these paths
     assert lib.vnl_set_workspace(fake_model, fake_work, need) == -1              # unknown model blob
     assert lib.vnl_register_blob(fake_model, m.ctypes.data, m.nbytes) == 0

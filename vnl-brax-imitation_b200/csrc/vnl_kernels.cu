@@ -78,30 +78,48 @@ __device__ __forceinline__ void group_sync(int groups) {
 
 __host__ __device__ inline int align4(int x) { return (x + 3) & ~3; }
 
+// Per-env shared-memory layout.  Three parts: arrays that live through the whole substep, and two recycled regions whose
+// tenants change with the phase of the substep (P1 kinematics, P2 com / cdof, P3 velocity + rne passes, P4 smooth forces,
+// P5 inertia build, P6 factorise + invert, P7 smooth solve, P8 constraint rows, P9 solver, P10 integrator):
+//   R0  P1-P8: xpos, xquat, cvel (P8 is their last reader; the caller's copies went to the output state in P1)
+//       P9-P10: Jaref and the solver vectors qacc .. qfrc_con
+//   R1  P1-P2: xipos, xanchor, xaxis | P3-P5: cacc, then crb * cdof ("fd") in the same place
+//       P2-P5: t16 = cinert / crb (10) + rne force (6) per body, behind them
+//       P5-P6, P10: F, the factorisation workspace (M, then L^T D L, then K), from behind fd / part+tmpv on (over t16)
+//       P7-P10: part, tmpv (mat-vec scratch) at the very start (fd is dead by then)
+//       P8-P9: the constraint rows (limit list, contacts, efcD, Jv) behind part / tmpv (F is dead: K went to the workspace)
+// Only M_diag, K_diag survive of the inertia; M and K themselves are streamed from the global workspace.
 __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   int o = 0;
 #define A(name, n) L.name = o; o += align4(n)
   A(qpos, d.nq); A(qvel, d.nv); A(act, d.na); A(ctrl, d.nu); A(warm, d.nv);
-  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cdof, d.nv * 6);
-  // cvel is dead once the contact rows are built (its last reader); Jaref and the limit list are born after that
-  { const int need = align4(d.nefc) + align4(d.nlimit); A(cvel, d.nbody * 6 > need ? d.nbody * 6 : need); }
-  L.Jaref = L.cvel; L.lim_dof = L.cvel + align4(d.nefc);
-  A(Mdiag, d.nv); A(rcom, d.nroot * 3);
-  const int ab = o;
-  A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3); A(t16, d.nbody * 16);
-  const int a_end = o;
-  o = ab;
-  A(K, d.nM + 1); A(efcD, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
-  if (a_end > o) o = a_end;
-  A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(qfrc_act, d.nv); A(act_dot, d.na);
-  A(limrow_of_dof, d.nv);
-  A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
-  A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv); A(tmpv, d.nv); A(part, d.naslot + d.ndslot);
+  A(cdof, d.nv * 6); A(Mdiag, d.nv); A(Kdiag, d.nv); A(rcom, d.nroot * 3);
+  A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(act_dot, d.na); A(ints, 16);
   L.Mn = L.H = L.jr = 0;
   if (d.solver == 2) { A(Mn, d.nM); A(H, d.nv * d.nv); A(jr, 3 * d.nv); }  // Newton: natural-order M, dense Hessian, row scratch
-  L.cacc = L.qacc;  // spatial accelerations / crb * cdof live where the solver vectors will be (dead until the solve)
-  if (o - L.qacc < (d.nbody > d.nv ? d.nbody : d.nv) * 6) o = L.qacc + align4((d.nbody > d.nv ? d.nbody : d.nv) * 6);
-  A(ints, 16);
+  const int r0 = o;
+  A(xpos, d.nbody * 3); A(xquat, d.nbody * 4); A(cvel, d.nbody * 6);
+  const int r0a = o;
+  o = r0;
+  A(Jaref, d.nefc); A(qacc, d.nv); A(Ma, d.nv); A(grad, d.nv); A(Mgrad, d.nv); A(search, d.nv); A(Mv, d.nv); A(qfrc_con, d.nv);
+  if (r0a > o) o = r0a;
+  const int r1 = o;
+  A(xipos, d.nbody * 3); A(xanchor, d.njnt * 3); A(xaxis, d.njnt * 3);
+  const int cacc_n = align4((d.nbody > d.nv ? d.nbody : d.nv) * 6);
+  if (o - r1 < cacc_n) o = r1 + cacc_n;
+  L.cacc = r1;
+  A(t16, d.nbody * 16);
+  int r1end = o;
+  o = r1;
+  A(part, d.naslot + d.ndslot); A(tmpv, d.nv);
+  const int scratch_end = o;
+  A(lim_dof, d.nlimit); A(limrow_of_dof, d.nv); A(cbody, d.ncon); A(crel, d.ncon * 3); A(cframe, d.ncon * 6); A(cmu, d.ncon);
+  A(efcD, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
+  if (o > r1end) r1end = o;
+  o = r1 + (cacc_n > scratch_end - r1 ? cacc_n : scratch_end - r1);  // F clears fd (P5) and part / tmpv (P10)
+  A(K, d.nM + 1);
+  if (o > r1end) r1end = o;
+  o = r1end;
 #undef A
   L.total = o;
 }
@@ -390,6 +408,13 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
     }
     i0 = i1;
   }
+  {  // K leaves shared memory: program-ordered copies for solve_m's two mat-vecs, 1 / D stays (Kdiag)
+    float* const wk = slot_work(c) + (c.TA + c.TD) * kEnvThreads;
+    spill_section(TB32(prog_a), c.TA, F, wk);
+    spill_section(TB32(prog_d), c.TD, F, wk + c.TA * kEnvThreads);
+    for (int i = tid; i < nv; i += kEnvThreads) s[c.L.Kdiag + i] = F[madr[i]];
+    env_sync();
+  }
   pf.mark(18);
 }
 
@@ -397,22 +422,22 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
 __device__ __noinline__ void solve_m(int so, int xo, int outo) {
   VNL_SMEM
   const int nv = c.d.nv, lane = LANE, tid = ETID;
-  float* const K = s + c.L.K;
+  const float* const Kdiag = s + c.L.Kdiag;
   const float* const x = s + xo;
   float* const pa = s + c.L.part;
   float* const pd = pa + c.d.naslot;
   float* const tmp = s + c.L.tmpv;
-  const uint16_t* const madr = TB16(madr);
   const uint8_t* const dpa = TB8(dpart_adr);
-  spmv_section(TB32(prog_d), c.TD, K, x, pd);   // K[nM] = 0 since factor()
+  const float* const wk = slot_work(c) + (c.TA + c.TD) * kEnvThreads;  // the program-ordered copies of K follow those of M
+  spmv_stream_g(TB32(prog_d), c.TD, 0, wk + c.TA * kEnvThreads, x, pd, 0);
   env_sync();
   for (int j = tid; j < nv; j += kEnvThreads) {
     float acc = x[j];
     for (int q = dpa[j]; q < dpa[j + 1]; ++q) acc += pd[q];
-    tmp[j] = acc * K[madr[j]];
+    tmp[j] = acc * Kdiag[j];
   }
   env_sync();
-  spmv_section(TB32(prog_a), c.TA, K, tmp, pa);
+  spmv_stream_g(TB32(prog_a), c.TA, c.TA, wk, tmp, pa, 0);
   env_sync();
   float* const out = s + outo;
   const uint8_t* const apa = TB8(apart_adr);

@@ -22,17 +22,16 @@ struct Dims {
       dump_efc, dump_qacc, dump_total;
 };
 
-// Per-env shared-memory layout (float offsets).  Region A (kinematic / inertial scratch) is dead once the joint-space
-// inertia is built and shares its storage with region B (inverse factor + constraint rows).
+// Per-env shared-memory layout (float offsets); see make_layout for the regions and who lives in them when.
 struct Lay {
-  int qpos, qvel, act, ctrl, warm, xpos, xquat, cdof, cvel, M, rcom;
-  int xipos, xanchor, xaxis, t16;                                         // region A
-  int cacc;                                                               // aliases the solver vectors (dead until the solve)
-  int K, efcD, Jaref, Jv;                                                 // region B
-  int qfrc_smooth, qacc_smooth, qfrc_act, act_dot;
-  int lim_dof, limrow_of_dof, cbody, crel, cframe, cmu, Mdiag;
+  int qpos, qvel, act, ctrl, warm, cdof, Mdiag, Kdiag, rcom, qfrc_smooth, qacc_smooth, act_dot, ints;  // whole substep
   int Mn, H, jr;                                                          // Newton solver only (dense Hessian)
-  int qacc, Ma, grad, Mgrad, search, Mv, qfrc_con, tmpv, part, ints, total;
+  int xpos, xquat, cvel;                                                  // region R0, kinematics .. constraint rows
+  int Jaref, qacc, Ma, grad, Mgrad, search, Mv, qfrc_con;                 // region R0, solver .. integrator
+  int xipos, xanchor, xaxis, cacc, t16;                                   // region R1, kinematic passes
+  int part, tmpv, lim_dof, limrow_of_dof, cbody, crel, cframe, cmu, efcD, Jv;  // region R1, solves / constraint rows
+  int K;                                                                  // region R1, factorisation workspace
+  int total;
 };
 
 struct Params {
@@ -58,8 +57,9 @@ struct Params {
 
 struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };  // warps_per_cta = env groups per CTA
 
-// floats of inertia workspace per resident env: the A-order and the D-order copy of the off-diagonal entries
-inline int work_stride(const Dims& d) { return ((d.TA + d.TD) * 32 * d.env_warps + 31) & ~31; }
+// floats of workspace per resident env: the A-order and the D-order copy of the off-diagonal entries of the inertia M,
+// then the same two copies of its inverse factor K
+inline int work_stride(const Dims& d) { return (2 * (d.TA + d.TD) * 32 * d.env_warps + 31) & ~31; }
 
 // vnl_kernels.cu is compiled once per env-group width (-DVNL_EW=1, 2) into its own namespace.
 namespace ew1 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
