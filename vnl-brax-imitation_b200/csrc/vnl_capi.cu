@@ -54,6 +54,7 @@ void fill_dims(const uint32_t* w, vnl::Dims& d) {
   d.dump_efc = d.dump_con + 13 * d.ncon;
   d.dump_qacc = d.dump_efc + 3 * d.nefc + d.nefc * nv;
   d.dump_total = d.dump_qacc + 2 * nv + d.nefc + 4;
+  vnl::any_decide_stream(d);
 }
 
 int check_blob(const void* host, size_t nbytes, uint32_t magic, int nfields) {
@@ -75,7 +76,7 @@ int prepare(const void* model, const void* task, bool need_task, vnl::Params& p)
   if (!model || !lookup(model, hm)) return -10;
   if (hm.w[0] != VNL_MAGIC_MODEL) return -11;
   fill_dims(hm.w, p.dims);
-  {
+  if (p.dims.stream) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto it = g_work.find(model);
     if (it == g_work.end()) return -20;

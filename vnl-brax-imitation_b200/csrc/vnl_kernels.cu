@@ -38,12 +38,16 @@
 #ifndef VNL_EW
 #define VNL_EW 1
 #endif
+#ifndef VNL_STREAM
+#define VNL_STREAM 1
+#endif
 #define VNL_CAT2(a, b) a##b
 #define VNL_CAT(a, b) VNL_CAT2(a, b)
 
 namespace vnl {
-namespace VNL_CAT(ew, VNL_EW) {  // one instantiation of everything below per env-group width (see Makefile)
+namespace VNL_CAT(VNL_CAT(ew, VNL_EW), VNL_CAT(s, VNL_STREAM)) {  // one instantiation of everything below per (env-group width, inertia home): see Makefile
 
+constexpr bool kStream = VNL_STREAM != 0;  // M and K streamed from the global workspace (1) or resident in shared memory (0): Dims::stream
 constexpr int kEnvWarps = VNL_EW;          // warps cooperating on one env
 constexpr int kEnvThreads = 32 * VNL_EW;   // = lanes of the mat-vec programs (VNL_MH_ENV_WARPS of the blob must agree)
 // envs per CTA upper bound: one-warp groups are bounded by shared memory (10 rodents) or by the register file (16 warps x 128
@@ -95,6 +99,8 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(qpos, d.nq); A(qvel, d.nv); A(act, d.na); A(ctrl, d.nu); A(warm, d.nv);
   A(cdof, d.nv * 6); A(Mdiag, d.nv); A(Kdiag, d.nv); A(rcom, d.nroot * 3);
   A(qfrc_smooth, d.nv); A(qacc_smooth, d.nv); A(act_dot, d.na); A(ints, 16);
+  L.Ms = L.Ks = 0;
+  if (!d.stream) { A(Ms, d.nM + 1); A(Ks, d.nM + 1); }
   L.Mn = L.H = L.jr = 0;
   if (d.solver == 2) { A(Mn, d.nM); A(H, d.nv * d.nv); A(jr, 3 * d.nv); }  // Newton: natural-order M, dense Hessian, row scratch
   const int r0 = o;
@@ -275,8 +281,12 @@ __device__ __noinline__ void mul_m(int so, int xo, int outo) {
   const float* const x = s + xo;
   float* const pa = s + c.L.part;
   float* const pd = pa + c.d.naslot;
-  const float* const wk = slot_work(c);
-  spmv_stream_g(TB32(prog_a), c.TA + c.TD, c.TA, wk, x, pa, c.d.naslot);  // PROG_D follows PROG_A in the staged tables
+  if (kStream) {
+    spmv_stream_g(TB32(prog_a), c.TA + c.TD, c.TA, slot_work(c), x, pa, c.d.naslot);  // PROG_D follows PROG_A in the staged tables
+  } else {
+    spmv_section(TB32(prog_a), c.TA, s + c.L.Ms, x, pa);
+    spmv_section(TB32(prog_d), c.TD, s + c.L.Ms, x, pd);
+  }
   env_sync();
   const uint8_t* const dpa = TB8(dpart_adr);
   const uint8_t* const apa = TB8(apart_adr);
@@ -304,7 +314,12 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
   if (damp) {
     const float* damping = c.ff(VNL_F_DOF_DAMPING);
     const float dt = c.d.timestep;
-    restore_section(TB32(prog_a), c.TA, F, slot_work(c), 4u * (uint32_t)nM);
+    if (kStream) {
+      restore_section(TB32(prog_a), c.TA, F, slot_work(c), 4u * (uint32_t)nM);
+    } else {
+      for (int e = tid; e < nM; e += kEnvThreads) F[e] = s[c.L.Ms + e];
+      env_sync();
+    }
     for (int i = tid; i < nv; i += kEnvThreads) F[madr[i]] = s[c.L.Mdiag + i] + dt * damping[i];
     if (tid == 0) F[nM] = 0.0f;
     env_sync();
@@ -409,9 +424,13 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
     i0 = i1;
   }
   {  // K leaves shared memory: program-ordered copies for solve_m's two mat-vecs, 1 / D stays (Kdiag)
-    float* const wk = slot_work(c) + (c.TA + c.TD) * kEnvThreads;
-    spill_section(TB32(prog_a), c.TA, F, wk);
-    spill_section(TB32(prog_d), c.TD, F, wk + c.TA * kEnvThreads);
+    if (kStream) {
+      float* const wk = slot_work(c) + (c.TA + c.TD) * kEnvThreads;
+      spill_section(TB32(prog_a), c.TA, F, wk);
+      spill_section(TB32(prog_d), c.TD, F, wk + c.TA * kEnvThreads);
+    } else {
+      for (int e = tid; e <= nM; e += kEnvThreads) s[c.L.Ks + e] = F[e];  // incl. the zero slot the padded terms point at
+    }
     for (int i = tid; i < nv; i += kEnvThreads) s[c.L.Kdiag + i] = F[madr[i]];
     env_sync();
   }
@@ -429,7 +448,8 @@ __device__ __noinline__ void solve_m(int so, int xo, int outo) {
   float* const tmp = s + c.L.tmpv;
   const uint8_t* const dpa = TB8(dpart_adr);
   const float* const wk = slot_work(c) + (c.TA + c.TD) * kEnvThreads;  // the program-ordered copies of K follow those of M
-  spmv_stream_g(TB32(prog_d), c.TD, 0, wk + c.TA * kEnvThreads, x, pd, 0);
+  if (kStream) spmv_stream_g(TB32(prog_d), c.TD, 0, wk + c.TA * kEnvThreads, x, pd, 0);
+  else spmv_section(TB32(prog_d), c.TD, s + c.L.Ks, x, pd);
   env_sync();
   for (int j = tid; j < nv; j += kEnvThreads) {
     float acc = x[j];
@@ -437,7 +457,8 @@ __device__ __noinline__ void solve_m(int so, int xo, int outo) {
     tmp[j] = acc * Kdiag[j];
   }
   env_sync();
-  spmv_stream_g(TB32(prog_a), c.TA, c.TA, wk, tmp, pa, 0);
+  if (kStream) spmv_stream_g(TB32(prog_a), c.TA, c.TA, wk, tmp, pa, 0);
+  else spmv_section(TB32(prog_a), c.TA, s + c.L.Ks, tmp, pa);
   env_sync();
   float* const out = s + outo;
   const uint8_t* const apa = TB8(apart_adr);
@@ -1114,12 +1135,14 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         dump[d.dump_qM + TB8(mcol)[q] * d.nv + TB8(mrow)[q]] = F[q];
       }
     }
-    {  // program-ordered copies of M for the solver's mat-vecs and for the integrator's second factorisation
+    if (kStream) {  // program-ordered copies of M for the solver's mat-vecs and for the integrator's second factorisation
       float* const wk = slot_work(c);
       spill_section(TB32(prog_a), c.TA, F, wk);
       spill_section(TB32(prog_d), c.TD, F, wk + c.TA * kEnvThreads);
+    } else {
+      for (int e = tid; e <= d.nM; e += kEnvThreads) s[L.Ms + e] = F[e];
     }
-    if (kEnvWarps > 1) env_sync();  // the factorisation rewrites F: every warp of the env must be done copying
+    if (kEnvWarps > 1 || !kStream) env_sync();  // the factorisation rewrites F: every thread of the env must be done copying
   }
   pf.mark(4);
   if (ls3) __syncthreads();
@@ -1884,6 +1907,22 @@ template __global__ void vnl_env_kernel<1>(Params);
 template __global__ void vnl_env_kernel<2>(Params);
 template __global__ void vnl_env_kernel<3>(Params);
 
+static int max_envs_per_cta(const Dims& d) {
+  Lay L;
+  make_layout(d, L);
+  const int w = (227 * 1024 - (kCtaFloats + align4(d.ktab_words)) * 4) / (L.total * 4);
+  return w > kMaxEnvs ? kMaxEnvs : w;
+}
+
+void decide_stream(Dims& d) {
+  Dims r = d, g = d;
+  r.stream = 0; g.stream = 1;
+  d.stream = max_envs_per_cta(r) >= max_envs_per_cta(g) ? 0 : 1;  // resident inertia only where it costs no resident env
+  static int force = -2;
+  if (force == -2) { const char* ev = getenv("VNL_STREAM"); force = ev ? atoi(ev) : -1; }
+  if (force == 0 || force == 1) d.stream = force;
+}
+
 LaunchInfo launch_info(const Dims& d, int B) {
   Lay L;
   make_layout(d, L);
@@ -1928,6 +1967,7 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   const LaunchInfo li = launch_info(p.dims, p.B);
   if (li.warps_per_cta < 1) return cudaErrorInvalidConfiguration;  // one env does not fit in shared memory
   if (p.dims.env_warps != kEnvWarps) return cudaErrorInvalidValue;   // the blob's lane programs are for another group width
+  if ((p.dims.stream != 0) != kStream) return cudaErrorInvalidValue;  // dispatched to the wrong instantiation
   void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;

@@ -15,6 +15,8 @@ struct Dims {
   int ktab_words;  // size of VNL_F_KTAB
   int ndslot;      // partial-sum slots of the descendant mat-vec program (VNL_KS_NDSLOT)
   int TA, TD;      // steps of the mat-vec lane programs (VNL_MH_TA / VNL_MH_TD)
+  int stream;      // 1: M and K live in the global workspace (large models: buys residency); 0: resident in shared memory
+                   // (small models whose residency is bound by the register file anyway).  Set by decide_stream().
   int naslot;      // partial-sum slots of the ancestor mat-vec program (VNL_MH_NASLOT)
   int env_warps;   // warps cooperating on one env (VNL_MH_ENV_WARPS): lane count of the mat-vec programs / 32
   // stage-dump offsets (layout of oracle.dump_layout)
@@ -31,6 +33,7 @@ struct Lay {
   int xipos, xanchor, xaxis, cacc, t16;                                   // region R1, kinematic passes
   int part, tmpv, lim_dof, limrow_of_dof, cbody, crel, cframe, cmu, efcD, Jv;  // region R1, solves / constraint rows
   int K;                                                                  // region R1, factorisation workspace
+  int Ms, Ks;                                                             // resident copies of M and K (stream == 0 only)
   int total;
 };
 
@@ -59,16 +62,23 @@ struct LaunchInfo { int smem_bytes, warps_per_cta, ctas; };  // warps_per_cta = 
 
 // floats of workspace per resident env: the A-order and the D-order copy of the off-diagonal entries of the inertia M,
 // then the same two copies of its inverse factor K
-inline int work_stride(const Dims& d) { return (2 * (d.TA + d.TD) * 32 * d.env_warps + 31) & ~31; }
+inline int work_stride(const Dims& d) { return d.stream ? (2 * (d.TA + d.TD) * 32 * d.env_warps + 31) & ~31 : 0; }
 
-// vnl_kernels.cu is compiled once per env-group width (-DVNL_EW=1, 2) into its own namespace.
-namespace ew1 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
-namespace ew2 { LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
+// vnl_kernels.cu is compiled once per (env-group width -DVNL_EW=1, 2; inertia home -DVNL_STREAM=0, 1) into its own namespace.
+// decide_stream() fills Dims::stream: resident inertia unless that would cost a resident env.
+#define VNL_DECL(ns) namespace ns { void decide_stream(Dims& d); LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
+VNL_DECL(ew1s0) VNL_DECL(ew1s1) VNL_DECL(ew2s0) VNL_DECL(ew2s1)
+#undef VNL_DECL
 
-inline LaunchInfo any_launch_info(const Dims& d, int B) { return d.env_warps == 2 ? ew2::launch_info(d, B) : ew1::launch_info(d, B); }
+inline void any_decide_stream(Dims& d) { if (d.env_warps == 2) ew2s1::decide_stream(d); else ew1s1::decide_stream(d); }
+inline LaunchInfo any_launch_info(const Dims& d, int B) {
+  if (d.env_warps == 2) return d.stream ? ew2s1::launch_info(d, B) : ew2s0::launch_info(d, B);
+  return d.stream ? ew1s1::launch_info(d, B) : ew1s0::launch_info(d, B);
+}
 inline cudaError_t any_launch(int mode, const Params& p, cudaStream_t stream) {
-  if (p.dims.env_warps == 2) return ew2::launch(mode, p, stream);
-  if (p.dims.env_warps == 1) return ew1::launch(mode, p, stream);
+  const bool st = p.dims.stream != 0;
+  if (p.dims.env_warps == 2) return st ? ew2s1::launch(mode, p, stream) : ew2s0::launch(mode, p, stream);
+  if (p.dims.env_warps == 1) return st ? ew1s1::launch(mode, p, stream) : ew1s0::launch(mode, p, stream);
   return cudaErrorInvalidValue;
 }
 
