@@ -198,7 +198,8 @@ enum VnlKtab {
   VNL_KT_KITEM,         /* u16 [sum of dof depths] c | dof << 8, grouped by dof depth, descending c inside a group */
   VNL_KT_KLVL,          /* u16 [maxdepth+2] offsets into KITEM by dof depth */
   /* Lane programs of the sparse mat-vecs with M and with the inverse factor K (same sparsity).  A program is
-   * [T][32 * env_warps] words, one term per lane per step: bits 0-13 entry * 4, bits 14-23 x index * 4, bits 24-31 the
+   * [T / 4][32 * env_warps][4] words (the four consecutive steps of a lane form one 16-byte word; T a multiple of 8),
+   * one term per lane per step: bits 0-13 entry * 4, bits 14-23 x index * 4, bits 24-31 the
    * partial-sum slot to flush into after this term (0xFF = keep accumulating).  PROG_A: strict-ancestor terms
    * (row i, entries madr[i]+1 ..), PROG_D: descendant terms (column j); long rows / columns are split into chunks,
    * the chunks' slots are listed by APART_ADR / DPART_ADR.  Lanes are load balanced on the host; lists are padded with a zero term. */

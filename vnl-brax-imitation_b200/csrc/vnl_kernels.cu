@@ -171,107 +171,103 @@ struct Prof {
 // sparse-inertia helpers (one env group).  Vector arguments are float offsets into the env slice.
 // ---------------------------------------------------------------------------------------------------------------------
 // One section of a lane program: part[slot] = sum over the lane's terms of V[entry] * x[index] (see VnlKtab).
-// T is a multiple of 4 (host pads).  The four program words and their eight operands of a batch are loaded before any
-// partial sum is flushed, so the loads of a batch overlap instead of queueing behind the previous term's store.
+// A program is stored as [T / 4][lanes][4] words: the four consecutive steps of a lane sit in one 16-byte word, so a
+// lane fetches them (and, from the workspace copies, their four V operands) with one 128-bit load.  T is a multiple
+// of 8 (host pads).  All loads of a batch are issued before any partial sum is flushed.
+#define VNL_LDV(w) (*reinterpret_cast<const float*>(Vb + ((w) & 0x3ffcu)))
+#define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
+#define VNL_FLUSHTO(pt, w) if ((w) < 0xff000000u) { (pt)[(w) >> 24] = acc; acc = 0.0f; }
 __device__ __forceinline__ void spmv_section(const uint32_t* __restrict__ prog, int T, const float* __restrict__ V,
                                              const float* __restrict__ x, float* __restrict__ part) {
   const char* Vb = reinterpret_cast<const char*>(V);
   const char* xb = reinterpret_cast<const char*>(x);
-  prog += ETID;
+  const uint4* pp = reinterpret_cast<const uint4*>(prog) + ETID;
   float acc = 0.0f;
-#define VNL_LDV(w) (*reinterpret_cast<const float*>(Vb + ((w) & 0x3ffcu)))
-#define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
-#define VNL_FLUSH(w) if ((w) < 0xff000000u) { part[(w) >> 24] = acc; acc = 0.0f; }
-  for (int t = 0; t < T; t += 4) {
-    const uint32_t w0 = prog[t * kEnvThreads], w1 = prog[(t + 1) * kEnvThreads], w2 = prog[(t + 2) * kEnvThreads], w3 = prog[(t + 3) * kEnvThreads];
-    const float v0 = VNL_LDV(w0), x0 = VNL_LDX(w0), v1 = VNL_LDV(w1), x1 = VNL_LDX(w1);
-    const float v2 = VNL_LDV(w2), x2 = VNL_LDX(w2), v3 = VNL_LDV(w3), x3 = VNL_LDX(w3);
-    acc += v0 * x0; VNL_FLUSH(w0)
-    acc += v1 * x1; VNL_FLUSH(w1)
-    acc += v2 * x2; VNL_FLUSH(w2)
-    acc += v3 * x3; VNL_FLUSH(w3)
+  for (int t = 0; t < T; t += 4, pp += kEnvThreads) {
+    const uint4 w = *pp;
+    const float v0 = VNL_LDV(w.x), x0 = VNL_LDX(w.x), v1 = VNL_LDV(w.y), x1 = VNL_LDX(w.y);
+    const float v2 = VNL_LDV(w.z), x2 = VNL_LDX(w.z), v3 = VNL_LDV(w.w), x3 = VNL_LDX(w.w);
+    acc += v0 * x0; VNL_FLUSHTO(part, w.x)
+    acc += v1 * x1; VNL_FLUSHTO(part, w.y)
+    acc += v2 * x2; VNL_FLUSHTO(part, w.z)
+    acc += v3 * x3; VNL_FLUSHTO(part, w.w)
   }
-#undef VNL_LDV
-#undef VNL_LDX
-#undef VNL_FLUSH
 }
 
 // The joint-space inertia M lives in GLOBAL memory (L2), one copy per mat-vec program, in the order the program's lanes
-// consume it: word (t, lane) of the copy is the V operand of program word (t, lane).  Every thread only ever reads the
-// words it wrote itself, so no fence is needed.  Loads / stores bypass L1 (.cg).
+// consume it: word (t, lane) of the copy is the V operand of program word (t, lane), same [T / 4][lanes][4] packing.
+// Every thread only ever reads the words it wrote itself, so no fence is needed.  Loads / stores bypass L1 (.cg).
 __device__ __forceinline__ float* slot_work(const Cta& c) {
   return c.work + (size_t)(blockIdx.x * (blockDim.x / kEnvThreads) + ESLOT) * (size_t)c.work_stride;
 }
 __device__ __forceinline__ void spill_section(const uint32_t* __restrict__ prog, int T, const float* __restrict__ V, float* __restrict__ g) {
   const char* Vb = reinterpret_cast<const char*>(V);
-  prog += ETID; g += ETID;
-  for (int t = 0; t < T; t += 4) {
-    const uint32_t w0 = prog[t * kEnvThreads], w1 = prog[(t + 1) * kEnvThreads], w2 = prog[(t + 2) * kEnvThreads], w3 = prog[(t + 3) * kEnvThreads];
-    const float v0 = *reinterpret_cast<const float*>(Vb + (w0 & 0x3ffcu)), v1 = *reinterpret_cast<const float*>(Vb + (w1 & 0x3ffcu));
-    const float v2 = *reinterpret_cast<const float*>(Vb + (w2 & 0x3ffcu)), v3 = *reinterpret_cast<const float*>(Vb + (w3 & 0x3ffcu));
-    __stcg(g + t * kEnvThreads, v0); __stcg(g + (t + 1) * kEnvThreads, v1);
-    __stcg(g + (t + 2) * kEnvThreads, v2); __stcg(g + (t + 3) * kEnvThreads, v3);
+  const uint4* pp = reinterpret_cast<const uint4*>(prog) + ETID;
+  float4* gp = reinterpret_cast<float4*>(g) + ETID;
+  for (int t = 0; t < T; t += 4, pp += kEnvThreads, gp += kEnvThreads) {
+    const uint4 w = *pp;
+    __stcg(gp, make_float4(VNL_LDV(w.x), VNL_LDV(w.y), VNL_LDV(w.z), VNL_LDV(w.w)));
   }
 }
 // the inverse of spill_section for the ancestor program (it covers every off-diagonal entry exactly once; padding
 // words point at the zero slot `pad` and are skipped)
 __device__ __forceinline__ void restore_section(const uint32_t* __restrict__ prog, int T, float* __restrict__ V, const float* __restrict__ g, uint32_t pad) {
   char* Vb = reinterpret_cast<char*>(V);
-  prog += ETID; g += ETID;
-  for (int t = 0; t < T; t += 4) {
-    const uint32_t w0 = prog[t * kEnvThreads] & 0x3ffcu, w1 = prog[(t + 1) * kEnvThreads] & 0x3ffcu;
-    const uint32_t w2 = prog[(t + 2) * kEnvThreads] & 0x3ffcu, w3 = prog[(t + 3) * kEnvThreads] & 0x3ffcu;
-    const float v0 = __ldcg(g + t * kEnvThreads), v1 = __ldcg(g + (t + 1) * kEnvThreads);
-    const float v2 = __ldcg(g + (t + 2) * kEnvThreads), v3 = __ldcg(g + (t + 3) * kEnvThreads);
-    if (w0 != pad) *reinterpret_cast<float*>(Vb + w0) = v0;
-    if (w1 != pad) *reinterpret_cast<float*>(Vb + w1) = v1;
-    if (w2 != pad) *reinterpret_cast<float*>(Vb + w2) = v2;
-    if (w3 != pad) *reinterpret_cast<float*>(Vb + w3) = v3;
+  const uint4* pp = reinterpret_cast<const uint4*>(prog) + ETID;
+  const float4* gp = reinterpret_cast<const float4*>(g) + ETID;
+  for (int t = 0; t < T; t += 4, pp += kEnvThreads, gp += kEnvThreads) {
+    const uint4 w = *pp;
+    const float4 v = __ldcg(gp);
+    const uint32_t e0 = w.x & 0x3ffcu, e1 = w.y & 0x3ffcu, e2 = w.z & 0x3ffcu, e3 = w.w & 0x3ffcu;
+    if (e0 != pad) *reinterpret_cast<float*>(Vb + e0) = v.x;
+    if (e1 != pad) *reinterpret_cast<float*>(Vb + e1) = v.y;
+    if (e2 != pad) *reinterpret_cast<float*>(Vb + e2) = v.z;
+    if (e3 != pad) *reinterpret_cast<float*>(Vb + e3) = v.w;
   }
 }
-// spmv_section with the V operands streamed from the workspace copy: eight terms per batch, three batches of V words in
-// flight (L2 latency is several batches long).  Walks the ancestor and the descendant program back to back -- they and
-// their workspace copies are contiguous -- so the stream never drains in between (T = TA + TD, a multiple of 8).  The
-// flush slots of the descendant program are offset by `dslot0`.
+// spmv_section with the V operands streamed from the workspace copy: eight terms (two 128-bit words) per batch, three
+// batches of V words in flight (L2 latency is several batches long).  Can walk the ancestor and the descendant program
+// back to back -- they and their workspace copies are contiguous -- so the stream never drains in between (T = TA + TD, a
+// multiple of 8).  The flush slots of the steps from TA on are offset by `dslot0`.
 __device__ __forceinline__ void spmv_stream_g(const uint32_t* __restrict__ prog, int T, int TA, const float* __restrict__ g,
                                               const float* __restrict__ x, float* __restrict__ part, int dslot0) {
   const char* xb = reinterpret_cast<const char*>(x);
-  prog += ETID; g += ETID;
+  const uint4* pp = reinterpret_cast<const uint4*>(prog) + ETID;  // running pointers: every access is base + immediate
+  const float4* gq = reinterpret_cast<const float4*>(g) + ETID;
   float acc = 0.0f;
-  float q0[8], q1[8], q2[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    q0[k] = __ldcg(g + k * kEnvThreads);
-    q1[k] = 8 < T ? __ldcg(g + (8 + k) * kEnvThreads) : 0.0f;
-    q2[k] = 16 < T ? __ldcg(g + (16 + k) * kEnvThreads) : 0.0f;
-  }
-#define VNL_LDX(w) (*reinterpret_cast<const float*>(xb + (((w) >> 14) & 0x3fcu)))
-#define VNL_BATCH(q, t0)                                                                          \
+  const float4 z4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  float4 q0a = __ldcg(gq), q0b = __ldcg(gq + kEnvThreads);
+  float4 q1a = 8 < T ? __ldcg(gq + 2 * kEnvThreads) : z4, q1b = 8 < T ? __ldcg(gq + 3 * kEnvThreads) : z4;
+  float4 q2a = 16 < T ? __ldcg(gq + 4 * kEnvThreads) : z4, q2b = 16 < T ? __ldcg(gq + 5 * kEnvThreads) : z4;
+  gq += 6 * kEnvThreads;
+#define VNL_BATCH(qa, qb, t0)                                                                     \
   if ((t0) < T) {                                                                                 \
-    float v[8], xv[8];                                                                            \
-    uint32_t w[8];                                                                                \
-    _Pragma("unroll") for (int k = 0; k < 8; ++k) { v[k] = q[k]; w[k] = pp[k * kEnvThreads]; }    \
-    if ((t0) + 24 < T) {                                                                          \
-      _Pragma("unroll") for (int k = 0; k < 8; ++k) q[k] = __ldcg(gq + k * kEnvThreads);          \
-    }                                                                                             \
-    pp += 8 * kEnvThreads; gq += 8 * kEnvThreads;                                                 \
-    _Pragma("unroll") for (int k = 0; k < 8; ++k) xv[k] = VNL_LDX(w[k]);                          \
+    const float4 va = qa, vb = qb;                                                                \
+    const uint4 wa = pp[0], wb = pp[kEnvThreads];                                                 \
+    if ((t0) + 24 < T) { qa = __ldcg(gq); qb = __ldcg(gq + kEnvThreads); }                        \
+    pp += 2 * kEnvThreads; gq += 2 * kEnvThreads;                                                 \
+    const float x0 = VNL_LDX(wa.x), x1 = VNL_LDX(wa.y), x2 = VNL_LDX(wa.z), x3 = VNL_LDX(wa.w);   \
+    const float x4 = VNL_LDX(wb.x), x5 = VNL_LDX(wb.y), x6 = VNL_LDX(wb.z), x7 = VNL_LDX(wb.w);   \
     float* const pt = (t0) >= TA ? part + dslot0 : part;                                          \
-    _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                               \
-      acc += v[k] * xv[k];                                                                        \
-      if (w[k] < 0xff000000u) { pt[w[k] >> 24] = acc; acc = 0.0f; }                               \
-    }                                                                                             \
+    acc += va.x * x0; VNL_FLUSHTO(pt, wa.x)                                                       \
+    acc += va.y * x1; VNL_FLUSHTO(pt, wa.y)                                                       \
+    acc += va.z * x2; VNL_FLUSHTO(pt, wa.z)                                                       \
+    acc += va.w * x3; VNL_FLUSHTO(pt, wa.w)                                                       \
+    acc += vb.x * x4; VNL_FLUSHTO(pt, wb.x)                                                       \
+    acc += vb.y * x5; VNL_FLUSHTO(pt, wb.y)                                                       \
+    acc += vb.z * x6; VNL_FLUSHTO(pt, wb.z)                                                       \
+    acc += vb.w * x7; VNL_FLUSHTO(pt, wb.w)                                                       \
   }
-  const uint32_t* pp = prog;                    // running pointers: every access is base + immediate
-  const float* gq = g + 24 * kEnvThreads;
   for (int t = 0; t < T; t += 24) {
-    VNL_BATCH(q0, t)
-    VNL_BATCH(q1, t + 8)
-    VNL_BATCH(q2, t + 16)
+    VNL_BATCH(q0a, q0b, t)
+    VNL_BATCH(q1a, q1b, t + 8)
+    VNL_BATCH(q2a, q2b, t + 16)
   }
 #undef VNL_BATCH
-#undef VNL_LDX
 }
+#undef VNL_LDV
+#undef VNL_LDX
+#undef VNL_FLUSHTO
 
 // out = M x   (tree-sparse symmetric M: diagonal + strict-ancestor terms + descendant terms)
 __device__ __noinline__ void mul_m(int so, int xo, int outo) {

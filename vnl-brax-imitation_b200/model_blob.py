@@ -188,7 +188,8 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
                     flush = slot if k == len(terms) - 1 else 0xFF
                     prog[t, l] = np.uint32((4 * int(e)) | ((4 * int(xi)) << 14) | (int(flush) << 24))
                     t += 1
-        return prog.reshape(-1), T
+        # [T / 4][lanes][4]: the four consecutive steps of a lane form one 16-byte word
+        return np.ascontiguousarray(prog.reshape(T // 4, 4, NL).transpose(0, 2, 1)).reshape(-1), T
 
     # long rows / columns are cut into chunks so that the lanes can be balanced; one warp per env keeps whole rows
     CH = 24 if env_warps == 1 else 12
@@ -286,13 +287,13 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
     kt[C["VNL_KT_PROG_A"]] = prog_a
     kt[C["VNL_KT_PROG_D"]] = prog_d
     nkt, nks = C["VNL_KT_COUNT"], C["VNL_KT_NSCALAR"]
-    ndir = (nkt + nks + 1) // 2 * 2  # directory padded to an even word count: tables start 8-byte aligned
+    ndir = (nkt + nks + 3) // 4 * 4  # directory padded to a multiple of four words: tables start 16-byte aligned
     off = 4 * ndir
     dirw = np.zeros(ndir, dtype=np.uint32)
     blobs = []
     for t, a in enumerate(kt):
         raw = a.tobytes()
-        raw += b"\0" * ((-len(raw)) % 8)  # every table 8-byte aligned (EROW is read as 64-bit words)
+        raw += b"\0" * ((-len(raw)) % 16)  # every table 16-byte aligned (the lane programs are read as 128-bit words)
         dirw[t] = off
         off += len(raw)
         blobs.append(raw)
