@@ -1337,16 +1337,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
   int niter = 0, lsiter = 0;
   {
     // candidate cost: 0.5 sum D Jaref^2 [Jaref<0] + 0.5 (Ma - qfrc_smooth).(qacc - qacc_smooth)
+    // The smooth candidate is evaluated FIRST: the warm start wins in all but the first substep after a reset, and the
+    // winner's Ma / Jaref are then already in place (the loser's would have to be recomputed).
     float cost_w, cost_s;
     {
-      mul_m(so, L.warm, L.Ma);
-      jmul(so, L.warm, L.Jaref);
-      float v0 = 0.0f, v1 = 0.0f;
-      for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) v0 += efcD[r] * ja * ja; }
-      for (int i = lane; i < d.nv; i += 32) v1 += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
-      v0 = warp_sum(v0); v1 = warp_sum(v1);
-      cost_w = 0.5f * v0 + 0.5f * v1;
-      env_sync();
       mul_m(so, L.qacc_smooth, L.Ma);
       jmul(so, L.qacc_smooth, L.Jaref);
       float w0 = 0.0f, w1 = 0.0f;
@@ -1355,14 +1349,22 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       w0 = warp_sum(w0); w1 = warp_sum(w1);
       cost_s = 0.5f * w0 + 0.5f * w1;
       env_sync();
+      mul_m(so, L.warm, L.Ma);
+      jmul(so, L.warm, L.Jaref);
+      float v0 = 0.0f, v1 = 0.0f;
+      for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) v0 += efcD[r] * ja * ja; }
+      for (int i = lane; i < d.nv; i += 32) v1 += (Ma[i] - qfrc_smooth[i]) * (s[L.warm + i] - qacc_smooth[i]);
+      v0 = warp_sum(v0); v1 = warp_sum(v1);
+      cost_w = 0.5f * v0 + 0.5f * v1;
+      env_sync();
     }
     if (cost_w < cost_s) {
-      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = s[L.warm + i];
+      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = s[L.warm + i];  // Ma, Jaref already hold the warm-start candidate
+    } else {
+      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = qacc_smooth[i];
       env_sync();
       mul_m(so, L.qacc, L.Ma);
       jmul(so, L.qacc, L.Jaref);
-    } else {
-      for (int i = tid; i < d.nv; i += kEnvThreads) qacc[i] = qacc_smooth[i];  // Ma, Jaref already hold the smooth candidate
     }
     env_sync();
     for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] -= arefv[r];
