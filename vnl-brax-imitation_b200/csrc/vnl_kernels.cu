@@ -757,7 +757,10 @@ __device__ __noinline__ void newton_mgrad(int so) {
 struct Sol { float cost, prev_cost, gauss, gradnorm; };
 
 // solver._update_constraint + _update_gradient (CG: Mgrad = M^-1 grad)
-__device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
+// `last`: no iteration can follow (the iteration budget is spent).  Returns true when the solver stops after this update
+// -- budget spent or converged by the test the next loop top would make -- in which case the gradient solve, whose
+// only consumer is the next search direction, is skipped (the reference computes and discards it).
+__device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool last, float scale) {
   VNL_SMEM
   const Lay& L = c.L;
   const int* ints = (const int*)(s + L.ints);
@@ -784,9 +787,14 @@ __device__ __noinline__ void update_constraint(int so, Sol& st, Prof& pf) {
   st.gradnorm = sqrtf(g);
   env_sync();
   pf.mark(23);
-  if (c.d.solver == 2) newton_mgrad(so);
-  else solve_m(so, L.grad, L.Mgrad);
+  bool stop = last;
+  if (c.d.iterations != 1) stop |= ((st.prev_cost - st.cost) / scale < c.d.tolerance) || (st.gradnorm / scale < c.d.tolerance);
+  if (!stop) {
+    if (c.d.solver == 2) newton_mgrad(so);
+    else solve_m(so, L.grad, L.Mgrad);
+  }
   pf.mark(24);
+  return stop;
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -1374,11 +1382,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
-    update_constraint(so, st, pf);
-    for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
+    bool done = update_constraint(so, st, pf, d.iterations < 1, scale);  // true: converged before the first iteration
+    if (!done) for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
     env_sync();
     pf.mark(9);
-    bool done = false;
     for (int itn = 0; itn < d.iterations; ++itn) {
       if (ls3) __syncthreads();
       if (!done && d.iterations != 1) {
@@ -1480,8 +1487,10 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; Mv[i] = Mgrad[i]; }  // Mv <- previous Mgrad
       for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] += Jv[r] * ia;
       env_sync();
-      update_constraint(so, st, pf);
-      if (d.solver == 2) {
+      done = update_constraint(so, st, pf, itn == d.iterations - 1, scale);
+      if (done) {
+        // no further iteration: the search direction is not needed
+      } else if (d.solver == 2) {
         for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
       } else {  // Polak-Ribiere
         float nb = 0.0f;
