@@ -31,8 +31,13 @@ def main(path, top=40):
             line = int(r[0])
         except ValueError:
             continue
-        inst = int(r[hdr.index("Instructions Executed")] or 0)
-        smp = int(r[hdr.index("# Samples")] or 0)
+        if len(r) != len(hdr):
+            continue  # a source line whose text broke the CSV quoting (inline asm with quotes): a handful of intrinsics
+        try:
+            inst = int(r[hdr.index("Instructions Executed")] or 0)
+            smp = int(r[hdr.index("# Samples")] or 0)
+        except ValueError:
+            continue
         key = (cur_file, line)
         agg[key][0] += inst
         agg[key][1] += smp
@@ -89,8 +94,13 @@ def ranges(path, spec):
             line = int(r[0])
         except ValueError:
             continue
-        inst = int(r[hdr.index("Instructions Executed")] or 0)
-        smp = int(r[hdr.index("# Samples")] or 0)
+        if len(r) != len(hdr):
+            continue
+        try:
+            inst = int(r[hdr.index("Instructions Executed")] or 0)
+            smp = int(r[hdr.index("# Samples")] or 0)
+        except ValueError:
+            continue
         tot_i += inst
         tot_s += smp
         hit = False
