@@ -123,7 +123,7 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   A(efcD, d.nefc); A(Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon);
   if (o > r1end) r1end = o;
   o = r1 + (cacc_n > scratch_end - r1 ? cacc_n : scratch_end - r1);  // F clears fd (P5) and part / tmpv (P10)
-  A(K, d.nM + 1);
+  A(K, d.nM + 40);  // + the zero slots the padded program terms and descendant lists point at
   if (o > r1end) r1end = o;
   o = r1end;
 #undef A
@@ -320,6 +320,9 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
     if (tid == 0) F[nM] = 0.0f;
     env_sync();
   }
+  // zero slots behind the entries: the padded tails of the descendant lists read F[nM] * F[nM + c], c < 40
+  for (int i = tid; i < 40; i += kEnvThreads) F[nM + i] = 0.0f;
+  env_sync();
   // Left-looking elimination by dof height, in Cholesky form.  A final row k holds C[k][a] = F[k][a] / sqrt(D_k)
   // (a >= 1) and 1 / sqrt(D_k) in its diagonal slot, so that row j (entries c = 0 .. dj) receives from every descendant
   // k at distance a just  F[j][c] -= C[k][a] * C[k][a + c].  Rows of one height are independent: one barrier per
@@ -343,13 +346,12 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
           const float* const Fc = F + (cc < n ? cc : 0);
           float acc = own ? Fb[cc] : 0.0f, accb = 0.0f;
           int t = (w.y & 0xffff) + g;
-          for (; t + 3 * G < d1; t += 4 * G) {
+          for (; t < d1; t += 4 * G) {  // the host pads every list to a multiple of 4 G with the zero slot: no remainder
             const int s0 = dsrc[t], s1 = dsrc[t + G], s2 = dsrc[t + 2 * G], s3 = dsrc[t + 3 * G];
             const float u0 = F[s0], u1 = F[s1], u2 = F[s2], u3 = F[s3];
             const float v0 = Fc[s0], v1 = Fc[s1], v2 = Fc[s2], v3 = Fc[s3];
             acc = fmaf(-u0, v0, acc); accb = fmaf(-u1, v1, accb); acc = fmaf(-u2, v2, acc); accb = fmaf(-u3, v3, accb);
           }
-          for (; t < d1; t += G) { const int s0 = dsrc[t]; acc = fmaf(-F[s0], Fc[s0], acc); }
           acc += accb;
           for (int o = 1 << lg; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
           const float rs = rsqrtf(__shfl_sync(FULLMASK, acc, 0));

@@ -233,6 +233,12 @@ def derived_tables(m: mjcf.Model, env_warps: int = 0) -> Dict[str, np.ndarray]:
         for k, a in desc_of[j]:
             desc_src.append(madr[k] + a)
             desc_k.append(k)
+        # the elimination walks a row's list four entries per lane group at a time: pad it to a multiple of 4 * groups with
+        # the zero slot behind the inertia entries (entry nM, and the 39 zeros the kernel keeps behind it), descendant 0
+        groups = 32 >> lg2c(ddepth[j] + 1) if ddepth[j] + 1 <= 32 else 1
+        while desc_of[j] and (len(desc_src) - desc_adr[-1]) % (4 * groups):
+            desc_src.append(nM_)
+            desc_k.append(0)
         desc_adr.append(len(desc_src))
     if nM_ >= (1 << 13) or len(desc_src) >= (1 << 16):
         raise NotImplementedError("model too large for the packed factorisation schedule")
