@@ -361,6 +361,11 @@ int vnl_resident_envs(const void* model_host);
 size_t vnl_workspace_bytes(const void* model_host);
 int vnl_set_workspace(const void* model_dev, void* workspace_dev, size_t nbytes);
 
+/* Test hook: (name, float offset, float size) of every array of the per-env shared-memory layout for this model, in the
+ * order of make_layout (csrc/vnl_kernels.cu); the last entry "total" carries the slice size as its offset.  Returns the
+ * number of entries.  tests/test_layout.py checks that arrays that are live in the same phase never share storage. */
+int vnl_debug_layout(const void* model_host, const char** names, int32_t* offsets, int32_t* sizes, int cap);
+
 /* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
  * size_t opaque_len)`), operand order documented in INTEGRATION.md. */
 void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len);

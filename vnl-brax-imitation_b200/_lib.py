@@ -35,7 +35,8 @@ class VnlOutputs(ctypes.Structure):
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
            "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
            "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta",
-           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace", "vnl_step_training")
+           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace", "vnl_step_training",
+           "vnl_debug_layout")
 
 
 def load_library() -> ctypes.CDLL:

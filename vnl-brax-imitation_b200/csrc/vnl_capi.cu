@@ -171,6 +171,15 @@ int vnl_resident_envs(const void* model_host) {
   return li.ctas * li.warps_per_cta;
 }
 
+int vnl_debug_layout(const void* model_host, const char** names, int32_t* offsets, int32_t* sizes, int cap) {
+  vnl::Dims d;
+  fill_dims((const uint32_t*)model_host, d);
+  vnl::LayoutEntry e[64];
+  const int n = vnl::ew1s1::layout_table(d, e, 64);
+  for (int i = 0; i < n && i < cap; ++i) { names[i] = e[i].name; offsets[i] = e[i].offset; sizes[i] = e[i].size; }
+  return n;
+}
+
 size_t vnl_dump_size(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);

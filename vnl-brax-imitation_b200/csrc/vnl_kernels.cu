@@ -1916,6 +1916,30 @@ template __global__ void vnl_env_kernel<1>(Params);
 template __global__ void vnl_env_kernel<2>(Params);
 template __global__ void vnl_env_kernel<3>(Params);
 
+// (name, offset, size) of every array of the per-env layout, for tests/test_layout.py (sizes as make_layout reserves them)
+int layout_table(const Dims& d, LayoutEntry* out, int cap) {
+  Lay L;
+  make_layout(d, L);
+  const int nb = d.nbody, nv = d.nv, big = (nb > nv ? nb : nv) * 6;
+  const LayoutEntry e[] = {
+      {"qpos", L.qpos, d.nq}, {"qvel", L.qvel, nv}, {"act", L.act, d.na}, {"ctrl", L.ctrl, d.nu}, {"warm", L.warm, nv},
+      {"cdof", L.cdof, 6 * nv}, {"Mdiag", L.Mdiag, nv}, {"Kdiag", L.Kdiag, nv}, {"rcom", L.rcom, 3 * d.nroot},
+      {"qfrc_smooth", L.qfrc_smooth, nv}, {"qacc_smooth", L.qacc_smooth, nv}, {"act_dot", L.act_dot, d.na}, {"ints", L.ints, 16},
+      {"Ms", L.Ms, d.stream ? 0 : d.nM + 1}, {"Ks", L.Ks, d.stream ? 0 : d.nM + 1},
+      {"Mn", L.Mn, d.solver == 2 ? d.nM : 0}, {"H", L.H, d.solver == 2 ? nv * nv : 0}, {"jr", L.jr, d.solver == 2 ? 3 * nv : 0},
+      {"xpos", L.xpos, 3 * nb}, {"xquat", L.xquat, 4 * nb}, {"cvel", L.cvel, 6 * nb},
+      {"Jaref", L.Jaref, d.nefc}, {"qacc", L.qacc, nv}, {"Ma", L.Ma, nv}, {"grad", L.grad, nv}, {"Mgrad", L.Mgrad, nv},
+      {"search", L.search, nv}, {"Mv", L.Mv, nv}, {"qfrc_con", L.qfrc_con, nv},
+      {"xipos", L.xipos, 3 * nb}, {"xanchor", L.xanchor, 3 * d.njnt}, {"xaxis", L.xaxis, 3 * d.njnt}, {"cacc", L.cacc, big},
+      {"t16", L.t16, 16 * nb}, {"part", L.part, d.naslot + d.ndslot}, {"tmpv", L.tmpv, nv},
+      {"lim_dof", L.lim_dof, d.nlimit}, {"limrow_of_dof", L.limrow_of_dof, nv}, {"cbody", L.cbody, d.ncon}, {"crel", L.crel, 3 * d.ncon},
+      {"cframe", L.cframe, 6 * d.ncon}, {"cmu", L.cmu, d.ncon}, {"efcD", L.efcD, d.nefc},
+      {"Jv", L.Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon}, {"K", L.K, d.nM + 40}, {"total", L.total, 0}};
+  const int n = (int)(sizeof(e) / sizeof(e[0]));
+  for (int i = 0; i < n && i < cap; ++i) out[i] = e[i];
+  return n;
+}
+
 static int max_envs_per_cta(const Dims& d) {
   Lay L;
   make_layout(d, L);

@@ -66,7 +66,8 @@ inline int work_stride(const Dims& d) { return d.stream ? (2 * (d.TA + d.TD) * 3
 
 // vnl_kernels.cu is compiled once per (env-group width -DVNL_EW=1, 2; inertia home -DVNL_STREAM=0, 1) into its own namespace.
 // decide_stream() fills Dims::stream: resident inertia unless that would cost a resident env.
-#define VNL_DECL(ns) namespace ns { void decide_stream(Dims& d); LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
+struct LayoutEntry { const char* name; int offset, size; };  // floats; for the layout / liveness test
+#define VNL_DECL(ns) namespace ns { int layout_table(const Dims& d, LayoutEntry* out, int cap); void decide_stream(Dims& d); LaunchInfo launch_info(const Dims& d, int B); cudaError_t launch(int mode, const Params& p, cudaStream_t stream); }
 VNL_DECL(ew1s0) VNL_DECL(ew1s1) VNL_DECL(ew2s0) VNL_DECL(ew2s1)
 #undef VNL_DECL
 
