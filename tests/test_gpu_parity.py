@@ -77,6 +77,37 @@ def test_forward_stages_match_oracle(gpu_env, rodent, oracle_mod):
     assert checked == len(tol)
 
 
+def test_rodent_newton_solver_matches_oracle(rodent, oracle_mod):
+    """The Newton branch on the big model (dense 73 x 73 Hessian in shared memory, inertia streamed from the workspace):
+    `solver: newton` is a legal setting of the reference's rodent config (envs/rodent.py:55-63).  One forward pass and a
+    few pipeline steps against the oracle's Newton branch, bounded by the oracle's own fp32-vs-fp64 spread."""
+    import copy
+    import torch
+    mb, libm, mj = pkg("model_blob"), pkg("_lib"), pkg("mjcf")
+    model = copy.deepcopy(rodent["model"])
+    model.solver, model.iterations, model.ls_iterations = mj.SOLVER_NEWTON, 2, 4
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    eng = libm.Engine(blob, None, device="cuda:0")
+    assert 1 <= eng.envs_per_cta < 14  # the Hessian costs residency: supported, not the fast path
+    B = 12
+    qpos, qvel, _ = start_states(rodent, B, seed=51)
+    qpos[:, 2] -= 0.01  # belly into the floor: contacts act
+    rng = np.random.default_rng(52)
+    ctrl = rng.uniform(-1, 1, size=(B, 30)).astype(np.float32)
+    st = dict(qpos=torch.tensor(qpos, device="cuda"), qvel=torch.tensor(qvel, device="cuda"))
+    g = oracle_mod.split_dump(dims, eng.forward_dump(st, torch.tensor(ctrl, device="cuda")).cpu().numpy().astype(np.float64))
+    ost = dict(qpos=qpos.astype(np.float64), qvel=qvel.astype(np.float64))
+    o32 = oracle_mod.forward_dump(blob, ost, ctrl.astype(np.float64), precision=32, dims=dims)
+    o64 = oracle_mod.forward_dump(blob, ost, ctrl.astype(np.float64), precision=64, dims=dims)
+    assert (o32["counters"][:, 2] > 0).all() and (o32["counters"][:, 0] == 2).all()
+    assert np.array_equal(g["counters"][:, [0, 2, 3]], o32["counters"][:, [0, 2, 3]])
+    for name in ("qacc", "qfrc_constraint"):
+        spread = rel(o32[name], o64[name])
+        assert np.isfinite(g[name]).all() and rel(g[name], o32[name]) < 10 * spread + 1e-3, (name, rel(g[name], o32[name]), spread)
+    assert rel(g["qacc_smooth"], o32["qacc_smooth"]) < 1e-4 and rel(g["qM"], o32["qM"]) < 5e-6
+
+
 def test_reset_matches_oracle(gpu_env, rodent, oracle_mod):
     B = 33
     qpos, qvel, start = start_states(rodent, B, seed=2)
