@@ -938,7 +938,7 @@ template <class T> void env_step(const ModelView& m, const TaskView& t, int e, c
   get_obs(m, t, d, obs.data());
   get_traj(m, t, d, t.traj_old_frame ? frame_old : cur_frame, traj.data());  // ant.py:182: window from the OLD info
   // _calculate_reward (rodent.py:266-316): every reference lookup uses the OLD cur_frame (Q3)
-  int f = clampi(frame_old, 0, t.T_ - 1), nj = m.nq - 7;
+  int f = clampi(frame_old, 0, t.T_ - 1);
   // humanoid.py:275 evaluates every term on the PRE-step state (`data_c = state.pipeline_state`), the rodent on the new one
   const bool old = t.reward_old_state != 0;
   const T* r_qvel = old ? qvel_old.data() : d.qvel.data();
