@@ -12,8 +12,10 @@ clip transform_snips_groom.p, 4096 envs per GPU, iid U(-1, 1) actions, weak scal
 no data-path collective).
 
 `value`      whole-job env-steps/s with state and pre-generated actions resident in HBM (CUDA events, max over ranks).
-`e2e`        the same metric through the public env API (`RodentTracking.step`) with HOST buffers: every step copies
-             the step's actions from pinned host memory and reads obs, traj, reward and done back to pinned host memory.
+`e2e`        the same metric through the public host-buffer API (`hostio.HostStepper.step`, the host form of `env.step` +
+             AutoReset): every step copies the step's actions from pinned host memory and returns once obs, traj, reward
+             and done are in pinned host memory (two launches cut at the last wave boundary; the first chunk's copy
+             overlaps the last wave's compute).
 `roofline`   HBM view of the fused kernel (algorithmic bytes at the step boundary / launch time) against the measured copy
              bandwidth; `roofline_fp32` is the binding one: algorithmic FLOPs / launch time against an FFMA
              microkernel measured in the same run.
