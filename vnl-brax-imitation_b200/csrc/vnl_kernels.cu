@@ -1351,13 +1351,13 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     // winner's Ma / Jaref are then already in place (the loser's would have to be recomputed).
     float cost_w, cost_s;
     {
-      mul_m(so, L.qacc_smooth, L.Ma);
+      // its Gauss term is (M qacc_smooth - qfrc_smooth) . (qacc_smooth - qacc_smooth) = 0 whatever M qacc_smooth rounds to,
+      // so the mat-vec is only done if this candidate wins (below)
       jmul(so, L.qacc_smooth, L.Jaref);
-      float w0 = 0.0f, w1 = 0.0f;
+      float w0 = 0.0f;
       for (int r = lane; r < nrow; r += 32) { const float ja = Jaref[r] - arefv[r]; if (ja < 0.0f) w0 += efcD[r] * ja * ja; }
-      for (int i = lane; i < d.nv; i += 32) w1 += (Ma[i] - qfrc_smooth[i]) * (qacc_smooth[i] - qacc_smooth[i]);
-      w0 = warp_sum(w0); w1 = warp_sum(w1);
-      cost_s = 0.5f * w0 + 0.5f * w1;
+      w0 = warp_sum(w0);
+      cost_s = 0.5f * w0;
       env_sync();
       mul_m(so, L.warm, L.Ma);
       jmul(so, L.warm, L.Jaref);
