@@ -29,7 +29,6 @@
 #include <stdint.h>
 #include <stdlib.h>
 
-#include <type_traits>
 
 #include "../../include/vnl_blob.h"
 #include "vnl_device.cuh"
@@ -1165,11 +1164,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     if (lane == 0) { ints[0] = 0; ints[1] = 0; }
     for (int i = tid; i < d.nv; i += kEnvThreads) ((int*)(s + L.limrow_of_dof))[i] = -1;
     env_sync();
-    // joint limits (constraint._instantiate_limit_slide_hinge).  Their rows come first, but the list itself is written
-    // AFTER the contact rows: it shares storage with cvel, whose last reader is the contact block -- so the limits are
-    // counted first (WRITE = false), the contacts instantiated, then the limit rows filled in.
-    auto limit_rows = [&](auto write_tag) {
-      constexpr bool WRITE = decltype(write_tag)::value;
+    // joint limits (constraint._instantiate_limit_slide_hinge): their rows come first
+    {
       const int* ljnt = c.fi(VNL_F_LIMIT_JNT);
       const int* jqadr = c.fi(VNL_F_JNT_QPOSADR);
       const float* range = c.ff(VNL_F_JNT_RANGE);
@@ -1192,7 +1188,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
           sign = (dmin < dmax) ? 1.0f : -1.0f;
         }
         const unsigned m = __ballot_sync(FULLMASK, active);
-        if (WRITE && active) {
+        if (active) {
           const int slot = base + __popc(m & ((1u << lane) - 1u));
           const int dof = jdofadr[j];
           ((int*)(s + L.lim_dof))[slot] = sign > 0.0f ? dof : ~dof;
@@ -1206,9 +1202,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         }
         base += __popc(m);
       }
-      if (!WRITE && lane == 0) ints[0] = base;
-    };
-    limit_rows(std::false_type{});
+      if (lane == 0) ints[0] = base;
+    }
     env_sync();
     {  // contacts (collision_driver + constraint._instantiate_contact, pyramidal condim 3)
       const int nl = ints[0];
@@ -1323,8 +1318,6 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       }
       if (lane == 0) ints[1] = base;
     }
-    env_sync();
-    limit_rows(std::true_type{});
     env_sync();
   }
   pf.mark(7);
