@@ -340,6 +340,10 @@ def test_nan_guard_and_autoreset_quirk(gpu_env, rodent):
     assert (np.array(dones)[9:] == 1).all() and (s.info["sub_clip_frame"].cpu().numpy() == 12).all()
 
 
+def eng_resident(env):
+    return env.engine.resident_envs
+
+
 def test_full_size_properties(gpu_env, rodent):
     """BASELINE config 2 size (4096 envs): size-independent properties + agreement of a slice with a small batch."""
     import torch
@@ -358,9 +362,12 @@ def test_full_size_properties(gpu_env, rodent):
     assert torch.equal(s.obs[:, 220:], s.pipeline_state["xpos"][:, ee].reshape(B, 12))
     total = sum(s.metrics[k] for k in ("rcom", "rvel", "rtrunk", "rquat", "ract", "rapp"))
     assert (s.reward - total).abs().max() < 1e-7
-    lo, hi = 2000, 2016
-    sm = _run_steps(gpu_env, qpos[lo:hi], qvel[lo:hi], start[lo:hi], acts[:, lo:hi])
-    assert torch.equal(sm.pipeline_state["qpos"], q[lo:hi]) and torch.equal(sm.reward, s.reward[lo:hi])
+    # a slice of the first wave of the persistent grid and one of the second (same CTA slots and workspace rows, reused)
+    assert B > eng_resident(gpu_env)
+    for lo, hi in ((2000, 2016), (B - 16, B)):
+        sm = _run_steps(gpu_env, qpos[lo:hi], qvel[lo:hi], start[lo:hi], acts[:, lo:hi])
+        assert torch.equal(sm.pipeline_state["qpos"], q[lo:hi]) and torch.equal(sm.reward, s.reward[lo:hi]), lo
+        assert torch.equal(sm.info["traj"], s.info["traj"][lo:hi]) and torch.equal(sm.pipeline_state["xpos"], s.pipeline_state["xpos"][lo:hi])
 
 
 def test_fused_autoreset_equals_wrapper_semantics(gpu_env, rodent):
