@@ -36,8 +36,8 @@ typedef struct VnlPolicyDims {
   int32_t nu;     /* action_size; the decoder emits 2 * nu  ppo_networks.py:99-113             */
 } VnlPolicyDims;
 
-/* 0 if the kernel supports these sizes (hidden sizes multiples of 32 and <= 256, latent a multiple of 16 and
- * 2 * latent <= 256, 2 * nu <= 256, tensor-memory and shared-memory budgets), else a negative code. */
+/* 0 if the kernel supports these sizes (hidden sizes multiples of 64 and <= 256, latent a multiple of 32 and
+ * 2 * latent <= 256, nu <= 64, tensor-memory and shared-memory budgets), else a negative code. */
 int vnl_policy_check(const VnlPolicyDims* dims);
 
 /* Size of the packed parameter blob for these sizes. */
@@ -68,7 +68,8 @@ int vnl_policy_forward(const void* blob_dev, const VnlPolicyDims* dims, int B, c
                        float* rand_log_prob, float* z_mean, float* z_logvar, void* stream);
 
 /* Test hook: the pre-activation of layer `layer` (0..5: the raw tcgen05 accumulators, no bias) for the first
- * min(B,128) envs, written row-major [128, N_layer] to `dump`. */
+ * min(B,128) envs, written row-major [128, N_layer] to `dump`.  layer -1: SM-clock stamps of CTA 0 at the phase
+ * boundaries (32 floats; developer profile, tools/gpu_policy.py). */
 int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, const float* traj, const float* obs,
                      const float* obs_mean, const float* obs_std, const float* eps_z, int layer, float* dump,
                      void* stream);

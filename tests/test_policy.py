@@ -179,6 +179,8 @@ def test_policy_forward_matches_restatement(B):
     for k, tol in TOL_BF16REF.items():
         assert torch.isfinite(out[k]).all(), k
         err = float((out[k] - ref[k]).abs().max())
+        if k == "rand_log_prob":  # -z^2 / 2 with z = (u - loc) / scale up to ~50: the bound is relative
+            tol += 2e-3 * float(ref[k].abs().max())
         assert err < tol, (k, err)
     for k, tol in TOL_FP32.items():
         err = float((out[k] - ref32[k]).abs().max())

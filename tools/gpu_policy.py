@@ -65,6 +65,15 @@ def main():
     us = e0.elapsed_time(e1) / 50 * 1e3
     flops = 2 * Bt * (795 * 256 + 256 * 128 + 128 * 128 + 296 * 128 + 128 * 256 + 256 * 60)
     tim = {"policy_forward_us_8192": us, "dense_tflops": flops / us * 1e-6}
+    import ctypes
+    stamps = torch.zeros(32, device=dev)
+    ptr = lambda x: None if x is None else x.data_ptr()
+    p.lib.vnl_policy_debug(p.blob_dev.data_ptr(), ctypes.byref(p.dims), Bt, ptr(traj), ptr(obs), ptr(p.obs_mean), ptr(p.obs_std),
+                           ptr(eps_z), -1, stamps.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    st = stamps.cpu().numpy()
+    names = ["setup", "L0c0", "L0c1", "L0c2", "L0c3", "L0_issued"] + [x for n in range(1, 6) for x in ("mma%d_done" % (n - 1), "epi%d_done" % (n - 1), "w%d_sync" % n)] + ["mma5_done", "end"]
+    tim["stamps_cycles"] = {n: int(v) for n, v in zip(names, st[:23])}
     P = {k: torch.as_tensor(v, device=dev) for k, v in params.items()}
     for _ in range(3):
         pol.reference_forward(P, traj, obs, eps_z, eps_a, None, mean, std, operand_dtype=None)

@@ -1,10 +1,13 @@
-"""BASELINE.json configs[3] (SURVEY section 8d config 4, rows f1 / f2 -- "next", measured here with LIBRARY kernels for the
-network so that the share of the rollout that is NOT the env step is known before anything is fused):
+"""BASELINE.json configs[3]:
 
   rollout = unroll_length (20) x [ intention-network policy forward (ppo_imitation/intention_policy_network.py:20-105:
-  Encoder 795->256->128->(60, 60) with ReLU + LayerNorm, reparameterise, Decoder 292->128->256->60, tanh-normal sample)
-  + running-statistics normalisation of obs/traj + the fused env step (vnl_step_autoreset) ], 8192 envs per GPU,
-  random-init weights (there is no checkpoint), torch / cuBLAS for the MLP.
+  Encoder 795->256->128->(64, 64) with ReLU + LayerNorm, reparameterise, Decoder 296->128->256->60, tanh-normal sample,
+  obs normalised by the running statistics) + the fused env step (vnl_step_autoreset) ], 8192 envs per GPU,
+  random-init weights (there is no checkpoint).
+
+  POLICY=kernel (default): the repo's tcgen05 policy kernel (vnl_policy_forward, one launch, row f1), normal draws
+  pre-generated for the whole unroll (the caller owns the RNG stream, like the reference's key argument);
+  POLICY=torch: the same network through torch / cuBLAS (library kernels, ~25 launches) -- the comparison line.
 
 Also times the PPO gradient all-reduce message (policy 341 k + value 1.289 M fp32 parameters = 6.5 MB,
 ppo_imitation/train.py:251-253) over NCCL when launched under torchrun.
@@ -42,7 +45,7 @@ class MLP(nn.Module):
 class IntentionPolicy(nn.Module):
     """Encoder(traj) -> (mean, logvar) -> z; Decoder([z, obs]) -> 2 * action_size logits (configs/train_config.yaml:15-17)."""
 
-    def __init__(self, traj_size, obs_size, nu, latents=60, enc=(256, 128), dec=(128, 256)):
+    def __init__(self, traj_size, obs_size, nu, latents=64, enc=(256, 128), dec=(128, 256)):
         super().__init__()
         self.enc = MLP([traj_size, *enc], True)
         self.mean = nn.Linear(enc[-1], latents)
@@ -73,23 +76,35 @@ def main():
     s0 = env.reset_from(qpos, qvel, start)
     first, first_obs = dict(s0.pipeline_state), s0.obs
     torch.manual_seed(rank)
-    policy = IntentionPolicy(eng.traj_size, eng.obs_size, env.action_size).to(dev).eval()
+    which = os.environ.get("POLICY", "kernel")
+    if which == "torch":
+        policy = IntentionPolicy(eng.traj_size, eng.obs_size, env.action_size).to(dev).eval()
+    else:
+        pol = importlib.import_module("vnl-brax-imitation_b200.policy")
+        params = pol.init_params(np.random.default_rng(rank), pol.param_shapes(eng.traj_size, eng.obs_size, env.action_size))
+        kpol = pol.IntentionPolicy(params, str(dev), torch.zeros(eng.obs_size), torch.ones(eng.obs_size))
+        pout = kpol.alloc_outputs(B)
+        gen = torch.Generator(device=dev).manual_seed(rank)
+        eps_z = torch.randn(unroll, B, kpol.latent, device=dev, generator=gen)
+        eps_a = torch.randn(unroll, B, env.action_size, device=dev, generator=gen)
     a_st = {k: v.clone() for k, v in first.items()}
     a_st["cur_frame"], a_st["sub_clip_frame"] = s0.info["cur_frame"].clone(), s0.info["sub_clip_frame"].clone()
     b_st, out = eng.alloc_state(B), eng.alloc_outputs(B)
     out["obs"].copy_(s0.obs); out["traj"].copy_(s0.info["traj"])
     mean_o, std_o = torch.zeros(eng.obs_size, device=dev), torch.ones(eng.obs_size, device=dev)
-    mean_t, std_t = torch.zeros(eng.traj_size, device=dev), torch.ones(eng.traj_size, device=dev)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     t_pol = t_env = 0.0
 
     def unroll_once(timed):
         nonlocal a_st, b_st, t_pol, t_env
-        for _ in range(unroll):
+        for t in range(unroll):
             e0, e1, e2 = ev(), ev(), ev()
             e0.record()
-            with torch.no_grad():
-                act = policy((out["traj"] - mean_t) / std_t, (out["obs"] - mean_o) / std_o).contiguous()
+            if which == "torch":
+                with torch.no_grad():
+                    act = policy(out["traj"], (out["obs"] - mean_o) / std_o).contiguous()  # obs only is normalised
+            else:
+                act, _ = kpol(out["traj"], out["obs"], eps_z[t], eps_a[t], out=pout)
             e1.record()
             eng.step_autoreset(a_st, act, b_st, out, first, first_obs)
             e2.record()
@@ -110,7 +125,8 @@ def main():
     ms = sh.reduce_scalars(dict(ms=w0.elapsed_time(w1)), op="max", device=dev)["ms"]
     t_pol = float(np.mean([a.elapsed_time(b) for a, b, _ in marks]))
     t_env = float(np.mean([b.elapsed_time(c) for _, b, c in marks]))
-    res = {"config": "rodent PPO rollout: %d envs/GPU x unroll %d, intention network forward (torch/cuBLAS, random init) + fused env step" % (B, unroll),
+    res = {"config": "rodent PPO rollout: %d envs/GPU x unroll %d, intention network forward (%s, random init) + fused env step" % (
+               B, unroll, "torch/cuBLAS" if which == "torch" else "vnl_policy_forward tcgen05 kernel"), "policy": which,
            "n_gpus": world, "rollout_env_steps_per_s": world * B * unroll * reps / (ms * 1e-3), "ms_per_unroll": ms / reps,
            "policy_forward_ms": t_pol, "env_step_ms": t_env, "policy_share": t_pol / (t_pol + t_env)}
     # gradient all-reduce message of one minibatch update (6.5 MB fp32)

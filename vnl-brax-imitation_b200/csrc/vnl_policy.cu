@@ -6,7 +6,7 @@
 // tensor memory); everything between two layers happens in the epilogue of the first, on the SM:
 //
 //   L0  traj[795 -> 832]  x W[.,256]  -> +b, relu, LayerNorm -> bf16 A-operand of L1     (K streamed in 64-wide chunks,
-//   L1  [256] x W[.,128]              -> +b, relu, LayerNorm                               2-deep ring, loads overlap MMA)
+//   L1  [256] x W[.,128]              -> +b, relu, LayerNorm                               3-slot ring, loads overlap MMA)
 //   L2  [128] x [W_mean | W_logvar]   -> +b, z = mean + eps_z * exp(logvar / 2)
 //   L3  [z | (obs - mu) / sigma] (296 -> 304) x W[.,128] -> +b, relu, LayerNorm
 //   L4  [128] x W[.,256]              -> +b, relu, LayerNorm
@@ -18,9 +18,9 @@
 // stride between 8-row groups (SBO) is 128.  Weights are packed into exactly this image on the host (vnl_policy_pack),
 // so a layer's B operand is one contiguous cp.async stream.
 //
-// Warps 0-3 own the epilogues (thread t = env t of the tile = its tensor-memory lane, 32x32b loads), warps 4-7
-// stream the next layer's weights (and the normalised obs columns of L3's A operand) while the epilogue runs; thread 0
-// issues the MMAs and commits them to an mbarrier.
+// All 8 warps run the epilogues (warps w and w + 4 share the tensor-memory lanes of quadrant w % 4 = env rows 32 (w % 4) ..
+// + 31 and split the accumulator columns in halves, 32x32b loads); the next layer's weights stream in by cp.async while the
+// epilogue computes; thread 0 issues the MMAs and commits them to an mbarrier.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,10 +36,11 @@ constexpr int THREADS = 256;
 constexpr int KCHUNK = 64;
 constexpr uint32_t LBO_A = TILE_M * 16 + 16;
 constexpr uint32_t SBO = 128;
-constexpr uint32_t R0_BYTES = 80 * 1024;  // A operands (activations), later the logits scratch
-constexpr uint32_t R1_BYTES = 80 * 1024;  // B operands (weights), later the log-prob scratch
+constexpr uint32_t R0_BYTES = 96 * 1024;  // A operands (activations), later the logits scratch
+constexpr uint32_t R1_BYTES = 100 * 1024; // B operands (weights; 3 ring slots in L0)
+constexpr int RING = 3;                   // L0 ring depth
 constexpr int MAX_PARAM_FLOATS = 3072;
-constexpr uint32_t SMEM_BYTES = R0_BYTES + R1_BYTES + MAX_PARAM_FLOATS * 4 + 64;
+constexpr uint32_t SMEM_BYTES = R0_BYTES + R1_BYTES + MAX_PARAM_FLOATS * 4 + 2 * TILE_M * 8 + 64;
 constexpr uint32_t POLICY_MAGIC = 0x4c4f5056u;  // "VPOL"
 constexpr uint32_t HEADER_BYTES = 64;
 constexpr int TMEM_COLS = 512;
@@ -75,20 +76,29 @@ __host__ __device__ inline void make_layout(const VnlPolicyDims& d, Layout& L) {
   L.total = off + pf * 4;
 }
 
+// K-group offset of the decoder input inside R0: its obs columns must clear the operand of L2 (e2 / 8 K-groups)
+__host__ __device__ inline int a3_base_kg(const VnlPolicyDims& d) { return d.e2 / 8 > d.latent / 8 ? d.e2 / 8 - d.latent / 8 : 0; }
+
+// where the action-noise draws of the tile are staged in R1: behind the weights of L4 (live when the copy is issued) and L5
+__host__ __device__ inline uint32_t draw_stage_offset(const Layout& L) {
+  const uint32_t m = L.bytesW[4] > L.bytesW[5] ? L.bytesW[4] : L.bytesW[5];
+  return (m + 127u) & ~127u;
+}
+
 int check_dims(const VnlPolicyDims* d) {
   if (!d) return -1;
   const int h[4] = {d->e1, d->e2, d->d1, d->d2};
   for (int i = 0; i < 4; ++i)
-    if (h[i] < 32 || h[i] > 256 || h[i] % 32) return -2;
-  if (d->latent < 16 || d->latent % 16 || 2 * d->latent > 256) return -3;
+    if (h[i] < 64 || h[i] > 256 || h[i] % 64) return -2;
+  if (d->latent < 32 || d->latent % 32 || d->latent > 64) return -3;
   if (d->nu < 1 || d->nu > 64 || d->traj < 1 || d->obs < 0) return -4;
   Layout L;
   make_layout(*d, L);
   if (d->e1 + d->e2 + 2 * d->latent > TMEM_COLS || d->d1 + d->d2 + L.N[5] > TMEM_COLS) return -5;
   for (int i = 1; i < 6; ++i)
-    if ((uint32_t)(L.K[i] / 8) * LBO_A > R0_BYTES || L.bytesW[i] > R1_BYTES) return -6;
-  if (2u * (KCHUNK / 8) * LBO_A > R0_BYTES || 2u * (KCHUNK / 8) * L.lboB[0] > R1_BYTES) return -6;
-  if ((uint32_t)TILE_M * (L.N[5] + 1) * 4 > R0_BYTES || (uint32_t)TILE_M * d->nu * 8 > R1_BYTES) return -6;
+    if ((uint32_t)(L.K[i] / 8 + (i == 3 ? a3_base_kg(*d) : 0)) * LBO_A > R0_BYTES || L.bytesW[i] > R1_BYTES) return -6;
+  if ((uint32_t)RING * (KCHUNK / 8) * LBO_A > R0_BYTES || (uint32_t)RING * (KCHUNK / 8) * L.lboB[0] > R1_BYTES) return -6;
+  if ((uint32_t)TILE_M * (L.N[5] + 1) * 4 > R0_BYTES || draw_stage_offset(L) + 2u * TILE_M * d->nu * 4 > R1_BYTES) return -6;
   if (L.nParamFloats > (uint32_t)MAX_PARAM_FLOATS) return -7;
   return 0;
 }
@@ -101,7 +111,6 @@ struct Args {
   float *action, *raw_action, *logits, *log_prob, *rand_log_prob, *z_mean, *z_logvar;
   int dump_layer;
   float* dump;
-  int desc_mode;  // developer knob (VNL_POLICY_DESC_MODE): 1 swaps the two descriptor strides
 };
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -124,9 +133,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 // smem matrix descriptor: K-major, no swizzle; LBO = stride between K-adjacent core matrices, SBO = between 8-row groups
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, int mode = 0) {
-  const uint32_t lead = mode ? SBO : lbo, stride = mode ? lbo : SBO;
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lead >> 4) << 16) | ((uint64_t)(stride >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128
 __device__ __forceinline__ uint32_t make_idesc(int N) {
@@ -145,25 +153,38 @@ __device__ __forceinline__ void cp_async_bytes(uint32_t dst, const uint8_t* src,
   for (uint32_t o = (uint32_t)tid * 16; o < bytes; o += (uint32_t)nthreads * 16)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+// bulk L2 prefetch of a contiguous global range (16-byte granules; the range is shrunk to whole granules)
+__device__ __noinline__ void l2_prefetch(const void* p, size_t bytes) {
+  const uintptr_t b = ((uintptr_t)p + 15) & ~(uintptr_t)15, e = ((uintptr_t)p + bytes) & ~(uintptr_t)15;
+  for (uintptr_t q = b; q < e; q += 65536) {
+    const uint32_t n = (uint32_t)((e - q) < 65536 ? (e - q) : 65536);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(q), "r"(n) : "memory");
+  }
 }
+__device__ __noinline__ void cp_async_words(uint32_t dst, const float* src, int count, int tid) {
+  for (int i = tid; i < count; i += THREADS)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src + i) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 #define VNL_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
-// 32 (16) consecutive accumulator columns of this thread's tensor-memory lane; the wait is part of the statement so
-// that no consumer can be scheduled between the load and its completion
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* f) {
-  uint32_t v[32];
+// split form: the load is issued into `v`, other work proceeds, tmem_ld32_wait(v) makes the registers valid (it lists them
+// as in/out operands, so no consumer of v can be scheduled before it)
+#define VNL_RW8(v, o) "+r"(v[o + 0]), "+r"(v[o + 1]), "+r"(v[o + 2]), "+r"(v[o + 3]), "+r"(v[o + 4]), "+r"(v[o + 5]), "+r"(v[o + 6]), "+r"(v[o + 7])
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-      "tcgen05.wait::ld.sync.aligned;"
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
       : VNL_R8(v, 0), VNL_R8(v, 8), VNL_R8(v, 16), VNL_R8(v, 24)
       : "r"(taddr)
       : "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
 }
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : VNL_RW8(v, 0), VNL_RW8(v, 8), VNL_RW8(v, 16), VNL_RW8(v, 24)::"memory");
+}
+// 16 consecutive accumulator columns, load and wait in one statement
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* f) {
   uint32_t v[16];
   asm volatile(
@@ -181,149 +202,236 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
 }
-__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.0f) + log1pf(expf(-fabsf(x))); }
-// brax TanhBijector.forward_log_det_jacobian
-__device__ __forceinline__ float tanh_log_det(float x) { return 2.0f * (0.69314718056f - x - softplus(-2.0f * x)); }
+__device__ __forceinline__ float softplus(float x) { return fmaxf(x, 0.0f) + __logf(1.0f + __expf(-fabsf(x))); }
+// tanh(x) and brax TanhBijector.forward_log_det_jacobian(x) = 2 (log 2 - x - softplus(-2x)) from one exponential
+__device__ __forceinline__ void tanh_and_log_det(float x, float& th, float& ld) {
+  const float t = __expf(-2.0f * fabsf(x));  // in (0, 1]
+  th = copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+  ld = 2.0f * (0.69314718056f - x - (fmaxf(-2.0f * x, 0.0f) + __logf(1.0f + t)));
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Coalesced activation loader: rows [r_begin, r_end) of the tile, 64 source columns from col0; lane l owns columns
+// Coalesced activation loader: NR rows of the tile from r_begin, 64 source columns from col0; lane l owns columns
 // col0 + 2l, col0 + 2l + 1 of a row and stores them as one bf16 pair into K-group kg0 + l / 4 of the operand image.
-// Out-of-range rows / columns store zeros.  (src rows are only 4-byte aligned: traj rows are 795 floats.)
-__device__ __forceinline__ void load_rows(const float* __restrict__ src, int ncols, int col0, int row0, int B, uint8_t* dst,
-                                          int kg0, int kg_limit, int r_begin, int r_end, const float* __restrict__ mu,
-                                          const float* __restrict__ sigma, int lane) {
+// Out-of-range rows / columns are zeros.  (src rows are only 4-byte aligned: traj rows are 795 floats.)  Split into a
+// fetch (all loads in flight at once) and a store so that the fetch of the next chunk can overlap the current MMA.
+template <int NR>
+struct RowRegs {
+  float x[NR][2];
+};
+
+template <int NR>
+__device__ __forceinline__ void fetch_rows(RowRegs<NR>& rr, const float* __restrict__ src, int ncols, int col0, int row0, int B,
+                                           int r_begin, int lane) {
+  const int j = col0 + 2 * lane;
+  const bool ok0 = j < ncols, ok1 = j + 1 < ncols;
+#pragma unroll
+  for (int u = 0; u < NR; ++u) {
+    const int grow = row0 + r_begin + u;
+    const float* p = src + (size_t)grow * ncols + j;
+    rr.x[u][0] = (ok0 && grow < B) ? __ldg(p) : 0.0f;
+    rr.x[u][1] = (ok1 && grow < B) ? __ldg(p + 1) : 0.0f;
+  }
+}
+
+template <int NR>
+__device__ __forceinline__ void store_rows(const RowRegs<NR>& rr, int ncols, int col0, int row0, int B, uint8_t* dst, int kg0,
+                                           int kg_limit, int r_begin, const float* __restrict__ mu,
+                                           const float* __restrict__ sigma, int lane) {
   const int j = col0 + 2 * lane;
   const bool ok0 = j < ncols, ok1 = j + 1 < ncols;
   const int kg = kg0 + (lane >> 2);
   if (kg >= kg_limit) return;
-  float m0 = 0.0f, m1 = 0.0f, s0 = 1.0f, s1 = 1.0f;
+  float m0 = 0.0f, m1 = 0.0f, s0 = 1.0f, s1 = 1.0f;  // s = 1 / sigma: one division per lane, not one per element
   if (mu) {
-    if (ok0) m0 = __ldg(mu + j), s0 = __ldg(sigma + j);
-    if (ok1) m1 = __ldg(mu + j + 1), s1 = __ldg(sigma + j + 1);
+    if (ok0) m0 = __ldg(mu + j), s0 = 1.0f / __ldg(sigma + j);
+    if (ok1) m1 = __ldg(mu + j + 1), s1 = 1.0f / __ldg(sigma + j + 1);
   }
   uint8_t* out = dst + (uint32_t)kg * LBO_A + (lane & 3) * 4;
-  for (int r = r_begin; r < r_end; r += 4) {
-    float x[4][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int grow = row0 + r + u;
-      const float* p = src + (size_t)grow * ncols + j;
-      x[u][0] = (ok0 && grow < B) ? __ldg(p) : 0.0f;
-      x[u][1] = (ok1 && grow < B) ? __ldg(p + 1) : 0.0f;
+  for (int u = 0; u < NR; ++u) {
+    const int grow = row0 + r_begin + u;
+    float a = rr.x[u][0], b = rr.x[u][1];
+    if (mu && grow < B) {
+      a = ok0 ? (a - m0) * s0 : 0.0f;
+      b = ok1 ? (b - m1) * s1 : 0.0f;
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int grow = row0 + r + u;
-      float a = x[u][0], b = x[u][1];
-      if (mu && grow < B) {
-        a = ok0 ? (a - m0) / s0 : 0.0f;
-        b = ok1 ? (b - m1) / s1 : 0.0f;
-      }
-      *reinterpret_cast<uint32_t*>(out + (r + u) * 16) = pack_bf16(a, b);
-    }
+    *reinterpret_cast<uint32_t*>(out + (r_begin + u) * 16) = pack_bf16(a, b);
   }
 }
 
-// +bias, relu, LayerNorm (flax: fast variance E[x^2] - E[x]^2 clipped at 0, eps 1e-6, scale and bias) of this thread's row,
-// written as the bf16 A operand of the next layer.  Two passes over tensor memory instead of a 256-float register row.
-__device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __restrict__ P, uint8_t* anext, int row) {
+// Epilogues run on all 8 warps: warps w and w + 4 share the tensor-memory lanes of quadrant w % 4 (thread = env row
+// 32 (w % 4) + lane) and split the accumulator columns in halves.
+
+// +bias, relu, LayerNorm (flax: fast variance E[x^2] - E[x]^2 clipped at 0, eps 1e-6, scale and bias) of this thread's half
+// row, written as the bf16 A operand of the next layer.  Two passes over tensor memory instead of a register row; the two
+// halves of a row exchange their partial sums through `stats` (one CTA barrier).
+__device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __restrict__ P, uint8_t* anext, int row, int half,
+                                            float2* stats) {
   const float* bias = P;
   const float* gamma = P + N;
   const float* beta = P + 2 * N;
+  const int cb = half * (N >> 1), nchunk = N >> 6;  // 32-column chunks of this thread's half row
+  uint32_t va[32], vb[32];
   float sum = 0.0f, sq = 0.0f;
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(tb + c0, v);
+  auto stat = [&](const uint32_t* v, int c0) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float x = fmaxf(v[j] + bias[c0 + j], 0.0f);
-      sum += x;
-      sq = fmaf(x, x, sq);
+    for (int q = 0; q < 8; ++q) {
+      const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);  // warp-uniform address: one broadcast wavefront
+      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float x = fmaxf(__uint_as_float(v[4 * q + j]) + bb[j], 0.0f);
+        sum += x;
+        sq = fmaf(x, x, sq);
+      }
+    }
+  };
+  tmem_ld32_issue(tb + cb, va);
+  for (int c = 0; c < nchunk; c += 2) {  // the load of chunk c + 1 is in flight while chunk c is reduced
+    tmem_ld32_wait(va);
+    if (c + 1 < nchunk) tmem_ld32_issue(tb + cb + (c + 1) * 32, vb);
+    stat(va, cb + c * 32);
+    if (c + 1 < nchunk) {
+      tmem_ld32_wait(vb);
+      if (c + 2 < nchunk) tmem_ld32_issue(tb + cb + (c + 2) * 32, va);
+      stat(vb, cb + (c + 1) * 32);
     }
   }
+  tmem_ld32_issue(tb + cb, va);  // first chunk of the second pass, in flight across the barrier
+  stats[half * TILE_M + row] = make_float2(sum, sq);
+  __syncthreads();
+  const float2 p0 = stats[row], p1 = stats[TILE_M + row];
   const float inv_n = 1.0f / (float)N;
-  const float mean = sum * inv_n;
-  const float var = fmaxf(sq * inv_n - mean * mean, 0.0f);
+  const float mean = (p0.x + p1.x) * inv_n;
+  const float var = fmaxf((p0.y + p1.y) * inv_n - mean * mean, 0.0f);
   const float rstd = rsqrtf(var + 1e-6f);
-  for (int c0 = 0; c0 < N; c0 += 32) {
-    float v[32];
-    tmem_ld32(tb + c0, v);
+  auto emit = [&](const uint32_t* v, int c0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint32_t w[4];
 #pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int c = c0 + q * 8 + h * 2;
-        const float x0 = fmaxf(v[q * 8 + h * 2] + bias[c], 0.0f), x1 = fmaxf(v[q * 8 + h * 2 + 1] + bias[c + 1], 0.0f);
-        w[h] = pack_bf16((x0 - mean) * rstd * gamma[c] + beta[c], (x1 - mean) * rstd * gamma[c + 1] + beta[c + 1]);
+      for (int h = 0; h < 2; ++h) {
+        const int c = c0 + q * 8 + h * 4;
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + c), g4 = *reinterpret_cast<const float4*>(gamma + c),
+                     e4 = *reinterpret_cast<const float4*>(beta + c);
+        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float x = fmaxf(__uint_as_float(v[q * 8 + h * 4 + j]) + bb[j], 0.0f);
+          y[j] = (x - mean) * rstd * gg[j] + ee[j];
+        }
+        w[2 * h] = pack_bf16(y[0], y[1]);
+        w[2 * h + 1] = pack_bf16(y[2], y[3]);
       }
       *reinterpret_cast<uint4*>(anext + (uint32_t)((c0 >> 3) + q) * LBO_A + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  };
+  for (int c = 0; c < nchunk; c += 2) {
+    tmem_ld32_wait(va);
+    if (c + 1 < nchunk) tmem_ld32_issue(tb + cb + (c + 1) * 32, vb);
+    emit(va, cb + c * 32);
+    if (c + 1 < nchunk) {
+      tmem_ld32_wait(vb);
+      if (c + 2 < nchunk) tmem_ld32_issue(tb + cb + (c + 2) * 32, va);
+      emit(vb, cb + (c + 1) * 32);
     }
   }
 }
 
 // [mean | logvar] heads -> z = mean + eps * exp(logvar / 2) (intention_policy_network.py:76-79), K-groups 0 .. latent/8 of
-// the decoder's A operand
+// the decoder's A operand; this thread owns latent columns [half * latent / 2, (half + 1) * latent / 2)
 __device__ __forceinline__ void epilogue_z(uint32_t tb, int latent, const float* __restrict__ P, uint8_t* anext, int row,
-                                           int grow, int B, const float* __restrict__ eps_z, float* z_mean, float* z_logvar) {
-  for (int c0 = 0; c0 < latent; c0 += 16) {
-    float m[16], lv[16], e[16];
-    tmem_ld16(tb + c0, m);
-    tmem_ld16(tb + latent + c0, lv);
+                                           int half, int grow, int B, const float4* ez, float* z_mean, float* z_logvar) {
+  const int cb = half * (latent >> 1);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      m[j] += P[c0 + j];
-      lv[j] += P[latent + c0 + j];
-      e[j] = 0.0f;
-    }
-    if (grow < B) {
+  for (int it = 0; it < 2; ++it) {  // latent / 2 <= 32 columns per thread, 16 at a time
+    const int c0 = cb + it * 16;
+    if (it * 16 < (latent >> 1)) {
+      float m[16], lv[16], e[16];
+      tmem_ld16(tb + c0, m);
+      tmem_ld16(tb + latent + c0, lv);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        m[j] += P[c0 + j];
+        lv[j] += P[latent + c0 + j];
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(eps_z + (size_t)grow * latent + c0) + q);
+        const float4 t = ez[it * 4 + q];
         e[4 * q] = t.x, e[4 * q + 1] = t.y, e[4 * q + 2] = t.z, e[4 * q + 3] = t.w;
-        if (z_mean)
-          reinterpret_cast<float4*>(z_mean + (size_t)grow * latent + c0)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-        if (z_logvar)
-          reinterpret_cast<float4*>(z_logvar + (size_t)grow * latent + c0)[q] = make_float4(lv[4 * q], lv[4 * q + 1], lv[4 * q + 2], lv[4 * q + 3]);
       }
-    }
+      if (grow < B) {
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t w[4];
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int j = q * 8 + h * 2;
-        w[h] = pack_bf16(m[j] + e[j] * expf(0.5f * lv[j]), m[j + 1] + e[j + 1] * expf(0.5f * lv[j + 1]));
+        for (int q = 0; q < 4; ++q) {
+          if (z_mean)
+            reinterpret_cast<float4*>(z_mean + (size_t)grow * latent + c0)[q] = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+          if (z_logvar)
+            reinterpret_cast<float4*>(z_logvar + (size_t)grow * latent + c0)[q] = make_float4(lv[4 * q], lv[4 * q + 1], lv[4 * q + 2], lv[4 * q + 3]);
+        }
       }
-      *reinterpret_cast<uint4*>(anext + (uint32_t)((c0 >> 3) + q) * LBO_A + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        uint32_t w[4];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int j = q * 8 + h * 2;
+          w[h] = pack_bf16(m[j] + e[j] * __expf(0.5f * lv[j]), m[j + 1] + e[j + 1] * __expf(0.5f * lv[j + 1]));
+        }
+        *reinterpret_cast<uint4*>(anext + (uint32_t)((c0 >> 3) + q) * LBO_A + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   }
 }
 
+// developer profile (vnl_policy_debug with layer -1): SM-clock stamps of CTA 0 at the phase boundaries, relative to entry
+#define VNL_STAMP(i) do { if (prof && tid == 0) a.dump[(i)] = (float)(clock64() - t_entry); } while (0)
+
 __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
+  const bool prof = a.dump && a.dump_layer == -1 && blockIdx.x == 0;
+  const long long t_entry = prof ? clock64() : 0;
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* R0 = smem;
   uint8_t* R1 = smem + R0_BYTES;
   float* P = reinterpret_cast<float*>(smem + R0_BYTES + R1_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(P + MAX_PARAM_FLOATS);
+  float2* stats = reinterpret_cast<float2*>(P + MAX_PARAM_FLOATS);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * TILE_M);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
 
   Layout L;
   make_layout(a.d, L);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row = (warp & 3) * 32 + lane, half = warp >> 2;  // epilogue role
   const int row0 = blockIdx.x * TILE_M;
   const uint32_t r0_s = smem_u32(R0), r1_s = smem_u32(R1);
-  const uint32_t bar_ring[2] = {smem_u32(bars), smem_u32(bars + 1)};
-  const uint32_t bar_layer = smem_u32(bars + 2);
+  const uint32_t bar_ring = smem_u32(bars), bar_layer = smem_u32(bars + RING);
 
-  {
-    const float* src = reinterpret_cast<const float*>(a.blob + L.offParams);
-    for (uint32_t i = tid; i < L.nParamFloats; i += THREADS) P[i] = __ldg(src + i);
-  }
+  // The tile's rows of every input are one contiguous range: ask for them in L2 now, so that the dependent phases below see
+  // L2 latency instead of HBM latency.
   if (tid == 0) {
-    mbar_init(bar_ring[0], 1);
-    mbar_init(bar_ring[1], 1);
-    mbar_init(bar_layer, 1);
+    const int rows = min(TILE_M, a.B - row0);
+    l2_prefetch(a.traj + (size_t)row0 * a.d.traj, (size_t)rows * a.d.traj * 4);
+    if (a.d.obs > 0) l2_prefetch(a.obs + (size_t)row0 * a.d.obs, (size_t)rows * a.d.obs * 4);
+    l2_prefetch(a.eps_z + (size_t)row0 * a.d.latent, (size_t)rows * a.d.latent * 4);
+    if (a.eps_a) l2_prefetch(a.eps_a + (size_t)row0 * a.d.nu, (size_t)rows * a.d.nu * 4);
+    if (a.rand_action) l2_prefetch(a.rand_action + (size_t)row0 * a.d.nu, (size_t)rows * a.d.nu * 4);
+  }
+
+  // ---- L0 prologue: the first two weight chunks and the first activation chunk are requested before anything else ----
+  const int nch = L.K[0] / KCHUNK;
+  const uint32_t a_stride = (KCHUNK / 8) * LBO_A, b_stride = (KCHUNK / 8) * L.lboB[0];
+  const uint8_t* w0 = a.blob + L.offW[0];
+  RowRegs<16> rr, rr2;  // activations of the even / odd chunks, fetched two iterations ahead
+  cp_async_bytes(r1_s, w0, b_stride, tid, THREADS);
+  cp_async_bytes(smem_u32(P), a.blob + L.offParams, (L.nParamFloats * 4 + 15) & ~15u, tid, THREADS);  // bias / LayerNorm vectors
+  cp_async_commit();
+  if (nch > 1) cp_async_bytes(r1_s + b_stride, w0 + b_stride, b_stride, tid, THREADS);
+  cp_async_commit();
+  fetch_rows<16>(rr, a.traj, a.d.traj, 0, row0, a.B, warp * 16, lane);
+  if (nch > 1) fetch_rows<16>(rr2, a.traj, a.d.traj, KCHUNK, row0, a.B, warp * 16, lane);
+  if (tid == 0) {
+    for (int i = 0; i <= RING; ++i) mbar_init(bar_ring + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -334,136 +442,205 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
+  VNL_STAMP(0);
 
-  // ---- L0: K streamed in 64-wide chunks through a 2-deep ring (A halves of R0, B halves of R1) ----
+  // ---- L0: K streamed in 64-wide chunks through a 3-slot ring (A slots in R0, B slots in R1).  In iteration c the
+  // weights of chunk c + 2 and the activations of chunk c + 1 are in flight while the MMAs of chunk c run. ----
   {
-    const int nch = L.K[0] / KCHUNK;
-    const uint32_t a_stride = (KCHUNK / 8) * LBO_A, b_stride = (KCHUNK / 8) * L.lboB[0];
     const uint32_t idesc = make_idesc(L.N[0]);
-    uint32_t ring_phase[2] = {0, 0};
-    for (int c = 0; c < nch; ++c) {
-      const int b = c & 1;
-      if (c >= 2) {  // the MMAs of chunk c - 2 have finished reading this slot
-        mbar_wait(bar_ring[b], ring_phase[b]);
-        ring_phase[b] ^= 1;
-      }
-      cp_async_bytes(r1_s + b * b_stride, a.blob + L.offW[0] + (size_t)c * b_stride, b_stride, tid, THREADS);
-      load_rows(a.traj, a.d.traj, c * KCHUNK, row0, a.B, R0 + b * a_stride, 0, KCHUNK / 8, warp * 16, warp * 16 + 16, nullptr,
-                nullptr, lane);
-      cp_async_wait_all();
+    auto step = [&](int c, RowRegs<16>& regs) {
+      const int slot = c % RING;
+      store_rows<16>(regs, a.d.traj, c * KCHUNK, row0, a.B, R0 + slot * a_stride, 0, KCHUNK / 8, warp * 16, nullptr, nullptr, lane);
+      if (c + 2 < nch) fetch_rows<16>(regs, a.traj, a.d.traj, (c + 2) * KCHUNK, row0, a.B, warp * 16, lane);
+      cp_async_wait_pending1();  // the weights of chunk c have landed (those of chunk c + 1 may still be in flight)
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < KCHUNK / 16; ++s)
-          mma_bf16(tmem + L.tcol[0], make_desc(r0_s + b * a_stride + s * 2 * LBO_A, LBO_A, a.desc_mode),
-                   make_desc(r1_s + b * b_stride + s * 2 * L.lboB[0], L.lboB[0], a.desc_mode), idesc, (c > 0 || s > 0) ? 1u : 0u);
-        mma_commit(bar_ring[b]);
+          mma_bf16(tmem + L.tcol[0], make_desc(r0_s + slot * a_stride + s * 2 * LBO_A, LBO_A),
+                   make_desc(r1_s + slot * b_stride + s * 2 * L.lboB[0], L.lboB[0]), idesc, (c > 0 || s > 0) ? 1u : 0u);
+        mma_commit(bar_ring + 8 * slot);
         if (c == nch - 1) mma_commit(bar_layer);
       }
+      if (c + 2 < nch) {
+        if (c >= 1) mbar_wait(bar_ring + 8 * ((c - 1) % RING), ((c - 1) / RING) & 1);  // slot of chunk c + 2 = slot of chunk c - 1
+        cp_async_bytes(r1_s + ((c + 2) % RING) * b_stride, w0 + (size_t)(c + 2) * b_stride, b_stride, tid, THREADS);
+      }
+      cp_async_commit();
+      if (c < 4) VNL_STAMP(1 + c);
+    };
+    for (int c = 0; c < nch; c += 2) {
+      step(c, rr);
+      if (c + 1 < nch) step(c + 1, rr2);
     }
   }
+  VNL_STAMP(5);
 
-  // ---- L1 .. L5: epilogue of layer n - 1 (warps 0-3) beside the weight stream of layer n (warps 4-7) ----
+  // ---- L1 .. L5: the weights of layer n stream in (cp.async) while all warps run the epilogue of layer n - 1.
+  // The decoder input [z | normalised obs | 0] sits a3_kg K-groups into R0 so that its obs columns can be staged early
+  // (first half beside the epilogue of L1, second half beside the z epilogue) without touching the live operand of L2.
+  const int kg_lat = a.d.latent / 8, kg_end3 = L.K[3] / 8;
+  const int a3_kg = a3_base_kg(a.d);
+  uint8_t* A3 = R0 + (uint32_t)a3_kg * LBO_A;
+  const int nobs = (L.K[3] - a.d.latent + KCHUNK - 1) / KCHUNK;
+  float4 ez[8];
+  auto obs_fetch = [&](RowRegs<16>& r, int ci) { fetch_rows<16>(r, a.obs, a.d.obs, ci * KCHUNK, row0, a.B, warp * 16, lane); };
+  auto obs_store = [&](const RowRegs<16>& r, int ci) {
+    store_rows<16>(r, a.d.obs, ci * KCHUNK, row0, a.B, A3, kg_lat + ci * (KCHUNK / 8), kg_end3, warp * 16, a.obs_mean, a.obs_std, lane);
+  };
   uint32_t layer_phase = 0;
   for (int n = 1; n < 6; ++n) {
+    // global operands of the coming epilogue are requested before the wait on the MMAs of layer n - 1
+    const int ob = (n == 2) ? 0 : nobs / 2, oe = (n == 2) ? nobs / 2 : ((n == 3) ? nobs : 0);
+    if (n == 2 || n == 3) {
+      if (ob < oe) obs_fetch(rr, ob);
+      if (ob + 1 < oe) obs_fetch(rr2, ob + 1);
+    }
+    if (n == 3) {
+      const int hw = a.d.latent >> 1, grow = row0 + row;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        ez[q] = (4 * q < hw && grow < a.B) ? __ldg(reinterpret_cast<const float4*>(a.eps_z + (size_t)grow * a.d.latent + half * hw) + q)
+                                           : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    if (n == 5) {  // the tile's action-noise draws -> shared memory behind the weights (consumed after L5)
+      const int cnt = min(TILE_M, a.B - row0) * a.d.nu;
+      const uint32_t dst = r1_s + draw_stage_offset(L);
+      if (a.eps_a) cp_async_words(dst, a.eps_a + (size_t)row0 * a.d.nu, cnt, tid);
+      if (a.rand_action) cp_async_words(dst + TILE_M * a.d.nu * 4, a.rand_action + (size_t)row0 * a.d.nu, cnt, tid);
+    }
     mbar_wait(bar_layer, layer_phase);
     layer_phase ^= 1;
     tc_fence_after();
-    if (warp >= 4) {
-      cp_async_bytes(r1_s, a.blob + L.offW[n], L.bytesW[n], tid - 128, 128);
-      if (n == 3) {  // decoder input = [z | normalised obs | 0]: the obs columns and the zero tail
-        const int w = warp - 4, kg_lat = a.d.latent / 8, kg_end = L.K[3] / 8;
-        for (int col0 = 0; kg_lat + col0 / 8 < kg_end; col0 += KCHUNK)
-          load_rows(a.obs, a.d.obs, col0, row0, a.B, R0, kg_lat + col0 / 8, kg_end, w * 32, w * 32 + 32, a.obs_mean, a.obs_std, lane);
-      }
-      cp_async_wait_all();
-      fence_proxy_async();
-    } else {
-      const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + L.tcol[n - 1];
-      if (a.dump && a.dump_layer == n - 1 && blockIdx.x == 0) {
-        for (int c0 = 0; c0 < L.N[n - 1]; c0 += 16) {
-          float v[16];
-          tmem_ld16(tb + c0, v);
+    VNL_STAMP(6 + 3 * (n - 1));
+    cp_async_bytes(r1_s, a.blob + L.offW[n], L.bytesW[n], tid, THREADS);
+    cp_async_commit();
+    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + L.tcol[n - 1];
+    if (a.dump && a.dump_layer == n - 1 && blockIdx.x == 0) {
+      const int hw = L.N[n - 1] >> 1;
+      for (int c0 = half * hw; c0 < (half + 1) * hw; c0 += 16) {
+        float v[16];
+        tmem_ld16(tb + c0, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a.dump[(size_t)tid * L.N[n - 1] + c0 + j] = v[j];
-        }
+        for (int j = 0; j < 16; ++j) a.dump[(size_t)row * L.N[n - 1] + c0 + j] = v[j];
       }
-      if (L.ln[n - 1])
-        epilogue_ln(tb, L.N[n - 1], P + L.offP[n - 1], R0, tid);
-      else
-        epilogue_z(tb, a.d.latent, P + L.offP[n - 1], R0, tid, row0 + tid, a.B, a.eps_z, a.z_mean, a.z_logvar);
-      fence_proxy_async();
-      tc_fence_before();
     }
+    if (n == 3)
+      epilogue_z(tb, a.d.latent, P + L.offP[2], A3, row, half, row0 + row, a.B, ez, a.z_mean, a.z_logvar);
+    else
+      epilogue_ln(tb, L.N[n - 1], P + L.offP[n - 1], R0, row, half, stats);
+    if (n == 2 || n == 3) {
+      if (ob < oe) obs_store(rr, ob);
+      if (ob + 1 < oe) obs_store(rr2, ob + 1);
+      for (int ci = ob + 2; ci < oe; ++ci) {  // wider obs than two chunks per phase: staged without overlap
+        obs_fetch(rr, ci);
+        obs_store(rr, ci);
+      }
+    }
+    VNL_STAMP(7 + 3 * (n - 1));
+    cp_async_wait_all();
+    fence_proxy_async();
+    tc_fence_before();
     __syncthreads();
+    VNL_STAMP(8 + 3 * (n - 1));
     if (tid == 0) {
       tc_fence_after();
       const uint32_t idesc = make_idesc(L.N[n]);
+      const uint32_t a_s = r0_s + (n == 3 ? (uint32_t)a3_kg * LBO_A : 0u);
       const int ksteps = L.K[n] / 16;
       for (int s = 0; s < ksteps; ++s)
-        mma_bf16(tmem + L.tcol[n], make_desc(r0_s + s * 2 * LBO_A, LBO_A, a.desc_mode), make_desc(r1_s + s * 2 * L.lboB[n], L.lboB[n], a.desc_mode), idesc,
+        mma_bf16(tmem + L.tcol[n], make_desc(a_s + s * 2 * LBO_A, LBO_A), make_desc(r1_s + s * 2 * L.lboB[n], L.lboB[n]), idesc,
                  s > 0 ? 1u : 0u);
       mma_commit(bar_layer);
     }
   }
 
-  // ---- logits -> NormalTanhDistribution sample / log-prob (ppo_networks.py:45-83) ----
+  // ---- logits -> NormalTanhDistribution sample / log-prob (ppo_networks.py:45-83).  Warp w owns tile rows w, w + 8, ..;
+  // lane i owns action dimensions i (and i + 32), so a row's log-prob is one warp reduction (fixed order).  The loops are
+  // kept rolled (4 rows per trip): this code runs once per CTA and its instruction-fetch footprint is what it costs. ----
+  const int nu = a.d.nu, nlog = 2 * nu, sstride = L.N[5] + 1;
   mbar_wait(bar_layer, layer_phase);
   tc_fence_after();
-  const int nu = a.d.nu, nlog = 2 * nu, sstride = L.N[5] + 1;
-  float* S = reinterpret_cast<float*>(R0);        // [128][N5 + 1] logits
-  float* LP = reinterpret_cast<float*>(R1);       // [128][nu] per-dimension log-prob terms
-  float* LPR = LP + TILE_M * nu;                  // same for the uniform draw
-  if (warp < 4) {
-    const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + L.tcol[5];
+  VNL_STAMP(21);
+  float* S = reinterpret_cast<float*>(R0);  // [128][N5 + 1] logits
+  const float* EA = reinterpret_cast<const float*>(R1 + draw_stage_offset(L));  // [128][nu] eps_a, then [128][nu] rand_action
+  const float* UA = EA + TILE_M * nu;
+  {
+    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + L.tcol[5];
     const float* bias = P + L.offP[5];
-    for (int c0 = 0; c0 < L.N[5]; c0 += 32) {
-      float v[32];
-      tmem_ld32(tb + c0, v);
+    const int hw = L.N[5] >> 1;
+#pragma unroll 1
+    for (int c0 = half * hw; c0 < (half + 1) * hw; c0 += 16) {
+      float v[16];
+      tmem_ld16(tb + c0, v);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (a.dump && a.dump_layer == 5 && blockIdx.x == 0) a.dump[(size_t)tid * L.N[5] + c0 + j] = v[j];
-        S[tid * sstride + c0 + j] = v[j] + bias[c0 + j];
+      for (int j = 0; j < 16; ++j) {
+        if (a.dump && a.dump_layer == 5 && blockIdx.x == 0) a.dump[(size_t)row * L.N[5] + c0 + j] = v[j];
+        S[row * sstride + c0 + j] = v[j] + bias[c0 + j];
       }
     }
     tc_fence_before();
   }
   __syncthreads();
-  for (int item = tid; item < TILE_M * nu; item += THREADS) {
-    const int r = item / nu, i = item - r * nu, grow = row0 + r;
-    if (grow >= a.B) continue;
-    const float loc = S[r * sstride + i];
-    const float scale = softplus(S[r * sstride + nu + i]) + 1e-3f;  // brax NormalTanhDistribution min_std
-    const float e = a.eps_a ? __ldg(a.eps_a + (size_t)grow * nu + i) : 0.0f;
-    const float raw = loc + scale * e;
-    const float log_scale = logf(scale);
-    if (a.action) a.action[(size_t)grow * nu + i] = tanhf(raw);
-    if (a.raw_action) a.raw_action[(size_t)grow * nu + i] = raw;
-    LP[item] = -0.5f * e * e - log_scale - 0.91893853321f - tanh_log_det(raw);
-    if (a.rand_action) {
-      const float ra = __ldg(a.rand_action + (size_t)grow * nu + i);
-      const float zr = (ra - loc) / scale;
-      LPR[item] = -0.5f * zr * zr - log_scale - 0.91893853321f - tanh_log_det(ra);
+#pragma unroll 1
+  for (int g = 0; g < TILE_M / 32; ++g) {
+    float lp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, lpr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int i = lane; i < nu; i += 32) {
+      float th[4], raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // four independent rows in flight, no stores in between
+        const int r = warp + 8 * (4 * g + u);
+        const float loc = S[r * sstride + i];
+        const float scale = softplus(S[r * sstride + nu + i]) + 1e-3f;  // brax NormalTanhDistribution min_std
+        const float e = a.eps_a ? EA[r * nu + i] : 0.0f;
+        raw[u] = loc + scale * e;
+        const float log_scale = __logf(scale);
+        float ld;
+        tanh_and_log_det(raw[u], th[u], ld);
+        lp[u] += -0.5f * e * e - log_scale - 0.91893853321f - ld;
+        if (a.rand_action) {
+          const float ua = UA[r * nu + i], zr = __fdividef(ua - loc, scale);
+          float t2;
+          tanh_and_log_det(ua, t2, ld);
+          lpr[u] += -0.5f * zr * zr - log_scale - 0.91893853321f - ld;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int grow = row0 + warp + 8 * (4 * g + u);
+        if (grow < a.B) {
+          if (a.action) a.action[(size_t)grow * nu + i] = th[u];
+          if (a.raw_action) a.raw_action[(size_t)grow * nu + i] = raw[u];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        lp[u] += __shfl_xor_sync(0xffffffffu, lp[u], o);
+        lpr[u] += __shfl_xor_sync(0xffffffffu, lpr[u], o);
+      }
+#pragma unroll 1
+    for (int u = 0; u < 4; ++u) {
+      const int r = warp + 8 * (4 * g + u), grow = row0 + r;
+      if (grow >= a.B) continue;
+      const float l = u == 0 ? lp[0] : u == 1 ? lp[1] : u == 2 ? lp[2] : lp[3];
+      const float lr = u == 0 ? lpr[0] : u == 1 ? lpr[1] : u == 2 ? lpr[2] : lpr[3];
+      if (lane == 0) {
+        if (a.log_prob) a.log_prob[grow] = l;
+        if (a.rand_action && a.rand_log_prob) a.rand_log_prob[grow] = lr;
+      }
+      if (a.logits)
+#pragma unroll 1
+        for (int i = lane; i < nlog; i += 32) a.logits[(size_t)grow * nlog + i] = S[r * sstride + i];
     }
   }
-  if (a.logits)
-    for (int item = tid; item < TILE_M * nlog; item += THREADS) {
-      const int r = item / nlog, i = item - r * nlog, grow = row0 + r;
-      if (grow < a.B) a.logits[(size_t)grow * nlog + i] = S[r * sstride + i];
-    }
   __syncthreads();
-  if (tid < TILE_M && row0 + tid < a.B) {
-    float s = 0.0f, sr = 0.0f;
-    for (int i = 0; i < nu; ++i) s += LP[tid * nu + i];
-    if (a.log_prob) a.log_prob[row0 + tid] = s;
-    if (a.rand_action && a.rand_log_prob) {
-      for (int i = 0; i < nu; ++i) sr += LPR[tid * nu + i];
-      a.rand_log_prob[row0 + tid] = sr;
-    }
-  }
-  __syncthreads();
+  VNL_STAMP(22);
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
 }
 
@@ -485,7 +662,7 @@ void pack_weight(const Layout& L, int li, const float* W, int K_true, int N_true
     }
 }
 
-int launch(Args a, void* stream) {
+int launch(const Args& a, void* stream) {
   static bool attr_set[64] = {};  // per device; idempotent, a race sets it twice
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -9;
@@ -494,8 +671,6 @@ int launch(Args a, void* stream) {
     if (e != cudaSuccess) return -(int)e;
     attr_set[dev] = true;
   }
-  static const int desc_mode = getenv("VNL_POLICY_DESC_MODE") ? atoi(getenv("VNL_POLICY_DESC_MODE")) : 0;
-  a.desc_mode = desc_mode;
   const int grid = (a.B + TILE_M - 1) / TILE_M;
   vnl_policy_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return -(int)cudaGetLastError();
@@ -556,7 +731,7 @@ int vnl_policy_forward(const void* blob_dev, const VnlPolicyDims* dims, int B, c
   if (!blob_dev || !traj || !eps_z || B < 0 || (dims->obs > 0 && !obs) || ((obs_mean == nullptr) != (obs_std == nullptr))) return -1;
   if (B == 0) return 0;
   Args a{*dims, B, static_cast<const uint8_t*>(blob_dev), traj, obs, obs_mean, obs_std, eps_z, eps_a, rand_action,
-         action, raw_action, logits, log_prob, rand_log_prob, z_mean, z_logvar, -1, nullptr, 0};
+         action, raw_action, logits, log_prob, rand_log_prob, z_mean, z_logvar, -1, nullptr};
   return launch(a, stream);
 }
 
@@ -564,9 +739,9 @@ int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, con
                      const float* obs_mean, const float* obs_std, const float* eps_z, int layer, float* dump, void* stream) {
   const int rc = check_dims(dims);
   if (rc) return rc;
-  if (!blob_dev || !traj || !eps_z || !dump || B <= 0 || layer < 0 || layer > 5) return -1;
+  if (!blob_dev || !traj || !eps_z || !dump || B <= 0 || layer < -1 || layer > 5) return -1;
   Args a{*dims, B, static_cast<const uint8_t*>(blob_dev), traj, obs, obs_mean, obs_std, eps_z, nullptr, nullptr,
-         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, layer, dump, 0};
+         nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, layer, dump};
   return launch(a, stream);
 }
 
