@@ -1,0 +1,92 @@
+"""rollout.Rollout == `generate_unroll` / `actor_step` of ppo_imitation/acting.py:30-80 around the wrapped env: field
+alignment of the transition, equality with a step-by-step loop over the two C entry points, and CUDA-graph replay ==
+eager launches (both kernels are capturable: no allocation, no sync, static geometry)."""
+import numpy as np
+import pytest
+
+from conftest import pkg, start_states
+
+pytestmark = pytest.mark.gpu
+
+T, B, EP = 6, 200, 4.0  # episode_length 4 < unroll: truncation + restore happen inside an unroll
+
+
+def _setup(gpu_env, rodent, seed):
+    import torch
+    pol = pkg("policy")
+    eng = gpu_env.engine
+    qpos, qvel, start = start_states(rodent, B, seed=seed)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    params = pol.init_params(np.random.default_rng(seed), pol.param_shapes(eng.traj_size, eng.obs_size, gpu_env.action_size), perturb=0.1)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    mean = torch.randn(eng.obs_size, device="cuda", generator=g) * 0.1
+    std = torch.rand(eng.obs_size, device="cuda", generator=g) + 0.5
+    policy = pol.IntentionPolicy(params, "cuda:0", mean, std)
+    draws = [(torch.randn(T, B, 64, device="cuda", generator=g), torch.randn(T, B, 30, device="cuda", generator=g)) for _ in range(3)]
+    return s0, policy, draws
+
+
+def test_unroll_equals_stepwise_loop(gpu_env, rodent):
+    import torch
+    s0, policy, draws = _setup(gpu_env, rodent, 51)
+    eng = gpu_env.engine
+    ro = pkg("rollout").Rollout(gpu_env, policy, s0, T, EP, use_graph=False)
+    # the reference loop, one call at a time with fresh buffers
+    first, first_obs = dict(s0.pipeline_state), s0.obs
+    st = dict({k: v.clone() for k, v in first.items()}, cur_frame=s0.info["cur_frame"].clone(), sub_clip_frame=s0.info["sub_clip_frame"].clone())
+    obs, traj = s0.obs.clone(), s0.info["traj"].clone()
+    steps, done = torch.zeros(B, device="cuda"), torch.zeros(B, device="cuda")
+    seen_trunc = False
+    for u in range(2):
+        tr = ro.generate_unroll(*draws[u])
+        torch.cuda.synchronize()
+        assert torch.equal(tr["next_observation"][:-1], tr["observation"][1:])
+        for t in range(T):
+            act, ex = policy(traj, obs, draws[u][0][t], draws[u][1][t])
+            nxt, out, trunc = eng.alloc_state(B), eng.alloc_outputs(B), torch.zeros(B, device="cuda")
+            eng.step_training(st, act, nxt, out, first, first_obs, steps, done, steps, trunc, EP)
+            torch.cuda.synchronize()
+            assert torch.equal(tr["observation"][t], obs) and torch.equal(tr["action"][t], act), (u, t)
+            assert torch.equal(tr["policy_extras"]["log_prob"][t], ex["log_prob"])
+            assert torch.equal(tr["policy_extras"]["raw_action"][t], ex["raw_action"])
+            assert torch.equal(tr["policy_extras"]["logits"][t], ex["logits"])
+            assert torch.equal(tr["reward"][t], out["reward"]) and torch.equal(tr["discount"][t], 1 - out["done"])
+            assert torch.equal(tr["next_observation"][t], out["obs"]) and torch.equal(tr["state_extras"]["traj"][t], out["traj"])
+            assert torch.equal(tr["state_extras"]["truncation"][t], trunc)
+            seen_trunc = seen_trunc or bool((trunc > 0).any())
+            st, obs, traj, done = nxt, out["obs"], out["traj"], out["done"].clone()
+        for k, v in st.items():
+            assert torch.equal(ro.env_state[k], v), k
+    assert seen_trunc and float(steps.max()) <= EP and ro.launches == 4 * T
+
+
+def test_graph_replay_equals_eager(gpu_env, rodent):
+    import torch
+    s0, policy, draws = _setup(gpu_env, rodent, 52)
+    eager = pkg("rollout").Rollout(gpu_env, policy, s0, T, EP, use_graph=False)
+    graph = pkg("rollout").Rollout(gpu_env, policy, s0, T, EP, use_graph=True)
+    for u in range(3):
+        a = eager.generate_unroll(*draws[u])
+        b = graph.generate_unroll(*draws[u])
+        torch.cuda.synchronize()
+        for k in ("observation", "next_observation", "action", "reward", "discount", "metrics"):
+            assert torch.equal(a[k], b[k]), (u, k)
+        for grp in ("policy_extras", "state_extras"):
+            for k in a[grp]:
+                assert torch.equal(a[grp][k], b[grp][k]), (u, grp, k)
+        for k, v in eager.env_state.items():
+            assert torch.equal(graph.env_state[k], v), (u, k)
+    assert graph.graph is not None
+
+
+def test_odd_unroll_length_carries_state(gpu_env, rodent):
+    import torch
+    s0, policy, draws = _setup(gpu_env, rodent, 53)
+    a = pkg("rollout").Rollout(gpu_env, policy, s0, 3, EP, use_graph=False)
+    b = pkg("rollout").Rollout(gpu_env, policy, s0, 6, EP, use_graph=False)
+    z, e = draws[0]
+    a.generate_unroll(z[:3], e[:3])
+    ta = {k: v.clone() for k, v in a.generate_unroll(z[3:], e[3:]).items() if k in ("reward", "action")}
+    tb = b.generate_unroll(z, e)
+    torch.cuda.synchronize()
+    assert torch.equal(ta["reward"], tb["reward"][3:]) and torch.equal(ta["action"], tb["action"][3:])

@@ -87,6 +87,30 @@ def main():
         gen = torch.Generator(device=dev).manual_seed(rank)
         eps_z = torch.randn(unroll, B, kpol.latent, device=dev, generator=gen)
         eps_a = torch.randn(unroll, B, env.action_size, device=dev, generator=gen)
+    if os.environ.get("GRAPH") == "1" and which != "torch":
+        # the packaged loop: rollout.Rollout = generate_unroll over vnl_policy_forward + vnl_step_training (Episode + AutoReset
+        # wrappers fused, episode_length 150), 2 x 20 launches replayed as one CUDA graph, draws refilled per unroll
+        ro = importlib.import_module("vnl-brax-imitation_b200.rollout").Rollout(env, kpol, s0, unroll, 150.0, use_graph=True)
+        ro.generate_unroll(eps_z, eps_a)
+        torch.cuda.synchronize()
+        sh.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(reps):
+            ro.eps_z.normal_(generator=gen)
+            ro.eps_a.normal_(generator=gen)
+            ro.generate_unroll()
+        g1.record()
+        torch.cuda.synchronize()
+        ms = sh.reduce_scalars(dict(ms=g0.elapsed_time(g1)), op="max", device=dev)["ms"]
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank == 0:
+            print(json.dumps({"config": "rodent PPO rollout (rollout.Rollout, CUDA graph of 2 x %d launches, draws generated inside the timed region): %d envs/GPU" % (unroll, B),
+                              "n_gpus": world, "rollout_env_steps_per_s": world * B * unroll * reps / (ms * 1e-3), "ms_per_unroll": ms / reps}), flush=True)
+        return
     a_st = {k: v.clone() for k, v in first.items()}
     a_st["cur_frame"], a_st["sub_clip_frame"] = s0.info["cur_frame"].clone(), s0.info["sub_clip_frame"].clone()
     b_st, out = eng.alloc_state(B), eng.alloc_outputs(B)
