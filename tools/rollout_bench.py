@@ -91,7 +91,9 @@ def main():
         # the packaged loop: rollout.Rollout = generate_unroll over vnl_policy_forward + vnl_step_training (Episode + AutoReset
         # wrappers fused, episode_length 150), 2 x 20 launches replayed as one CUDA graph, draws refilled per unroll
         ro = importlib.import_module("vnl-brax-imitation_b200.rollout").Rollout(env, kpol, s0, unroll, 150.0, use_graph=True)
-        ro.generate_unroll(eps_z, eps_a)
+        stats = importlib.import_module("vnl-brax-imitation_b200.normalizer").RunningStatistics(eng.obs_size, str(dev))
+        kpol.set_normalizer(stats.mean, stats.std)  # shared tensors: every update is seen by the next policy launch
+        stats.update(ro.generate_unroll(eps_z, eps_a)["observation"])
         torch.cuda.synchronize()
         sh.barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -99,7 +101,7 @@ def main():
         for _ in range(reps):
             ro.eps_z.normal_(generator=gen)
             ro.eps_a.normal_(generator=gen)
-            ro.generate_unroll()
+            stats.update(ro.generate_unroll()["observation"])  # running_statistics.update + its psum (train.py:330-334)
         g1.record()
         torch.cuda.synchronize()
         ms = sh.reduce_scalars(dict(ms=g0.elapsed_time(g1)), op="max", device=dev)["ms"]
@@ -108,7 +110,7 @@ def main():
             dist.barrier()
             dist.destroy_process_group()
         if rank == 0:
-            print(json.dumps({"config": "rodent PPO rollout (rollout.Rollout, CUDA graph of 2 x %d launches, draws generated inside the timed region): %d envs/GPU" % (unroll, B),
+            print(json.dumps({"config": "rodent PPO rollout (rollout.Rollout, CUDA graph of 2 x %d launches; draws generated and the obs normaliser updated + all-reduced inside the timed region): %d envs/GPU" % (unroll, B),
                               "n_gpus": world, "rollout_env_steps_per_s": world * B * unroll * reps / (ms * 1e-3), "ms_per_unroll": ms / reps}), flush=True)
         return
     a_st = {k: v.clone() for k, v in first.items()}
