@@ -31,7 +31,7 @@ def brax_update(state, batches, std_min=1e-6, std_max=1e6):
 
 def test_header_and_binding_agree():
     txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vnl_normalizer.h")).read(), flags=re.S)
-    declared = sorted(set(re.findall(r"\b(vnl_obs_[a-z_0-9]+)\s*\(", txt)))
+    declared = sorted(set(re.findall(r"\b(vnl_(?:xla_)?obs_[a-z_0-9]+)\s*\(", txt)))
     assert set(declared) == set(nz.NORMALIZER_EXPORTS)
     if not os.path.exists(libm.LIB_PATH):
         import __graft_entry__
@@ -119,3 +119,32 @@ def test_update_is_deterministic_and_accepts_time_major_batches():
         assert torch.equal(getattr(a, k), getattr(b, k)), k
     with pytest.raises(ValueError):
         a.update(x[:, :, :100])
+
+
+@pytest.mark.gpu
+def test_xla_custom_call_trampolines_equal_direct_calls():
+    """Legacy XLA custom-call ABI: uninitialised scratch / result buffers, state passed functionally (operands -> results)."""
+    import ctypes
+    import struct
+    W, n = 232, 5000
+    x = torch.randn(n, W, generator=torch.Generator().manual_seed(2)).cuda() * 2 + 1
+    st = nz.RunningStatistics(W)
+    st.update(x[:2000].contiguous())
+    old = {k: getattr(st, k).clone() for k in ("count", "mean", "summed_variance", "std")}
+    st.update(x[2000:].contiguous())
+    torch.cuda.synchronize()
+    lib, stream = st.lib, torch.cuda.current_stream().cuda_stream
+    garbage = lambda m: torch.full((m,), float("nan"), device="cuda")
+    sums, work = garbage(2 * W + 1), garbage(st.workspace.numel())
+    batch = x[2000:].contiguous()
+    arr = (ctypes.c_void_p * 4)(batch.data_ptr(), old["mean"].data_ptr(), sums.data_ptr(), work.data_ptr())
+    op = struct.pack("<qi", n - 2000, W)
+    lib.vnl_xla_obs_stats_partial(stream, arr, op, len(op))
+    new = {k: garbage(v.numel()) for k, v in old.items()}
+    arr = (ctypes.c_void_p * 9)(sums.data_ptr(), *[old[k].data_ptr() for k in ("count", "mean", "summed_variance", "std")],
+                                *[new[k].data_ptr() for k in ("count", "mean", "summed_variance", "std")])
+    op = struct.pack("<iff", W, 1e-6, 1e6)
+    lib.vnl_xla_obs_stats_finish(stream, arr, op, len(op))
+    torch.cuda.synchronize()
+    for k in new:
+        assert torch.equal(new[k], getattr(st, k)), k

@@ -26,7 +26,7 @@ RODENT = dict(traj_size=795, obs_size=232, action_size=30)  # SURVEY App. A; lat
 def _declared():
     txt = open(os.path.join(ROOT, "include", "vnl_policy.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(vnl_policy_[a-z_0-9]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(vnl_(?:xla_)?policy_[a-z_0-9]+)\s*\(", txt)))
 
 
 @pytest.fixture(scope="module")
@@ -233,3 +233,23 @@ def test_policy_rows_are_independent_and_deterministic():
     torch.cuda.synchronize()
     for k in ("logits", "action", "log_prob"):
         assert torch.equal(a[k][perm], b[k]), k
+
+
+@pytest.mark.gpu
+def test_xla_custom_call_trampoline_equals_direct_call():
+    """`vnl_xla_policy_forward(stream, buffers, opaque, len)` (legacy XLA custom-call ABI) == vnl_policy_forward."""
+    import struct
+    params, x, mean, std = _case(257, seed=9)
+    p = pol.IntentionPolicy(params, "cuda:0", mean, std)
+    _, a = p(x["traj"], x["obs"], x["eps_z"], x["eps_a"], x["rand"])
+    a = {k: v.clone() for k, v in a.items()}
+    b = p.alloc_outputs(257)
+    bufs = [p.blob_dev, x["traj"], x["obs"], mean, std, x["eps_z"], x["eps_a"], x["rand"],
+            b["action"], b["raw_action"], b["logits"], b["log_prob"], b["rand_log_prob"]]
+    arr = (ctypes.c_void_p * len(bufs))(*[t.data_ptr() for t in bufs])
+    d = p.dims
+    opaque = struct.pack("<9i", d.traj, d.obs, d.latent, d.e1, d.e2, d.d1, d.d2, d.nu, 257)
+    p.lib.vnl_xla_policy_forward(torch.cuda.current_stream().cuda_stream, arr, opaque, len(opaque))
+    torch.cuda.synchronize()
+    for k in ("action", "raw_action", "logits", "log_prob", "rand_log_prob"):
+        assert torch.equal(a[k], b[k]), k

@@ -745,4 +745,19 @@ int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, con
   return launch(a, stream);
 }
 
+// Legacy XLA custom call (`void f(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)`).
+// opaque = 9 little-endian int32: the VnlPolicyDims fields (traj, obs, latent, e1, e2, d1, d2, nu), then B.
+// buffers: [blob, traj, obs, obs_mean, obs_std, eps_z, eps_a, rand_action,
+//           (outputs) action, raw_action, logits, log_prob, rand_log_prob]
+void vnl_xla_policy_forward(void* stream, void** b, const char* opaque, size_t opaque_len) {
+  if (opaque_len < 9 * sizeof(int32_t)) return;
+  VnlPolicyDims d;
+  int32_t B;
+  memcpy(&d, opaque, sizeof(d));
+  memcpy(&B, opaque + sizeof(d), sizeof(B));
+  vnl_policy_forward(b[0], &d, B, (const float*)b[1], (const float*)b[2], (const float*)b[3], (const float*)b[4],
+                     (const float*)b[5], (const float*)b[6], (const float*)b[7], (float*)b[8], (float*)b[9], (float*)b[10],
+                     (float*)b[11], (float*)b[12], nullptr, nullptr, stream);
+}
+
 }  // extern "C"

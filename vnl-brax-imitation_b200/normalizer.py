@@ -16,7 +16,8 @@ import ctypes
 
 from . import _lib
 
-NORMALIZER_EXPORTS = ("vnl_obs_stats_workspace_bytes", "vnl_obs_stats_partial", "vnl_obs_stats_finish")
+NORMALIZER_EXPORTS = ("vnl_obs_stats_workspace_bytes", "vnl_obs_stats_partial", "vnl_obs_stats_finish",
+                      "vnl_xla_obs_stats_partial", "vnl_xla_obs_stats_finish")
 
 
 def _bind(lib):
@@ -25,6 +26,9 @@ def _bind(lib):
     lib.vnl_obs_stats_workspace_bytes.restype = ctypes.c_size_t
     lib.vnl_obs_stats_partial.argtypes = [v, ctypes.c_longlong, ctypes.c_int, v, v, v, v]
     lib.vnl_obs_stats_finish.argtypes = [v, ctypes.c_int, v, v, v, v, ctypes.c_float, ctypes.c_float, v]
+    for n in ("vnl_xla_obs_stats_partial", "vnl_xla_obs_stats_finish"):
+        getattr(lib, n).argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t]
+        getattr(lib, n).restype = None
     return lib
 
 

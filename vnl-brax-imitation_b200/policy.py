@@ -31,7 +31,8 @@ class VnlPolicyDims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("traj", "obs", "latent", "e1", "e2", "d1", "d2", "nu")]
 
 
-POLICY_EXPORTS = ("vnl_policy_check", "vnl_policy_blob_bytes", "vnl_policy_pack", "vnl_policy_forward", "vnl_policy_debug")
+POLICY_EXPORTS = ("vnl_policy_check", "vnl_policy_blob_bytes", "vnl_policy_pack", "vnl_policy_forward", "vnl_policy_debug",
+                  "vnl_xla_policy_forward")
 
 
 def _bind(lib):
@@ -43,6 +44,8 @@ def _bind(lib):
     lib.vnl_policy_pack.argtypes = [P, ctypes.POINTER(v), v, ctypes.c_size_t]
     lib.vnl_policy_forward.argtypes = [v, P, ctypes.c_int] + [v] * 15
     lib.vnl_policy_debug.argtypes = [v, P, ctypes.c_int, v, v, v, v, v, ctypes.c_int, v, v]
+    lib.vnl_xla_policy_forward.argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t]
+    lib.vnl_xla_policy_forward.restype = None
     return lib
 
 
