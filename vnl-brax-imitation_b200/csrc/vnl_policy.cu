@@ -399,9 +399,13 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * TILE_M);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
 
+  // the layer table: a per-thread copy for the compile-time indices (stays in registers) and one in shared memory for the
+  // layer loop's run-time indices (a dynamically indexed local array would live on the stack, behind L1)
+  __shared__ Layout Ls;
   Layout L;
   make_layout(a.d, L);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) Ls = L;
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;  // epilogue role
   const int row0 = blockIdx.x * TILE_M;
   const uint32_t r0_s = smem_u32(R0), r1_s = smem_u32(R1);
@@ -515,22 +519,22 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     layer_phase ^= 1;
     tc_fence_after();
     VNL_STAMP(6 + 3 * (n - 1));
-    cp_async_bytes(r1_s, a.blob + L.offW[n], L.bytesW[n], tid, THREADS);
+    cp_async_bytes(r1_s, a.blob + Ls.offW[n], Ls.bytesW[n], tid, THREADS);
     cp_async_commit();
-    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + L.tcol[n - 1];
+    const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Ls.tcol[n - 1];
     if (a.dump && a.dump_layer == n - 1 && blockIdx.x == 0) {
-      const int hw = L.N[n - 1] >> 1;
+      const int hw = Ls.N[n - 1] >> 1;
       for (int c0 = half * hw; c0 < (half + 1) * hw; c0 += 16) {
         float v[16];
         tmem_ld16(tb + c0, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) a.dump[(size_t)row * L.N[n - 1] + c0 + j] = v[j];
+        for (int j = 0; j < 16; ++j) a.dump[(size_t)row * Ls.N[n - 1] + c0 + j] = v[j];
       }
     }
     if (n == 3)
       epilogue_z(tb, a.d.latent, P + L.offP[2], A3, row, half, row0 + row, a.B, ez, a.z_mean, a.z_logvar);
     else
-      epilogue_ln(tb, L.N[n - 1], P + L.offP[n - 1], R0, row, half, stats);
+      epilogue_ln(tb, Ls.N[n - 1], P + Ls.offP[n - 1], R0, row, half, stats);
     if (n == 2 || n == 3) {
       if (ob < oe) obs_store(rr, ob);
       if (ob + 1 < oe) obs_store(rr2, ob + 1);
@@ -547,11 +551,11 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     VNL_STAMP(8 + 3 * (n - 1));
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t idesc = make_idesc(L.N[n]);
+      const uint32_t idesc = make_idesc(Ls.N[n]);
       const uint32_t a_s = r0_s + (n == 3 ? (uint32_t)a3_kg * LBO_A : 0u);
-      const int ksteps = L.K[n] / 16;
+      const int ksteps = Ls.K[n] / 16;
       for (int s = 0; s < ksteps; ++s)
-        mma_bf16(tmem + L.tcol[n], make_desc(a_s + s * 2 * LBO_A, LBO_A), make_desc(r1_s + s * 2 * L.lboB[n], L.lboB[n]), idesc,
+        mma_bf16(tmem + Ls.tcol[n], make_desc(a_s + s * 2 * LBO_A, LBO_A), make_desc(r1_s + s * 2 * Ls.lboB[n], Ls.lboB[n]), idesc,
                  s > 0 ? 1u : 0u);
       mma_commit(bar_layer);
     }
