@@ -27,6 +27,10 @@ PARAM_ORDER = (
 )
 
 
+# the same entries as (module, layer, leaf) of the flax dict `params["params"]`
+PARAM_ORDER_TUPLES = tuple(tuple(k.split("/")) for k in PARAM_ORDER)
+
+
 class VnlPolicyDims(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("traj", "obs", "latent", "e1", "e2", "d1", "d2", "nu")]
 
