@@ -148,3 +148,19 @@ def test_xla_custom_call_trampolines_equal_direct_calls():
     torch.cuda.synchronize()
     for k in new:
         assert torch.equal(new[k], getattr(st, k)), k
+
+
+@pytest.mark.gpu
+def test_empty_batches():
+    """rows = 0 (a rank with no envs this step) contributes zeros to the exchange; an all-empty update keeps init_state."""
+    st = nz.RunningStatistics(232)
+    st.update(torch.zeros(0, 232, device="cuda"))
+    torch.cuda.synchronize()
+    assert float(st.count) == 0 and float(st.std.min()) == 1.0 and not torch.isnan(st.mean).any()
+    x = torch.randn(100, 232, device="cuda")
+    st.update(x)
+    before = {k: getattr(st, k).clone() for k in ("count", "mean", "summed_variance", "std")}
+    st.update(torch.zeros(0, 232, device="cuda"))
+    torch.cuda.synchronize()
+    for k, v in before.items():
+        assert torch.equal(getattr(st, k), v), k

@@ -253,3 +253,19 @@ def test_xla_custom_call_trampoline_equals_direct_call():
     torch.cuda.synchronize()
     for k in ("action", "raw_action", "logits", "log_prob", "rand_log_prob"):
         assert torch.equal(a[k], b[k]), k
+
+
+@pytest.mark.gpu
+def test_empty_batch_and_argument_errors(lib):
+    params, x, mean, std = _case(4, seed=1)
+    p = pol.IntentionPolicy(params, "cuda:0", mean, std)
+    z = lambda w: torch.zeros(0, w, device="cuda")
+    act, out = p(z(795), z(232), z(64), z(30))  # B = 0: nothing is launched, nothing fails
+    torch.cuda.synchronize()
+    assert act.shape == (0, 30)
+    with pytest.raises(ValueError):
+        p(x["traj"][:, :100].contiguous(), x["obs"], x["eps_z"], x["eps_a"])
+    with pytest.raises(ValueError):
+        p(x["traj"].double(), x["obs"], x["eps_z"], x["eps_a"])
+    d = p.dims
+    assert lib.vnl_policy_forward(None, ctypes.byref(d), 4, *([None] * 15)) < 0  # null blob: argument error, no launch

@@ -90,3 +90,33 @@ def test_odd_unroll_length_carries_state(gpu_env, rodent):
     tb = b.generate_unroll(z, e)
     torch.cuda.synchronize()
     assert torch.equal(ta["reward"], tb["reward"][3:]) and torch.equal(ta["action"], tb["action"][3:])
+
+
+def test_long_rollout_with_normaliser_stays_finite(gpu_env, rodent):
+    """200 env steps of 512 envs through the packaged loop (graph replay), the obs normaliser updated every unroll and feeding
+    the policy: everything stays finite, actions stay in (-1, 1), the normaliser counts every observation, episodes end."""
+    import torch
+    pol, nzm = pkg("policy"), pkg("normalizer")
+    eng = gpu_env.engine
+    Bn, Tn, U = 512, 20, 10
+    qpos, qvel, start = start_states(rodent, Bn, seed=61)
+    s0 = gpu_env.reset_from(qpos, qvel, start)
+    params = pol.init_params(np.random.default_rng(61), pol.param_shapes(eng.traj_size, eng.obs_size, gpu_env.action_size))
+    stats = nzm.RunningStatistics(eng.obs_size)
+    policy = pol.IntentionPolicy(params, "cuda:0", stats.mean, stats.std)
+    assert policy.obs_mean.data_ptr() == stats.mean.data_ptr()  # shared: updates reach the next launch
+    ro = pkg("rollout").Rollout(gpu_env, policy, s0, Tn, 150.0, use_graph=True)
+    g = torch.Generator(device="cuda").manual_seed(61)
+    ended = 0.0
+    for u in range(U):
+        ro.eps_z.normal_(generator=g)
+        ro.eps_a.normal_(generator=g)
+        tr = ro.generate_unroll()
+        stats.update(tr["observation"])
+        torch.cuda.synchronize()
+        for k in ("observation", "action", "reward"):
+            assert torch.isfinite(tr[k]).all(), (u, k)
+        assert torch.isfinite(tr["policy_extras"]["log_prob"]).all() and float(tr["action"].abs().max()) <= 1.0
+        ended += float((1 - tr["discount"]).sum())
+    assert float(stats.count) == U * Tn * Bn and torch.isfinite(stats.std).all() and float(stats.std.min()) > 0
+    assert ended > 0  # sub-clips of 10 frames end inside 200 steps (Q7: and stay ended)

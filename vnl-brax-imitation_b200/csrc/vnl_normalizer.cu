@@ -117,6 +117,7 @@ __global__ void obs_stats_finish_kernel(const float* __restrict__ sums, int widt
                                         float std_min, float std_max) {
   const float cnt = *count + sums[2 * width];
   __syncthreads();  // every thread has read the old count before thread 0 replaces it
+  if (!(cnt > 0.0f)) return;  // nothing seen yet (all ranks sent empty batches): keep init_state, no 0 / 0
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     const float s1 = sums[c], s2 = sums[width + c];
     const float mu = s1 / cnt;  // mean' - mean

@@ -732,8 +732,8 @@ int vnl_policy_forward(const void* blob_dev, const VnlPolicyDims* dims, int B, c
                        float* rand_log_prob, float* z_mean, float* z_logvar, void* stream) {
   const int rc = check_dims(dims);
   if (rc) return rc;
+  if (B == 0) return 0;  // an empty batch launches nothing (its buffers may be null)
   if (!blob_dev || !traj || !eps_z || B < 0 || (dims->obs > 0 && !obs) || ((obs_mean == nullptr) != (obs_std == nullptr))) return -1;
-  if (B == 0) return 0;
   Args a{*dims, B, static_cast<const uint8_t*>(blob_dev), traj, obs, obs_mean, obs_std, eps_z, eps_a, rand_action,
          action, raw_action, logits, log_prob, rand_log_prob, z_mean, z_logvar, -1, nullptr};
   return launch(a, stream);

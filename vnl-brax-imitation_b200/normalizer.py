@@ -67,6 +67,8 @@ class RunningStatistics:
         if batch.dtype != t.float32 or not batch.is_contiguous() or batch.shape[-1] != self.width or batch.device != self.device:
             raise ValueError("batch must be a contiguous fp32 [..., width] tensor on the normaliser's device")
         rows = batch.numel() // self.width
+        if rows == 0 and not group_reduce:
+            return  # empty batch, nobody to exchange with: the state is unchanged (brax: step_increment 0)
         stream = t.cuda.current_stream(self.device).cuda_stream
         with t.cuda.device(self.device):
             rc = self.lib.vnl_obs_stats_partial(batch.data_ptr(), rows, self.width, self.mean.data_ptr(), self.workspace.data_ptr(),
