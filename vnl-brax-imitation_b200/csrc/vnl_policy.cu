@@ -16,11 +16,12 @@
 // sits at (k / 8) * LBO + r * 16 + (k % 8) * 2 with LBO = R * 16 + 16.  The 16 bytes of slack per K-group rotate the
 // banks so that the coalesced activation loader (a lane owns 2 consecutive k of one row) stores conflict-free; the
 // stride between 8-row groups (SBO) is 128.  Weights are packed into exactly this image on the host (vnl_policy_pack),
-// so a layer's B operand is one contiguous cp.async stream.
+// so a layer's B operand (or a K chunk of it) is ONE contiguous TMA bulk copy (cp.async.bulk, completion counted in bytes
+// on an mbarrier): written by the async proxy, read by the tensor core, no thread touches it.
 //
 // All 8 warps run the epilogues (warps w and w + 4 share the tensor-memory lanes of quadrant w % 4 = env rows 32 (w % 4) ..
-// + 31 and split the accumulator columns in halves, 32x32b loads); the next layer's weights stream in by cp.async while the
-// epilogue computes; thread 0 issues the MMAs and commits them to an mbarrier.
+// + 31 and split the accumulator columns in halves, 32x32b loads); the next layer's weights stream in by TMA while the
+// epilogue computes; thread 0 issues the MMAs and commits them to an mbarrier, thread 32 issues the weight copies.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -40,7 +41,7 @@ constexpr uint32_t R0_BYTES = 96 * 1024;  // A operands (activations), later the
 constexpr uint32_t R1_BYTES = 100 * 1024; // B operands (weights; 3 ring slots in L0)
 constexpr int RING = 3;                   // L0 ring depth
 constexpr int MAX_PARAM_FLOATS = 3072;
-constexpr uint32_t SMEM_BYTES = R0_BYTES + R1_BYTES + MAX_PARAM_FLOATS * 4 + 2 * TILE_M * 8 + 64;
+constexpr uint32_t SMEM_BYTES = R0_BYTES + R1_BYTES + MAX_PARAM_FLOATS * 4 + 2 * TILE_M * 8 + 16 * 8 + 64;
 constexpr uint32_t POLICY_MAGIC = 0x4c4f5056u;  // "VPOL"
 constexpr uint32_t HEADER_BYTES = 64;
 constexpr int TMEM_COLS = 512;
@@ -73,7 +74,7 @@ __host__ __device__ inline void make_layout(const VnlPolicyDims& d, Layout& L) {
   }
   L.offParams = off;
   L.nParamFloats = pf;
-  L.total = off + pf * 4;
+  L.total = (off + pf * 4 + 15u) & ~15u;  // whole 16-byte granules (TMA bulk copies)
 }
 
 // K-group offset of the decoder input inside R0: its obs columns must clear the operand of L2 (e2 / 8 K-groups)
@@ -149,10 +150,6 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t 
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void cp_async_bytes(uint32_t dst, const uint8_t* src, uint32_t bytes, int tid, int nthreads) {
-  for (uint32_t o = (uint32_t)tid * 16; o < bytes; o += (uint32_t)nthreads * 16)
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + o), "l"(src + o) : "memory");
-}
 // bulk L2 prefetch of a contiguous global range (16-byte granules; the range is shrunk to whole granules)
 __device__ __noinline__ void l2_prefetch(const void* p, size_t bytes) {
   const uintptr_t b = ((uintptr_t)p + 15) & ~(uintptr_t)15, e = ((uintptr_t)p + bytes) & ~(uintptr_t)15;
@@ -165,9 +162,17 @@ __device__ __noinline__ void cp_async_words(uint32_t dst, const float* src, int 
   for (int i = tid; i < count; i += THREADS)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * i), "l"(src + i) : "memory");
 }
+// TMA bulk copy global -> shared (contiguous, 16-byte granules), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+               "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 #define VNL_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
 // split form: the load is issued into `v`, other work proceeds, tmem_ld32_wait(v) makes the registers valid (it lists them
@@ -397,7 +402,7 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   float* P = reinterpret_cast<float*>(smem + R0_BYTES + R1_BYTES);
   float2* stats = reinterpret_cast<float2*>(P + MAX_PARAM_FLOATS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(stats + 2 * TILE_M);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 16);
 
   // the layer table: a per-thread copy for the compile-time indices (stays in registers) and one in shared memory for the
   // layer loop's run-time indices (a dynamically indexed local array would live on the stack, behind L1)
@@ -409,7 +414,11 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;  // epilogue role
   const int row0 = blockIdx.x * TILE_M;
   const uint32_t r0_s = smem_u32(R0), r1_s = smem_u32(R1);
-  const uint32_t bar_ring = smem_u32(bars), bar_layer = smem_u32(bars + RING);
+  // mbarriers: ring slot released (MMA commit) x3, layer done (MMA commit), ring slot filled (TMA bytes) x3, layer weights
+  // filled, bias / LayerNorm vectors filled
+  const uint32_t bar_ring = smem_u32(bars), bar_layer = smem_u32(bars + RING), bar_full = smem_u32(bars + RING + 1),
+                 bar_wfull = smem_u32(bars + 2 * RING + 1), bar_pfull = smem_u32(bars + 2 * RING + 2);
+  constexpr int PRODUCER = 32;  // the thread that issues the weight copies (warp 1; thread 0 issues the MMAs)
 
   // The tile's rows of every input are one contiguous range: ask for them in L2 now, so that the dependent phases below see
   // L2 latency instead of HBM latency.
@@ -427,17 +436,19 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   const uint32_t a_stride = (KCHUNK / 8) * LBO_A, b_stride = (KCHUNK / 8) * L.lboB[0];
   const uint8_t* w0 = a.blob + L.offW[0];
   RowRegs<16> rr, rr2;  // activations of the even / odd chunks, fetched two iterations ahead
-  cp_async_bytes(r1_s, w0, b_stride, tid, THREADS);
-  cp_async_bytes(smem_u32(P), a.blob + L.offParams, (L.nParamFloats * 4 + 15) & ~15u, tid, THREADS);  // bias / LayerNorm vectors
-  cp_async_commit();
-  if (nch > 1) cp_async_bytes(r1_s + b_stride, w0 + b_stride, b_stride, tid, THREADS);
-  cp_async_commit();
+  if (tid == PRODUCER) {
+    for (int i = 0; i < 2 * RING + 3; ++i) mbar_init(bar_ring + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t pbytes = (L.nParamFloats * 4 + 15) & ~15u;
+    mbar_expect_tx(bar_pfull, pbytes);
+    bulk_g2s(smem_u32(P), a.blob + L.offParams, pbytes, bar_pfull);  // bias / LayerNorm vectors
+    for (int c = 0; c < 2 && c < nch; ++c) {
+      mbar_expect_tx(bar_full + 8 * c, b_stride);
+      bulk_g2s(r1_s + c * b_stride, w0 + (size_t)c * b_stride, b_stride, bar_full + 8 * c);
+    }
+  }
   fetch_rows<16>(rr, a.traj, a.d.traj, 0, row0, a.B, warp * 16, lane);
   if (nch > 1) fetch_rows<16>(rr2, a.traj, a.d.traj, KCHUNK, row0, a.B, warp * 16, lane);
-  if (tid == 0) {
-    for (int i = 0; i <= RING; ++i) mbar_init(bar_ring + 8 * i, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -454,12 +465,13 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     const uint32_t idesc = make_idesc(L.N[0]);
     auto step = [&](int c, RowRegs<16>& regs) {
       const int slot = c % RING;
+      if (c >= RING) mbar_wait(bar_ring + 8 * slot, ((c - RING) / RING) & 1);  // the MMAs of chunk c - 3 have left this A slot
       store_rows<16>(regs, a.d.traj, c * KCHUNK, row0, a.B, R0 + slot * a_stride, 0, KCHUNK / 8, warp * 16, nullptr, nullptr, lane);
       if (c + 2 < nch) fetch_rows<16>(regs, a.traj, a.d.traj, (c + 2) * KCHUNK, row0, a.B, warp * 16, lane);
-      cp_async_wait_pending1();  // the weights of chunk c have landed (those of chunk c + 1 may still be in flight)
       fence_proxy_async();
       __syncthreads();
       if (tid == 0) {
+        mbar_wait(bar_full + 8 * slot, (c / RING) & 1);  // the weights of chunk c have landed (TMA)
         tc_fence_after();
 #pragma unroll
         for (int s = 0; s < KCHUNK / 16; ++s)
@@ -467,12 +479,12 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
                    make_desc(r1_s + slot * b_stride + s * 2 * L.lboB[0], L.lboB[0]), idesc, (c > 0 || s > 0) ? 1u : 0u);
         mma_commit(bar_ring + 8 * slot);
         if (c == nch - 1) mma_commit(bar_layer);
+      } else if (tid == PRODUCER && c + 2 < nch) {
+        const int ns = (c + 2) % RING;  // = slot of chunk c - 1: refill once its MMAs are done
+        if (c >= 1) mbar_wait(bar_ring + 8 * ns, ((c - 1) / RING) & 1);
+        mbar_expect_tx(bar_full + 8 * ns, b_stride);
+        bulk_g2s(r1_s + ns * b_stride, w0 + (size_t)(c + 2) * b_stride, b_stride, bar_full + 8 * ns);
       }
-      if (c + 2 < nch) {
-        if (c >= 1) mbar_wait(bar_ring + 8 * ((c - 1) % RING), ((c - 1) / RING) & 1);  // slot of chunk c + 2 = slot of chunk c - 1
-        cp_async_bytes(r1_s + ((c + 2) % RING) * b_stride, w0 + (size_t)(c + 2) * b_stride, b_stride, tid, THREADS);
-      }
-      cp_async_commit();
       if (c < 4) VNL_STAMP(1 + c);
     };
     for (int c = 0; c < nch; c += 2) {
@@ -519,7 +531,11 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     layer_phase ^= 1;
     tc_fence_after();
     VNL_STAMP(6 + 3 * (n - 1));
-    cp_async_bytes(r1_s, a.blob + Ls.offW[n], Ls.bytesW[n], tid, THREADS);
+    if (tid == PRODUCER) {  // the weights of layer n: one TMA bulk copy (R1 is free: the MMAs of layer n - 1 are done)
+      mbar_expect_tx(bar_wfull, Ls.bytesW[n]);
+      bulk_g2s(r1_s, a.blob + Ls.offW[n], Ls.bytesW[n], bar_wfull);
+    }
+    if (n == 1) mbar_wait(bar_pfull, 0);  // bias / LayerNorm vectors (landed long ago; the wait is the acquire)
     cp_async_commit();
     const uint32_t tb = tmem + ((uint32_t)((warp & 3) * 32) << 16) + Ls.tcol[n - 1];
     if (a.dump && a.dump_layer == n - 1 && blockIdx.x == 0) {
@@ -550,6 +566,7 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     __syncthreads();
     VNL_STAMP(8 + 3 * (n - 1));
     if (tid == 0) {
+      mbar_wait(bar_wfull, (n - 1) & 1);
       tc_fence_after();
       const uint32_t idesc = make_idesc(Ls.N[n]);
       const uint32_t a_s = r0_s + (n == 3 ? (uint32_t)a3_kg * LBO_A : 0u);
