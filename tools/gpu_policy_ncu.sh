@@ -1,0 +1,4 @@
+timeout -s KILL 150 python tools/gpu_policy.py 300 > gpurun_out/pol0.log 2>&1 && \
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:vnl_policy_kernel -s 8 -c 1 -f -o gpurun_out/prof_policy python tools/gpu_policy.py 300 > gpurun_out/pol_ncu_full.log 2>&1
+echo "ncu rc=$?"; tail -1 gpurun_out/pol0.log | cut -c1-200
+POLICY=kernel timeout -s KILL 300 python tools/rollout_bench.py > gpurun_out/rollout_kernel_n1.log 2>&1; tail -1 gpurun_out/rollout_kernel_n1.log
