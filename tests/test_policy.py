@@ -269,3 +269,14 @@ def test_empty_batch_and_argument_errors(lib):
         p(x["traj"].double(), x["obs"], x["eps_z"], x["eps_a"])
     d = p.dims
     assert lib.vnl_policy_forward(None, ctypes.byref(d), 4, *([None] * 15)) < 0  # null blob: argument error, no launch
+
+
+@pytest.mark.gpu
+def test_deterministic_mode_is_tanh_of_loc():
+    """make_policy(params, deterministic=True) (ppo_networks.py:63-64): action = distribution.mode(logits) = tanh(loc)."""
+    params, x, mean, std = _case(200, seed=13)
+    p = pol.IntentionPolicy(params, "cuda:0", mean, std)
+    act, out = p(x["traj"], x["obs"], x["eps_z"], None)
+    torch.cuda.synchronize()
+    loc = out["logits"][:, :30]
+    assert float((act - torch.tanh(loc)).abs().max()) < 2e-6 and torch.equal(out["raw_action"], loc)

@@ -137,10 +137,13 @@ class IntentionPolicy:
 
     def __call__(self, traj, obs, eps_z, eps_a, rand_action=None, out: Optional[dict] = None, heads: bool = False):
         """One launch: (action [B,nu], extras) as `policy(trajectories, observations, key)` of ppo_networks.py:55-83.
-        eps_z [B,latent], eps_a [B,nu]: standard-normal draws; rand_action [B,nu]: the uniform(-1,1) draw (optional)."""
+        eps_z [B,latent], eps_a [B,nu]: standard-normal draws; rand_action [B,nu]: the uniform(-1,1) draw (optional).
+        eps_a=None gives the deterministic policy of evaluation (`mode(logits)`; the latent is still sampled, as there)."""
         t = self.torch
         B = traj.shape[0]
         for x, w in ((traj, self.traj_size), (obs, self.obs_size), (eps_z, self.latent), (eps_a, self.action_size)):
+            if x is None and w == self.action_size:
+                continue  # eps_a=None: `deterministic=True` of make_policy (ppo_networks.py:63-64), action = mode = tanh(loc)
             if x.dtype != t.float32 or not x.is_contiguous() or x.shape != (B, w) or x.device != self.device:
                 raise ValueError("policy operands must be contiguous fp32 [B, width] tensors on the policy's device")
         if out is None:
