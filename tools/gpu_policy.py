@@ -73,7 +73,8 @@ def main():
     torch.cuda.synchronize()
     st = stamps.cpu().numpy()
     names = ["setup", "L0c0", "L0c1", "L0c2", "L0c3", "L0_issued"] + [x for n in range(1, 6) for x in ("mma%d_done" % (n - 1), "epi%d_done" % (n - 1), "w%d_sync" % n)] + ["mma5_done", "end"]
-    tim["stamps_cycles"] = {n: int(v) for n, v in zip(names, st[:23])}
+    names += ["(unused)"] + ["mma%d_issued" % n for n in range(1, 6)]
+    tim["stamps_cycles"] = {n: int(v) for n, v in zip(names, st[:29]) if n != "(unused)"}
     P = {k: torch.as_tensor(v, device=dev) for k, v in params.items()}
     for _ in range(3):
         pol.reference_forward(P, traj, obs, eps_z, eps_a, None, mean, std, operand_dtype=None)

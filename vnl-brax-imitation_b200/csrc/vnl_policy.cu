@@ -568,13 +568,15 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     if (tid == 0) {
       mbar_wait(bar_wfull, (n - 1) & 1);
       tc_fence_after();
-      const uint32_t idesc = make_idesc(Ls.N[n]);
-      const uint32_t a_s = r0_s + (n == 3 ? (uint32_t)a3_kg * LBO_A : 0u);
+      // everything the issue loop needs sits in registers before it starts (the asm statements clobber memory, so a table
+      // read inside the loop would be a shared-memory round trip per MMA); the descriptors advance by constant increments
+      const uint32_t idesc = make_idesc(Ls.N[n]), lbo_b = Ls.lboB[n], d_tmem = tmem + Ls.tcol[n];
       const int ksteps = Ls.K[n] / 16;
-      for (int s = 0; s < ksteps; ++s)
-        mma_bf16(tmem + Ls.tcol[n], make_desc(a_s + s * 2 * LBO_A, LBO_A), make_desc(r1_s + s * 2 * Ls.lboB[n], Ls.lboB[n]), idesc,
-                 s > 0 ? 1u : 0u);
+      uint64_t da = make_desc(r0_s + (n == 3 ? (uint32_t)a3_kg * LBO_A : 0u), LBO_A), db = make_desc(r1_s, lbo_b);
+      const uint64_t sa = (2 * LBO_A) >> 4, sb = (2 * lbo_b) >> 4;  // one K step of 16 = two K-groups, in 16-byte units
+      for (int s = 0; s < ksteps; ++s, da += sa, db += sb) mma_bf16(d_tmem, da, db, idesc, s > 0 ? 1u : 0u);
       mma_commit(bar_layer);
+      VNL_STAMP(23 + n);
     }
   }
 
