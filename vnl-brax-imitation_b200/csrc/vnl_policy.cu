@@ -123,6 +123,9 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -174,6 +177,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+constexpr int LROWS = 19;  // rows per loader warp in layer 0: 128 = 5 x 18 + 2 x 19 over warps 1-7 (warp 0 issues)
 #define VNL_R8(v, o) "=r"(v[o + 0]), "=r"(v[o + 1]), "=r"(v[o + 2]), "=r"(v[o + 3]), "=r"(v[o + 4]), "=r"(v[o + 5]), "=r"(v[o + 6]), "=r"(v[o + 7])
 // split form: the load is issued into `v`, other work proceeds, tmem_ld32_wait(v) makes the registers valid (it lists them
 // as in/out operands, so no consumer of v can be scheduled before it)
@@ -227,22 +231,22 @@ struct RowRegs {
 
 template <int NR>
 __device__ __forceinline__ void fetch_rows(RowRegs<NR>& rr, const float* __restrict__ src, int ncols, int col0, int row0, int B,
-                                           int r_begin, int lane) {
+                                           int r_begin, int lane, int count = NR) {
   const int j = col0 + 2 * lane;
   const bool ok0 = j < ncols, ok1 = j + 1 < ncols;
 #pragma unroll
   for (int u = 0; u < NR; ++u) {
     const int grow = row0 + r_begin + u;
     const float* p = src + (size_t)grow * ncols + j;
-    rr.x[u][0] = (ok0 && grow < B) ? __ldg(p) : 0.0f;
-    rr.x[u][1] = (ok1 && grow < B) ? __ldg(p + 1) : 0.0f;
+    rr.x[u][0] = (ok0 && grow < B && u < count) ? __ldg(p) : 0.0f;
+    rr.x[u][1] = (ok1 && grow < B && u < count) ? __ldg(p + 1) : 0.0f;
   }
 }
 
 template <int NR>
 __device__ __forceinline__ void store_rows(const RowRegs<NR>& rr, int ncols, int col0, int row0, int B, uint8_t* dst, int kg0,
                                            int kg_limit, int r_begin, const float* __restrict__ mu,
-                                           const float* __restrict__ sigma, int lane) {
+                                           const float* __restrict__ sigma, int lane, int count = NR) {
   const int j = col0 + 2 * lane;
   const bool ok0 = j < ncols, ok1 = j + 1 < ncols;
   const int kg = kg0 + (lane >> 2);
@@ -261,7 +265,7 @@ __device__ __forceinline__ void store_rows(const RowRegs<NR>& rr, int ncols, int
       a = ok0 ? (a - m0) * s0 : 0.0f;
       b = ok1 ? (b - m1) * s1 : 0.0f;
     }
-    *reinterpret_cast<uint32_t*>(out + (r_begin + u) * 16) = pack_bf16(a, b);
+    if (u < count) *reinterpret_cast<uint32_t*>(out + (r_begin + u) * 16) = pack_bf16(a, b);
   }
 }
 
@@ -417,8 +421,12 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   // mbarriers: ring slot released (MMA commit) x3, layer done (MMA commit), ring slot filled (TMA bytes) x3, layer weights
   // filled, bias / LayerNorm vectors filled
   const uint32_t bar_ring = smem_u32(bars), bar_layer = smem_u32(bars + RING), bar_full = smem_u32(bars + RING + 1),
-                 bar_wfull = smem_u32(bars + 2 * RING + 1), bar_pfull = smem_u32(bars + 2 * RING + 2);
-  constexpr int PRODUCER = 32;  // the thread that issues the weight copies (warp 1; thread 0 issues the MMAs)
+                 bar_wfull = smem_u32(bars + 2 * RING + 1), bar_pfull = smem_u32(bars + 2 * RING + 2),
+                 bar_afull = smem_u32(bars + 2 * RING + 3);  // x3: the activations of a ring slot are stored (7 warp arrivals)
+  constexpr int PRODUCER = 0;  // thread 0 issues the weight copies and the MMAs
+  // layer-0 loader rows of this warp: warps 1-5 take 18 rows, warps 6-7 take 19, warp 0 none (it only issues)
+  const int l0_begin = warp == 0 ? 0 : (warp <= 5 ? (warp - 1) * 18 : 90 + (warp - 6) * 19);
+  const int l0_count = warp == 0 ? 0 : (warp <= 5 ? 18 : 19);
 
   // The tile's rows of every input are one contiguous range: ask for them in L2 now, so that the dependent phases below see
   // L2 latency instead of HBM latency.
@@ -435,9 +443,10 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   const int nch = L.K[0] / KCHUNK;
   const uint32_t a_stride = (KCHUNK / 8) * LBO_A, b_stride = (KCHUNK / 8) * L.lboB[0];
   const uint8_t* w0 = a.blob + L.offW[0];
-  RowRegs<16> rr, rr2;  // activations of the even / odd chunks, fetched two iterations ahead
+  RowRegs<LROWS> rr, rr2;  // activations of the even / odd chunks, fetched two iterations ahead
   if (tid == PRODUCER) {
     for (int i = 0; i < 2 * RING + 3; ++i) mbar_init(bar_ring + 8 * i, 1);
+    for (int i = 0; i < RING; ++i) mbar_init(bar_afull + 8 * i, 7);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t pbytes = (L.nParamFloats * 4 + 15) & ~15u;
     mbar_expect_tx(bar_pfull, pbytes);
@@ -447,8 +456,10 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
       bulk_g2s(r1_s + c * b_stride, w0 + (size_t)c * b_stride, b_stride, bar_full + 8 * c);
     }
   }
-  fetch_rows<16>(rr, a.traj, a.d.traj, 0, row0, a.B, warp * 16, lane);
-  if (nch > 1) fetch_rows<16>(rr2, a.traj, a.d.traj, KCHUNK, row0, a.B, warp * 16, lane);
+  if (warp > 0) {
+    fetch_rows<LROWS>(rr, a.traj, a.d.traj, 0, row0, a.B, l0_begin, lane, l0_count);
+    if (nch > 1) fetch_rows<LROWS>(rr2, a.traj, a.d.traj, KCHUNK, row0, a.B, l0_begin, lane, l0_count);
+  }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tslot)), "r"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -459,39 +470,48 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   const uint32_t tmem = *tslot;
   VNL_STAMP(0);
 
-  // ---- L0: K streamed in 64-wide chunks through a 3-slot ring (A slots in R0, B slots in R1).  In iteration c the
-  // weights of chunk c + 2 and the activations of chunk c + 1 are in flight while the MMAs of chunk c run. ----
-  {
-    const uint32_t idesc = make_idesc(L.N[0]);
-    auto step = [&](int c, RowRegs<16>& regs) {
+  // ---- L0: K streamed in 64-wide chunks through a 3-slot ring (A slots in R0, B slots in R1), two decoupled loops:
+  // warps 1-7 convert and store the activations of chunk c (those of chunk c + 2 in flight in registers) and arrive on the
+  // slot's `afull` barrier; thread 0 waits for the activations and the TMA'd weights of chunk c, issues its MMAs (4 x ~130
+  // cycles that no loader waits for), and refills the weight slot of chunk c - 1 with chunk c + 2. ----
+  if (warp > 0) {
+    auto step = [&](int c, RowRegs<LROWS>& regs) {
       const int slot = c % RING;
       if (c >= RING) mbar_wait(bar_ring + 8 * slot, ((c - RING) / RING) & 1);  // the MMAs of chunk c - 3 have left this A slot
-      store_rows<16>(regs, a.d.traj, c * KCHUNK, row0, a.B, R0 + slot * a_stride, 0, KCHUNK / 8, warp * 16, nullptr, nullptr, lane);
-      if (c + 2 < nch) fetch_rows<16>(regs, a.traj, a.d.traj, (c + 2) * KCHUNK, row0, a.B, warp * 16, lane);
-      fence_proxy_async();
-      __syncthreads();
-      if (tid == 0) {
-        mbar_wait(bar_full + 8 * slot, (c / RING) & 1);  // the weights of chunk c have landed (TMA)
-        tc_fence_after();
+      store_rows<LROWS>(regs, a.d.traj, c * KCHUNK, row0, a.B, R0 + slot * a_stride, 0, KCHUNK / 8, l0_begin, nullptr, nullptr, lane,
+                        l0_count);
+      if (c + 2 < nch) fetch_rows<LROWS>(regs, a.traj, a.d.traj, (c + 2) * KCHUNK, row0, a.B, l0_begin, lane, l0_count);
+      fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_afull + 8 * slot);
+    };
+    for (int c = 0; c < nch; c += 2) {
+      step(c, rr);
+      if (c + 1 < nch) step(c + 1, rr2);
+    }
+  } else if (tid == 0) {
+    const uint32_t idesc = make_idesc(L.N[0]), d_tmem = tmem + L.tcol[0], lbo_b = L.lboB[0];
+    const uint64_t sa = (2 * LBO_A) >> 4, sb = (2 * lbo_b) >> 4;
+    for (int c = 0; c < nch; ++c) {
+      const int slot = c % RING;
+      mbar_wait(bar_afull + 8 * slot, (c / RING) & 1);  // activations stored by the 7 loader warps
+      mbar_wait(bar_full + 8 * slot, (c / RING) & 1);   // weights landed (TMA)
+      tc_fence_after();
+      uint64_t da = make_desc(r0_s + slot * a_stride, LBO_A), db = make_desc(r1_s + slot * b_stride, lbo_b);
 #pragma unroll
-        for (int s = 0; s < KCHUNK / 16; ++s)
-          mma_bf16(tmem + L.tcol[0], make_desc(r0_s + slot * a_stride + s * 2 * LBO_A, LBO_A),
-                   make_desc(r1_s + slot * b_stride + s * 2 * L.lboB[0], L.lboB[0]), idesc, (c > 0 || s > 0) ? 1u : 0u);
-        mma_commit(bar_ring + 8 * slot);
-        if (c == nch - 1) mma_commit(bar_layer);
-      } else if (tid == PRODUCER && c + 2 < nch) {
+      for (int s = 0; s < KCHUNK / 16; ++s, da += sa, db += sb) mma_bf16(d_tmem, da, db, idesc, (c > 0 || s > 0) ? 1u : 0u);
+      mma_commit(bar_ring + 8 * slot);
+      if (c == nch - 1) mma_commit(bar_layer);
+      if (c + 2 < nch) {
         const int ns = (c + 2) % RING;  // = slot of chunk c - 1: refill once its MMAs are done
         if (c >= 1) mbar_wait(bar_ring + 8 * ns, ((c - 1) / RING) & 1);
         mbar_expect_tx(bar_full + 8 * ns, b_stride);
         bulk_g2s(r1_s + ns * b_stride, w0 + (size_t)(c + 2) * b_stride, b_stride, bar_full + 8 * ns);
       }
       if (c < 4) VNL_STAMP(1 + c);
-    };
-    for (int c = 0; c < nch; c += 2) {
-      step(c, rr);
-      if (c + 1 < nch) step(c + 1, rr2);
     }
   }
+  __syncwarp();
   VNL_STAMP(5);
 
   // ---- L1 .. L5: the weights of layer n stream in (cp.async) while all warps run the epilogue of layer n - 1.
@@ -502,9 +522,9 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
   uint8_t* A3 = R0 + (uint32_t)a3_kg * LBO_A;
   const int nobs = (L.K[3] - a.d.latent + KCHUNK - 1) / KCHUNK;
   float4 ez[8];
-  auto obs_fetch = [&](RowRegs<16>& r, int ci) { fetch_rows<16>(r, a.obs, a.d.obs, ci * KCHUNK, row0, a.B, warp * 16, lane); };
-  auto obs_store = [&](const RowRegs<16>& r, int ci) {
-    store_rows<16>(r, a.d.obs, ci * KCHUNK, row0, a.B, A3, kg_lat + ci * (KCHUNK / 8), kg_end3, warp * 16, a.obs_mean, a.obs_std, lane);
+  auto obs_fetch = [&](RowRegs<LROWS>& r, int ci) { fetch_rows<LROWS>(r, a.obs, a.d.obs, ci * KCHUNK, row0, a.B, warp * 16, lane, 16); };
+  auto obs_store = [&](const RowRegs<LROWS>& r, int ci) {
+    store_rows<LROWS>(r, a.d.obs, ci * KCHUNK, row0, a.B, A3, kg_lat + ci * (KCHUNK / 8), kg_end3, warp * 16, a.obs_mean, a.obs_std, lane, 16);
   };
   uint32_t layer_phase = 0;
   for (int n = 1; n < 6; ++n) {
