@@ -627,15 +627,18 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     tc_fence_before();
   }
   __syncthreads();
+  constexpr int RG = 8;  // rows of a warp in flight per trip (16 rows per warp: two trips)
 #pragma unroll 1
-  for (int g = 0; g < TILE_M / 32; ++g) {
-    float lp[4] = {0.0f, 0.0f, 0.0f, 0.0f}, lpr[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  for (int g = 0; g < TILE_M / (8 * RG); ++g) {
+    float lp[RG], lpr[RG];
+#pragma unroll
+    for (int u = 0; u < RG; ++u) lp[u] = lpr[u] = 0.0f;
 #pragma unroll 1
     for (int i = lane; i < nu; i += 32) {
-      float th[4], raw[4];
+      float th[RG], raw[RG];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // four independent rows in flight, no stores in between
-        const int r = warp + 8 * (4 * g + u);
+      for (int u = 0; u < RG; ++u) {  // independent rows in flight, no stores in between
+        const int r = warp + 8 * (RG * g + u);
         const float loc = S[r * sstride + i];
         const float scale = softplus(S[r * sstride + nu + i]) + 1e-3f;  // brax NormalTanhDistribution min_std
         const float e = a.eps_a ? EA[r * nu + i] : 0.0f;
@@ -652,8 +655,8 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int grow = row0 + warp + 8 * (4 * g + u);
+      for (int u = 0; u < RG; ++u) {
+        const int grow = row0 + warp + 8 * (RG * g + u);
         if (grow < a.B) {
           if (a.action) a.action[(size_t)grow * nu + i] = th[u];
           if (a.raw_action) a.raw_action[(size_t)grow * nu + i] = raw[u];
@@ -663,22 +666,28 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < RG; ++u) {
         lp[u] += __shfl_xor_sync(0xffffffffu, lp[u], o);
         lpr[u] += __shfl_xor_sync(0xffffffffu, lpr[u], o);
       }
-#pragma unroll 1
-    for (int u = 0; u < 4; ++u) {
-      const int r = warp + 8 * (4 * g + u), grow = row0 + r;
-      if (grow >= a.B) continue;
-      const float l = u == 0 ? lp[0] : u == 1 ? lp[1] : u == 2 ? lp[2] : lp[3];
-      const float lr = u == 0 ? lpr[0] : u == 1 ? lpr[1] : u == 2 ? lpr[2] : lpr[3];
-      if (lane == 0) {
+    // lane u keeps row u's sums, so that the scalar stores below are one predicated store per array
+    float l = 0.0f, lr = 0.0f;
+#pragma unroll
+    for (int u = 0; u < RG; ++u)
+      if (lane == u) l = lp[u], lr = lpr[u];
+    if (lane < RG) {
+      const int grow = row0 + warp + 8 * (RG * g + lane);
+      if (grow < a.B) {
         if (a.log_prob) a.log_prob[grow] = l;
         if (a.rand_action && a.rand_log_prob) a.rand_log_prob[grow] = lr;
       }
-      if (a.logits)
-#pragma unroll 1
+    }
+  }
+  if (a.logits) {  // [128, 2 nu] row-major out of the scratch: a warp per row, coalesced
+#pragma unroll 4
+    for (int k = 0; k < TILE_M / 8; ++k) {
+      const int r = warp + 8 * k, grow = row0 + r;
+      if (grow < a.B)
         for (int i = lane; i < nlog; i += 32) a.logits[(size_t)grow * nlog + i] = S[r * sstride + i];
     }
   }
