@@ -37,7 +37,7 @@ typedef struct VnlPolicyDims {
 } VnlPolicyDims;
 
 /* 0 if the kernel supports these sizes (hidden sizes multiples of 64 and <= 256, latent a multiple of 32 and
- * 2 * latent <= 256, nu <= 64, tensor-memory and shared-memory budgets), else a negative code. */
+ * 2 * latent <= 256, nu <= 64, obs <= 256, tensor-memory and shared-memory budgets), else a negative code. */
 int vnl_policy_check(const VnlPolicyDims* dims);
 
 /* Size of the packed parameter blob for these sizes. */

@@ -92,7 +92,7 @@ int check_dims(const VnlPolicyDims* d) {
   for (int i = 0; i < 4; ++i)
     if (h[i] < 64 || h[i] > 256 || h[i] % 64) return -2;
   if (d->latent < 32 || d->latent % 32 || d->latent > 64) return -3;
-  if (d->nu < 1 || d->nu > 64 || d->traj < 1 || d->obs < 0) return -4;
+  if (d->nu < 1 || d->nu > 64 || d->traj < 1 || d->obs < 0 || d->obs > 4 * KCHUNK) return -4;  // obs: two staging phases x two chunks
   Layout L;
   make_layout(*d, L);
   if (d->e1 + d->e2 + 2 * d->latent > TMEM_COLS || d->d1 + d->d2 + L.N[5] > TMEM_COLS) return -5;
@@ -574,10 +574,6 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     if (n == 2 || n == 3) {
       if (ob < oe) obs_store(rr, ob);
       if (ob + 1 < oe) obs_store(rr2, ob + 1);
-      for (int ci = ob + 2; ci < oe; ++ci) {  // wider obs than two chunks per phase: staged without overlap
-        obs_fetch(rr, ci);
-        obs_store(rr, ci);
-      }
     }
     VNL_STAMP(7 + 3 * (n - 1));
     cp_async_wait_all();
@@ -684,10 +680,11 @@ __global__ void __launch_bounds__(THREADS, 1) vnl_policy_kernel(const Args a) {
     }
   }
   if (a.logits) {  // [128, 2 nu] row-major out of the scratch: a warp per row, coalesced
-#pragma unroll 4
+#pragma unroll 1
     for (int k = 0; k < TILE_M / 8; ++k) {
       const int r = warp + 8 * k, grow = row0 + r;
       if (grow < a.B)
+#pragma unroll 2
         for (int i = lane; i < nlog; i += 32) a.logits[(size_t)grow * nlog + i] = S[r * sstride + i];
     }
   }
