@@ -15,7 +15,8 @@
  * activations never leave the SM.  Random draws are operands (eps_z, eps_a), so the caller owns the RNG stream, as
  * the reference's `key` argument does.
  *
- * All pointers are caller-owned; `blob_dev`, the inputs and outputs are device memory, `dims` is host memory.
+ * All pointers are caller-owned; `blob_dev` (16-byte aligned: it is streamed by TMA bulk copies), the inputs and outputs
+ * are device memory, `dims` is host memory.
  * Enqueue-only on `stream`, no allocation, no synchronisation, CUDA-graph capturable.  Returns 0 or a negative error
  * code / cudaError.
  */

@@ -269,6 +269,9 @@ def test_empty_batch_and_argument_errors(lib):
         p(x["traj"].double(), x["obs"], x["eps_z"], x["eps_a"])
     d = p.dims
     assert lib.vnl_policy_forward(None, ctypes.byref(d), 4, *([None] * 15)) < 0  # null blob: argument error, no launch
+    ptr = lambda t: t.data_ptr()
+    assert lib.vnl_policy_forward(ptr(p.blob_dev) + 4, ctypes.byref(d), 4, ptr(x["traj"]), ptr(x["obs"]), None, None, ptr(x["eps_z"]),
+                                  *([None] * 10)) == -10  # misaligned blob: refused, not mis-streamed
 
 
 @pytest.mark.gpu

@@ -779,6 +779,7 @@ int vnl_policy_forward(const void* blob_dev, const VnlPolicyDims* dims, int B, c
   if (rc) return rc;
   if (B == 0) return 0;  // an empty batch launches nothing (its buffers may be null)
   if (!blob_dev || !traj || !eps_z || B < 0 || (dims->obs > 0 && !obs) || ((obs_mean == nullptr) != (obs_std == nullptr))) return -1;
+  if (reinterpret_cast<uintptr_t>(blob_dev) & 15) return -10;  // TMA bulk copies stream the blob in 16-byte granules
   Args a{*dims, B, static_cast<const uint8_t*>(blob_dev), traj, obs, obs_mean, obs_std, eps_z, eps_a, rand_action,
          action, raw_action, logits, log_prob, rand_log_prob, z_mean, z_logvar, -1, nullptr};
   return launch(a, stream);
@@ -789,6 +790,7 @@ int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, con
   const int rc = check_dims(dims);
   if (rc) return rc;
   if (!blob_dev || !traj || !eps_z || !dump || B <= 0 || layer < -1 || layer > 5) return -1;
+  if (reinterpret_cast<uintptr_t>(blob_dev) & 15) return -10;
   Args a{*dims, B, static_cast<const uint8_t*>(blob_dev), traj, obs, obs_mean, obs_std, eps_z, nullptr, nullptr,
          nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, layer, dump};
   return launch(a, stream);
