@@ -5,8 +5,8 @@
 // Six dense layers run as tcgen05.mma.cta_group::1.kind::f16 (bf16 operands from shared memory, fp32 accumulators in
 // tensor memory); everything between two layers happens in the epilogue of the first, on the SM:
 //
-//   L0  traj[795 -> 832]  x W[.,256]  -> +b, relu, LayerNorm -> bf16 A-operand of L1     (K streamed in 64-wide chunks,
-//   L1  [256] x W[.,128]              -> +b, relu, LayerNorm                               3-slot ring, loads overlap MMA)
+//   L0  traj[795 -> 832]  x W[.,256]  -> +b, relu, LayerNorm -> bf16 A-operand of L1     (K streamed in 64-wide chunks through
+//   L1  [256] x W[.,128]              -> +b, relu, LayerNorm                               a 3-slot ring: warps 1-7 load, thread 0 issues)
 //   L2  [128] x [W_mean | W_logvar]   -> +b, z = mean + eps_z * exp(logvar / 2)
 //   L3  [z | (obs - mu) / sigma] (296 -> 304) x W[.,128] -> +b, relu, LayerNorm
 //   L4  [128] x W[.,256]              -> +b, relu, LayerNorm
@@ -21,7 +21,9 @@
 //
 // All 8 warps run the epilogues (warps w and w + 4 share the tensor-memory lanes of quadrant w % 4 = env rows 32 (w % 4) ..
 // + 31 and split the accumulator columns in halves, 32x32b loads); the next layer's weights stream in by TMA while the
-// epilogue computes; thread 0 issues the MMAs and commits them to an mbarrier, thread 32 issues the weight copies.
+// epilogue computes; thread 0 issues the weight copies and the MMAs (committed to mbarriers).  In layer 0 warp 0 does
+// nothing else: the seven other warps load, convert and store the activations and signal per-slot mbarriers, so the
+// ~130 cycles each MMA takes to issue are in nobody's load iteration.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
