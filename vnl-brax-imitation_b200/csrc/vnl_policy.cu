@@ -209,6 +209,35 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* f) {
   for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
 }
 
+// Blackwell packed fp32 arithmetic (FADD2 / FMUL2 / FFMA2): two lanes per instruction on an aligned register pair
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// relu(v + b) on a pair
+__device__ __forceinline__ f32x2 bias_relu2(uint32_t v0, uint32_t v1, float b0, float b1) {
+  float x0, x1;
+  upk2(add2(pk2(__uint_as_float(v0), __uint_as_float(v1)), pk2(b0, b1)), x0, x1);
+  return pk2(fmaxf(x0, 0.0f), fmaxf(x1, 0.0f));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&p);
@@ -284,18 +313,14 @@ __device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __r
   const float* beta = P + 2 * N;
   const int cb = half * (N >> 1), nchunk = N >> 6;  // 32-column chunks of this thread's half row
   uint32_t va[32], vb[32];
-  float sum = 0.0f, sq = 0.0f;
+  f32x2 sum2 = pk2(0.0f, 0.0f), sq2 = pk2(0.0f, 0.0f);  // even / odd columns
   auto stat = [&](const uint32_t* v, int c0) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const float4 b4 = *reinterpret_cast<const float4*>(bias + c0 + 4 * q);  // warp-uniform address: one broadcast wavefront
-      const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float x = fmaxf(__uint_as_float(v[4 * q + j]) + bb[j], 0.0f);
-        sum += x;
-        sq = fmaf(x, x, sq);
-      }
+      const f32x2 x01 = bias_relu2(v[4 * q], v[4 * q + 1], b4.x, b4.y), x23 = bias_relu2(v[4 * q + 2], v[4 * q + 3], b4.z, b4.w);
+      sum2 = add2(sum2, add2(x01, x23));
+      sq2 = fma2(x01, x01, fma2(x23, x23, sq2));
     }
   };
   tmem_ld32_issue(tb + cb, va);
@@ -310,6 +335,11 @@ __device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __r
     }
   }
   tmem_ld32_issue(tb + cb, va);  // first chunk of the second pass, in flight across the barrier
+  float sum, sq, sum_hi, sq_hi;
+  upk2(sum2, sum, sum_hi);
+  upk2(sq2, sq, sq_hi);
+  sum += sum_hi;
+  sq += sq_hi;
   stats[half * TILE_M + row] = make_float2(sum, sq);
   __syncthreads();
   const float2 p0 = stats[row], p1 = stats[TILE_M + row];
@@ -317,6 +347,7 @@ __device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __r
   const float mean = (p0.x + p1.x) * inv_n;
   const float var = fmaxf((p0.y + p1.y) * inv_n - mean * mean, 0.0f);
   const float rstd = rsqrtf(var + 1e-6f);
+  const f32x2 nmean2 = pk2(-mean, -mean), rstd2 = pk2(rstd, rstd);
   auto emit = [&](const uint32_t* v, int c0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -326,15 +357,14 @@ __device__ __forceinline__ void epilogue_ln(uint32_t tb, int N, const float* __r
         const int c = c0 + q * 8 + h * 4;
         const float4 b4 = *reinterpret_cast<const float4*>(bias + c), g4 = *reinterpret_cast<const float4*>(gamma + c),
                      e4 = *reinterpret_cast<const float4*>(beta + c);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, gg[4] = {g4.x, g4.y, g4.z, g4.w}, ee[4] = {e4.x, e4.y, e4.z, e4.w};
-        float y[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float x = fmaxf(__uint_as_float(v[q * 8 + h * 4 + j]) + bb[j], 0.0f);
-          y[j] = (x - mean) * rstd * gg[j] + ee[j];
-        }
-        w[2 * h] = pack_bf16(y[0], y[1]);
-        w[2 * h + 1] = pack_bf16(y[2], y[3]);
+        const uint32_t* vv = v + q * 8 + h * 4;
+        const f32x2 y01 = fma2(mul2(add2(bias_relu2(vv[0], vv[1], b4.x, b4.y), nmean2), rstd2), pk2(g4.x, g4.y), pk2(e4.x, e4.y));
+        const f32x2 y23 = fma2(mul2(add2(bias_relu2(vv[2], vv[3], b4.z, b4.w), nmean2), rstd2), pk2(g4.z, g4.w), pk2(e4.z, e4.w));
+        float y0, y1, y2, y3;
+        upk2(y01, y0, y1);
+        upk2(y23, y2, y3);
+        w[2 * h] = pack_bf16(y0, y1);
+        w[2 * h + 1] = pack_bf16(y2, y3);
       }
       *reinterpret_cast<uint4*>(anext + (uint32_t)((c0 >> 3) + q) * LBO_A + row * 16) = make_uint4(w[0], w[1], w[2], w[3]);
     }
