@@ -222,20 +222,39 @@ def cpu_oracle_rate(seconds_target=12.0, nthreads=0, steps=None, sample_envs=Non
                 sample="%d envs x %d env steps of the bench workload (fp32 oracle, OpenMP over envs)" % (sample_envs, nsteps))
 
 
+def workload_config(workload, B, world):
+    """`config` keys shared verbatim by both arms (the driver compares them)."""
+    wl = WORKLOADS[workload]
+    return {"workload": "%s, %d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "
+                        "reference's info-not-reset quirk" % (wl["text"], B),
+            "envs_per_gpu": B, "global_envs": B * world, "parallelism": "env shards, dp%d, no data-path collective" % world}
+
+
 def run_reference(args):
+    """Reference arm: the CPU implementation of the same path on the box's host cores.  The reference's own arithmetic
+    (mujoco-mjx / brax on JAX-CPU) is not installable here, so this times the repo's CPU restatement of it
+    (`kind: "port"`): the same workload, the same K timed + W warm-up steps as our arm, each step over a bounded sample of
+    the 4096-env batch sized so that the run ends within a few minutes (the whole batch when the cores allow)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    r = cpu_oracle_rate(seconds_target=10.0, steps=max(1, min(args.steps, 8)), warmup=max(1, min(args.warmup, 2)))
+    K, W = args.steps, args.warmup
+    B = args.envs_per_gpu or WORKLOADS["rodent"]["envs"]
+    nt = len(os.sched_getaffinity(0))
+    pilot = cpu_oracle_rate(steps=1, sample_envs=8 * nt, warmup=1)
+    budget_s = 90.0
+    sample = int(min(B, max(8 * nt, pilot["value"] * budget_s / (K + W))))
+    r = cpu_oracle_rate(steps=K, sample_envs=sample, warmup=W)
+    cfg = workload_config("rodent", B, 1)
+    cfg["reference_sample"] = "each step advances %d of the %d envs (bounded sample); CPU port of the path on %d host cores" % (sample, B, r["cores"])
     line = {"impl": "reference", "metric": "rodent imitation env-steps/s", "value": r["value"], "unit": "env-steps/s",
-            "n_gpus": args.gpus, "steps": r["steps"], "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_per_step"],
+            "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "rodent imitation env step (rodent.xml, transform_snips_groom.p clip), CPU path, "
-                                   "bounded sample of the 4096-env workload", "envs_per_step": r["envs"]},
+            "config": cfg,
             "cpu_baseline": {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference's own arithmetic lives in mujoco-mjx/brax/jax, none installable here (SURVEY 8c): this arm "
-                    "times the repo's CPU restatement (oracle port), not the reference's JAX-CPU path"}
+            "note": "CPU PORT, not the reference's JAX-CPU path: mujoco-mjx / brax / jax are not installable in this image "
+                    "(SURVEY 8c), so this arm times the repo's C++ restatement of the path (oracle/, fp32, OpenMP over envs)"}
     print(json.dumps(line), flush=True)
 
 
@@ -402,9 +421,7 @@ def run_ours(args):
         "metric": "%s imitation env-steps/s" % args.workload, "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": ms_total / K, "rank_ms_per_step": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s, %d envs per GPU, 5 physics substeps per env step, U(-1,1) actions, AutoReset with the "
-                               "reference's info-not-reset quirk" % (wl["text"], B),
-                   "envs_per_gpu": B, "global_envs": total, "parallelism": "env shards, dp%d, no data-path collective" % world,
+        "config": {**workload_config(args.workload, B, world),
                    "l2": "not flushed: the whole batch state (%.0f MB) is L2-resident; numbers are L2-warm as in the rollout loop"
                          % (B * nbytes / 1e6), "done_fraction": done_frac},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -18,11 +18,17 @@
  *
  * Conventions
  *   - every array is a caller-allocated DEVICE buffer, fp32 / int32, batch-major contiguous
- *     [B, n]; the library allocates nothing per call, keeps no mutable global state, only
+ *     [B, n]; the library allocates nothing per call, keeps NO global state (no registry, no lock), only
  *     enqueues work on `stream` (a cudaStream_t passed as void*), never synchronises and is
  *     CUDA-graph capturable.
  *   - `model` and `task` are device copies of the flat blobs described below (constant
- *     tables; pass them as operands so the caller owns their lifetime).
+ *     tables; pass them as operands so the caller owns their lifetime).  They may live at a
+ *     different device address on every call (XLA copies / donates / replicates operands).
+ *   - `ctx` is a small HOST struct (VnlContext) the caller fills once per model: the host copy
+ *     of the blobs' scalar headers (launch geometry) and the caller-owned device workspace.
+ *     It is read-only for the library: nothing is cached between calls, there is no registry,
+ *     no lock and no global state; two host threads may call concurrently as long as each
+ *     passes its own workspace (one workspace serves one stream at a time).
  *   - return value 0 = ok, negative = argument error, positive = cudaError_t of the launch.
  *     Numerical failure is data, not an error (nan flag -> done = 1, NaN -> 0).
  */
@@ -49,7 +55,7 @@ extern "C" {
  * ---------------------------------------------------------------------------------------- */
 #define VNL_MAGIC_MODEL 0x4d4c4e56u /* "VNLM" */
 #define VNL_MAGIC_TASK 0x544c4e56u  /* "VNLT" */
-#define VNL_BLOB_VERSION 6
+#define VNL_BLOB_VERSION 7
 #define VNL_TABLE_OFF 64
 #define VNL_MAX_FIELDS 96
 #define VNL_DATA_OFF (VNL_TABLE_OFF + 2 * VNL_MAX_FIELDS)
@@ -237,6 +243,8 @@ enum VnlTaskHdr {
                            * before the increment); 0: at NEW cur_frame + 1 (rodent.py:188-190) */
   VNL_TH_RACT_ACTION,     /* 1: ract = 0.01 * -0.015 * sum(action^2) / nu (ant.py:251); 0: -0.015 * mean(qfrc_actuator^2) */
   VNL_TH_METRICS_RAW,     /* 1: metrics hold the UNWEIGHTED reward terms (ant.py:203-210); 0: the weighted ones (rodent.py:193-199) */
+  VNL_TH_NCLIPS,          /* clips stacked in the tables: every VNL_T_* clip table is [nclips, T, ...], the env's
+                           * VnlState.clip_id picks one; 0 or 1 = the single-clip task of the reference */
   VNL_TH_HEALTHY_LO = 32, VNL_TH_HEALTHY_HI, VNL_TH_TERM_THRESHOLD, VNL_TH_BODY_ERR_MULT,
   VNL_TH_W_RCOM, VNL_TH_W_RVEL, VNL_TH_W_RTRUNK, VNL_TH_W_RQUAT, VNL_TH_W_RACT, VNL_TH_W_RAPP, /* reward weights:
                            * rodent / humanoid 0.01 x4, 1e-4, 0.01 (rodent.py:193-199); ant 0.05 0.01 0.20 0.01 0.001 0 (ant.py:186-192) */
@@ -278,7 +286,23 @@ typedef struct VnlState {
   float* qfrc_actuator;  /* [B,nv] */
   int32_t* cur_frame;      /* [B] info["cur_frame"] */
   int32_t* sub_clip_frame; /* [B] info["sub_clip_frame"] */
+  int32_t* clip_id;        /* [B] which clip of a multi-clip task blob the env tracks; NULL = clip 0.
+                              Read from `in`, copied to `out` when both are given; never changed by a step. */
 } VnlState;
+
+/* Host-side call context: everything the host needs to size a launch, so that no call depends on a registry keyed by
+ * device pointers.  Fill it once with vnl_context_init and set the workspace; pass it to every call (read-only). */
+typedef struct VnlContext {
+  uint32_t model_hdr[VNL_DATA_OFF]; /* host copy of the first VNL_DATA_OFF words of the MODEL blob (scalars + field table) */
+  uint32_t task_hdr[VNL_TABLE_OFF]; /* host copy of the scalar header of the TASK blob; task_hdr[0] == 0: physics only */
+  void* workspace;                  /* device scratch of vnl_workspace_bytes() bytes (inertia of the resident envs); the
+                                       kernels write before they read, so it may be uninitialised (an XLA scratch result) */
+  uint64_t workspace_bytes;
+} VnlContext;
+
+/* Validates the two host blobs (vnl_check_model / vnl_check_task) and copies their headers; `task_host` may be NULL.
+ * Leaves workspace = NULL.  0 = ok. */
+int vnl_context_init(VnlContext* ctx, const void* model_host, size_t model_bytes, const void* task_host, size_t task_bytes);
 
 typedef struct VnlOutputs {
   float* obs;     /* [B,obs_size]  State.obs (rodent.py:318-344), NaN -> 0 */
@@ -292,14 +316,14 @@ typedef struct VnlOutputs {
 
 /* One env step for B envs: `in` is read, `out` and `outputs` are written (in and out may alias
  * buffer by buffer).  Replaces RodentTracking.step (envs/rodent.py:178-239). */
-int vnl_step(const void* model, const void* task, int B, const VnlState* in, const float* action,
+int vnl_step(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action,
              const VnlState* out, const VnlOutputs* outputs, void* stream);
 
 /* vnl_step followed by brax's AutoResetWrapper.step (brax/envs/wrappers/training.py, installed around the env at
  * ppo_imitation/train.py:204-214), in the same launch: where the step's done flag is set, the state leaves written to
  * `out` (qpos .. qfrc_actuator) and `outputs->obs` are replaced by `first` / `first_obs` (the cached reset state);
  * info (cur_frame, sub_clip_frame, traj), reward, done and metrics are NOT restored. */
-int vnl_step_autoreset(const void* model, const void* task, int B, const VnlState* in, const float* action,
+int vnl_step_autoreset(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action,
                        const VnlState* out, const VnlOutputs* outputs, const VnlState* first, const float* first_obs,
                        void* stream);
 
@@ -316,36 +340,42 @@ typedef struct VnlEpisode {
 /* vnl_step wrapped the way the reference trains (ppo_imitation/train.py:204-214): AutoResetWrapper(EpisodeWrapper(env)),
  * action_repeat 1, all in the one launch.  steps = (done_in ? 0 : steps_in) + 1; where steps >= episode_length:
  * truncation = 1 - done, done = 1; then the AutoReset restore of vnl_step_autoreset on that final done flag. */
-int vnl_step_training(const void* model, const void* task, int B, const VnlState* in, const float* action,
+int vnl_step_training(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action,
                       const VnlState* out, const VnlOutputs* outputs, const VnlState* first, const float* first_obs,
                       const VnlEpisode* episode, void* stream);
 
 /* Reset tail for B envs: qpos/qvel/cur_frame(start_frame) are read from `in` (act, ctrl and
  * qacc_warmstart are zero as in mjx.make_data), `out` receives the mjx.forward state, obs,
  * traj and info["termination_error"] (metrics[6]).  Replaces envs/rodent.py:148-176. */
-int vnl_reset(const void* model, const void* task, int B, const VnlState* in, const VnlState* out,
+int vnl_reset(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const VnlState* out,
               const VnlOutputs* outputs, void* stream);
 
 /* Physics only: `nsteps` x mjx.step (forward; euler) with a constant ctrl, no task logic.
  * Replaces PipelineEnv.pipeline_step (envs/rodent.py:181). */
-int vnl_pipeline_step(const void* model, int B, int nsteps, const VnlState* in, const float* ctrl,
+int vnl_pipeline_step(const VnlContext* ctx, const void* model, int B, int nsteps, const VnlState* in, const float* ctrl,
                       const VnlState* out, int32_t* stats, void* stream);
 
 /* Stage dump of one mjx.forward for parity tests: writes the arrays listed in
  * VNL_DUMP_* order into `dump` ([B, vnl_dump_size(model)] floats).  Test hook. */
-int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* ctrl, float* dump,
+int vnl_forward_dump(const VnlContext* ctx, const void* model, int B, const VnlState* in, const float* ctrl, float* dump,
                      void* stream);
 size_t vnl_dump_size(const void* model_host);
+
+/* Clip preprocessing on the GPU.  Replaces `process_clip` after the pickle load
+ * (preprocessing/mjx_preprocess.py:88-105): `extract_features` (set_position -> smooth.kinematics per frame, :109-134) and
+ * `compute_velocity_from_kinematics` + the joint-velocity clip (:170-193, :96-99), for `nclips` clips of T frames at once.
+ *   qpos             [nclips, T, nq]  raw mocap qpos (free joint first)
+ *   qpos_out         [nclips, T, nq]  qpos after kinematics (free-joint quaternion normalised): position | quaternion | joints
+ *   body_positions   [nclips, T, nbody, 3], body_quaternions [nclips, T, nbody, 4]   xpos / xquat of every body
+ *   qvel_out         [nclips, T, nq-1] velocity | angular_velocity | joints_velocity (joint block clipped to +-max_qvel);
+ *                    each clip is padded with its own last frame, as the reference does (last row = 0)
+ * The task blob stacks these per clip (VNL_TH_NCLIPS); needs no task blob itself. */
+int vnl_process_clip(const VnlContext* ctx, const void* model, int nclips, int T, const float* qpos, float dt, float max_qvel,
+                     float* qpos_out, float* body_positions, float* body_quaternions, float* qvel_out, void* stream);
 
 /* Blob validation on the host (magic, version, sizes).  0 = ok. */
 int vnl_check_model(const void* model_host, size_t nbytes);
 int vnl_check_task(const void* task_host, size_t nbytes);
-
-/* The launch geometry depends on the blob's scalar header.  Blobs handed to the calls above are
- * device buffers, so each one is registered once (host copy of the same bytes -> cached 256-byte
- * header keyed by the device pointer); the step path then never copies or synchronises. */
-int vnl_register_blob(const void* blob_dev, const void* blob_host, size_t nbytes);
-int vnl_unregister_blob(const void* blob_dev);
 
 /* Dynamic shared memory of one CTA for this model, and the number of envs (one warp each) a CTA holds. */
 int vnl_step_smem_bytes(const void* model_host);
@@ -355,28 +385,51 @@ int vnl_envs_per_cta(const void* model_host);
 int vnl_resident_envs(const void* model_host);
 
 /* Device workspace of the step kernels: the joint-space inertia of every RESIDENT env lives in global memory (L2),
- * laid out in the order the mat-vec lane programs consume it, which is what lets ten rodent envs share an SM.
- * The caller allocates vnl_workspace_bytes() bytes on the device once and binds them to the (registered) model blob;
- * one workspace serves one stream at a time.  Every step / reset / pipeline call fails with -20 without it. */
+ * laid out in the order the mat-vec lane programs consume it, which is what lets fourteen rodent envs share an SM.
+ * The caller allocates vnl_workspace_bytes() bytes on the device (the bound over every launch geometry the library can
+ * pick on the current device) and passes them in VnlContext; one workspace serves one stream at a time.  A model that
+ * streams its inertia fails with -20 without a workspace and with -21 if the ACTUAL launch geometry of the call (grid x
+ * envs per CTA for this B) would index past workspace_bytes. */
 size_t vnl_workspace_bytes(const void* model_host);
-int vnl_set_workspace(const void* model_dev, void* workspace_dev, size_t nbytes);
 
 /* Test hook: (name, float offset, float size) of every array of the per-env shared-memory layout for this model, in the
  * order of make_layout (csrc/vnl_kernels.cu); the last entry "total" carries the slice size as its offset.  Returns the
  * number of entries.  tests/test_layout.py checks that arrays that are live in the same phase never share storage. */
 int vnl_debug_layout(const void* model_host, const char** names, int32_t* offsets, int32_t* sizes, int cap);
 
-/* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque,
- * size_t opaque_len)`), operand order documented in INTEGRATION.md. */
-void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len);
-void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* XLA custom-call entry points, STATUS-RETURNING legacy signature (API_VERSION_STATUS_RETURNING = 2):
+ *     void f(cudaStream_t stream, void** buffers, const char* opaque, size_t opaque_len, XlaCustomCallStatus* status)
+ * Stateless: everything the host needs travels in `opaque` (VnlXlaOpaque: B, the blobs' headers), the workspace is the
+ * LAST buffer (declare it as a scratch result of vnl_workspace_bytes() bytes), model and task blobs are ordinary operands
+ * at whatever address XLA placed them.  A non-zero return code of the underlying call is reported through
+ * XlaCustomCallStatusSetFailure (resolved with dlsym from the hosting process, i.e. jaxlib) -- never silently dropped.
+ *   buffers: [model, task, qpos, qvel, act, warm, xpos, xquat, subtree_com, qfrc_actuator, cur_frame, sub_clip_frame, clip_id,
+ *             action,
+ *             (results) qpos', qvel', act', warm', xpos', xquat', subtree_com', qfrc_actuator', cur_frame', sub_clip_frame',
+ *             clip_id', obs, traj, reward, done, metrics, stats, workspace]
+ * vnl_xla_reset takes the same list (action is ignored).  The `_rc` forms return the code instead (tests, other hosts). */
+typedef struct VnlXlaOpaque {
+  int32_t B;        /* envs: product of all leading (vmap) dimensions */
+  int32_t version;  /* VNL_XLA_OPAQUE_VERSION */
+  uint32_t model_hdr[VNL_DATA_OFF];
+  uint32_t task_hdr[VNL_TABLE_OFF];
+  uint64_t workspace_bytes;
+} VnlXlaOpaque;
+#define VNL_XLA_OPAQUE_VERSION 2
+#define VNL_XLA_STEP_NBUF 32
+void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+int vnl_xla_step_rc(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+int vnl_xla_reset_rc(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+/* Fills `opaque` for B envs from a context (host helper for bindings). */
+int vnl_xla_make_opaque(const VnlContext* ctx, int B, VnlXlaOpaque* opaque);
 
 /* Measurement helper (bench.py): FFMA-saturating microkernel, flops = blocks * 256 * iters * 32.  `out` needs
  * blocks * 256 floats (never written in practice).  Gives the FP32 roofline denominator of the device. */
 int vnl_ffma_probe(int blocks, int iters, float* out, void* stream);
 
 /* vnl_step with one env's per-phase clock64 accumulators written to prof[32] (developer hook, tools/gpu_prof.py). */
-int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action,
+int vnl_step_profiled(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action,
                       const VnlState* out, const VnlOutputs* outputs, void* stream, long long* prof, int block);
 
 const char* vnl_version(void);

@@ -37,14 +37,14 @@ int vnl_obs_stats_partial(const float* batch, long long rows, int width, const f
 int vnl_obs_stats_finish(const float* sums, int width, float* count, float* mean, float* summed_variance, float* std,
                          float std_min_value, float std_max_value, void* stream);
 
-/* Legacy XLA custom-call entry points (`void f(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)`).
+/* XLA custom-call entry points, status-returning legacy ABI (`void f(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len, XlaCustomCallStatus* status)`, api_version 2; a non-zero code of the underlying call is reported through XlaCustomCallStatusSetFailure).
  * XLA result buffers are uninitialised and never alias operands: `partial` zeroes the scratch result's ticket itself,
  * `finish` copies the state operands into the state results before updating them in place.
  *   partial: opaque = int64 rows, int32 width;                 buffers = [batch, mean, (outputs) sums, workspace]
  *   finish:  opaque = int32 width, float std_min, float std_max; buffers = [sums, count, mean, summed_variance, std,
  *                                                                          (outputs) count', mean', summed_variance', std'] */
-void vnl_xla_obs_stats_partial(void* stream, void** buffers, const char* opaque, size_t opaque_len);
-void vnl_xla_obs_stats_finish(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void vnl_xla_obs_stats_partial(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
+void vnl_xla_obs_stats_finish(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
 
 #ifdef __cplusplus
 }

@@ -75,10 +75,11 @@ int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, con
                      const float* obs_mean, const float* obs_std, const float* eps_z, int layer, float* dump,
                      void* stream);
 
-/* Legacy XLA custom-call entry point (`void f(cudaStream_t, void** buffers, const char* opaque, size_t opaque_len)`):
+/* XLA custom-call entry point, status-returning legacy ABI (`void f(cudaStream_t, void** buffers, const char* opaque,
+ * size_t opaque_len, XlaCustomCallStatus* status)`, api_version 2; failures reported through XlaCustomCallStatusSetFailure):
  * opaque = 9 little-endian int32 (the VnlPolicyDims fields in order, then B); buffers = [blob, traj, obs, obs_mean,
  * obs_std, eps_z, eps_a, rand_action, (outputs) action, raw_action, logits, log_prob, rand_log_prob]. */
-void vnl_xla_policy_forward(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void vnl_xla_policy_forward(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
 
 #ifdef __cplusplus
 }

@@ -23,9 +23,9 @@ extern "C" {
 int vnl_gae(int T, int B, const float* truncation, const float* termination, const float* rewards, const float* values,
             const float* bootstrap_value, float lambda_, float discount, float* vs, float* advantages, void* stream);
 
-/* Legacy XLA custom call: opaque = int32 T, int32 B, float lambda, float discount;
+/* XLA custom call (status-returning legacy ABI, api_version 2): opaque = int32 T, int32 B, float lambda, float discount;
  * buffers = [truncation, termination, rewards, values, bootstrap_value, (outputs) vs, advantages]. */
-void vnl_xla_gae(void* stream, void** buffers, const char* opaque, size_t opaque_len);
+void vnl_xla_gae(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status);
 
 #ifdef __cplusplus
 }

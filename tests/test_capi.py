@@ -62,38 +62,72 @@ def test_sizes(lib, rodent, oracle_mod):
     assert lib.vnl_dump_size(m.ctypes.data) == oracle_mod.lib().vnl_oracle_dump_size(m.ctypes.data_as(ctypes.c_void_p))
 
 
-def test_unregistered_blob_is_an_argument_error(lib):
+def _ctx(lib, m, t=None):
+    ctx = libm.VnlContext()
+    rc = lib.vnl_context_init(ctypes.byref(ctx), m.ctypes.data, m.nbytes, None if t is None else t.ctypes.data, 0 if t is None else t.nbytes)
+    return rc, ctx
+
+
+def test_bad_context_is_an_argument_error(lib, rodent):
     st = libm.VnlState(); out = libm.VnlOutputs()
     dummy = np.zeros(8, dtype=np.float32)
-    rc = lib.vnl_step(dummy.ctypes.data, dummy.ctypes.data, 4, ctypes.byref(st), dummy.ctypes.data, ctypes.byref(st),
+    empty = libm.VnlContext()  # never initialised: no model header
+    rc = lib.vnl_step(ctypes.byref(empty), dummy.ctypes.data, dummy.ctypes.data, 4, ctypes.byref(st), dummy.ctypes.data, ctypes.byref(st),
                       ctypes.byref(out), None)
-    assert rc < 0  # never launches: the model pointer was not registered
-    assert lib.vnl_step(None, None, 0, None, None, None, None, None) < 0
-    assert lib.vnl_unregister_blob(dummy.ctypes.data) != 0
+    assert rc == -11  # never launches
+    assert lib.vnl_step(None, None, None, 0, None, None, None, None, None) < 0
+    bad = rodent["model_blob"].copy(); bad[0] ^= 1
+    assert _ctx(lib, bad)[0] == -2
+    rc, ctx = _ctx(lib, rodent["model_blob"], rodent["task_blob"])
+    assert rc == 0 and ctx.workspace is None and ctx.model_hdr[0] == rodent["model_blob"][0] and ctx.task_hdr[0] == rodent["task_blob"][0]
+    badt = rodent["task_blob"].copy(); badt[1] += 1
+    assert _ctx(lib, rodent["model_blob"], badt)[0] == -103
 
 
 def test_workspace_is_required_and_sized(lib, rodent):
-    """The step entry points refuse to launch (-20 / -21, before any device access) until a big enough inertia
-    workspace is bound to the registered model blob; sizing follows the resident-env count and both lane-program lengths."""
+    """Stateless boundary: the workspace is an ARGUMENT (VnlContext).  The step entry points refuse to launch (-20 / -21,
+    before any device access) without one that is big enough for the geometry of THIS call; sizing follows the resident-env
+    count and both lane-program lengths.  Nothing is registered: the same host context serves any device address."""
     mb = pkg("model_blob")
     m, t = rodent["model_blob"], rodent["task_blob"]
-    lib.vnl_workspace_bytes.restype = ctypes.c_size_t
     need = lib.vnl_workspace_bytes(m.ctypes.data)
     d = mb.model_dims(rodent["model"])
     per_env = (2 * (d["TA"] + d["TD"]) * 32 + 31) // 32 * 32 * 4  # M and K, one copy per lane program each
     assert need == lib.vnl_resident_envs(m.ctypes.data) * per_env and per_env == 20480
     assert lib.vnl_resident_envs(m.ctypes.data) % lib.vnl_envs_per_cta(m.ctypes.data) == 0 and lib.vnl_envs_per_cta(m.ctypes.data) == 14
     fake_model, fake_task, fake_work = 0x7000000000, 0x7100000000, 0x7200000000  # never dereferenced on these paths
-    assert lib.vnl_set_workspace(fake_model, fake_work, need) == -1              # unknown model blob
-    assert lib.vnl_register_blob(fake_model, m.ctypes.data, m.nbytes) == 0
-    assert lib.vnl_register_blob(fake_task, t.ctypes.data, t.nbytes) == 0
+    rc, ctx = _ctx(lib, m, t)
+    assert rc == 0
     st = libm.VnlState(); out = libm.VnlOutputs()
     dummy = np.zeros(8, dtype=np.float32)
-    call = lambda: lib.vnl_step(fake_model, fake_task, 4, ctypes.byref(st), dummy.ctypes.data, ctypes.byref(st), ctypes.byref(out), None)
+    call = lambda B=4096, model=fake_model: lib.vnl_step(ctypes.byref(ctx), model, fake_task, B, ctypes.byref(st), dummy.ctypes.data,
+                                                         ctypes.byref(st), ctypes.byref(out), None)
     assert call() == -20
-    assert lib.vnl_set_workspace(fake_model, fake_work, need - 4) == 0 and call() == -21
-    assert lib.vnl_set_workspace(fake_model, None, 0) == 0 and call() == -20   # unbound again
-    assert lib.vnl_unregister_blob(fake_model) == 0 and lib.vnl_unregister_blob(fake_task) == 0
+    ctx.workspace, ctx.workspace_bytes = fake_work, need - 4
+    assert call() == -21 and call(model=fake_model + 4096) == -21   # no dependence on the blob's device address
+    ctx.workspace_bytes = 4 * per_env
+    assert call(B=4096) == -21  # checked against the geometry of the actual batch: 4 env slots are not enough for 4096 envs
+    ctx.workspace = None
+    assert call() == -20
+    # the XLA trampolines carry the same bytes in `opaque`: a short or wrong-version opaque never launches
+    op = libm.VnlXlaOpaque()
+    ctx.workspace_bytes = need
+    assert lib.vnl_xla_make_opaque(ctypes.byref(ctx), 4096, ctypes.byref(op)) == 0 and op.B == 4096 and op.version == 2
+    bufs = (ctypes.c_void_p * libm.VNL_XLA_STEP_NBUF)()
+    raw = bytes(op)
+    assert lib.vnl_xla_step_rc(None, bufs, raw[:100], 100) == -30
+    op.version = 1
+    assert lib.vnl_xla_step_rc(None, bufs, bytes(op), len(bytes(op))) == -31
+    assert lib.vnl_xla_reset_rc(None, bufs, raw, len(raw)) == -10  # NULL model buffer: argument error, still no launch
+
+
+def test_no_mutable_globals_in_the_abi():
+    """no registry / lock / global state behind the C ABI (round-1 kept pointer-keyed maps)."""
+    src = open(os.path.join(ROOT, "vnl-brax-imitation_b200", "csrc", "vnl_capi.cu")).read()
+    for needle in ("std::mutex", "unordered_map", "g_headers", "g_work", "vnl_register_blob", "vnl_set_workspace"):
+        assert needle not in src, needle
+    hdr = open(os.path.join(ROOT, "include", "vnl_b200.h")).read()
+    assert "vnl_register_blob" not in hdr and "vnl_set_workspace" not in hdr
 
 
 def test_two_warp_blob_has_wider_lane_programs(rodent):

@@ -139,12 +139,12 @@ def test_xla_custom_call_trampolines_equal_direct_calls():
     batch = x[2000:].contiguous()
     arr = (ctypes.c_void_p * 4)(batch.data_ptr(), old["mean"].data_ptr(), sums.data_ptr(), work.data_ptr())
     op = struct.pack("<qi", n - 2000, W)
-    lib.vnl_xla_obs_stats_partial(stream, arr, op, len(op))
+    lib.vnl_xla_obs_stats_partial(stream, arr, op, len(op), None)
     new = {k: garbage(v.numel()) for k, v in old.items()}
     arr = (ctypes.c_void_p * 9)(sums.data_ptr(), *[old[k].data_ptr() for k in ("count", "mean", "summed_variance", "std")],
                                 *[new[k].data_ptr() for k in ("count", "mean", "summed_variance", "std")])
     op = struct.pack("<iff", W, 1e-6, 1e6)
-    lib.vnl_xla_obs_stats_finish(stream, arr, op, len(op))
+    lib.vnl_xla_obs_stats_finish(stream, arr, op, len(op), None)
     torch.cuda.synchronize()
     for k in new:
         assert torch.equal(new[k], getattr(st, k)), k

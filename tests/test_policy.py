@@ -249,7 +249,7 @@ def test_xla_custom_call_trampoline_equals_direct_call():
     arr = (ctypes.c_void_p * len(bufs))(*[t.data_ptr() for t in bufs])
     d = p.dims
     opaque = struct.pack("<9i", d.traj, d.obs, d.latent, d.e1, d.e2, d.d1, d.d2, d.nu, 257)
-    p.lib.vnl_xla_policy_forward(torch.cuda.current_stream().cuda_stream, arr, opaque, len(opaque))
+    p.lib.vnl_xla_policy_forward(torch.cuda.current_stream().cuda_stream, arr, opaque, len(opaque), None)
     torch.cuda.synchronize()
     for k in ("action", "raw_action", "logits", "log_prob", "rand_log_prob"):
         assert torch.equal(a[k], b[k]), k

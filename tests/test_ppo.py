@@ -82,7 +82,7 @@ def test_gae_xla_trampoline_and_argument_errors():
     lib = ppo._bind(libm.load_library())
     arr = (ctypes.c_void_p * 7)(*[x.data_ptr() for x in c], vs2.data_ptr(), adv2.data_ptr())
     op = struct.pack("<iiff", T, B, 0.95, 0.9)
-    lib.vnl_xla_gae(torch.cuda.current_stream().cuda_stream, arr, op, len(op))
+    lib.vnl_xla_gae(torch.cuda.current_stream().cuda_stream, arr, op, len(op), None)
     torch.cuda.synchronize()
     assert torch.equal(vs, vs2) and torch.equal(adv, adv2)
     with pytest.raises(ValueError):

@@ -79,6 +79,35 @@ def test_graph_replay_equals_eager(gpu_env, rodent):
     assert graph.graph is not None
 
 
+def test_graph_replay_sees_reloaded_params_and_normaliser(gpu_env, rodent):
+    """after a PPO update `load_params` / `set_normalizer` must reach a rollout graph that was captured
+    before them — the device blob and the mean / std operands keep their addresses and are overwritten in place."""
+    import torch
+    pol = pkg("policy")
+    s0, policy, draws = _setup(gpu_env, rodent, 53)
+    eng = gpu_env.engine
+    graph = pkg("rollout").Rollout(gpu_env, policy, s0, T, EP, use_graph=True)
+    graph.generate_unroll(*draws[0])  # capture + first replay with the old weights
+    torch.cuda.synchronize()
+    ptr = policy.blob_dev.data_ptr(), policy.obs_mean.data_ptr(), policy.obs_std.data_ptr()
+    new = pol.init_params(np.random.default_rng(530), pol.param_shapes(eng.traj_size, eng.obs_size, gpu_env.action_size), perturb=0.2)
+    policy.load_params(new)
+    policy.set_normalizer(policy.obs_mean * 0.5 + 0.01, policy.obs_std * 1.5)
+    assert ptr == (policy.blob_dev.data_ptr(), policy.obs_mean.data_ptr(), policy.obs_std.data_ptr())
+    b = {k: v.clone() for k, v in graph.generate_unroll(*draws[1]).items() if k in ("action", "reward")}
+    # an eager twin that saw the same first unroll with the OLD weights and the second with the NEW ones
+    policy2 = pol.IntentionPolicy(new, "cuda:0", policy.obs_mean.clone(), policy.obs_std.clone())
+    old = _setup(gpu_env, rodent, 53)[1]
+    eager = pkg("rollout").Rollout(gpu_env, old, s0, T, EP, use_graph=False)
+    eager.generate_unroll(*draws[0])
+    eager.policy = policy2
+    a = eager.generate_unroll(*draws[1])
+    torch.cuda.synchronize()
+    assert torch.equal(a["action"], b["action"]) and torch.equal(a["reward"], b["reward"])
+    with pytest.raises(ValueError):
+        policy.set_normalizer(None, None)  # captured operands cannot silently become the identity
+
+
 def test_odd_unroll_length_carries_state(gpu_env, rodent):
     import torch
     s0, policy, draws = _setup(gpu_env, rodent, 53)

@@ -36,7 +36,7 @@ def main():
     torch.cuda.synchronize()
     prof = torch.zeros(32, dtype=torch.int64, device="cuda")
     A, Bs, O = eng._state(st_a), eng._state(st_b), eng._outputs(out)
-    rc = eng.lib.vnl_step_profiled(eng.model_dev.data_ptr(), eng.task_dev.data_ptr(), BB, ctypes.byref(A), a.data_ptr(),
+    rc = eng.lib.vnl_step_profiled(eng._cref, eng.model_dev.data_ptr(), eng.task_dev.data_ptr(), BB, ctypes.byref(A), a.data_ptr(),
                                    ctypes.byref(Bs), ctypes.byref(O), eng._stream(), prof.data_ptr(), BB // 2)
     torch.cuda.synchronize()
     assert rc == 0

@@ -15,8 +15,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("VNL_B200_LIB") or os.path.join(_HERE, "libvnl_b200.so")  # override: developer A/B builds
 
 STATE_F = ("qpos", "qvel", "act", "qacc_warmstart", "xpos", "xquat", "subtree_com", "qfrc_actuator")
-STATE_I = ("cur_frame", "sub_clip_frame")
+STATE_I = ("cur_frame", "sub_clip_frame", "clip_id")
 OUT_F = ("obs", "traj", "reward", "done", "metrics")
+VNL_TABLE_OFF, VNL_MAX_FIELDS = 64, 96  # include/vnl_b200.h
+VNL_DATA_OFF = VNL_TABLE_OFF + 2 * VNL_MAX_FIELDS
+VNL_XLA_STEP_NBUF = 32
 
 
 class VnlState(ctypes.Structure):
@@ -32,11 +35,23 @@ class VnlOutputs(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in OUT_F + ("stats",)]
 
 
+class VnlContext(ctypes.Structure):
+    """Host-side call context (include/vnl_b200.h): header copies + the caller-owned workspace.  Read-only for the library."""
+    _fields_ = [("model_hdr", ctypes.c_uint32 * VNL_DATA_OFF), ("task_hdr", ctypes.c_uint32 * VNL_TABLE_OFF),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_uint64)]
+
+
+class VnlXlaOpaque(ctypes.Structure):
+    """`opaque` of the XLA custom calls: batch size + the same header copies (stateless boundary)."""
+    _fields_ = [("B", ctypes.c_int32), ("version", ctypes.c_int32), ("model_hdr", ctypes.c_uint32 * VNL_DATA_OFF),
+                ("task_hdr", ctypes.c_uint32 * VNL_TABLE_OFF), ("workspace_bytes", ctypes.c_uint64)]
+
+
 EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vnl_dump_size", "vnl_check_model",
-           "vnl_check_task", "vnl_register_blob", "vnl_unregister_blob", "vnl_step_smem_bytes", "vnl_xla_step",
-           "vnl_xla_reset", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled", "vnl_step_autoreset", "vnl_envs_per_cta",
-           "vnl_resident_envs", "vnl_workspace_bytes", "vnl_set_workspace", "vnl_step_training",
-           "vnl_debug_layout")
+           "vnl_check_task", "vnl_context_init", "vnl_step_smem_bytes", "vnl_xla_step", "vnl_xla_reset", "vnl_xla_step_rc",
+           "vnl_xla_reset_rc", "vnl_xla_make_opaque", "vnl_version", "vnl_ffma_probe", "vnl_step_profiled",
+           "vnl_step_autoreset", "vnl_envs_per_cta", "vnl_resident_envs", "vnl_workspace_bytes", "vnl_step_training",
+           "vnl_debug_layout", "vnl_process_clip")
 
 
 def load_library() -> ctypes.CDLL:
@@ -44,37 +59,34 @@ def load_library() -> ctypes.CDLL:
         raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
                            "There is no CPU fallback for the product path.")
     lib = ctypes.CDLL(LIB_PATH)
+    CTX, ST, OUT = ctypes.POINTER(VnlContext), ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs)
+    v, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     lib.vnl_version.restype = ctypes.c_char_p
-    lib.vnl_dump_size.restype = ctypes.c_size_t
-    lib.vnl_dump_size.argtypes = [ctypes.c_void_p]
-    lib.vnl_step_smem_bytes.argtypes = [ctypes.c_void_p]
-    lib.vnl_envs_per_cta.argtypes = [ctypes.c_void_p]
-    lib.vnl_resident_envs.argtypes = [ctypes.c_void_p]
-    lib.vnl_workspace_bytes.restype = ctypes.c_size_t
-    lib.vnl_workspace_bytes.argtypes = [ctypes.c_void_p]
-    lib.vnl_set_workspace.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-    lib.vnl_check_model.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
-    lib.vnl_check_task.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
-    lib.vnl_register_blob.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
-    lib.vnl_unregister_blob.argtypes = [ctypes.c_void_p]
-    lib.vnl_step.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                             ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p]
-    lib.vnl_step_autoreset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                                       ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.POINTER(VnlState),
-                                       ctypes.c_void_p, ctypes.c_void_p]
-    lib.vnl_step_training.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                                      ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.POINTER(VnlState),
-                                      ctypes.c_void_p, ctypes.POINTER(VnlEpisode), ctypes.c_void_p]
-    lib.vnl_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState),
-                              ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p]
-    lib.vnl_pipeline_step.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                                      ctypes.POINTER(VnlState), ctypes.c_void_p, ctypes.c_void_p]
-    lib.vnl_forward_dump.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                                     ctypes.c_void_p, ctypes.c_void_p]
-    lib.vnl_ffma_probe.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
-    lib.vnl_step_profiled.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(VnlState), ctypes.c_void_p,
-                                      ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs), ctypes.c_void_p, ctypes.c_void_p,
-                                      ctypes.c_int]
+    lib.vnl_dump_size.restype = sz
+    lib.vnl_dump_size.argtypes = [v]
+    lib.vnl_step_smem_bytes.argtypes = [v]
+    lib.vnl_envs_per_cta.argtypes = [v]
+    lib.vnl_resident_envs.argtypes = [v]
+    lib.vnl_workspace_bytes.restype = sz
+    lib.vnl_workspace_bytes.argtypes = [v]
+    lib.vnl_check_model.argtypes = [v, sz]
+    lib.vnl_check_task.argtypes = [v, sz]
+    lib.vnl_context_init.argtypes = [CTX, v, sz, v, sz]
+    lib.vnl_step.argtypes = [CTX, v, v, i, ST, v, ST, OUT, v]
+    lib.vnl_step_autoreset.argtypes = [CTX, v, v, i, ST, v, ST, OUT, ST, v, v]
+    lib.vnl_step_training.argtypes = [CTX, v, v, i, ST, v, ST, OUT, ST, v, ctypes.POINTER(VnlEpisode), v]
+    lib.vnl_reset.argtypes = [CTX, v, v, i, ST, ST, OUT, v]
+    lib.vnl_pipeline_step.argtypes = [CTX, v, i, i, ST, v, ST, v, v]
+    lib.vnl_forward_dump.argtypes = [CTX, v, i, ST, v, v, v]
+    lib.vnl_step_profiled.argtypes = [CTX, v, v, i, ST, v, ST, OUT, v, v, i]
+    lib.vnl_ffma_probe.argtypes = [i, i, v, v]
+    for name in ("vnl_xla_step", "vnl_xla_reset"):
+        getattr(lib, name).argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, sz, v]
+        getattr(lib, name).restype = None
+        getattr(lib, name + "_rc").argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, sz]
+    lib.vnl_xla_make_opaque.argtypes = [CTX, i, ctypes.POINTER(VnlXlaOpaque)]
+    # clip preprocessing on the GPU: qpos [n, T, nq] -> the ReferenceClip tables
+    lib.vnl_process_clip.argtypes = [CTX, v, i, i, v, ctypes.c_float, ctypes.c_float, v, v, v, v, v]
     return lib
 
 
@@ -100,7 +112,6 @@ class Engine:
         if rc:
             raise ValueError(f"bad model blob ({rc})")
         self.model_dev = torch.from_numpy(self.model_host.view(np.int32)).to(self.device)
-        self._register(self.model_dev, self.model_host)
         self.task_host = self.task_dev = None
         if task_blob is not None:
             self.task_host = np.ascontiguousarray(task_blob, dtype=np.uint32)
@@ -108,7 +119,13 @@ class Engine:
             if rc:
                 raise ValueError(f"bad task blob ({rc})")
             self.task_dev = torch.from_numpy(self.task_host.view(np.int32)).to(self.device)
-            self._register(self.task_dev, self.task_host)
+        # the call context: header copies + this engine's workspace.  Nothing is registered with the library.
+        self.ctx = VnlContext()
+        rc = self.lib.vnl_context_init(ctypes.byref(self.ctx), self.model_host.ctypes.data, self.model_host.nbytes,
+                                       None if self.task_host is None else self.task_host.ctypes.data,
+                                       0 if self.task_host is None else self.task_host.nbytes)
+        if rc:
+            raise ValueError(f"vnl_context_init failed ({rc})")
         from . import model_blob as mb
         self.dims = mb.read_dims(self.model_host)
         self.dump_size = int(self.lib.vnl_dump_size(self.model_host.ctypes.data))
@@ -119,24 +136,34 @@ class Engine:
             nbytes = int(self.lib.vnl_workspace_bytes(self.model_host.ctypes.data))
         # inertia workspace of the resident envs (L2-resident scratch the kernels address by CTA / env slot)
         self.workspace = torch.empty(max(nbytes, 4) // 4, dtype=torch.float32, device=self.device)
-        rc = self.lib.vnl_set_workspace(self.model_dev.data_ptr(), self.workspace.data_ptr(), self.workspace.numel() * 4)
-        if rc:
-            raise RuntimeError(f"vnl_set_workspace failed ({rc})")
+        self.ctx.workspace, self.ctx.workspace_bytes = self.workspace.data_ptr(), nbytes
+        self._cref = ctypes.byref(self.ctx)
         if self.task_host is not None:
             self.obs_size = int(self.task_host[mb.C["VNL_TH_OBS_SIZE"]])
             self.traj_size = int(self.task_host[mb.C["VNL_TH_TRAJ_SIZE"]])
             self.n_frames = int(self.task_host[mb.C["VNL_TH_NFRAMES"]])
         self.launches = 0
 
-    def _register(self, dev, host):
-        rc = self.lib.vnl_register_blob(dev.data_ptr(), host.ctypes.data, host.nbytes)
-        if rc:
-            raise RuntimeError(f"vnl_register_blob failed ({rc})")
-
     def close(self):
-        for t in (self.model_dev, self.task_dev):
-            if t is not None:
-                self.lib.vnl_unregister_blob(t.data_ptr())
+        """Nothing to release in the library (it keeps no state); kept for callers of the round-1 API."""
+
+    def context_for_stream(self):
+        """A second context with its OWN workspace: one workspace serves one stream at a time, so a caller that steps
+        the same model from several streams / host threads takes one context per stream."""
+        t = self.torch
+        ctx = VnlContext()
+        ctypes.memmove(ctypes.byref(ctx), ctypes.byref(self.ctx), ctypes.sizeof(VnlContext))
+        work = t.empty_like(self.workspace)
+        ctx.workspace = work.data_ptr()
+        return ctx, work
+
+    def xla_opaque(self, B: int, ctx: Optional[VnlContext] = None) -> bytes:
+        """The `opaque` bytes of vnl_xla_step / vnl_xla_reset for a batch of B envs."""
+        op = VnlXlaOpaque()
+        rc = self.lib.vnl_xla_make_opaque(ctypes.byref(ctx or self.ctx), int(B), ctypes.byref(op))
+        if rc:
+            raise ValueError(f"vnl_xla_make_opaque failed ({rc})")
+        return bytes(op)
 
     # ---- allocation helpers ---------------------------------------------------------------
     def alloc_state(self, B: int) -> Dict[str, "torch.Tensor"]:
@@ -144,7 +171,8 @@ class Engine:
         z = lambda *s: t.zeros(*s, dtype=t.float32, device=dev)
         return dict(qpos=z(B, d["nq"]), qvel=z(B, d["nv"]), act=z(B, d["na"]), qacc_warmstart=z(B, d["nv"]),
                     xpos=z(B, d["nbody"], 3), xquat=z(B, d["nbody"], 4), subtree_com=z(B, 3), qfrc_actuator=z(B, d["nv"]),
-                    cur_frame=t.zeros(B, dtype=t.int32, device=dev), sub_clip_frame=t.zeros(B, dtype=t.int32, device=dev))
+                    cur_frame=t.zeros(B, dtype=t.int32, device=dev), sub_clip_frame=t.zeros(B, dtype=t.int32, device=dev),
+                    clip_id=t.zeros(B, dtype=t.int32, device=dev))
 
     def alloc_outputs(self, B: int) -> Dict[str, "torch.Tensor"]:
         t, dev = self.torch, self.device
@@ -189,7 +217,7 @@ class Engine:
         B = state["qpos"].shape[0]
         a, b, o = self._state(state), self._state(out_state), self._outputs(outputs)
         assert action.is_contiguous() and action.shape == (B, self.dims["nu"])
-        self._check(self.lib.vnl_step(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+        self._check(self.lib.vnl_step(self._cref, self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                       action.data_ptr(), ctypes.byref(b), ctypes.byref(o), self._stream()), "vnl_step")
 
     def step_autoreset(self, state: Dict, action, out_state: Dict, outputs: Dict, first: Dict, first_obs):
@@ -197,7 +225,7 @@ class Engine:
         B = state["qpos"].shape[0]
         a, b, o, f = self._state(state), self._state(out_state), self._outputs(outputs), self._state(first)
         assert action.is_contiguous() and action.shape == (B, self.dims["nu"]) and first_obs.is_contiguous()
-        self._check(self.lib.vnl_step_autoreset(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+        self._check(self.lib.vnl_step_autoreset(self._cref, self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                                 action.data_ptr(), ctypes.byref(b), ctypes.byref(o), ctypes.byref(f),
                                                 first_obs.data_ptr(), self._stream()), "vnl_step_autoreset")
 
@@ -210,20 +238,20 @@ class Engine:
         for t in (steps, done_in, steps_out, truncation):
             assert t.is_contiguous() and t.shape == (B,) and t.element_size() == 4 and t.dtype.is_floating_point
         ep = VnlEpisode(steps.data_ptr(), done_in.data_ptr(), steps_out.data_ptr(), truncation.data_ptr(), float(episode_length))
-        self._check(self.lib.vnl_step_training(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+        self._check(self.lib.vnl_step_training(self._cref, self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                                action.data_ptr(), ctypes.byref(b), ctypes.byref(o), ctypes.byref(f),
                                                first_obs.data_ptr(), ctypes.byref(ep), self._stream()), "vnl_step_training")
 
     def reset(self, state: Dict, out_state: Dict, outputs: Dict):
         B = state["qpos"].shape[0]
         a, b, o = self._state(state), self._state(out_state), self._outputs(outputs)
-        self._check(self.lib.vnl_reset(self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
+        self._check(self.lib.vnl_reset(self._cref, self.model_dev.data_ptr(), self.task_dev.data_ptr(), B, ctypes.byref(a),
                                        ctypes.byref(b), ctypes.byref(o), self._stream()), "vnl_reset")
 
     def pipeline_step(self, state: Dict, ctrl, out_state: Dict, nsteps: int, stats=None):
         B = state["qpos"].shape[0]
         a, b = self._state(state), self._state(out_state)
-        self._check(self.lib.vnl_pipeline_step(self.model_dev.data_ptr(), B, int(nsteps), ctypes.byref(a), _ptr(ctrl),
+        self._check(self.lib.vnl_pipeline_step(self._cref, self.model_dev.data_ptr(), B, int(nsteps), ctypes.byref(a), _ptr(ctrl),
                                                ctypes.byref(b), _ptr(stats), self._stream()), "vnl_pipeline_step")
 
     def forward_dump(self, state: Dict, ctrl=None):
@@ -231,6 +259,6 @@ class Engine:
         B = state["qpos"].shape[0]
         dump = t.empty(B, self.dump_size, dtype=t.float32, device=self.device)
         a = self._state(state)
-        self._check(self.lib.vnl_forward_dump(self.model_dev.data_ptr(), B, ctypes.byref(a), _ptr(ctrl), dump.data_ptr(),
+        self._check(self.lib.vnl_forward_dump(self._cref, self.model_dev.data_ptr(), B, ctypes.byref(a), _ptr(ctrl), dump.data_ptr(),
                                               self._stream()), "vnl_forward_dump")
         return dump

@@ -1,34 +1,18 @@
 // vnl_capi.cu -- extern "C" boundary of include/vnl_b200.h.
 //
-// The model dimensions needed for the launch geometry live in the blob header.  The blobs
-// passed to vnl_step & co. are DEVICE buffers, so the (tiny) header is cached host-side per
-// device pointer the first time a blob is registered with vnl_register_blob(); no call on
-// the step path copies, allocates or synchronises.
+// STATELESS: the model dimensions needed for the launch geometry travel with every call in a caller-owned host struct
+// (VnlContext: host copies of the blobs' scalar headers + the device workspace; for the XLA custom calls the same bytes
+// arrive in `opaque` and the workspace is a scratch buffer).  There is no registry, no lock and no global: the model /
+// task blobs are plain device operands that may sit at a different address on every call.  No call on the step path
+// copies, allocates or synchronises.
 #include <cuda_runtime.h>
 #include <string.h>
 
-#include <mutex>
-#include <unordered_map>
-#include <vector>
-
 #include "../../include/vnl_blob.h"
 #include "vnl_kernels.h"
+#include "vnl_xla_status.h"
 
 namespace {
-
-struct Header { uint32_t w[VNL_DATA_OFF]; };  // scalar header + field table
-std::mutex g_mu;
-std::unordered_map<const void*, Header> g_headers;  // device blob pointer -> host copy of its scalar header
-struct Work { float* p; size_t bytes; };
-std::unordered_map<const void*, Work> g_work;        // device model blob pointer -> bound inertia workspace
-
-bool lookup(const void* dev, Header& h) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  auto it = g_headers.find(dev);
-  if (it == g_headers.end()) return false;
-  h = it->second;
-  return true;
-}
 
 void fill_dims(const uint32_t* w, vnl::Dims& d) {
   d.nq = vnl_hdr_i(w, VNL_MH_NQ); d.nv = vnl_hdr_i(w, VNL_MH_NV); d.nu = vnl_hdr_i(w, VNL_MH_NU); d.na = vnl_hdr_i(w, VNL_MH_NA);
@@ -71,26 +55,24 @@ int check_blob(const void* host, size_t nbytes, uint32_t magic, int nfields) {
   return 0;
 }
 
-int prepare(const void* model, const void* task, bool need_task, vnl::Params& p) {
-  Header hm;
-  if (!model || !lookup(model, hm)) return -10;
-  if (hm.w[0] != VNL_MAGIC_MODEL) return -11;
-  fill_dims(hm.w, p.dims);
+// Argument checks + launch parameters common to every entry point.  `B` is the ACTUAL batch: the workspace bound is
+// checked against the geometry this very launch will use.
+int prepare(const VnlContext* ctx, const void* model, const void* task, bool need_task, int B, vnl::Params& p) {
+  if (!ctx || !model) return -10;
+  if (ctx->model_hdr[0] != VNL_MAGIC_MODEL || ctx->model_hdr[1] != VNL_BLOB_VERSION) return -11;
+  fill_dims(ctx->model_hdr, p.dims);
   if (p.dims.stream) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    auto it = g_work.find(model);
-    if (it == g_work.end()) return -20;
-    const vnl::LaunchInfo li = vnl::any_launch_info(p.dims, 1 << 20);
+    if (!ctx->workspace) return -20;
+    const vnl::LaunchInfo li = vnl::any_launch_info(p.dims, B);
     p.work_stride = vnl::work_stride(p.dims);
-    if ((size_t)li.ctas * li.warps_per_cta * p.work_stride * sizeof(float) > it->second.bytes) return -21;
-    p.work = it->second.p;
+    if ((uint64_t)li.ctas * li.warps_per_cta * p.work_stride * sizeof(float) > ctx->workspace_bytes) return -21;
+    p.work = static_cast<float*>(ctx->workspace);
   }
   p.model = (const uint32_t*)model;
   p.task = (const uint32_t*)task;
   if (need_task) {
-    Header ht;
-    if (!task || !lookup(task, ht)) return -12;
-    if (ht.w[0] != VNL_MAGIC_TASK) return -13;
+    if (!task) return -12;
+    if (ctx->task_hdr[0] != VNL_MAGIC_TASK || ctx->task_hdr[1] != VNL_BLOB_VERSION) return -13;
   }
   return 0;
 }
@@ -112,6 +94,48 @@ __global__ void vnl_ffma_probe_kernel(int iters, float* out) {
   if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // keeps the chains alive; practically never true
 }
 
+// compute_velocity_from_kinematics + the joint-velocity clip of process_clip (preprocessing/mjx_preprocess.py:88-105,
+// 170-193; quaternion helpers preprocessing/transformations.py:86-139), one thread per (clip, frame, column block).
+// The trajectory is padded with its last frame (mjx_preprocess.py:91), so the last frame's velocity is zero.  Works on the
+// RAW qpos (the reference differentiates mocap_qpos, not the kinematics-normalised copy).
+__global__ void clip_velocity_kernel(const float* __restrict__ qpos, int nclips, int T, int nq, float dt, float max_qvel,
+                                     float* __restrict__ qvel) {
+  const int nv = nq - 1;
+  const long long total = (long long)nclips * T * nv;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(idx % nv);
+    const long long row = idx / nv;
+    const int t = (int)(row % T);
+    const float* q0 = qpos + row * nq;
+    const float* q1 = (t + 1 < T) ? q0 + nq : q0;  // padded frame = the last one
+    float v;
+    if (col < 3) {
+      v = (q1[col] - q0[col]) / dt;
+    } else if (col < 6) {
+      // quat_diff(source, target) = conj(source) * target, normalised, then quat_to_axisangle / dt
+      const float sw = q0[3], sx = -q0[4], sy = -q0[5], sz = -q0[6];
+      const float tw = q1[3], tx = q1[4], ty = q1[5], tz = q1[6];
+      float d[4] = {sw * tw - sx * tx - sy * ty - sz * tz, sw * tx + sx * tw + sy * tz - sz * ty,
+                    sw * ty - sx * tz + sy * tw + sz * tx, sw * tz + sx * ty - sy * tx + sz * tw};
+      const float n = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2] + d[3] * d[3]);
+      for (int k = 0; k < 4; ++k) d[k] /= n;
+      float angle = 2.0f * acosf(fminf(fmaxf(d[0], -1.0f), 1.0f));
+      if (angle < 1e-10f) {
+        v = 0.0f;
+      } else {
+        const float qn = sinf(angle / 2.0f);
+        const float pi = 3.14159265358979323846f, x = angle + pi;
+        angle = (x - floorf(x / (2.0f * pi)) * (2.0f * pi)) - pi;  // python floor-mod
+        v = d[1 + col - 3] / qn * angle / dt;
+      }
+    } else {
+      v = (q1[col + 1] - q0[col + 1]) / dt;
+      v = fminf(fmaxf(v, -max_qvel), max_qvel);
+    }
+    qvel[row * nv + col] = v;
+  }
+}
+
 extern "C" {
 
 const char* vnl_version(void) { return "vnl_b200 0.1 (sm_100a)"; }
@@ -119,37 +143,34 @@ const char* vnl_version(void) { return "vnl_b200 0.1 (sm_100a)"; }
 int vnl_check_model(const void* model_host, size_t nbytes) { return check_blob(model_host, nbytes, VNL_MAGIC_MODEL, VNL_F_MODEL_COUNT); }
 int vnl_check_task(const void* task_host, size_t nbytes) { return check_blob(task_host, nbytes, VNL_MAGIC_TASK, VNL_TASK_COUNT); }
 
-int vnl_register_blob(const void* blob_dev, const void* blob_host, size_t nbytes) {
-  const uint32_t* w = (const uint32_t*)blob_host;
-  if (!blob_dev || !w) return -1;
-  const int rc = (w[0] == VNL_MAGIC_MODEL) ? vnl_check_model(blob_host, nbytes) : vnl_check_task(blob_host, nbytes);
+int vnl_context_init(VnlContext* ctx, const void* model_host, size_t model_bytes, const void* task_host, size_t task_bytes) {
+  if (!ctx) return -1;
+  memset(ctx, 0, sizeof(*ctx));
+  int rc = vnl_check_model(model_host, model_bytes);
   if (rc) return rc;
-  Header h;
-  memcpy(h.w, w, sizeof(h.w));
-  std::lock_guard<std::mutex> lk(g_mu);
-  g_headers[blob_dev] = h;
+  memcpy(ctx->model_hdr, model_host, sizeof(ctx->model_hdr));
+  if (task_host) {
+    rc = vnl_check_task(task_host, task_bytes);
+    if (rc) return rc - 100;
+    memcpy(ctx->task_hdr, task_host, sizeof(ctx->task_hdr));
+  }
   return 0;
-}
-
-int vnl_unregister_blob(const void* blob_dev) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  g_work.erase(blob_dev);
-  return g_headers.erase(blob_dev) ? 0 : -1;
 }
 
 size_t vnl_workspace_bytes(const void* model_host) {
   vnl::Dims d;
   fill_dims((const uint32_t*)model_host, d);
-  const vnl::LaunchInfo li = vnl::any_launch_info(d, 1 << 20);
-  return (size_t)li.ctas * li.warps_per_cta * vnl::work_stride(d) * sizeof(float);
-}
-
-int vnl_set_workspace(const void* model_dev, void* workspace_dev, size_t nbytes) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!model_dev || g_headers.find(model_dev) == g_headers.end()) return -1;
-  if (!workspace_dev) { g_work.erase(model_dev); return 0; }
-  g_work[model_dev] = Work{(float*)workspace_dev, nbytes};
-  return 0;
+  if (!d.stream) return 0;
+  // bound over every geometry launch_info can pick on this device: batch sizes from one CTA's worth to many rounds
+  size_t best = 0;
+  for (int B = 1; B <= (1 << 20); B <<= 1) {
+    const vnl::LaunchInfo li = vnl::any_launch_info(d, B);
+    const size_t n = (size_t)li.ctas * li.warps_per_cta;
+    if (n > best) best = n;
+  }
+  const vnl::LaunchInfo li = vnl::any_launch_info(d, (1 << 20) + 12345);
+  if ((size_t)li.ctas * li.warps_per_cta > best) best = (size_t)li.ctas * li.warps_per_cta;
+  return best * vnl::work_stride(d) * sizeof(float);
 }
 
 int vnl_step_smem_bytes(const void* model_host) {
@@ -186,91 +207,83 @@ size_t vnl_dump_size(const void* model_host) {
   return (size_t)d.dump_total;
 }
 
-int vnl_step(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+int vnl_step(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
              const VnlOutputs* outputs, void* stream) {
   if (B <= 0 || !in || !out || !outputs || !action) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, task, true, p);
+  int rc = prepare(ctx, model, task, true, B, p);
   if (rc) return rc;
-  Header ht;
-  lookup(task, ht);
-  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.B = B; p.nsteps = vnl_hdr_i(ctx->task_hdr, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
-int vnl_step_autoreset(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+int vnl_step_autoreset(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
                        const VnlOutputs* outputs, const VnlState* first, const float* first_obs, void* stream) {
   if (B <= 0 || !in || !out || !outputs || !action || !first || !first->qpos) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, task, true, p);
+  int rc = prepare(ctx, model, task, true, B, p);
   if (rc) return rc;
-  Header ht;
-  lookup(task, ht);
-  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.B = B; p.nsteps = vnl_hdr_i(ctx->task_hdr, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   p.first = *first; p.first_obs = first_obs;
   return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
-int vnl_step_training(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+int vnl_step_training(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
                       const VnlOutputs* outputs, const VnlState* first, const float* first_obs, const VnlEpisode* episode,
                       void* stream) {
   if (B <= 0 || !in || !out || !outputs || !action || !first || !first->qpos || !episode) return -1;
   if (!episode->steps_in || !episode->done_in || !episode->steps_out || !episode->truncation_out) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, task, true, p);
+  int rc = prepare(ctx, model, task, true, B, p);
   if (rc) return rc;
-  Header ht;
-  lookup(task, ht);
-  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.B = B; p.nsteps = vnl_hdr_i(ctx->task_hdr, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   p.first = *first; p.first_obs = first_obs; p.episode = *episode;
   return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
 // Developer hook: vnl_step with per-phase clock64 accumulation for CTA `block` into prof[32].
-int vnl_step_profiled(const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
+int vnl_step_profiled(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const float* action, const VnlState* out,
                       const VnlOutputs* outputs, void* stream, long long* prof, int block) {
   if (B <= 0 || !in || !out || !outputs || !action) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, task, true, p);
+  int rc = prepare(ctx, model, task, true, B, p);
   if (rc) return rc;
-  Header ht;
-  lookup(task, ht);
-  p.B = B; p.nsteps = vnl_hdr_i(ht.w, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
+  p.B = B; p.nsteps = vnl_hdr_i(ctx->task_hdr, VNL_TH_NFRAMES); p.in = *in; p.out = *out; p.ctrl = action; p.outputs = *outputs;
   p.prof = prof; p.prof_env = block;
   return (int)vnl::any_launch(0, p, (cudaStream_t)stream);
 }
 
-int vnl_reset(const void* model, const void* task, int B, const VnlState* in, const VnlState* out, const VnlOutputs* outputs,
+int vnl_reset(const VnlContext* ctx, const void* model, const void* task, int B, const VnlState* in, const VnlState* out, const VnlOutputs* outputs,
               void* stream) {
   if (B <= 0 || !in || !out || !outputs) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, task, true, p);
+  int rc = prepare(ctx, model, task, true, B, p);
   if (rc) return rc;
   p.B = B; p.nsteps = 1; p.in = *in; p.out = *out; p.outputs = *outputs;
   return (int)vnl::any_launch(1, p, (cudaStream_t)stream);
 }
 
-int vnl_pipeline_step(const void* model, int B, int nsteps, const VnlState* in, const float* ctrl, const VnlState* out,
+int vnl_pipeline_step(const VnlContext* ctx, const void* model, int B, int nsteps, const VnlState* in, const float* ctrl, const VnlState* out,
                       int32_t* stats, void* stream) {
   if (B <= 0 || nsteps <= 0 || !in || !out) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, nullptr, false, p);
+  int rc = prepare(ctx, model, nullptr, false, B, p);
   if (rc) return rc;
   p.B = B; p.nsteps = nsteps; p.in = *in; p.out = *out; p.ctrl = ctrl; p.stats = stats;
   return (int)vnl::any_launch(2, p, (cudaStream_t)stream);
 }
 
-int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* ctrl, float* dump, void* stream) {
+int vnl_forward_dump(const VnlContext* ctx, const void* model, int B, const VnlState* in, const float* ctrl, float* dump, void* stream) {
   if (B <= 0 || !in || !dump) return -1;
   vnl::Params p;
   memset(&p, 0, sizeof(p));
-  int rc = prepare(model, nullptr, false, p);
+  int rc = prepare(ctx, model, nullptr, false, B, p);
   if (rc) return rc;
   p.B = B; p.nsteps = 1; p.in = *in; p.ctrl = ctrl; p.dump = dump;
   cudaError_t err = cudaMemsetAsync(dump, 0xFF, (size_t)B * p.dims.dump_total * sizeof(float), (cudaStream_t)stream);
@@ -278,38 +291,72 @@ int vnl_forward_dump(const void* model, int B, const VnlState* in, const float* 
   return (int)vnl::any_launch(3, p, (cudaStream_t)stream);
 }
 
-// Legacy XLA custom calls.  `opaque` = two little-endian int32: B, then the operand layout version (1).
-// buffers: [model, task, qpos, qvel, act, warm, xpos, xquat, subtree_com, qfrc_actuator, cur_frame, sub_clip_frame, action,
-//           (outputs) qpos', qvel', act', warm', xpos', xquat', subtree_com', qfrc_actuator', cur_frame', sub_clip_frame',
-//           obs, traj, reward, done, metrics, stats]
+// process_clip on the GPU: kinematics of every frame with the env kernel's own kinematic pass (mode 4:
+// one warp per frame) + one elementwise kernel for the finite-difference velocities.
+int vnl_process_clip(const VnlContext* ctx, const void* model, int nclips, int T, const float* qpos, float dt, float max_qvel,
+                     float* qpos_out, float* body_positions, float* body_quaternions, float* qvel_out, void* stream) {
+  if (nclips <= 0 || T <= 0 || !qpos || !qpos_out || !body_positions || !body_quaternions || !qvel_out || !(dt > 0.0f)) return -1;
+  if ((long long)nclips * T > (1 << 24)) return -2;
+  const int B = nclips * T;
+  vnl::Params p;
+  memset(&p, 0, sizeof(p));
+  int rc = prepare(ctx, model, nullptr, false, B, p);
+  if (rc) return rc;
+  p.B = B; p.nsteps = 1;
+  p.in.qpos = const_cast<float*>(qpos);
+  p.out.qpos = qpos_out; p.out.xpos = body_positions; p.out.xquat = body_quaternions;
+  cudaError_t err = vnl::any_launch(4, p, (cudaStream_t)stream);
+  if (err != cudaSuccess) return (int)err;
+  const long long total = (long long)B * (p.dims.nq - 1);
+  const int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  clip_velocity_kernel<<<(int)blocks, threads, 0, (cudaStream_t)stream>>>(qpos, nclips, T, p.dims.nq, dt, max_qvel, qvel_out);
+  return (int)cudaGetLastError();
+}
+
+// XLA custom calls (status-returning legacy ABI), stateless: see include/vnl_b200.h for the buffer list.
 static void unpack(void** b, int first, VnlState& s) {
   s.qpos = (float*)b[first]; s.qvel = (float*)b[first + 1]; s.act = (float*)b[first + 2]; s.qacc_warmstart = (float*)b[first + 3];
   s.xpos = (float*)b[first + 4]; s.xquat = (float*)b[first + 5]; s.subtree_com = (float*)b[first + 6];
   s.qfrc_actuator = (float*)b[first + 7]; s.cur_frame = (int32_t*)b[first + 8]; s.sub_clip_frame = (int32_t*)b[first + 9];
+  s.clip_id = (int32_t*)b[first + 10];
 }
-void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 4) return;
-  int B;
-  memcpy(&B, opaque, 4);
+static int xla_call(bool reset, void* stream, void** buffers, const char* opaque, size_t opaque_len) {
+  if (!buffers || !opaque || opaque_len < sizeof(VnlXlaOpaque)) return -30;
+  VnlXlaOpaque op;  // opaque bytes carry no alignment guarantee
+  memcpy(&op, opaque, sizeof(op));
+  if (op.version != VNL_XLA_OPAQUE_VERSION) return -31;
+  VnlContext ctx;
+  memcpy(ctx.model_hdr, op.model_hdr, sizeof(ctx.model_hdr));
+  memcpy(ctx.task_hdr, op.task_hdr, sizeof(ctx.task_hdr));
+  ctx.workspace = buffers[VNL_XLA_STEP_NBUF - 1];
+  ctx.workspace_bytes = op.workspace_bytes;
   VnlState in, out;
   unpack(buffers, 2, in);
-  unpack(buffers, 13, out);
+  unpack(buffers, 14, out);
   VnlOutputs o;
-  o.obs = (float*)buffers[23]; o.traj = (float*)buffers[24]; o.reward = (float*)buffers[25]; o.done = (float*)buffers[26];
-  o.metrics = (float*)buffers[27]; o.stats = (int32_t*)buffers[28];
-  vnl_step(buffers[0], buffers[1], B, &in, (const float*)buffers[12], &out, &o, stream);
+  o.obs = (float*)buffers[25]; o.traj = (float*)buffers[26]; o.reward = (float*)buffers[27]; o.done = (float*)buffers[28];
+  o.metrics = (float*)buffers[29]; o.stats = (int32_t*)buffers[30];
+  if (reset) return vnl_reset(&ctx, buffers[0], buffers[1], op.B, &in, &out, &o, stream);
+  return vnl_step(&ctx, buffers[0], buffers[1], op.B, &in, (const float*)buffers[13], &out, &o, stream);
 }
-void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 4) return;
-  int B;
-  memcpy(&B, opaque, 4);
-  VnlState in, out;
-  unpack(buffers, 2, in);
-  unpack(buffers, 13, out);
-  VnlOutputs o;
-  o.obs = (float*)buffers[23]; o.traj = (float*)buffers[24]; o.reward = (float*)buffers[25]; o.done = (float*)buffers[26];
-  o.metrics = (float*)buffers[27]; o.stats = (int32_t*)buffers[28];
-  vnl_reset(buffers[0], buffers[1], B, &in, &out, &o, stream);
+int vnl_xla_step_rc(void* stream, void** buffers, const char* opaque, size_t opaque_len) { return xla_call(false, stream, buffers, opaque, opaque_len); }
+int vnl_xla_reset_rc(void* stream, void** buffers, const char* opaque, size_t opaque_len) { return xla_call(true, stream, buffers, opaque, opaque_len); }
+void vnl_xla_step(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status) {
+  vnl::xla_report(status, "vnl_xla_step", xla_call(false, stream, buffers, opaque, opaque_len));
+}
+void vnl_xla_reset(void* stream, void** buffers, const char* opaque, size_t opaque_len, void* status) {
+  vnl::xla_report(status, "vnl_xla_reset", xla_call(true, stream, buffers, opaque, opaque_len));
+}
+int vnl_xla_make_opaque(const VnlContext* ctx, int B, VnlXlaOpaque* opaque) {
+  if (!ctx || !opaque || B <= 0) return -1;
+  memset(opaque, 0, sizeof(*opaque));
+  opaque->B = B; opaque->version = VNL_XLA_OPAQUE_VERSION;
+  memcpy(opaque->model_hdr, ctx->model_hdr, sizeof(opaque->model_hdr));
+  memcpy(opaque->task_hdr, ctx->task_hdr, sizeof(opaque->task_hdr));
+  opaque->workspace_bytes = ctx->workspace_bytes;
+  return 0;
 }
 
 // Measurement helper for bench.py: an FFMA-saturating microkernel (8 independent chains per thread) that gives the

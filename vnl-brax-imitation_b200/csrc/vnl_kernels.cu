@@ -806,8 +806,9 @@ struct LSP { float alpha, cost, d0, d1; };
 // `gx` != nullptr (the last substep of a call): xpos / xquat / qfrc_actuator of this forward pass are the ones the caller
 // sees; they are stored to the env's rows of the output state right where they are produced (gx -> xpos, gq -> xquat,
 // gf -> qfrc_actuator), because their shared-memory homes are recycled by the solver.
+// `kin_only`: stop after smooth.kinematics (the clip-preprocessing mode: process_clip's set_position runs kinematics only).
 template <bool DUMP>
-__device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, float* gq, float* gf) {
+__device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, float* gq, float* gf, bool kin_only = false) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
@@ -900,6 +901,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     env_sync();
   }
   pf.mark(0);
+  if (kin_only) return;
   if (ls3) __syncthreads();
   // ---- smooth.com_pos: xipos, tree COM, cinert (t16[0..9]), cdof ------------------------------------------------------
   const int* dof_jnt = c.fi(VNL_F_DOF_JNTID);
@@ -1590,7 +1592,8 @@ __device__ __noinline__ RewardTerms reward_state_terms(const uint32_t* tb, int n
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// one env, one env group.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump
+// one env, one env group.  MODE 0 = env step, 1 = env reset tail, 2 = physics only, 3 = forward stage dump,
+// 4 = kinematics only (clip preprocessing: qpos -> normalised qpos, xpos, xquat)
 // ---------------------------------------------------------------------------------------------------------------------
 template <int MODE>
 __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool active) {
@@ -1598,6 +1601,16 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   const Dims& d = c.d;
   const Lay& L = c.L;
   const int lane = LANE, tid = ETID;
+  if (MODE == 4) {  // preprocessing/mjx_preprocess.py:109-134 `extract_features`: set_position -> smooth.kinematics, per frame
+    if (!active) return;  // no CTA-wide barriers on this path
+    Prof pf4; pf4.p = nullptr; pf4.t0 = 0;
+    for (int i = tid; i < d.nq; i += kEnvThreads) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
+    env_sync();
+    forward<false>(so, nullptr, pf4, p.out.xpos + (size_t)e * d.nbody * 3, p.out.xquat + (size_t)e * d.nbody * 4, nullptr, true);
+    for (int i = tid; i < d.nq; i += kEnvThreads) p.out.qpos[(size_t)e * d.nq + i] = s[L.qpos + i];  // free-joint quaternion normalised
+    env_sync();
+    return;
+  }
   if (!active) {  // a warp without an env in this round only keeps the CTA's phase barriers company
     if (p.lockstep) {
       const int ns = (MODE == 1 || MODE == 3) ? 1 : p.nsteps;
@@ -1635,14 +1648,21 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   // inputs, so evaluate it before the physics overwrites them.
   float rtrunk = 0.0f;
   int frame_old = 0;
+  // multi-clip task tables: every clip table is [nclips, T, ...]; the env's clip only offsets the row
+  int fbase = 0, clip = 0;
+  if (MODE == 0 || MODE == 1) {
+    const int nclips = max(1, vnl_hdr_i(tb, VNL_TH_NCLIPS));
+    clip = p.in.clip_id ? min(max(p.in.clip_id[e], 0), nclips - 1) : 0;
+    fbase = clip * vnl_hdr_i(tb, VNL_TH_CLIP_LEN);
+  }
   RewardTerms rt;
   rt.rcom = rt.rvel = rt.rquat = rt.ract = rt.healthy = 0.0f;
   if (MODE == 0) {
     frame_old = p.in.cur_frame[e];
     const int T = vnl_hdr_i(tb, VNL_TH_CLIP_LEN), ntrack = vnl_hdr_i(tb, VNL_TH_NTRACK), nj = d.nq - 7;
     const int f = min(max(frame_old, 0), T - 1);
-    const float* rj = vnl_field_f(tb, VNL_T_JOINTS) + (size_t)f * nj;
-    const float* rb = vnl_field_f(tb, VNL_T_BODY_POSITIONS) + (size_t)f * ntrack * 3;
+    const float* rj = vnl_field_f(tb, VNL_T_JOINTS) + (size_t)(fbase + f) * nj;
+    const float* rb = vnl_field_f(tb, VNL_T_BODY_POSITIONS) + (size_t)(fbase + f) * ntrack * 3;
     const int* bidx = vnl_field_i(tb, VNL_T_BODY_IDXS);
     const float* xold = p.in.xpos + (size_t)e * d.nbody * 3;
     float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;
@@ -1658,7 +1678,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     const float err = 0.5f * vnl_hdr_f(tb, VNL_TH_BODY_ERR_MULT) * eb + 0.5f * v0;
     rtrunk = 1.0f - err / vnl_hdr_f(tb, VNL_TH_TERM_THRESHOLD);
     if (vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE))  // humanoid.py:275: the whole reward reads the pre-step state
-      rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, p.in.qfrc_actuator + (size_t)e * d.nv, p.in.subtree_com + (size_t)e * 3);
+      rt = reward_state_terms(tb, d.nv, fbase + f, s + L.qvel, s + L.qpos, p.in.qfrc_actuator + (size_t)e * d.nv, p.in.subtree_com + (size_t)e * 3);
   }
 
   int* stats = ints + 4;  // [4..7]
@@ -1727,7 +1747,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   int cur_frame, sub_clip_frame;
   if (MODE == 0) { cur_frame = frame_old + 1; sub_clip_frame = p.in.sub_clip_frame[e] + 1; }
   else { cur_frame = p.in.cur_frame[e]; sub_clip_frame = 0; }
-  if (lane == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; }
+  if (lane == 0) { o.cur_frame[e] = cur_frame; o.sub_clip_frame[e] = sub_clip_frame; if (o.clip_id) o.clip_id[e] = clip; }
   {
     float* obs = p.outputs.obs + (size_t)e * obs_size;
     for (int i = tid; i < obs_size; i += kEnvThreads) {  // [qpos, qvel (, qfrc_actuator, xpos[end effectors])]
@@ -1742,7 +1762,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
     quat_to_mat(ld4(gxq + 4 * vnl_hdr_i(tb, VNL_TH_ROT_BODY)), R);  // rodent.py:385 xmat[1]; ant.py:333 xmat[0]
     // window start: NEW cur_frame + 1 (rodent.py:188-190); the ant hands the not yet incremented info to _get_obs (ant.py:182)
     const int wf = (MODE == 0 && vnl_hdr_i(tb, VNL_TH_TRAJ_OLD_FRAME)) ? frame_old : cur_frame;
-    const int ws = min(max(wf + 1, 0), T - ref_len);
+    const int ws = fbase + min(max(wf + 1, 0), T - ref_len);
     float* traj = p.outputs.traj + (size_t)e * traj_size;
     const int n_app = ref_len * napp * 3, n_bod = ref_len * ntrack * 3, n_root = ref_len * 3;
     for (int i = tid; i < traj_size; i += kEnvThreads) {
@@ -1771,7 +1791,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   }
   if (MODE == 1) {
     // info["termination_error"] of the fresh state (rodent.py:169)
-    const int f = min(max(cur_frame, 0), T - 1);
+    const int f = fbase + min(max(cur_frame, 0), T - 1);
     float v0 = 0.0f, v1 = 0.0f, v2 = 0.0f, v3_ = 0.0f;
     for (int j = lane; j < nj; j += 32) v0 += fabsf(rjoints[(size_t)f * nj + j] - s[L.qpos + 7 + j]);
     for (int b = lane; b < ntrack; b += 32) {
@@ -1795,7 +1815,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   }
   // _calculate_reward (rodent.py:266-316 / humanoid.py:264-311): every reference lookup uses the OLD cur_frame
   {
-    const int f = min(max(frame_old, 0), T - 1);
+    const int f = fbase + min(max(frame_old, 0), T - 1);
     if (!vnl_hdr_i(tb, VNL_TH_REWARD_OLD_STATE)) rt = reward_state_terms(tb, d.nv, f, s + L.qvel, s + L.qpos, gfa, rcom);
     float v2 = 0.0f, v3_ = 0.0f;  // |app - ref|^2, nan count
     for (int i = lane; i < d.nv; i += 32)
@@ -1908,6 +1928,7 @@ template __global__ void vnl_env_kernel<0>(Params);
 template __global__ void vnl_env_kernel<1>(Params);
 template __global__ void vnl_env_kernel<2>(Params);
 template __global__ void vnl_env_kernel<3>(Params);
+template __global__ void vnl_env_kernel<4>(Params);
 
 // (name, offset, size) of every array of the per-env layout, for tests/test_layout.py (sizes as make_layout reserves them)
 int layout_table(const Dims& d, LayoutEntry* out, int cap) {
@@ -1994,7 +2015,7 @@ cudaError_t launch(int mode, const Params& p, cudaStream_t stream) {
   if (li.warps_per_cta < 1) return cudaErrorInvalidConfiguration;  // one env does not fit in shared memory
   if (p.dims.env_warps != kEnvWarps) return cudaErrorInvalidValue;   // the blob's lane programs are for another group width
   if ((p.dims.stream != 0) != kStream) return cudaErrorInvalidValue;  // dispatched to the wrong instantiation
-  void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : vnl_env_kernel<3>;
+  void (*k)(Params) = mode == 0 ? vnl_env_kernel<0> : mode == 1 ? vnl_env_kernel<1> : mode == 2 ? vnl_env_kernel<2> : mode == 3 ? vnl_env_kernel<3> : vnl_env_kernel<4>;
   cudaError_t err = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, li.smem_bytes);
   if (err != cudaSuccess) return err;
   static int lockstep = -1;

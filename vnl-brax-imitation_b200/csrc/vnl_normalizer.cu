@@ -12,6 +12,7 @@
 #include <string.h>
 
 #include "../../include/vnl_normalizer.h"
+#include "vnl_xla_status.h"
 
 namespace {
 
@@ -173,30 +174,32 @@ int vnl_obs_stats_finish(const float* sums, int width, float* count, float* mean
 // Legacy XLA custom calls.  XLA hands out uninitialised result buffers and never aliases operands with results, so the
 // trampolines zero the arrival ticket of the scratch result and copy the state operands into the state results first.
 // partial: opaque = int64 rows, int32 width; buffers = [batch, mean, (outputs) sums, workspace]
-void vnl_xla_obs_stats_partial(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 12) return;
+void vnl_xla_obs_stats_partial(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < 12) { vnl::xla_report(status, "vnl_xla_obs_stats_partial", -30); return; }
   long long rows;
   int32_t width;
   memcpy(&rows, opaque, 8);
   memcpy(&width, opaque + 8, 4);
-  if (width < 1 || width > MAX_WIDTH) return;
+  if (width < 1 || width > MAX_WIDTH) { vnl::xla_report(status, "vnl_xla_obs_stats_partial", -1); return; }
   cudaMemsetAsync(static_cast<float*>(b[3]) + (size_t)GRID * 2 * width, 0, 16, (cudaStream_t)stream);
-  vnl_obs_stats_partial((const float*)b[0], rows, width, (const float*)b[1], b[3], (float*)b[2], stream);
+  vnl::xla_report(status, "vnl_xla_obs_stats_partial",
+                  vnl_obs_stats_partial((const float*)b[0], rows, width, (const float*)b[1], b[3], (float*)b[2], stream));
 }
 // finish: opaque = int32 width, float std_min, float std_max; buffers = [sums, count, mean, summed_variance, std,
 //         (outputs) count', mean', summed_variance', std']
-void vnl_xla_obs_stats_finish(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 12) return;
+void vnl_xla_obs_stats_finish(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < 12) { vnl::xla_report(status, "vnl_xla_obs_stats_finish", -30); return; }
   int32_t width;
   float lo, hi;
   memcpy(&width, opaque, 4);
   memcpy(&lo, opaque + 4, 4);
   memcpy(&hi, opaque + 8, 4);
-  if (width < 1 || width > MAX_WIDTH) return;
+  if (width < 1 || width > MAX_WIDTH) { vnl::xla_report(status, "vnl_xla_obs_stats_finish", -1); return; }
   cudaStream_t st = (cudaStream_t)stream;
   cudaMemcpyAsync(b[5], b[1], sizeof(float), cudaMemcpyDeviceToDevice, st);
   for (int i = 0; i < 3; ++i) cudaMemcpyAsync(b[6 + i], b[2 + i], (size_t)width * sizeof(float), cudaMemcpyDeviceToDevice, st);
-  vnl_obs_stats_finish((const float*)b[0], width, (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[8], lo, hi, stream);
+  vnl::xla_report(status, "vnl_xla_obs_stats_finish",
+                  vnl_obs_stats_finish((const float*)b[0], width, (float*)b[5], (float*)b[6], (float*)b[7], (float*)b[8], lo, hi, stream));
 }
 
 }  // extern "C"

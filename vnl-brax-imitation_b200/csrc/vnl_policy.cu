@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include "../../include/vnl_policy.h"
+#include "vnl_xla_status.h"
 
 namespace {
 
@@ -832,15 +833,16 @@ int vnl_policy_debug(const void* blob_dev, const VnlPolicyDims* dims, int B, con
 // opaque = 9 little-endian int32: the VnlPolicyDims fields (traj, obs, latent, e1, e2, d1, d2, nu), then B.
 // buffers: [blob, traj, obs, obs_mean, obs_std, eps_z, eps_a, rand_action,
 //           (outputs) action, raw_action, logits, log_prob, rand_log_prob]
-void vnl_xla_policy_forward(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 9 * sizeof(int32_t)) return;
+void vnl_xla_policy_forward(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < 9 * sizeof(int32_t)) { vnl::xla_report(status, "vnl_xla_policy_forward", -30); return; }
   VnlPolicyDims d;
   int32_t B;
   memcpy(&d, opaque, sizeof(d));
   memcpy(&B, opaque + sizeof(d), sizeof(B));
-  vnl_policy_forward(b[0], &d, B, (const float*)b[1], (const float*)b[2], (const float*)b[3], (const float*)b[4],
-                     (const float*)b[5], (const float*)b[6], (const float*)b[7], (float*)b[8], (float*)b[9], (float*)b[10],
-                     (float*)b[11], (float*)b[12], nullptr, nullptr, stream);
+  const int rc = vnl_policy_forward(b[0], &d, B, (const float*)b[1], (const float*)b[2], (const float*)b[3], (const float*)b[4],
+                                    (const float*)b[5], (const float*)b[6], (const float*)b[7], (float*)b[8], (float*)b[9],
+                                    (float*)b[10], (float*)b[11], (float*)b[12], nullptr, nullptr, stream);
+  vnl::xla_report(status, "vnl_xla_policy_forward", rc);
 }
 
 }  // extern "C"

@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "../../include/vnl_ppo.h"
+#include "vnl_xla_status.h"
 
 namespace {
 
@@ -54,16 +55,16 @@ int vnl_gae(int T, int B, const float* truncation, const float* termination, con
   return -(int)cudaGetLastError();
 }
 
-void vnl_xla_gae(void* stream, void** b, const char* opaque, size_t opaque_len) {
-  if (opaque_len < 16) return;
+void vnl_xla_gae(void* stream, void** b, const char* opaque, size_t opaque_len, void* status) {
+  if (!b || !opaque || opaque_len < 16) { vnl::xla_report(status, "vnl_xla_gae", -30); return; }
   int32_t T, B;
   float lam, disc;
   memcpy(&T, opaque, 4);
   memcpy(&B, opaque + 4, 4);
   memcpy(&lam, opaque + 8, 4);
   memcpy(&disc, opaque + 12, 4);
-  vnl_gae(T, B, (const float*)b[0], (const float*)b[1], (const float*)b[2], (const float*)b[3], (const float*)b[4], lam, disc,
-          (float*)b[5], (float*)b[6], stream);
+  vnl::xla_report(status, "vnl_xla_gae", vnl_gae(T, B, (const float*)b[0], (const float*)b[1], (const float*)b[2], (const float*)b[3],
+                                                 (const float*)b[4], lam, disc, (float*)b[5], (float*)b[6], stream));
 }
 
 }  // extern "C"

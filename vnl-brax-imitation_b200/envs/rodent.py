@@ -59,7 +59,7 @@ def rodent_task_tables(model: mjcf.Model, reference_clip, *, end_eff_names, appe
     body_idxs = [model.body_id(n) for n in walker_body_names]
     joint_idxs = [model.jnt_id(n) for n in joint_names]
     bp = np.asarray(reference_clip.body_positions)
-    filtered = bp[:, body_idxs] if bp.shape[1] != len(body_idxs) else bp  # rodent.py:114
+    filtered = bp[..., body_idxs, :] if bp.shape[-2] != len(body_idxs) else bp  # rodent.py:114 (works on stacked clips too)
     clip = reference_clip.replace(body_positions=filtered)
     nj = model.nq - 7
     obs_size = model.nq + 2 * model.nv + 3 * len(end_eff_idx)
@@ -141,7 +141,7 @@ class RodentTracking:
         m = out["metrics"]
         metrics = {k: m[:, i] for i, k in enumerate(METRIC_KEYS)}
         info = dict(cur_frame=st["cur_frame"], sub_clip_frame=st["sub_clip_frame"], traj=out["traj"],
-                    termination_error=m[:, 6], solver_stats=out["stats"])
+                    termination_error=m[:, 6], solver_stats=out["stats"], clip_idx=st["clip_id"])
         return State(ps, out["obs"], out["reward"], out["done"], metrics, info)
 
     def reset(self, rng, batch_size: int = 1, start_frame=None) -> State:
@@ -161,7 +161,7 @@ class RodentTracking:
         qvel = np.hstack([rt.velocity[start_frame], rt.angular_velocity[start_frame], rt.joints_velocity[start_frame]]).astype(np.float32)
         return self.reset_from(qpos + noise, qvel, start_frame)
 
-    def reset_from(self, qpos, qvel, start_frame) -> State:
+    def reset_from(self, qpos, qvel, start_frame, clip_id=None) -> State:
         """Reset tail after the random draws: `pipeline_init` + traj / obs / termination error."""
         import torch
 
@@ -170,6 +170,8 @@ class RodentTracking:
         st_in = dict(qpos=torch.as_tensor(qpos, dtype=torch.float32, device=dev).contiguous(),
                      qvel=torch.as_tensor(qvel, dtype=torch.float32, device=dev).contiguous(),
                      cur_frame=torch.as_tensor(start_frame, dtype=torch.int32, device=dev).contiguous())
+        if clip_id is not None:
+            st_in["clip_id"] = torch.as_tensor(clip_id, dtype=torch.int32, device=dev).contiguous()
         st, out = self.engine.alloc_state(B), self.engine.alloc_outputs(B)
         self.engine.reset(st_in, st, out)
         return self._wrap(st, out)
@@ -183,7 +185,83 @@ class RodentTracking:
         st_in = dict(ps)
         st_in["cur_frame"] = state.info["cur_frame"]
         st_in["sub_clip_frame"] = state.info["sub_clip_frame"]
+        st_in["clip_id"] = state.info.get("clip_idx")
         action = torch.as_tensor(action, dtype=torch.float32, device=self.device).reshape(B, self.sys.nu).contiguous()
         st, out = self.engine.alloc_state(B), self.engine.alloc_outputs(B)
         self.engine.step(st_in, action, st, out)
         return self._wrap(st, out)
+
+
+def stack_clips(clips):
+    """[ReferenceClip] (equal lengths) -> one ReferenceClip whose fields carry a leading clip axis [nclips, T, ...]."""
+    from dataclasses import fields
+    out = {}
+    for f in fields(clipm.ReferenceClip):
+        vals = [getattr(c, f.name) for c in clips]
+        if all(v is not None for v in vals):
+            out[f.name] = np.stack([np.asarray(v) for v in vals])
+    return clipm.ReferenceClip(**out)
+
+
+class RodentMultiClipTracking(RodentTracking):
+    """The env the reference only stubs (`envs/rodent.py:473-475`): `RodentTracking` over a SET of clips.  The clip tables
+    are stacked `[nclips, T, ...]` in one task blob (VNL_TH_NCLIPS); every env carries `info["clip_idx"]` (VnlState.clip_id),
+    drawn uniformly at reset; everything else (`step`, rewards, termination, quirks) is `RodentTracking` on that env's
+    clip, in the same fused launch.  `reference_clips`: a list of ReferenceClip of equal length, or one already stacked."""
+
+    def __init__(self, reference_clips=None, **kw):
+        if isinstance(reference_clips, (list, tuple)):
+            reference_clips = stack_clips(reference_clips)
+        super().__init__(reference_clip=reference_clips, **kw)
+        self.nclips = int(np.asarray(self._ref_traj.position).shape[0])
+
+    def reset(self, rng, batch_size: int = 1, start_frame=None, clip_id=None) -> State:
+        if not isinstance(rng, np.random.Generator):
+            rng = np.random.default_rng(rng)
+        B = int(batch_size)
+        if clip_id is None:
+            clip_id = rng.integers(0, self.nclips, size=B)
+        clip_id = np.asarray(clip_id, dtype=np.int32).reshape(B)
+        hi = self._clip_length - self._sub_clip_length - self._ref_traj_length
+        if start_frame is None:
+            start_frame = rng.integers(0, hi, size=B)
+        start_frame = np.asarray(start_frame, dtype=np.int32).reshape(B)
+        noise = (self._reset_noise_scale * rng.standard_normal((B, self.sys.nq))).astype(np.float32)
+        rt = self._ref_traj
+        g = lambda a: np.asarray(a)[clip_id, start_frame]
+        qpos = np.hstack([g(rt.position), g(rt.quaternion), g(rt.joints)]).astype(np.float32)
+        qvel = np.hstack([g(rt.velocity), g(rt.angular_velocity), g(rt.joints_velocity)]).astype(np.float32)
+        return self.reset_from(qpos + noise, qvel, start_frame, clip_id)
+
+
+def process_clips_gpu(model: mjcf.Model, mocap_qpos, max_qvel: float = 20.0, dt: float = 0.02, device: str = "cuda:0"):
+    """`process_clip` (`preprocessing/mjx_preprocess.py:43-107`) for a stack of clips `[nclips, T, nq]` (or one `[T, nq]`)
+    on the GPU: `vnl_process_clip` = the env kernel's kinematics pass per frame + the finite-difference velocity kernel.
+    Returns a ReferenceClip with a leading clip axis (squeezed for a single 2-D input)."""
+    import ctypes
+
+    import torch
+
+    from .._lib import Engine
+    q = np.asarray(mocap_qpos, dtype=np.float32)
+    single = q.ndim == 2
+    if single:
+        q = q[None]
+    n, T, nq = q.shape
+    eng = Engine(mb.build_model_blob(model), None, device=device)
+    dev = eng.device
+    qd = torch.as_tensor(q, device=dev).contiguous()
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    qo, bp, bq, qv = f(n, T, nq), f(n, T, model.nbody, 3), f(n, T, model.nbody, 4), f(n, T, nq - 1)
+    with torch.cuda.device(dev):
+        rc = eng.lib.vnl_process_clip(ctypes.byref(eng.ctx), eng.model_dev.data_ptr(), n, T, qd.data_ptr(), float(dt), float(max_qvel),
+                                      qo.data_ptr(), bp.data_ptr(), bq.data_ptr(), qv.data_ptr(), eng._stream())
+    if rc:
+        raise RuntimeError(f"vnl_process_clip failed ({rc})")
+    torch.cuda.synchronize(dev)
+    qo, bp, bq, qv = (x.cpu().numpy() for x in (qo, bp, bq, qv))
+    sq = (lambda a: a[0]) if single else (lambda a: a)
+    c = np.ascontiguousarray
+    return clipm.ReferenceClip(position=c(sq(qo[..., :3])), quaternion=c(sq(qo[..., 3:7])), joints=c(sq(qo[..., 7:])),
+                               body_positions=c(sq(bp)), velocity=c(sq(qv[..., :3])), joints_velocity=c(sq(qv[..., 6:])),
+                               angular_velocity=c(sq(qv[..., 3:6])), body_quaternions=c(sq(bq)))

@@ -451,7 +451,17 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
     MODEL body ids and relies on JAX clamping out-of-range gathers; the
     clamped indices are baked here so kernels only gather."""
     ntrack = len(body_idxs)
+    # multi-clip tables (SURVEY 8 row f4): fields with a leading clip axis [nclips, T, ...] are stored clip-major, flattened
+    # to [nclips * T, ...]; the kernel offsets every row by clip_id * T
+    nclips = 1
+    if np.asarray(clip.position).ndim == 3:
+        nclips = int(np.asarray(clip.position).shape[0])
+        flat = lambda a: None if a is None else np.asarray(a).reshape((-1,) + np.asarray(a).shape[2:])
+        clip = clip.replace(**{k: flat(getattr(clip, k)) for k in ("position", "quaternion", "joints", "body_positions", "velocity",
+                                                                  "angular_velocity", "joints_velocity", "body_quaternions",
+                                                                  "center_of_mass") if getattr(clip, k, None) is not None})
     w = _BlobWriter(C["VNL_MAGIC_TASK"], C["VNL_TASK_COUNT"])
+    w.set_i("VNL_TH_NCLIPS", nclips)
     w.set_i("VNL_TH_KIND", kind)
     w.set_i("VNL_TH_REWARD_OLD_STATE", int(reward_old_state))
     w.set_i("VNL_TH_TERM_MEAN", int(term_mean))
@@ -465,7 +475,7 @@ def build_task_blob(clip, *, body_idxs, end_eff_idx, app_idx, joint_idxs, com_id
     w.set_i("VNL_TH_METRICS_RAW", int(metrics_raw))
     for slot, v in zip(("RCOM", "RVEL", "RTRUNK", "RQUAT", "RACT", "RAPP"), weights):
         w.set_f("VNL_TH_W_" + slot, v)
-    w.set_i("VNL_TH_CLIP_LEN", clip.position.shape[0])
+    w.set_i("VNL_TH_CLIP_LEN", clip.position.shape[0] // nclips)
     w.set_i("VNL_TH_REF_LEN", ref_traj_length)
     w.set_i("VNL_TH_SUB_CLIP_LEN", sub_clip_length)
     w.set_i("VNL_TH_NTRACK", ntrack)

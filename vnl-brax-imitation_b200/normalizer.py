@@ -27,7 +27,7 @@ def _bind(lib):
     lib.vnl_obs_stats_partial.argtypes = [v, ctypes.c_longlong, ctypes.c_int, v, v, v, v]
     lib.vnl_obs_stats_finish.argtypes = [v, ctypes.c_int, v, v, v, v, ctypes.c_float, ctypes.c_float, v]
     for n in ("vnl_xla_obs_stats_partial", "vnl_xla_obs_stats_finish"):
-        getattr(lib, n).argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t]
+        getattr(lib, n).argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t, v]
         getattr(lib, n).restype = None
     return lib
 

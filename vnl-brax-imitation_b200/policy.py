@@ -48,7 +48,7 @@ def _bind(lib):
     lib.vnl_policy_pack.argtypes = [P, ctypes.POINTER(v), v, ctypes.c_size_t]
     lib.vnl_policy_forward.argtypes = [v, P, ctypes.c_int] + [v] * 15
     lib.vnl_policy_debug.argtypes = [v, P, ctypes.c_int, v, v, v, v, v, ctypes.c_int, v, v]
-    lib.vnl_xla_policy_forward.argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t]
+    lib.vnl_xla_policy_forward.argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t, v]
     lib.vnl_xla_policy_forward.restype = None
     return lib
 
@@ -119,13 +119,42 @@ class IntentionPolicy:
         if rc:
             raise RuntimeError(f"vnl_policy_pack failed ({rc})")
         self.blob_host = host
-        self.blob_dev = self.torch.from_numpy(host).to(self.device)
+        # The device blob keeps ONE address for the life of the policy: `rollout.Rollout` captures `blob_dev.data_ptr()` into
+        # its CUDA graph, so a re-upload after a PPO update must land in the same buffer (stream-ordered copy).
+        if getattr(self, "blob_dev", None) is None:
+            self.blob_dev = self.torch.from_numpy(host).to(self.device)
+        else:
+            self.blob_dev.copy_(self.torch.from_numpy(host), non_blocking=False)
 
     def set_normalizer(self, mean, std) -> None:
         """brax running_statistics.normalize parameters for obs (ppo_imitation/train.py:220-229); None = identity."""
         t = self.torch
-        self.obs_mean = None if mean is None else t.as_tensor(mean, dtype=t.float32, device=self.device).contiguous()
-        self.obs_std = None if std is None else t.as_tensor(std, dtype=t.float32, device=self.device).contiguous()
+        # like the blob, the mean / std operands keep their device addresses once they exist (captured by CUDA graphs);
+        # switching between identity (None) and a real normaliser after a capture is refused instead of silently ignored
+        for name, val in (("obs_mean", mean), ("obs_std", std)):
+            cur = getattr(self, name, None)
+            if val is None:
+                if cur is not None and getattr(self, "_norm_pinned", False):
+                    raise ValueError("the normaliser operands were captured; pass tensors (e.g. zeros / ones), not None")
+                setattr(self, name, None)
+                continue
+            src = t.as_tensor(val, dtype=t.float32)
+            if cur is None:
+                if getattr(self, "_norm_pinned", False):
+                    raise ValueError("the policy was captured without a normaliser; build it with obs_mean / obs_std instead")
+                # a contiguous fp32 tensor already on the device is ADOPTED (shared with e.g. normalizer.RunningStatistics,
+                # whose in-place updates then reach the next launch); anything else is uploaded once
+                setattr(self, name, src.to(self.device).contiguous())
+            elif isinstance(val, t.Tensor) and val.data_ptr() == cur.data_ptr():
+                pass  # the shared tensor itself
+            else:
+                if tuple(src.shape) != tuple(cur.shape):
+                    raise ValueError("normaliser shape changed")
+                cur.copy_(src)
+
+    def pin_operands(self) -> None:
+        """Called by a capturer (rollout.Rollout) once the operand addresses are baked into a CUDA graph."""
+        self._norm_pinned = True
 
     def alloc_outputs(self, B: int, heads: bool = False):
         t, nu = self.torch, self.action_size

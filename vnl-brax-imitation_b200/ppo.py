@@ -14,7 +14,7 @@ _LIB = None
 def _bind(lib):
     v = ctypes.c_void_p
     lib.vnl_gae.argtypes = [ctypes.c_int, ctypes.c_int, v, v, v, v, v, ctypes.c_float, ctypes.c_float, v, v, v]
-    lib.vnl_xla_gae.argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t]
+    lib.vnl_xla_gae.argtypes = [v, ctypes.POINTER(v), ctypes.c_char_p, ctypes.c_size_t, v]
     lib.vnl_xla_gae.restype = None
     return lib
 

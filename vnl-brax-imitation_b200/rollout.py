@@ -39,6 +39,8 @@ class Rollout:
         # env state ping-pong + episode counters of EpisodeWrapper / AutoResetWrapper
         self.state = [dict({k: v.clone() for k, v in self.first.items()}, cur_frame=first_state.info["cur_frame"].clone(),
                            sub_clip_frame=first_state.info["sub_clip_frame"].clone()), self.eng.alloc_state(B)]
+        if first_state.info.get("clip_idx") is not None:  # multi-clip env: every env keeps tracking its own clip
+            self.state[0]["clip_id"] = first_state.info["clip_idx"].clone()
         self.cur = 0
         self.steps, self.done_prev = f(B), f(B)
         # transition buffers (time-major, like `data` after the swapaxes of intention_losses.py:133)
@@ -103,6 +105,14 @@ class Rollout:
                 with t.cuda.graph(self.graph):
                     self._enqueue()
                 self._restore(snap)
+                # the graph holds the policy's operand addresses: `load_params` / `set_normalizer` copy into them from now on
+                self._captured = (self.policy.blob_dev.data_ptr(), None if self.policy.obs_mean is None else self.policy.obs_mean.data_ptr(),
+                                  None if self.policy.obs_std is None else self.policy.obs_std.data_ptr())
+                self.policy.pin_operands()
+            now = (self.policy.blob_dev.data_ptr(), None if self.policy.obs_mean is None else self.policy.obs_mean.data_ptr(),
+                   None if self.policy.obs_std is None else self.policy.obs_std.data_ptr())
+            if now != self._captured:  # someone swapped a tensor behind the policy's back: never replay stale addresses
+                raise RuntimeError("policy operands moved after the rollout graph was captured")
             self.graph.replay()
         self.launches += 2 * self.T
         return {"observation": self.obs[:self.T], "next_observation": self.obs[1:], "action": self.action, "reward": self.reward,
