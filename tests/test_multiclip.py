@@ -54,16 +54,27 @@ def test_multiclip_step_equals_single_clip_step_of_each_envs_clip(rodent, oracle
     assert multi.nclips == 4
     B = 96
     rng = np.random.default_rng(5)
-    s = multi.reset(rng, batch_size=B)
-    clip_id = s.info["clip_idx"].cpu().numpy()
-    assert set(clip_id.tolist()) == {0, 1, 2, 3}
+    # the draws of RodentMultiClipTracking.reset, done here so that the single-clip envs see the very same raw inputs
+    clip_id = rng.integers(0, 4, size=B).astype(np.int32)
+    start = rng.integers(0, 235, size=B).astype(np.int32)
+    rt = multi._ref_traj
+    g = lambda a: np.asarray(a)[clip_id, start]
+    qpos = np.hstack([g(rt.position), g(rt.quaternion), g(rt.joints)]).astype(np.float32)
+    qpos += (1e-3 * rng.standard_normal(qpos.shape)).astype(np.float32)
+    qvel = np.hstack([g(rt.velocity), g(rt.angular_velocity), g(rt.joints_velocity)]).astype(np.float32)
+    s = multi.reset_from(qpos, qvel, start, clip_id)
+    assert np.array_equal(s.info["clip_idx"].cpu().numpy(), clip_id) and set(clip_id.tolist()) == {0, 1, 2, 3}
+    s2 = multi.reset(np.random.default_rng(6), batch_size=B)  # the public reset draws clips itself
+    assert s2.info["clip_idx"].min() >= 0 and s2.info["clip_idx"].max() <= 3 and torch.isfinite(s2.obs).all()
     singles = [envs.RodentTracking(reference_clip=c, model=rodent["model"], device="cuda:0", **rod.RODENT_ENV_ARGS) for c in clips]
     acts = torch.tensor(rng.uniform(-1, 1, size=(3, B, 30)).astype(np.float32), device="cuda")
     # reset parity: the multi-clip reset equals each clip's own reset from the same qpos / qvel / frame
     for c in range(4):
-        m = torch.tensor(np.nonzero(clip_id == c)[0], device="cuda")
-        one = singles[c].reset_from(s.pipeline_state["qpos"][m].clone(), s.pipeline_state["qvel"][m].clone(), s.info["cur_frame"][m].clone())
-        assert torch.equal(one.obs, s.obs[m]) and torch.equal(one.info["traj"], s.info["traj"][m])
+        mi = np.nonzero(clip_id == c)[0]
+        m = torch.tensor(mi, device="cuda")
+        one = singles[c].reset_from(qpos[mi], qvel[mi], start[mi])
+        assert torch.equal(one.obs, s.obs[m])
+        assert torch.equal(one.info["traj"], s.info["traj"][m])
         assert torch.equal(one.metrics["termination_error"], s.metrics["termination_error"][m])
     st = s
     for t in range(3):
