@@ -1,0 +1,386 @@
+"""Pins for the parts of the dynamics oracle that CAN be pinned without MuJoCo / MJX in the image (VERDICT r1, next-round
+item 1).  The reference's arithmetic lives in mujoco-mjx, which is not installable here, so dynamics
+parity stays "unpinned" against the real thing; what is pinned here is everything that has an independent answer:
+
+  (a) compile constants the kernel and the oracle SHARE (both consume the blob built by mjcf.py, so kernel-vs-oracle tests
+      cannot see an error in them): geom volumes / inertias against numerical quadrature, the principal-axes body inertia
+      against the summed geom tensors, `dof_invweight0` / `body_invweight0` / `meaninertia` against their definition
+      evaluated with the ORACLE's composite-rigid-body M and cdof (a different code path from mjcf.mass_matrix), and the
+      contact-parameter mixing of the rodent's floor pairs against the values written in rodent.xml;
+  (b) closed forms of MuJoCo's soft-constraint model (Computation chapter: `aref = -b v - k imp r`, `R = (1 - imp) / imp *
+      invweight`, pyramidal invweight, impedance curve) that pin `_kbi`, the impedance, `efc_D`, `aref`, the pyramid
+      and the integrator end to end: a sphere at rest on a plane (equilibrium penetration, and the whole transient against a
+      scalar recurrence of the same semi-implicit Euler step: critically damped with time constant solref[0]), a hinge
+      pendulum (period), and a limited hinge pressed into its stop by gravity (equilibrium violation).
+"""
+import math
+import xml.etree.ElementTree as ET
+
+import numpy as np
+import pytest
+
+from conftest import pkg
+
+mjcf = pkg("mjcf")
+mb = pkg("model_blob")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (a) compile constants
+# ---------------------------------------------------------------------------------------------------------------------
+def _inside(gtype, size, p):
+    x, y, z = p[:, 0], p[:, 1], p[:, 2]
+    if gtype == mjcf.GEOM_SPHERE:
+        return x * x + y * y + z * z <= size[0] ** 2
+    if gtype == mjcf.GEOM_CAPSULE:
+        r, h = size[0], size[1]
+        zc = np.clip(z, -h, h)
+        return x * x + y * y + (z - zc) ** 2 <= r * r
+    if gtype == mjcf.GEOM_ELLIPSOID:
+        return (x / size[0]) ** 2 + (y / size[1]) ** 2 + (z / size[2]) ** 2 <= 1.0
+    if gtype == mjcf.GEOM_BOX:
+        return (np.abs(x) <= size[0]) & (np.abs(y) <= size[1]) & (np.abs(z) <= size[2])
+    if gtype == mjcf.GEOM_CYLINDER:
+        return (x * x + y * y <= size[0] ** 2) & (np.abs(z) <= size[1])
+    raise ValueError(gtype)
+
+
+def _quadrature(gtype, size, n=120):
+    """Midpoint-rule volume and diagonal inertia (unit density, geom frame) on an n^3 grid of the bounding box."""
+    if gtype in (mjcf.GEOM_SPHERE,):
+        half = np.array([size[0]] * 3)
+    elif gtype == mjcf.GEOM_CAPSULE:
+        half = np.array([size[0], size[0], size[1] + size[0]])
+    elif gtype == mjcf.GEOM_CYLINDER:
+        half = np.array([size[0], size[0], size[1]])
+    else:
+        half = np.array(size[:3], dtype=float)
+    ax = [(np.arange(n) + 0.5) / n * 2 * h - h for h in half]
+    g = np.stack(np.meshgrid(*ax, indexing="ij"), -1).reshape(-1, 3)
+    inside = _inside(gtype, size, g)
+    dv = np.prod(2 * half / n)
+    p = g[inside]
+    vol = inside.sum() * dv
+    inertia = np.array([(p[:, 1] ** 2 + p[:, 2] ** 2).sum(), (p[:, 0] ** 2 + p[:, 2] ** 2).sum(), (p[:, 0] ** 2 + p[:, 1] ** 2).sum()]) * dv
+    return vol, inertia
+
+
+@pytest.mark.parametrize("gtype,size", [("GEOM_SPHERE", (0.03, 0, 0)), ("GEOM_CAPSULE", (0.012, 0.04, 0)), ("GEOM_CAPSULE", (0.03, 0.005, 0)),
+                                        ("GEOM_ELLIPSOID", (0.02, 0.035, 0.011)), ("GEOM_BOX", (0.02, 0.03, 0.01)),
+                                        ("GEOM_CYLINDER", (0.02, 0.05, 0))])
+def test_geom_volume_and_inertia_against_quadrature(gtype, size):
+    """mjcf._geom_volume_inertia (mjCGeom::GetVolume / SetInertia) against brute-force integration of the solid."""
+    t = getattr(mjcf, gtype)
+    v, i = mjcf._geom_volume_inertia(t, np.array(size, dtype=float))
+    qv, qi = _quadrature(t, size)
+    assert abs(v - qv) / qv < 4e-3, (v, qv)
+    assert np.abs(i - qi).max() / qi.max() < 6e-3, (i, qi)
+
+
+def test_body_inertia_is_the_principal_frame_of_the_summed_geom_tensors(rodent):
+    """body_mass / body_ipos / body_iquat / body_inertia of every rodent body that carries mass: the full tensor
+    R(iquat) diag(inertia) R^T about ipos must equal the sum over the body's geoms of their (quadrature-checked) tensors
+    moved to the body COM by the parallel-axis theorem; masses add; the COM is the mass-weighted mean."""
+    m = rodent["model"]
+    A = m.arrays
+    checked = 0
+    for b in range(1, m.nbody):
+        gs = [g for g in range(m.ngeom) if A["geom_bodyid"][g] == b and A["geom_mass"][g] > 0]
+        if not gs or A["body_mass"][b] <= 0:
+            continue
+        ms = A["geom_mass"][gs]
+        assert abs(ms.sum() - A["body_mass"][b]) <= 1e-12 * A["body_mass"][b], b
+        coms = A["geom_pos"][gs]
+        com = (ms[:, None] * coms).sum(0) / ms.sum()
+        assert np.abs(com - A["body_ipos"][b]).max() < 1e-12, b
+        I = np.zeros((3, 3))
+        for g, mg, cg in zip(gs, ms, coms):
+            v, iu = mjcf._geom_volume_inertia(int(A["geom_type"][g]), A["geom_size"][g])
+            R = mjcf.quat_to_mat(A["geom_quat"][g])
+            d = cg - com
+            I += (mg / v) * (R @ np.diag(iu) @ R.T) + mg * (d @ d * np.eye(3) - np.outer(d, d))
+        Rb = mjcf.quat_to_mat(A["body_iquat"][b])
+        assert abs(np.linalg.det(Rb) - 1) < 1e-9 and abs(np.linalg.norm(A["body_iquat"][b]) - 1) < 1e-12
+        got = Rb @ np.diag(A["body_inertia"][b]) @ Rb.T
+        assert np.abs(got - I).max() <= 1e-9 * np.abs(I).max(), b
+        assert np.all(np.diff(A["body_inertia"][b]) <= 1e-18)  # mju_eig3 orders the principal moments descending
+        # a physical inertia tensor: positive, triangle inequality
+        w = A["body_inertia"][b]
+        assert w[2] > 0 and w[1] + w[2] >= w[0] * (1 - 1e-9)
+        checked += 1
+    assert checked >= 50
+    assert abs(A["body_mass"].sum() - 0.186791) < 2e-6  # the whole-body mass the reference clip's COM pins
+
+
+def test_invweights_and_meaninertia_from_the_oracles_crb_inertia(rodent, oracle_mod):
+    """mj_setConst: dof_invweight0 = diag(M^-1) (free-joint translations / rotations averaged), body_invweight0 = mean diagonal
+    of the translational / rotational blocks of J M^-1 J^T at the body COM, stat.meaninertia = mean diag(M), all at qpos0.
+    M and J come from the ORACLE's forward pass (composite rigid body algorithm; cdof about the subtree COM) -- not from
+    mjcf.mass_matrix / body_jacobian, which produced the blob's values."""
+    m = rodent["model"]
+    A = m.arrays
+    qpos0 = A["qpos0"].copy()
+    st = dict(qpos=qpos0[None], qvel=np.zeros((1, m.nv)), act=np.zeros((1, m.na)), qacc_warmstart=np.zeros((1, m.nv)))
+    d = oracle_mod.forward_dump(rodent["model_blob"], st, None, precision=64, dims=rodent["dims"])
+    M = d["qM"][0]
+    assert np.abs(M - M.T).max() < 1e-15
+    Minv = np.linalg.inv(M)
+    # the oracle reads the blob's fp32 constants, mjcf.py computed in float64: agreement to fp32 rounding of the inputs
+    assert abs(M.diagonal().mean() - m.meaninertia) <= 1e-7 * m.meaninertia
+    dinv = Minv.diagonal().copy()
+    dinv[0:3] = dinv[0:3].mean(); dinv[3:6] = dinv[3:6].mean()
+    rel = np.abs(dinv - A["dof_invweight0"]) / np.abs(dinv)
+    assert rel.max() < 2e-5, rel.max()
+    cdof, com, xipos = d["cdof"][0], d["subtree_com"][0][1], d["xipos"][0]
+    dof_body = A["dof_bodyid"]
+    parent = A["body_parentid"]
+    for b in range(1, m.nbody):
+        anc = set()
+        bb = b
+        while bb != 0:
+            anc.add(bb); bb = parent[bb]
+        cols = [i for i in range(m.nv) if dof_body[i] in anc]
+        jr = np.zeros((3, m.nv)); jp_ = np.zeros((3, m.nv))
+        for i in cols:  # spatial motion axis about the subtree COM -> point velocity at the body COM
+            jr[:, i] = cdof[i, :3]
+            jp_[:, i] = cdof[i, 3:] + np.cross(cdof[i, :3], xipos[b] - com)
+        t = np.trace(jp_ @ Minv @ jp_.T) / 3.0
+        r = np.trace(jr @ Minv @ jr.T) / 3.0
+        assert abs(t - A["body_invweight0"][b][0]) <= 2e-5 * t and abs(r - A["body_invweight0"][b][1]) <= 2e-5 * r, (b, t, r, A["body_invweight0"][b])
+
+
+def _xml_geom_params(root):
+    """A minimal, independent resolver of MJCF geom defaults (nested <default> classes, childclass inheritance) for the three
+    attributes the contact mixing reads.  Not mjcf._Defaults."""
+    parent, attrs = {}, {}
+
+    def walk(d, par):
+        name = d.get("class", "main")
+        parent[name] = par
+        g = d.find("geom")
+        attrs[name] = dict(g.attrib) if g is not None else {}
+        for c in d.findall("default"):
+            walk(c, name)
+    walk(root.find("default"), None)
+
+    def resolve(cls, key, default):
+        while cls is not None:
+            if key in attrs[cls]:
+                return attrs[cls][key]
+            cls = parent[cls]
+        return default
+    out = {}
+
+    def body(el, childclass):
+        cc = el.get("childclass", childclass)
+        for g in el.findall("geom"):
+            cls = g.get("class", cc or "main")
+            get = lambda k, dflt: g.get(k) if g.get(k) is not None else resolve(cls, k, dflt)
+            fr = [float(x) for x in get("friction", "1 0.005 0.0001").split()]
+            out[g.get("name")] = dict(priority=int(get("priority", "0")), friction=fr + [1.0, 0.005, 0.0001][len(fr):],
+                                      solref=[float(x) for x in get("solref", "0.02 1").split()], solmix=float(get("solmix", "1")))
+        for b in el.findall("body"):
+            body(b, cc)
+    body(root.find("worldbody"), None)
+    return out
+
+
+def test_contact_parameter_mixing_of_the_rodent_floor_pairs(rodent):
+    """rodent.xml:20-44: every geom inherits friction 0.7 / solref (0.005, 1); the paw classes add priority 1 and friction 1.5;
+    the floor (class collision_floor) keeps priority 0.  mj_contactParam / mjCPair::Compile: the higher priority wins outright,
+    equal priority -> element-wise max friction and solmix-weighted solref.  The expectation is re-derived from the XML with
+    an independent default resolver and compared with the compiled pair tables the kernel and the oracle consume."""
+    import os
+    m = rodent["model"]
+    A = m.arrays
+    n = len(A["pair_geom1"])
+    assert n == 32  # 27 capsules + 5 ellipsoids against the floor
+    assert set(A["pair_type"].tolist()) == {mjcf.GEOM_CAPSULE, mjcf.GEOM_ELLIPSOID}
+    assert np.all(A["geom_type"][A["pair_geom1"]] == mjcf.GEOM_PLANE)
+    fr = A["pair_friction"]
+    assert np.array_equal(fr[:, 0], fr[:, 1]) and np.array_equal(fr[:, 3], fr[:, 4])  # [slide, slide, spin, roll, roll]
+    # the numbers written in the file: one solref everywhere, default solimp, friction 0.7 (default) or 1.5 (paw classes)
+    assert np.allclose(A["pair_solref"], [0.005, 1.0]) and np.allclose(A["pair_solimp"], [0.9, 0.95, 0.001, 0.5, 2.0])
+    assert set(np.round(fr[:, 0], 9).tolist()) <= {0.7, 1.5} and np.allclose(fr[:, 2], 0.005) and np.allclose(fr[:, 3], 0.0001)
+    assert np.allclose(A["pair_includemargin"], 0.0)
+    path = os.path.join("/root/reference", "assets", "rodent.xml")
+    if not os.path.exists(path):
+        pytest.skip("reference checkout absent (GPU box): the XML-derived expectation needs rodent.xml")
+    prm = _xml_geom_params(ET.parse(path).getroot())
+    npaw = 0
+    for p in range(n):
+        a, b = prm[m.geom_names[A["pair_geom1"][p]]], prm[m.geom_names[A["pair_geom2"][p]]]
+        if a["priority"] != b["priority"]:
+            w = a if a["priority"] > b["priority"] else b
+            want_fr, want_sr = w["friction"], w["solref"]
+            npaw += 1
+        else:
+            want_fr = np.maximum(a["friction"], b["friction"])
+            mix = a["solmix"] / (a["solmix"] + b["solmix"])
+            want_sr = mix * np.array(a["solref"]) + (1 - mix) * np.array(b["solref"])
+        assert np.allclose(fr[p, [0, 2, 3]], want_fr) and np.allclose(A["pair_solref"][p], want_sr), p
+        assert np.allclose(A["geom_friction"][A["pair_geom2"][p]], b["friction"])
+    assert npaw == int((fr[:, 0] == 1.5).sum()) and npaw >= 4
+
+
+def test_mix_params_rules():
+    """mj_contactParam rules one by one on hand-made geoms: priority wins outright; equal priority -> max friction, max condim,
+    solmix-weighted solref / solimp, minimum solref when one is non-positive (direct stiffness / damping form)."""
+    base = dict(priority=0, condim=3, friction=np.array([1.0, 0.005, 0.0001]), solref=np.array([0.02, 1.0]),
+                solimp=np.array([0.9, 0.95, 0.001, 0.5, 2.0]), solmix=1.0, margin=0.0, gap=0.0)
+    g1 = dict(base, friction=np.array([0.7, 0.01, 0.0002]), solref=np.array([0.01, 1.0]), solmix=3.0, margin=0.002)
+    g2 = dict(base, friction=np.array([0.9, 0.002, 0.0001]), solref=np.array([0.03, 0.5]), solmix=1.0, gap=0.001)
+    condim, fr5, solref, solimp, margin, gap = mjcf._mix_params(g1, g2)
+    assert condim == 3 and np.allclose(fr5, [0.9, 0.9, 0.01, 0.0002, 0.0002])
+    assert np.allclose(solref, 0.75 * np.array([0.01, 1.0]) + 0.25 * np.array([0.03, 0.5])) and margin == 0.002 and gap == 0.001
+    hi = dict(g2, priority=1)
+    _, fr5, solref, _, _, _ = mjcf._mix_params(g1, hi)
+    assert np.allclose(fr5, [0.9, 0.9, 0.002, 0.0001, 0.0001]) and np.allclose(solref, [0.03, 0.5])
+    neg = dict(g2, solref=np.array([-1000.0, -10.0]))
+    _, _, solref, _, _, _ = mjcf._mix_params(g1, neg)
+    assert np.allclose(solref, [-1000.0, -10.0])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# (b) closed forms of the soft-constraint model
+# ---------------------------------------------------------------------------------------------------------------------
+def _impedance(solimp, r):
+    dmin, dmax, width, mid, power = solimp
+    x = abs(r) / width
+    if x >= 1.0:
+        return dmax
+    y = x ** power / mid ** (power - 1) if x < mid else 1.0 - (1.0 - x) ** power / (1.0 - mid) ** (power - 1)
+    return dmin + y * (dmax - dmin)
+
+
+def _kb(solref, solimp, dt):
+    tc, dr = max(solref[0], 2 * dt), solref[1]
+    dmax = solimp[1]
+    return 1.0 / (dmax * dmax * tc * tc * dr * dr), 2.0 / (dmax * tc)
+
+
+def _run(oracle_mod, model, qpos, qvel, nsteps, chunks=1, precision=64, ctrl=None):
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    st = dict(qpos=np.array([qpos], dtype=np.float64), qvel=np.array([qvel], dtype=np.float64), act=np.zeros((1, model.na)),
+              qacc_warmstart=np.zeros((1, model.nv)))
+    traj = []
+    for _ in range(chunks):
+        st, _ = oracle_mod.pipeline_step(blob, st, ctrl, nsteps, precision=precision, dims=dims)
+        traj.append((st["qpos"][0].copy(), st["qvel"][0].copy()))
+    return traj
+
+
+BALL = '''<mujoco model="ball"><option timestep="0.002"/>
+<worldbody><geom name="floor" type="plane" size="5 5 .1" friction="{mu} 0.005 0.0001"/>
+<body name="ball" pos="0 0 0.1"><freejoint/><geom name="g" type="sphere" size="0.05" density="{rho}" friction="{mu} 0.005 0.0001"
+ solref="{tc} {dr}"/></body></worldbody></mujoco>'''
+
+
+@pytest.mark.parametrize("mu,rho,tc,dr", [(1.0, 1000.0, 0.02, 1.0), (0.6, 400.0, 0.01, 1.0), (1.3, 2500.0, 0.03, 0.7)])
+def test_sphere_on_plane_equilibrium_and_transient(oracle_mod, mu, rho, tc, dr):
+    """A free sphere released at rest, touching the floor.  Four pyramid rows with normal Jacobian entry 1: per row
+    f = D (aref - a_n),  D = imp / ((1 - imp) w),  w = (1/m)(1 + mu^2) 2 mu^2 / impratio,  aref = -b v - k imp r.
+    Vertical dynamics: m a = -m g + 4 f  =>  a = (-g + c aref) / (1 + c),  c = 4 D / m.   (i) fixed point: 4 D k imp |r| = m g;
+    (ii) the whole transient equals the scalar recurrence  v += dt a;  z += dt v  (semi-implicit Euler) with the impedance
+    re-evaluated every step -- for mu = 1 that is the critically damped oscillator with time constant solref[0]."""
+    model = mjcf.compile_model(ET.fromstring(BALL.format(mu=mu, rho=rho, tc=tc, dr=dr)), solver="cg", iterations=100, ls_iterations=50)
+    A = model.arrays
+    mass = A["body_mass"][1]
+    assert abs(mass - rho * 4 / 3 * math.pi * 0.05 ** 3) < 1e-12 and abs(A["body_invweight0"][1][0] - 1 / mass) < 1e-9 / mass
+    solimp = A["pair_solimp"][0]
+    solref = 0.5 * (np.array([tc, dr]) + np.array([0.02, 1.0]))  # equal solmix: the floor's default solref mixes in
+    assert np.allclose(A["pair_solref"][0], solref) and np.allclose(A["pair_friction"][0][:2], mu)
+    dt, g = model.timestep, 9.81
+    k, b = _kb(solref, solimp, dt)
+    w = (1 / mass) * (1 + mu * mu) * 2 * mu * mu / model.impratio
+
+    def accel(r, v):  # r = signed distance (negative in penetration)
+        if r >= 0:
+            return -g
+        imp = _impedance(solimp, r)
+        c = 4 * (imp / ((1 - imp) * w)) / mass
+        a = (-g + c * (-b * v - k * imp * r)) / (1 + c)
+        return a if (a - (-b * v - k * imp * r)) < 0 else -g  # rows only push
+
+    # (ii) transient: 600 steps, compare every 20th state
+    z, v = -1e-4, 0.0
+    rec = []
+    for i in range(600):
+        v += dt * accel(z, v)
+        z += dt * v
+        if (i + 1) % 20 == 0:
+            rec.append((z, v))
+    traj = _run(oracle_mod, model, [0, 0, 0.05 - 1e-4, 1, 0, 0, 0], np.zeros(6), 20, chunks=30)
+    for (qz, qv), (rz, rv) in zip(traj, rec):
+        assert abs((qz[2] - 0.05) - rz) < 2e-9 and abs(qv[2] - rv) < 2e-7, ((qz[2] - 0.05, rz), (qv[2], rv))
+        assert np.abs(qz[:2]).max() < 1e-12 and np.abs(qv[[0, 1, 3, 4, 5]]).max() < 1e-10  # the tangential pyramid parts cancel
+    # (i) fixed point after 1.2 s (60 time constants): 4 D k imp |r| = m g with imp = imp(|r|); what is left is the solver's
+    # stopping tolerance (1e-8 x meaninertia x nv on cost improvement / gradient)
+    r_eq = traj[-1][0][2] - 0.05
+    imp = _impedance(solimp, r_eq)
+    lhs = 4 * (imp / ((1 - imp) * w)) * k * imp * abs(r_eq)
+    assert r_eq < 0 and abs(lhs - mass * g) < 2e-5 * mass * g
+    if mu == 1.0:  # closed form: |r| = g (1 - imp) / (k imp^2)
+        assert abs(abs(r_eq) - g * (1 - imp) / (k * imp * imp)) < 2e-5 * abs(r_eq)
+
+
+def test_sphere_on_plane_fp32_oracle_agrees(oracle_mod):
+    """The fp32 build of the oracle (the one the GPU kernel is compared with) settles at the same penetration."""
+    model = mjcf.compile_model(ET.fromstring(BALL.format(mu=1.0, rho=1000.0, tc=0.02, dr=1.0)), solver="cg", iterations=100, ls_iterations=50)
+    t64 = _run(oracle_mod, model, [0, 0, 0.0499, 1, 0, 0, 0], np.zeros(6), 600)[-1][0][2]
+    t32 = _run(oracle_mod, model, [0, 0, 0.0499, 1, 0, 0, 0], np.zeros(6), 600, precision=32)[-1][0][2]
+    assert abs(t64 - t32) < 2e-6 and abs((t64 - 0.05) + 3.6718e-4) < 1e-7
+
+
+PEND = '''<mujoco model="pend"><option timestep="0.001"><flag eulerdamp="{ed}"/></option>
+<worldbody><body name="arm" pos="0 0 1"><joint name="h" type="hinge" axis="0 1 0" damping="{damp}" {limit}/>
+<geom name="g" type="capsule" fromto="0 0 0 0 0 -0.4" size="0.02" density="1200"/></body></worldbody></mujoco>'''
+
+
+def test_hinge_pendulum_period(oracle_mod):
+    """Small oscillations of a compound pendulum: T = 2 pi sqrt(I_pivot / (m g l)).  Pins the CRB inertia, the RNE gravity
+    bias and the integrator's step (semi-implicit Euler: period error O(dt^2))."""
+    model = mjcf.compile_model(ET.fromstring(PEND.format(ed="disable", damp="0", limit="")), solver="cg", iterations=6, ls_iterations=6)
+    A = model.arrays
+    mass, l = A["body_mass"][1], abs(A["body_ipos"][1][2])
+    R = mjcf.quat_to_mat(A["body_iquat"][1])
+    Icom = (R @ np.diag(A["body_inertia"][1]) @ R.T)[1, 1]
+    Ipiv = Icom + mass * l * l
+    T = 2 * math.pi * math.sqrt(Ipiv / (mass * 9.81 * l))
+    th0 = 0.01
+    traj = _run(oracle_mod, model, [th0], [0.0], 1, chunks=3000)
+    th = np.array([q[0] for q, _ in traj])
+    t = (np.arange(len(th)) + 1) * model.timestep
+    zc = [i for i in range(1, len(th)) if th[i - 1] > 0 >= th[i]]  # downward zero crossings, linearly interpolated
+    tz = [t[i - 1] + (t[i] - t[i - 1]) * th[i - 1] / (th[i - 1] - th[i]) for i in zc]
+    period = float(np.mean(np.diff(tz)))
+    assert len(tz) >= 2 and abs(period - T) / T < 2e-4, (period, T)
+    assert abs(th.max() - th0) < 2e-5 and abs(th.min() + th0) < 2e-5  # no numerical damping to first order
+
+
+def test_limited_hinge_pressed_into_its_stop(oracle_mod):
+    """Gravity presses the arm into the upper joint limit.  One limit row, J = -1 on the dof, invweight = dof_invweight0 = 1 / I:
+    D = I imp / (1 - imp).  Rest: torque_g = D k imp |r|  =>  |r| = tau (1 - imp) / (I k imp^2), tau = m g l sin(theta)."""
+    lim = math.radians(40.0)
+    model = mjcf.compile_model(ET.fromstring(PEND.format(ed="enable", damp="0.002", limit='range="-20 40" limited="true"')),
+                               solver="cg", iterations=50, ls_iterations=50)
+    A = model.arrays
+    assert abs(A["jnt_range"][0][1] - lim) < 1e-12
+    mass, l = A["body_mass"][1], abs(A["body_ipos"][1][2])
+    R = mjcf.quat_to_mat(A["body_iquat"][1])
+    I = (R @ np.diag(A["body_inertia"][1]) @ R.T)[1, 1] + mass * l * l
+    assert abs(A["dof_invweight0"][0] - 1 / I) < 1e-9 / I
+    # start past the stop with the arm raised so that gravity pushes further into it: axis +y, theta > 0 swings towards -x;
+    # flip gravity's lever by starting on the far side: use a tilted gravity instead (keeps the model one-liner)
+    model.gravity = np.array([-9.81, 0.0, 0.0])  # pushes theta up for a downward-hanging arm
+    th = _run(oracle_mod, model, [lim + 1e-3], [0.0], 4000)[-1]
+    theta, vel = th[0][0], th[1][0]
+    r = lim - theta
+    assert r < 0 and abs(vel) < 1e-9
+    solimp, solref = A["jnt_solimp"][0], A["jnt_solref"][0]
+    k, _ = _kb(solref, solimp, model.timestep)
+    imp = _impedance(solimp, r)
+    tau = mass * 9.81 * l * math.cos(theta)  # gravity along -x on an arm hanging along -z rotated by theta about y
+    want = tau * (1 - imp) / (I * k * imp * imp)
+    assert abs(abs(r) - want) < 2e-4 * want, (r, want)  # what is left is the solver's stopping tolerance on a 1e-5 N m torque balance

@@ -54,11 +54,15 @@ EXPORTS = ("vnl_step", "vnl_reset", "vnl_pipeline_step", "vnl_forward_dump", "vn
            "vnl_debug_layout", "vnl_process_clip")
 
 
-def load_library() -> ctypes.CDLL:
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
+IEEE_LIB_PATH = os.path.join(_HERE, "libvnl_b200_ieee.so")  # A/B twin: IEEE div / sqrt in the physics kernels (tests only)
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with __graft_entry__.build() (nvcc, sm_100a). "
                            "There is no CPU fallback for the product path.")
-    lib = ctypes.CDLL(LIB_PATH)
+    lib = ctypes.CDLL(path)
     CTX, ST, OUT = ctypes.POINTER(VnlContext), ctypes.POINTER(VnlState), ctypes.POINTER(VnlOutputs)
     v, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
     lib.vnl_version.restype = ctypes.c_char_p
@@ -99,13 +103,14 @@ class Engine:
 
     All tensors are torch CUDA tensors (fp32 / int32, contiguous, batch-major)."""
 
-    def __init__(self, model_blob: np.ndarray, task_blob: Optional[np.ndarray] = None, device: str = "cuda:0"):
+    def __init__(self, model_blob: np.ndarray, task_blob: Optional[np.ndarray] = None, device: str = "cuda:0",
+                 lib_path: Optional[str] = None):
         import torch
 
         if not torch.cuda.is_available():
             raise RuntimeError("vnl_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.torch = torch
-        self.lib = load_library()
+        self.lib = load_library(lib_path)
         self.device = torch.device(device)
         self.model_host = np.ascontiguousarray(model_blob, dtype=np.uint32)
         rc = self.lib.vnl_check_model(self.model_host.ctypes.data, self.model_host.nbytes)

@@ -40,6 +40,11 @@
 #ifndef VNL_STREAM
 #define VNL_STREAM 1
 #endif
+#ifdef VNL_IEEE  // A/B build (Makefile: libvnl_b200_ieee.so): exact reciprocal square root instead of the 2-ulp intrinsic
+#define VNL_RSQRT(x) (1.0f / sqrtf(x))
+#else
+#define VNL_RSQRT(x) rsqrtf(x)
+#endif
 #define VNL_CAT2(a, b) a##b
 #define VNL_CAT(a, b) VNL_CAT2(a, b)
 
@@ -353,7 +358,7 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
           }
           acc += accb;
           for (int o = 1 << lg; o < 32; o <<= 1) acc += __shfl_xor_sync(FULLMASK, acc, o);
-          const float rs = rsqrtf(__shfl_sync(FULLMASK, acc, 0));
+          const float rs = VNL_RSQRT(__shfl_sync(FULLMASK, acc, 0));
           if (own) Fb[cc] = cc == 0 ? rs : acc * rs;
         } else {  // rows longer than a warp: lane owns columns lane and lane + 32 (few descendants down there)
           const bool on2 = lane + 32 < n;
@@ -365,7 +370,7 @@ __device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
             acc = fmaf(-u, F[s0 + lane], acc);
             acc2 = fmaf(-u, F[s0 + c1], acc2);
           }
-          const float rs = rsqrtf(__shfl_sync(FULLMASK, acc, 0));
+          const float rs = VNL_RSQRT(__shfl_sync(FULLMASK, acc, 0));
           Fb[lane] = lane == 0 ? rs : acc * rs;
           if (on2) Fb[c1] = acc2 * rs;
         }

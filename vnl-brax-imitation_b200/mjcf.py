@@ -658,6 +658,10 @@ def compile_model(root: ET.Element, *, name: str = "", solver: Optional[str] = N
             V[:, 2] = -V[:, 2]
         body_mass[bi], body_ipos[bi], body_iquat[bi], body_inertia[bi] = M, com, mat_to_quat(V), w
     A["body_mass"], A["body_ipos"], A["body_iquat"], A["body_inertia"] = body_mass, body_ipos, body_iquat, body_inertia
+    # per-geom mass (explicit `mass` or density x volume; 0 where the body carries an explicit <inertial>) and friction:
+    # mjModel fields the kernels never read, kept so that tests can re-derive the body constants independently
+    A["geom_mass"] = np.array([g.get("_mass", 0.0) for g in geoms]).reshape(len(geoms))
+    A["geom_friction"] = np.array([g["friction"] for g in geoms]).reshape(len(geoms), 3)
 
     # ---- actuators -----------------------------------------------------------------
     acts = []
