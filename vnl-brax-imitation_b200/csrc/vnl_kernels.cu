@@ -58,6 +58,12 @@ constexpr int kEnvThreads = 32 * VNL_EW;   // = lanes of the mat-vec programs (V
 // registers: humanoid, ant), two-warp groups by the register
 // file (16 warps x 128 registers) and by the named barriers (1 .. 8 for the groups)
 constexpr int kMaxEnvs = VNL_EW == 1 ? 16 : 8;
+// floats per body of t16 (cinert / crb 10 + rne force 6): an ODD stride, so that lane-per-body accesses (cinert build,
+// local rne, inert_mul / dot6 by dof_body) hit 32 different banks instead of 2 (stride 16 = 16-way conflicts)
+#ifndef VNL_TS
+#define VNL_TS 17
+#endif
+constexpr int kTS = VNL_TS;
 
 #define LANE ((int)(threadIdx.x & 31))
 #define FULLMASK 0xffffffffu
@@ -118,7 +124,7 @@ __host__ __device__ inline void make_layout(const Dims& d, Lay& L) {
   const int cacc_n = align4((d.nbody > d.nv ? d.nbody : d.nv) * 6);
   if (o - r1 < cacc_n) o = r1 + cacc_n;
   L.cacc = r1;
-  A(t16, d.nbody * 16);
+  A(t16, d.nbody * kTS);
   int r1end = o;
   o = r1;
   A(part, d.naslot + d.ndslot); A(tmpv, d.nv);
@@ -935,7 +941,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     const float* iquat = c.ff(VNL_F_BODY_IQUAT);
     const float* inertia = c.ff(VNL_F_BODY_INERTIA);
     for (int b = tid; b < d.nbody; b += kEnvThreads) {
-      float* ci = s + L.t16 + 16 * b;
+      float* ci = s + L.t16 + kTS * b;
       if (b == 0) {
 #pragma unroll
         for (int q = 0; q < 16; ++q) ci[q] = 0.0f;
@@ -985,7 +991,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     if (DUMP) {
       for (int i = tid; i < d.nbody * 3; i += kEnvThreads) dump[d.dump_xipos + i] = s[L.xipos + i];
       for (int i = tid; i < d.njnt * 3; i += kEnvThreads) { dump[d.dump_xanchor + i] = s[L.xanchor + i]; dump[d.dump_xanchor + d.njnt * 3 + i] = s[L.xaxis + i]; }
-      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + i] = s[L.t16 + kTS * (i / 10) + i % 10];
       for (int t = tid; t < d.nroot; t += kEnvThreads) st3(dump + d.dump_subtree_com + 3 * TB8(roots)[t], ld3(s + L.rcom + 3 * t));
     }
   }
@@ -1045,11 +1051,11 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     // local RNE force of each body: cfrc = I cacc + cvel x* (I cvel)   -> t16[10..15]
     for (int b = tid; b < d.nbody; b += kEnvThreads) {
       float f1[6], iv[6], f2[6];
-      inert_mul(s + L.t16 + 16 * b, s + L.cacc + 6 * b, f1);
-      inert_mul(s + L.t16 + 16 * b, s + L.cvel + 6 * b, iv);
+      inert_mul(s + L.t16 + kTS * b, s + L.cacc + 6 * b, f1);
+      inert_mul(s + L.t16 + kTS * b, s + L.cvel + 6 * b, iv);
       motion_cross_force(s + L.cvel + 6 * b, iv, f2);
 #pragma unroll
-      for (int q = 0; q < 6; ++q) s[L.t16 + 16 * b + 10 + q] = f1[q] + f2[q];
+      for (int q = 0; q < 6; ++q) s[L.t16 + kTS * b + 10 + q] = f1[q] + f2[q];
     }
     env_sync();
     pf.mark(28);
@@ -1061,15 +1067,15 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         const int ce = TB8(child_adr)[b + 1];
         int ch = TB8(child_adr)[b];
         if (ch < ce) {
-          float acc = s[L.t16 + 16 * b + q];
-          for (; ch < ce; ++ch) acc += s[L.t16 + 16 * TB8(child_list)[ch] + q];
-          s[L.t16 + 16 * b + q] = acc;
+          float acc = s[L.t16 + kTS * b + q];
+          for (; ch < ce; ++ch) acc += s[L.t16 + kTS * TB8(child_list)[ch] + q];
+          s[L.t16 + kTS * b + q] = acc;
         }
       }
       env_sync();
     }
     if (DUMP) {
-      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + d.nbody * 10 + d.nv * 6 + i] = s[L.t16 + 16 * (i / 10) + i % 10];
+      for (int i = tid; i < d.nbody * 10; i += kEnvThreads) dump[d.dump_cinert + d.nbody * 10 + d.nv * 6 + i] = s[L.t16 + kTS * (i / 10) + i % 10];
       for (int i = tid; i < d.nbody * 6; i += kEnvThreads) dump[d.dump_cvel + i] = s[L.cvel + i];
     }
   }
@@ -1115,7 +1121,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         pas = -stiff[j] * (s[L.qpos + jqadr[j]] - qspring[jqadr[j]]);
       }
       pas -= damping[i] * s[L.qvel + i];
-      const float bias = dot6(s + L.cdof + 6 * i, s + L.t16 + 16 * dof_body[i] + 10);
+      const float bias = dot6(s + L.cdof + 6 * i, s + L.t16 + kTS * dof_body[i] + 10);
       s[L.qfrc_smooth + i] = pas - bias + acc;
       if (DUMP) { dump[d.dump_passive + i] = pas; dump[d.dump_passive + d.nv + i] = bias; }
     }
@@ -1127,7 +1133,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
   {
     const float* armature = c.ff(VNL_F_DOF_ARMATURE);
     float* fd = s + L.cacc;  // cacc is dead: reuse as crb * cdof
-    for (int i = tid; i < d.nv; i += kEnvThreads) inert_mul(s + L.t16 + 16 * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
+    for (int i = tid; i < d.nv; i += kEnvThreads) inert_mul(s + L.t16 + kTS * dof_body[i], s + L.cdof + 6 * i, fd + 6 * i);
     env_sync();
     float* const F = s + L.K;  // built straight into the factorisation's workspace (region A's head is dead by now)
     for (int e = tid; e < d.nM; e += kEnvThreads) {
@@ -1950,7 +1956,7 @@ int layout_table(const Dims& d, LayoutEntry* out, int cap) {
       {"Jaref", L.Jaref, d.nefc}, {"qacc", L.qacc, nv}, {"Ma", L.Ma, nv}, {"grad", L.grad, nv}, {"Mgrad", L.Mgrad, nv},
       {"search", L.search, nv}, {"Mv", L.Mv, nv}, {"qfrc_con", L.qfrc_con, nv},
       {"xipos", L.xipos, 3 * nb}, {"xanchor", L.xanchor, 3 * d.njnt}, {"xaxis", L.xaxis, 3 * d.njnt}, {"cacc", L.cacc, big},
-      {"t16", L.t16, 16 * nb}, {"part", L.part, d.naslot + d.ndslot}, {"tmpv", L.tmpv, nv},
+      {"t16", L.t16, kTS * nb}, {"part", L.part, d.naslot + d.ndslot}, {"tmpv", L.tmpv, nv},
       {"lim_dof", L.lim_dof, d.nlimit}, {"limrow_of_dof", L.limrow_of_dof, nv}, {"cbody", L.cbody, d.ncon}, {"crel", L.crel, 3 * d.ncon},
       {"cframe", L.cframe, 6 * d.ncon}, {"cmu", L.cmu, d.ncon}, {"efcD", L.efcD, d.nefc},
       {"Jv", L.Jv, d.nefc > 6 * d.ncon ? d.nefc : 6 * d.ncon}, {"K", L.K, d.nM + 40}, {"total", L.total, 0}};
