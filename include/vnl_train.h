@@ -67,6 +67,14 @@ int vnl_rowdot(const float* h, int ld, int rows, int n, const float* w, const fl
 /* dh[r, c] = dv[r] * w[c]   (value head backward) */
 int vnl_outer(const float* dv, int rows, const float* w, int n, float* dh, int ld, void* stream);
 
+/* Rollout-side sampling of brax NormalTanhDistribution (ppo_imitation/ppo_networks.py:55-83) on fp32 logits [rows, 2 nu]:
+ * raw_action = loc + scale * eps_a (eps_a = NULL: the mode, `deterministic=True`), action = tanh(raw_action), log_prob(raw_action),
+ * and rand_log_prob = log_prob of `rand_action` [nu] -- ONE uniform(-1, 1) draw of shape (action_size,) broadcast over the batch,
+ * as the reference draws it (ppo_networks.py:68-73); rand_action / rand_log_prob may be NULL.  The fp32-accurate rollout policy
+ * (policy.PrecisePolicy) = the learner's forward kernels + this one. */
+int vnl_policy_sample(const float* logits, int ld, const float* eps_a, const float* rand_action, int rows, int nu, float* action,
+                      float* raw_action, float* log_prob, float* rand_log_prob, void* stream);
+
 /* Loss, part 1 (per row; intention_losses.py:149-166,189): brax NormalTanhDistribution on logits [rows, 2 nu]:
  *   target_lp[r] = log_prob(logits, raw_action), ent[r] = entropy(logits) with the sample loc + scale * eps_ent;
  *   termination[r] = (1 - discount[r]) * (1 - truncation[r]); rewards_s[r] = reward[r] * reward_scaling. */

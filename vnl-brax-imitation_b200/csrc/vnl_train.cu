@@ -220,6 +220,34 @@ __global__ void ppo_rows_kernel(const float* __restrict__ logits, int ld, const 
   }
 }
 
+// rollout-side sampling (ppo_networks.py:55-83): raw = loc + scale * eps (or the mode, eps == NULL), log_prob(raw), action = tanh(raw),
+// rand_log_prob = log_prob of ONE uniform(-1, 1) draw of shape (nu,) broadcast over the batch (ppo_networks.py:68-73)
+__global__ void policy_sample_kernel(const float* __restrict__ logits, int ld, const float* __restrict__ eps_a, const float* __restrict__ rand_action,
+                                     int rows, int nu, float* __restrict__ action, float* __restrict__ raw_action, float* __restrict__ log_prob,
+                                     float* __restrict__ rand_log_prob) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    float lp = 0.0f, rlp = 0.0f;
+    if (lane < nu) {
+      const float loc = logits[(size_t)r * ld + lane], scale = softplus(logits[(size_t)r * ld + nu + lane]) + 0.001f, ls = logf(scale);
+      const float raw = eps_a ? loc + scale * eps_a[(size_t)r * nu + lane] : loc;
+      raw_action[(size_t)r * nu + lane] = raw;
+      action[(size_t)r * nu + lane] = tanhf(raw);
+      const float z = (raw - loc) / scale;
+      lp = -0.5f * z * z - ls - kHalfLog2Pi - log_det_jac(raw);
+      if (rand_action) {
+        const float a = rand_action[lane], zr = (a - loc) / scale;
+        rlp = -0.5f * zr * zr - ls - kHalfLog2Pi - log_det_jac(a);
+      }
+    }
+    lp = warp_sum(lp); rlp = warp_sum(rlp);
+    if (lane == 0) {
+      log_prob[r] = lp;
+      if (rand_log_prob && rand_action) rand_log_prob[r] = rlp;
+    }
+  }
+}
+
 // mean and population std of `rows` values (jnp.mean / jnp.std), one block, fixed order
 __global__ void mean_std_kernel(const float* __restrict__ x, int rows, float* __restrict__ out2) {
   __shared__ double r1[32], r2[32];
@@ -389,6 +417,14 @@ int vnl_rowdot(const float* h, int ld, int rows, int n, const float* w, const fl
 int vnl_outer(const float* dv, int rows, const float* w, int n, float* dh, int ld, void* stream) {
   if (!dv || !w || !dh || rows <= 0 || n <= 0 || ld < n) return -1;
   outer_kernel<<<grid_for((size_t)rows * n, 256), 256, 0, (cudaStream_t)stream>>>(dv, rows, w, n, dh, ld);
+  return rc();
+}
+
+int vnl_policy_sample(const float* logits, int ld, const float* eps_a, const float* rand_action, int rows, int nu, float* action,
+                      float* raw_action, float* log_prob, float* rand_log_prob, void* stream) {
+  if (!logits || !action || !raw_action || !log_prob || rows <= 0 || nu <= 0 || nu > 32 || ld < 2 * nu) return -1;
+  policy_sample_kernel<<<grid_for((size_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(logits, ld, eps_a, rand_action, rows, nu, action, raw_action,
+                                                                                          log_prob, rand_log_prob);
   return rc();
 }
 

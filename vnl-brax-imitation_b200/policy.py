@@ -205,6 +205,149 @@ class IntentionPolicy:
         return dump
 
 
+class PrecisePolicy:
+    """The same `policy(traj, obs, draws)` call as IntentionPolicy at the REFERENCE's precision (fp32 network, VERDICT r1 / ADVICE r1:
+    the bf16 kernel's behaviour log-probs are 0.05-0.35 away from the fp32 network the learner re-evaluates, the size of the PPO
+    clip range).  Runs the learner's forward kernels: `vnl_gemm_tf32` on the tensor cores -- `precision="3xtf32"` (default, fp32-class:
+    log-probs within ~1e-4 of an fp32 / float64 evaluation) or `"tf32"` (one pass, what XLA runs for the reference on a GPU) -- plus
+    relu + LayerNorm, reparameterisation and `vnl_policy_sample`.  ~25 launches instead of one (0.25 ms at 8192 envs beside a 7.7 ms
+    env step), all CUDA-graph capturable: every buffer is allocated once per batch size, weights and their 3xTF32 splits are
+    refreshed in place by `load_params`.  Drop-in for IntentionPolicy in rollout.Rollout (same attributes and call)."""
+
+    def __init__(self, params: Dict[str, np.ndarray], device: str = "cuda:0", obs_mean=None, obs_std=None, precision: str = "3xtf32"):
+        import torch
+
+        from . import train_kernels as tk
+        if not torch.cuda.is_available():
+            raise RuntimeError("vnl_b200 policy needs a CUDA device (sm_100a); there is no CPU fallback")
+        if precision not in ("3xtf32", "tf32"):
+            raise ValueError("precision must be '3xtf32' or 'tf32'")
+        self.torch, self.tk, self.x3 = torch, tk, precision == "3xtf32"
+        self.device = torch.device(device)
+        traj, e1 = params["encoder/hidden_0/kernel"].shape
+        e2, latent = params["encoder/fc2_mean/kernel"].shape
+        k4, d1 = params["decoder/hidden_0/kernel"].shape
+        d2, nlog = params["decoder/hidden_2/kernel"].shape
+        self.traj_size, self.obs_size, self.latent, self.action_size = traj, k4 - latent, latent, nlog // 2
+        self.widths = (e1, e2, 2 * latent, d1, d2, nlog)
+        if max(self.widths) > 1024 or self.action_size > 32 or any(w % 4 for w in self.widths) or self.obs_size % 4 or latent % 4:
+            raise ValueError("layer sizes not supported by the fp32 policy path")
+        f = lambda *sh: torch.zeros(*sh, dtype=torch.float32, device=self.device)
+        self.W = {"e0": f(traj, e1), "e1": f(e1, e2), "eh": f(e2, 2 * latent), "d0": f(k4, d1), "d1": f(d1, d2), "d2": f(d2, nlog)}
+        self.Wsplit = {k: (torch.empty_like(v), torch.empty_like(v)) for k, v in self.W.items()}
+        self.b = {"e0": f(e1), "e1": f(e2), "eh": f(2 * latent), "d0": f(d1), "d1": f(d2), "d2": f(nlog)}
+        self.ln = {k: (f(n), f(n)) for k, n in (("e0", e1), ("e1", e2), ("d0", d1), ("d1", d2))}
+        self.blob_dev = self.W["e0"]  # an address that identifies "the parameters" for capturers (rollout.Rollout)
+        self.obs_mean, self.obs_std = f(self.obs_size), torch.ones(self.obs_size, dtype=torch.float32, device=self.device)
+        self._identity = True
+        self.bufs = {}
+        self.launches = 0
+        self.load_params(params)
+        self.set_normalizer(obs_mean, obs_std)
+
+    def load_params(self, params) -> None:
+        t = self.torch
+        up = lambda a: t.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=self.device)
+        self.W["e0"].copy_(up(params["encoder/hidden_0/kernel"])); self.b["e0"].copy_(up(params["encoder/hidden_0/bias"]))
+        self.W["e1"].copy_(up(params["encoder/hidden_1/kernel"])); self.b["e1"].copy_(up(params["encoder/hidden_1/bias"]))
+        self.W["eh"].copy_(t.cat([up(params["encoder/fc2_mean/kernel"]), up(params["encoder/fc2_logvar/kernel"])], 1))
+        self.b["eh"].copy_(t.cat([up(params["encoder/fc2_mean/bias"]), up(params["encoder/fc2_logvar/bias"])]))
+        for k, n in (("d0", "decoder/hidden_0"), ("d1", "decoder/hidden_1"), ("d2", "decoder/hidden_2")):
+            self.W[k].copy_(up(params[n + "/kernel"])); self.b[k].copy_(up(params[n + "/bias"]))
+        for k, n in (("e0", "encoder/LayerNorm_0"), ("e1", "encoder/LayerNorm_1"), ("d0", "decoder/LayerNorm_0"), ("d1", "decoder/LayerNorm_1")):
+            self.ln[k][0].copy_(up(params[n + "/scale"])); self.ln[k][1].copy_(up(params[n + "/bias"]))
+        if self.x3:
+            for k, w in self.W.items():
+                self.tk.split_into(w, *self.Wsplit[k])
+
+    def set_normalizer(self, mean, std) -> None:
+        """None = identity.  Tensors already on the device are ADOPTED when first given (shared with normalizer.RunningStatistics),
+        later calls copy into the same storage."""
+        t = self.torch
+        for name, val, ident in (("obs_mean", mean, 0.0), ("obs_std", std, 1.0)):
+            cur = getattr(self, name)
+            if val is None:
+                cur.fill_(ident)
+            elif isinstance(val, t.Tensor) and val.is_cuda and val.dtype == t.float32 and val.is_contiguous() and self._identity and not getattr(self, "_norm_pinned", False):
+                setattr(self, name, val)
+            elif not (isinstance(val, t.Tensor) and val.data_ptr() == cur.data_ptr()):
+                cur.copy_(t.as_tensor(val, dtype=t.float32))
+        self._identity = mean is None and std is None and self._identity
+
+    def pin_operands(self) -> None:
+        self._norm_pinned = True
+
+    def alloc_outputs(self, B: int, heads: bool = False):
+        t, nu = self.torch, self.action_size
+        f = lambda *s: t.empty(*s, dtype=t.float32, device=self.device)
+        out = {"action": f(B, nu), "raw_action": f(B, nu), "logits": f(B, 2 * nu), "log_prob": f(B), "rand_log_prob": f(B)}
+        if heads:
+            out["z_mean"], out["z_logvar"] = f(B, self.latent), f(B, self.latent)
+        return out
+
+    def _buffers(self, B: int):
+        if B not in self.bufs:
+            t = self.torch
+            f = lambda *s: t.zeros(*s, dtype=t.float32, device=self.device)
+            e1, e2, h2, d1, d2, nlog = self.widths
+            ld = (self.traj_size + 3) // 4 * 4
+            b = dict(traj=f(B, ld), idx=t.arange(B, dtype=t.int32, device=self.device), pre0=f(B, e1), h0=f(B, e1), pre1=f(B, e2), h1=f(B, e2),
+                     heads=f(B, h2), dec_in=f(B, self.latent + self.obs_size), pre2=f(B, d1), h2=f(B, d1), pre3=f(B, d2), h3=f(B, d2), st=f(B, 2))
+            if self.x3:
+                for k in ("traj", "h0", "h1", "dec_in", "h2", "h3"):
+                    b[k + "_hi"], b[k + "_lo"] = t.empty_like(b[k]), t.empty_like(b[k])
+            self.bufs[B] = b
+        return self.bufs[B]
+
+    def _dense(self, b, xname, rows, wname, out):
+        tk = self.tk
+        W = self.W[wname]
+        K, N = W.shape
+        parts, sk = None, 1
+        if self.x3:
+            tk.split_into(b[xname], b[xname + "_hi"], b[xname + "_lo"])
+            parts = ((b[xname + "_hi"], b[xname + "_lo"]), self.Wsplit[wname])
+            sk = max(1, ((K + 31) // 32 + 7) // 8)  # accumulation chains of <= 8 K blocks (the tensor core's accumulator truncates)
+        tk.gemm(b[xname], 0, W, 1, out, rows, N, K, bias=self.b[wname], x3=self.x3, splitk=sk, parts=parts)
+
+    def __call__(self, traj, obs, eps_z, eps_a, rand_action=None, out: Optional[dict] = None, heads: bool = False):
+        """(action [B, nu], extras) as IntentionPolicy.__call__; rand_action: the reference's ONE uniform draw of shape (nu,)
+        (a [B, nu] tensor is accepted for compatibility: its first row is used)."""
+        t, tk = self.torch, self.tk
+        L_ = tk.lib()
+        B = traj.shape[0]
+        for x, w in ((traj, self.traj_size), (obs, self.obs_size), (eps_z, self.latent)):
+            if x.dtype != t.float32 or not x.is_contiguous() or x.shape != (B, w) or x.device != self.device:
+                raise ValueError("policy operands must be contiguous fp32 [B, width] tensors on the policy's device")
+        if out is None:
+            out = self.alloc_outputs(B, heads)
+        if B == 0:
+            return out["action"], out
+        b, st, ptr = self._buffers(B), tk.stream(traj), (lambda x: None if x is None else x.data_ptr())
+        chk = tk.check
+        with t.cuda.device(self.device):
+            chk(L_.vnl_gather_rows(ptr(traj), 1, B, self.traj_size, ptr(b["idx"]), B, ptr(b["traj"]), b["traj"].shape[1], st), "pad traj")
+            Ld = self.latent + self.obs_size
+            chk(L_.vnl_obs_normalize(ptr(obs), self.obs_size, B, self.obs_size, ptr(self.obs_mean), ptr(self.obs_std), ptr(b["dec_in"]) + 4 * self.latent, Ld, st), "normalize")
+            relu_ln = lambda pre, name, dst: chk(L_.vnl_relu_ln_fwd(ptr(pre), pre.shape[1], B, pre.shape[1], ptr(self.ln[name][0]), ptr(self.ln[name][1]), ptr(dst), dst.shape[1], ptr(b["st"]), st), "relu_ln")
+            self._dense(b, "traj", B, "e0", b["pre0"]); relu_ln(b["pre0"], "e0", b["h0"])
+            self._dense(b, "h0", B, "e1", b["pre1"]); relu_ln(b["pre1"], "e1", b["h1"])
+            self._dense(b, "h1", B, "eh", b["heads"])
+            chk(L_.vnl_reparam_fwd(ptr(b["heads"]), ptr(eps_z), B, self.latent, ptr(b["dec_in"]), Ld, st), "reparam")
+            self._dense(b, "dec_in", B, "d0", b["pre2"]); relu_ln(b["pre2"], "d0", b["h2"])
+            self._dense(b, "h2", B, "d1", b["pre3"]); relu_ln(b["pre3"], "d1", b["h3"])
+            self._dense(b, "h3", B, "d2", out["logits"])
+            if rand_action is not None and rand_action.dim() == 2:
+                rand_action = rand_action[0].contiguous()
+            chk(L_.vnl_policy_sample(ptr(out["logits"]), 2 * self.action_size, ptr(eps_a), ptr(rand_action), B, self.action_size, ptr(out["action"]),
+                                     ptr(out["raw_action"]), ptr(out["log_prob"]), ptr(out["rand_log_prob"]) if rand_action is not None else None, st),
+                "policy_sample")
+            if heads:
+                out["z_mean"].copy_(b["heads"][:, :self.latent]); out["z_logvar"].copy_(b["heads"][:, self.latent:])
+        self.launches += 1
+        return out["action"], out
+
+
 def reference_forward(params, traj, obs, eps_z, eps_a, rand_action=None, obs_mean=None, obs_std=None, operand_dtype=None):
     """fp32 torch restatement of the reference policy (checker for tests / tools; works on CPU tensors too).
     `operand_dtype=torch.bfloat16` rounds the operands of every dense layer the way the kernel does (fp32 accumulation)."""

@@ -1,0 +1,111 @@
+"""`training_step` of the reference (ppo_imitation/train.py:296-349) on the GPU: rollout -> normaliser update -> SGD phase.
+
+    (state, _), data = scan(generate_unroll, ...)                      rollout.Rollout (policy kernel + fused env step, CUDA graph)
+    normalizer_params = running_statistics.update(..., pmap_axis_name)  normalizer.RunningStatistics (one pass + one all-reduce)
+    for _ in range(num_updates_per_batch):                              sgd_step (train.py:270-294)
+        permutation of the env axis, reshape to num_minibatches
+        for each minibatch: gradient_update_fn(loss, adam, pmean)       learner.PPOLearner.update (tcgen05 TF32 GEMMs + row kernels)
+    policy <- new parameters                                            policy.load_params (same device blob: captured graphs keep working)
+
+The transition buffers stay on the device from the env kernel to the loss: a minibatch is an index list over the env axis
+(`vnl_gather_rows`, which also pads traj rows 795 -> 796 floats for TMA).  One minibatch update (gathers + ~80 launches + the two
+gradient buckets + Adam) is captured once into a CUDA graph and replayed with fresh indices / noise.  torch = memory, streams,
+RNG for the noise operands and `torch.distributed`; no torch math on the data path, no CPU fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+from . import learner as lrn
+from . import train_kernels as tk
+
+
+class Trainer:
+    def __init__(self, env, policy, learner: "lrn.PPOLearner", rollout, stats, num_minibatches: int, num_updates_per_batch: int,
+                 use_graph: bool = True, seed: int = 0):
+        import torch
+
+        self.torch = t = torch
+        self.env, self.policy, self.learner, self.rollout, self.stats = env, policy, learner, rollout, stats
+        self.B, self.T = rollout.B, rollout.T
+        if self.B % num_minibatches:
+            raise ValueError("num_envs must be divisible by num_minibatches")
+        self.Bm = self.B // num_minibatches
+        if (learner.T, learner.Bm) != (self.T, self.Bm):
+            raise ValueError("learner was built for another minibatch shape")
+        self.num_minibatches, self.num_updates = int(num_minibatches), int(num_updates_per_batch)
+        dev = learner.device
+        L = learner
+        f = lambda *s: t.zeros(*s, dtype=t.float32, device=dev)
+        R = self.T * self.Bm
+        # static minibatch operands (graph-captured addresses)
+        self.idx = t.zeros(self.Bm, dtype=t.int32, device=dev)
+        self.mb = dict(traj=f(R, L.ld_traj), observation=f(R, L.obs), next_observation_last=f(self.Bm, L.obs), reward=f(R), discount=f(R),
+                       truncation=f(R), log_prob=f(R), raw_action=f(R, L.nu), eps_z=f(R, L.L), eps_ent=f(R, L.nu))
+        self.gen = t.Generator(device=dev).manual_seed(seed)
+        self.use_graph, self.graph = bool(use_graph), None
+        self.discount_buf = f(self.T, self.B)
+        self.env_steps = 0
+        self.sgd_launches = 0
+
+    # ---- one minibatch ----------------------------------------------------------------------------------------------------
+    def _gather(self, tr):
+        """`convert_data` (train.py:279-283) for one minibatch: rows of the time-major transition buffers picked by self.idx."""
+        L_, st = tk.lib(), tk.stream(self.idx)
+        T, B, Bm, mb = self.T, self.B, self.Bm, self.mb
+        g = lambda src, width, dst, ld, T_=T: tk.check(L_.vnl_gather_rows(src.data_ptr(), T_, B, width, self.idx.data_ptr(), Bm, dst.data_ptr(), ld, st), "vnl_gather_rows")
+        lr = self.learner
+        g(tr["state_extras_traj_in"], lr.traj, mb["traj"], lr.ld_traj)
+        g(tr["observation"], lr.obs, mb["observation"], lr.obs)
+        g(tr["next_observation"][T - 1:T], lr.obs, mb["next_observation_last"], lr.obs, 1)
+        g(tr["policy_extras"]["raw_action"], lr.nu, mb["raw_action"], lr.nu)
+        for k, src in (("reward", tr["reward"]), ("discount", self.discount_buf), ("truncation", tr["state_extras"]["truncation"]),
+                       ("log_prob", tr["policy_extras"]["log_prob"])):
+            g(src, 1, mb[k], 1)
+        self.sgd_launches += 8
+
+    def _minibatch(self, tr):
+        self._gather(tr)
+        self.learner.update(self.mb)
+
+    def sgd_phase(self, tr) -> None:
+        """num_updates_per_batch x num_minibatches gradient updates on the unroll `tr` (train.py:336-341)."""
+        t = self.torch
+        self.discount_buf.copy_(tr["discount"])  # `1 - done` view materialised once per unroll
+        # the policy's INPUT trajectory of step t is traj[t] (acting.py:47: state.info["traj"]), i.e. rollout.traj[:T]
+        tr = dict(tr, state_extras_traj_in=self.rollout.traj[:self.T])
+        for _ in range(self.num_updates):
+            perm = t.randperm(self.B, device=self.idx.device, generator=self.gen).to(t.int32)
+            for mbi in range(self.num_minibatches):
+                self.idx.copy_(perm[mbi * self.Bm:(mbi + 1) * self.Bm])
+                self.mb["eps_z"].normal_(generator=self.gen)
+                self.mb["eps_ent"].normal_(generator=self.gen)
+                if not self.use_graph:
+                    self._minibatch(tr)
+                    continue
+                if self.graph is None:
+                    side = t.cuda.Stream(device=self.idx.device)  # warm-up outside capture (lazy module loads, attribute sets)
+                    side.wait_stream(t.cuda.current_stream(self.idx.device))
+                    with t.cuda.stream(side):
+                        self._minibatch(tr)
+                    t.cuda.current_stream(self.idx.device).wait_stream(side)
+                    self.graph = t.cuda.CUDAGraph()
+                    with t.cuda.graph(self.graph):
+                        self._minibatch(tr)
+                    self.learner.updates -= 1  # the capture pass went through the host-side counter without executing
+                    continue  # the capture does not execute: this minibatch was the warm-up run
+                self.graph.replay()
+                self.learner.updates += 1  # host-side counter (the device-side step counter advanced inside the graph)
+
+    def training_step(self) -> Dict[str, float]:
+        """One `training_step`: unroll, normaliser update, SGD phase, policy refresh.  Returns the last minibatch's loss metrics."""
+        ro = self.rollout
+        ro.eps_z.normal_(generator=self.gen)
+        ro.eps_a.normal_(generator=self.gen)
+        tr = ro.generate_unroll()
+        self.stats.update(tr["observation"])  # running_statistics.update with its psum (train.py:330-334)
+        self.learner.set_normalizer(self.stats.mean, self.stats.std)
+        self.sgd_phase(tr)
+        self.policy.load_params(self.learner.policy_params())
+        self.env_steps += self.B * self.T
+        return self.learner.metrics_dict()
