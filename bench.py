@@ -132,6 +132,13 @@ WORKLOADS = {
     "rodent": dict(envs=4096, nu=30, text="rodent imitation env step+reward/obs (envs/rodent.py, rodent.xml, transform_snips_groom.p)"),
     "humanoid": dict(envs=8192, nu=21, text="CMU humanoid imitation env step+reward/obs (envs/humanoid.py, humanoid.xml, synthetic "
                                             "standing clip: qpos0 tiled x256 -- the reference clip humanoid_traj_stand.p is absent)"),
+    # BASELINE.json configs[3]: the PPO rollout / the whole training_step, and configs[4]: the two-agent physics sweep point
+    "rollout": dict(envs=8192, nu=30, text="rodent PPO rollout (ppo_imitation/acting.py:30-80: intention-network policy + fused env step with the "
+                                           "Episode / AutoReset wrappers, one CUDA graph per unroll, normaliser updated per unroll)"),
+    "train": dict(envs=8192, nu=30, text="rodent PPO training_step (ppo_imitation/train.py:296-349: rollout + normaliser + 16 x 32 minibatch "
+                                         "updates of 5120 rows: loss fwd / bwd on tcgen05 TF32 GEMMs, Adam, gradient all-reduce)"),
+    "rodent_pair": dict(envs=16384, nu=60, text="rodent_pair.xml two-agent physics env step (5 substeps, U(-1,1) controls, no task logic: the "
+                                                "reference has no env class for this model)"),
     # BASELINE.json configs[0]: the reference's own CPU-runnable plumbing case (a parity case; benched only on request)
     "ant": dict(envs=256, nu=8, text="ant imitation env step+reward/obs (envs/ant.py, ant.xml brax-style fused, Newton 1x4, still clip: "
                                      "init_qpos tiled -- the reference clip ant_traj_still.p is absent)"),
@@ -446,6 +453,153 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[3] / configs[4] as driver-runnable workloads
+# ------------------------------------------------------------------------------------------------------------------
+def _finish_extra(args, line_fn, ms_total, e2e_ms_total, K, dev, sampler, launches):
+    """max over ranks, clocks, one JSON line from rank 0."""
+    import torch.distributed as dist
+    sh = pkg("sharding")
+    rank, _, world = sh.env_info()
+    clocks = sampler.finish()
+    red = sh.reduce_scalars(dict(ms=ms_total, e2e=e2e_ms_total), op="max", device=dev)
+    sums = sh.reduce_scalars(dict(launches=float(launches)), op="sum", device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        line = line_fn(red["ms"], red["e2e"], int(sums["launches"]))
+        line.update({"n_gpus": world, "steps": K, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                     "dtype": "f32", "data": "synthetic", "clocks": clocks, "cpu_baseline": None})
+        print(json.dumps(line), flush=True)
+
+
+def run_pair(args):
+    """configs[4]: rodent_pair.xml physics env steps (5 substeps, no task logic: the reference has no env class for this model)."""
+    import torch
+    sh, mjcf, mb, lib = pkg("sharding"), pkg("mjcf"), pkg("model_blob"), pkg("_lib")
+    rank, local_rank, world = sh.env_info()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sh.init_process_group("nccl")
+    model = mjcf.load_model(os.path.join(ROOT, "vnl-brax-imitation_b200", "data", "rodent_pair_model.npz"))
+    eng = lib.Engine(mb.build_model_blob(model), None, device=str(dev))
+    B = args.envs_per_gpu or WORKLOADS["rodent_pair"]["envs"]
+    K, W = args.steps, args.warmup
+    rng = np.random.default_rng(rank)
+    qpos = np.tile(model.arrays["qpos0"], (B, 1)).astype(np.float32) + (1e-3 * rng.standard_normal((B, model.nq))).astype(np.float32)
+    a, b = eng.alloc_state(B), eng.alloc_state(B)
+    a["qpos"].copy_(torch.tensor(qpos, device=dev))
+    ctrl = torch.rand(W + K, B, model.nu, device=dev) * 2 - 1
+    stats = torch.zeros(B, 4, dtype=torch.int32, device=dev)
+    host_ctrl = torch.empty(K, B, model.nu).pin_memory()
+    host_ctrl.copy_(ctrl[W:].cpu())
+    host_q = torch.empty(B, model.nq).pin_memory()
+
+    def step(c):
+        nonlocal a, b
+        eng.pipeline_step(a, c, b, 5, stats)
+        a, b = b, a
+    for i in range(W):
+        step(ctrl[i])
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = eng.launches
+    sh.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step(ctrl[W + i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    dctrl = torch.empty(B, model.nu, device=dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(K):  # host-buffer form: controls from pinned memory in, qpos back to pinned memory, every step
+        dctrl.copy_(host_ctrl[i], non_blocking=True)
+        step(dctrl)
+        host_q.copy_(a["qpos"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    t1.record()
+    torch.cuda.synchronize()
+    total = B * world
+
+    def line(ms_t, e2e_t, launches):
+        return {"metric": "rodent_pair physics env-steps/s", "value": total * K / (ms_t * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_t / K,
+                "config": {"workload": WORKLOADS["rodent_pair"]["text"] + ", %d envs per GPU" % B, "envs_per_gpu": B, "global_envs": total,
+                           "parallelism": "env shards, dp%d, no data-path collective" % world, "envs_per_cta": eng.envs_per_cta},
+                "e2e": {"value": total * K / (e2e_t * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": B * model.nu * 4, "d2h_bytes_per_step": B * model.nq * 4},
+                "gpu_launches": launches, "roofline": None}
+    _finish_extra(args, line, ms, t0.elapsed_time(t1), K, dev, sampler, eng.launches - l0)
+
+
+def run_train(args, sgd: bool):
+    """configs[3]: rollout of 8192 envs/GPU x unroll 20 (policy + fused env step); with `sgd` the whole training_step of the
+    reference (ppo_imitation/train.py:296-349): + normaliser update + SGD phase (16 x 32 minibatch updates, gradient all-reduce)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import train_bench
+    sh = pkg("sharding")
+    rank, local_rank, world = sh.env_info()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        sh.init_process_group("nccl")
+    name = "train" if sgd else "rollout"
+    B, unroll = args.envs_per_gpu or WORKLOADS[name]["envs"], 20
+    nmb, nup = 32, (16 if sgd else 0)
+    tr = train_bench.build(dev, rank, world, B, unroll, nmb, max(nup, 1), True, False)
+    K, W = args.steps, args.warmup
+    host_metric = torch.empty(8).pin_memory()
+
+    def one(read_back):
+        tr.rollout.eps_z.normal_(generator=tr.gen); tr.rollout.eps_a.normal_(generator=tr.gen)
+        data = tr.rollout.generate_unroll()
+        tr.stats.update(data["observation"])
+        if sgd:
+            tr.learner.set_normalizer(tr.stats.mean, tr.stats.std)
+            tr.sgd_phase(data)
+            tr.policy.load_params(tr.learner.policy_params())
+        if read_back:  # the step's result on the host: loss metrics (train) / mean reward of the unroll (rollout)
+            host_metric[:1].copy_(data["reward"].mean().reshape(1), non_blocking=True)
+            if sgd:
+                host_metric.copy_(tr.learner.ws["metrics"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+    for _ in range(min(W, 3)):
+        one(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = tr.rollout.launches + tr.learner.launches
+    sh.barrier()
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    for _ in range(K):
+        one(False)
+    e1.record()
+    for _ in range(K):
+        one(True)
+    e2.record()
+    torch.cuda.synchronize()
+    total = B * world * unroll
+    launches = tr.rollout.launches + tr.learner.launches - l0
+
+    def line(ms_t, e2e_t, launches_):
+        return {"metric": ("rodent PPO training env-steps/s" if sgd else "rodent PPO rollout env-steps/s"), "value": total * K / (ms_t * 1e-3),
+                "unit": "env-steps/s", "ms_per_step": ms_t / K,
+                "config": {"workload": WORKLOADS[name]["text"] + ", %d envs per GPU" % B, "envs_per_gpu": B, "global_envs": B * world, "unroll_length": unroll,
+                           "parallelism": "env shards, dp%d; collectives: normaliser all-reduce (1.9 KB)%s" % (world, ", gradient all-reduce 6.5 MB per minibatch update (2 buckets)" if sgd else ""),
+                           "step": "one training_step" if sgd else "one unroll of 20 env steps", "minibatch_updates_per_step": nup * nmb,
+                           "policy": "PrecisePolicy (3xTF32)", "learner": "TF32 (one tensor-core pass)"},
+                "e2e": {"value": total * K / (e2e_t * 1e-3), "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 32,
+                        "note": "the rollout loop has no host input; the step's result (loss metrics / mean reward) is read back every step"},
+                "gpu_launches": launches_ // 2, "roofline": None}
+    _finish_extra(args, line, e0.elapsed_time(e1), e1.elapsed_time(e2), K, dev, sampler, launches)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -459,6 +613,10 @@ def main():
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "rodent_pair":
+        run_pair(args)
+    elif args.workload in ("rollout", "train"):
+        run_train(args, args.workload == "train")
     else:
         run_ours(args)
 
