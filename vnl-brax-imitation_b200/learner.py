@@ -203,7 +203,7 @@ class PPOLearner:
         self.launches += 1
 
     # ---- one loss + gradient evaluation ------------------------------------------------------------------------------------
-    def loss_and_grads(self, batch: Dict[str, "torch.Tensor"]):
+    def loss_and_grads(self, batch: Dict[str, "torch.Tensor"], exchange: bool = True):
         """batch (time-major, contiguous fp32 CUDA tensors, R = T * Bm rows):
         traj [R, ld_traj] (row stride padded to a multiple of 4: vnl_gather_rows does it), observation [R, obs],
         next_observation_last [Bm, obs], reward / discount / truncation / log_prob [R], raw_action [R, nu],
@@ -292,7 +292,9 @@ class PPOLearner:
         relu_ln_bwd(ws["dh0"], ws["h0pre"], ws["s0"], "encoder/LayerNorm_0", ws["dh0pre"])
         self._wgrad(traj, ws["dh0pre"], R, G("encoder/hidden_0/kernel"))
         colsum(ws["dh0pre"], self.widths["e1"], G("encoder/hidden_0/bias"))
-        self._policy_bucket_ready()
+        self._pending = None
+        if exchange:
+            self._policy_bucket_ready()
         # ---- backward: value (only the R baseline rows carry gradient; the bootstrap rows feed the stop-gradient GAE) ------------------------
         chk(L_.vnl_colsum(ptr(ws["v1"]), self.vh[1], R, self.vh[1], ptr(ws["dval"]), ptr(GV("hidden_2/kernel")), st), "colsum")
         chk(L_.vnl_colsum(ptr(ws["dval"]), 1, R, 1, None, ptr(GV("hidden_2/bias")), st), "colsum")
@@ -324,11 +326,12 @@ class PPOLearner:
         with t.cuda.stream(self.side):
             self._pending = start_bucket(dist, self.grads, 0, self.n_policy)
 
-    def apply_gradients(self):
-        """value bucket all-reduce + join the policy bucket, then optax.adam on the flat buffers (mean over ranks folded into Adam)."""
+    def apply_gradients(self, exchange: bool = True, scale: float = 1.0):
+        """value bucket all-reduce + join the policy bucket, then optax.adam on the flat buffers (mean over ranks folded into Adam).
+        `exchange=False`: the caller has already all-reduced self.grads (trainer.Trainer: eager NCCL call between two CUDA graphs)
+        and passes `scale` = 1 / world."""
         t, L_ = self.torch, tk.lib()
-        dist = self._dist()
-        scale = 1.0
+        dist = self._dist() if exchange else None
         if dist is not None:
             scale = finish_buckets(dist, self.grads, self.n_policy, self._pending)
             t.cuda.current_stream(self.device).wait_stream(self.side)

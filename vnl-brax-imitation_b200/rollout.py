@@ -101,8 +101,10 @@ class Rollout:
                     self._enqueue()
                 t.cuda.current_stream(self.eng.device).wait_stream(side)
                 self._restore(snap)
+                t.cuda.synchronize(self.eng.device)
                 self.graph = t.cuda.CUDAGraph()
-                with t.cuda.graph(self.graph):
+                # thread_local: event queries of other threads (NCCL's watchdog when a process group exists) do not invalidate the capture
+                with t.cuda.graph(self.graph, capture_error_mode="thread_local"):
                     self._enqueue()
                 self._restore(snap)
                 # the graph holds the policy's operand addresses: `load_params` / `set_normalizer` copy into them from now on

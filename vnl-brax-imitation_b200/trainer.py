@@ -9,7 +9,8 @@
 
 The transition buffers stay on the device from the env kernel to the loss: a minibatch is an index list over the env axis
 (`vnl_gather_rows`, which also pads traj rows 795 -> 796 floats for TMA).  One minibatch update (gathers + ~80 launches + the two
-gradient buckets + Adam) is captured once into a CUDA graph and replayed with fresh indices / noise.  torch = memory, streams,
+gradient exchange + Adam) is captured once into CUDA graphs (collective-free: with a process group the NCCL all-reduce runs eagerly
+between the gradient graph and the Adam graph) and replayed with fresh indices / noise.  torch = memory, streams,
 RNG for the noise operands and `torch.distributed`; no torch math on the data path, no CPU fallback.
 """
 from __future__ import annotations
@@ -68,9 +69,22 @@ class Trainer:
         self._gather(tr)
         self.learner.update(self.mb)
 
+    def _capture(self, fn):
+        """Capture `fn` into a CUDA graph.  The graphs of the SGD phase never contain a collective: with a process group the gradient
+        all-reduce runs eagerly BETWEEN two graphs (loss + gradients | Adam), so NCCL's watchdog thread and the capture never meet
+        (`capture_error_mode="thread_local"`: calls from other threads -- the watchdog's event queries -- do not invalidate it)."""
+        t = self.torch
+        t.cuda.synchronize(self.idx.device)
+        g = t.cuda.CUDAGraph()
+        with t.cuda.graph(g, capture_error_mode="thread_local"):
+            fn()
+        return g
+
     def sgd_phase(self, tr) -> None:
         """num_updates_per_batch x num_minibatches gradient updates on the unroll `tr` (train.py:336-341)."""
         t = self.torch
+        lr = self.learner
+        dist = lr._dist()
         self.discount_buf.copy_(tr["discount"])  # `1 - done` view materialised once per unroll
         # the policy's INPUT trajectory of step t is traj[t] (acting.py:47: state.info["traj"]), i.e. rollout.traj[:T]
         tr = dict(tr, state_extras_traj_in=self.rollout.traj[:self.T])
@@ -89,13 +103,21 @@ class Trainer:
                     with t.cuda.stream(side):
                         self._minibatch(tr)
                     t.cuda.current_stream(self.idx.device).wait_stream(side)
-                    self.graph = t.cuda.CUDAGraph()
-                    with t.cuda.graph(self.graph):
-                        self._minibatch(tr)
-                    self.learner.updates -= 1  # the capture pass went through the host-side counter without executing
-                    continue  # the capture does not execute: this minibatch was the warm-up run
-                self.graph.replay()
-                self.learner.updates += 1  # host-side counter (the device-side step counter advanced inside the graph)
+                    n0 = lr.updates
+                    if dist is None:
+                        self.graph = (self._capture(lambda: self._minibatch(tr)),)
+                    else:
+                        def grads_only():
+                            self._gather(tr)
+                            lr.loss_and_grads(self.mb, exchange=False)
+                        self.graph = (self._capture(grads_only), self._capture(lambda: lr.apply_gradients(exchange=False, scale=1.0 / dist.get_world_size())))
+                    lr.updates = n0  # the capture passes went through the host-side counter without executing
+                    continue  # this minibatch was the warm-up run
+                self.graph[0].replay()
+                if dist is not None:
+                    dist.all_reduce(lr.grads, op=dist.ReduceOp.SUM)  # lax.pmean of the gradients: one NCCL call, 6.5 MB; 1 / world in Adam
+                    self.graph[1].replay()
+                lr.updates += 1  # host-side counter (the device-side step counter advanced inside the graph)
 
     def training_step(self) -> Dict[str, float]:
         """One `training_step`: unroll, normaliser update, SGD phase, policy refresh.  Returns the last minibatch's loss metrics."""
