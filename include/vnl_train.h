@@ -75,6 +75,13 @@ int vnl_outer(const float* dv, int rows, const float* w, int n, float* dh, int l
 int vnl_policy_sample(const float* logits, int ld, const float* eps_a, const float* rand_action, int rows, int nu, float* action,
                       float* raw_action, float* log_prob, float* rand_log_prob, void* stream);
 
+/* brax `EvalWrapper` (envs/wrappers/training.py; installed by Evaluator at ppo_imitation/acting.py:109) folded over an unroll of T steps
+ * that starts at reset: per env, episode_metrics[k] = sum_t metrics[t, k] * active_t (k < nm) and [nm] = the same for the reward,
+ * active_{t+1} = active_t * (1 - done_t), episode_steps = steps of the first episode (info["steps"] while active).
+ * metrics [T, B, nm], reward / done [T, B]; outputs episode_metrics [B, nm + 1], active [B], episode_steps [B]. */
+int vnl_eval_metrics(int T, int B, int nm, const float* metrics, const float* reward, const float* done, float* episode_metrics, float* active,
+                     float* episode_steps, void* stream);
+
 /* Loss, part 1 (per row; intention_losses.py:149-166,189): brax NormalTanhDistribution on logits [rows, 2 nu]:
  *   target_lp[r] = log_prob(logits, raw_action), ent[r] = entropy(logits) with the sample loc + scale * eps_ent;
  *   termination[r] = (1 - discount[r]) * (1 - truncation[r]); rewards_s[r] = reward[r] * reward_scaling. */

@@ -252,7 +252,9 @@ int vnl_gemm_tf32(int M, int N, int K, int npairs, const float* const* A, int ld
   if (M <= 0 || N <= 0 || K <= 0 || npairs < 1 || npairs > 3 || !A || !B || !C || ldc < N) return -1;
   EncodeFn enc = encode_fn();
   if (!enc) return -4;
-  const int bn = N > 64 ? 128 : 64;
+  // tile width: 256 where it still fills the machine (>= 148 tiles), else 128; 64 for narrow outputs
+  const long tiles256 = (long)((N + 255) / 256) * ((M + BM - 1) / BM);
+  const int bn = N <= 64 ? 64 : ((N % 256 == 0 && tiles256 >= 148 && splitk <= 1) ? 256 : 128);
   CUtensorMap ta[3], tb[3];
   for (int p = 0; p < 3; ++p) {
     const int q = p < npairs ? p : 0;
@@ -270,6 +272,7 @@ int vnl_gemm_tf32(int M, int N, int K, int npairs, const float* const* A, int ld
   splits = (kblocks + g.kb_per_split - 1) / g.kb_per_split;
   g.atomic = splits > 1 ? 1 : 0;  // split-K partial tiles are added with red.global.add: the caller zeroes C first
   g.C = C; g.bias = bias;
+  if (bn == 256) return launch<256>(ta, tb, g, splits, (cudaStream_t)stream);
   return bn == 128 ? launch<128>(ta, tb, g, splits, (cudaStream_t)stream) : launch<64>(ta, tb, g, splits, (cudaStream_t)stream);
 }
 

@@ -248,6 +248,26 @@ __global__ void policy_sample_kernel(const float* __restrict__ logits, int ld, c
   }
 }
 
+// brax EvalWrapper.step folded over an unroll that starts at reset: one thread per env walks its T steps.
+__global__ void eval_metrics_kernel(int T, int B, int nm, const float* __restrict__ metrics, const float* __restrict__ reward,
+                                    const float* __restrict__ done, float* __restrict__ episode_metrics, float* __restrict__ active,
+                                    float* __restrict__ episode_steps) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float act = 1.0f, steps = 0.0f, acc[16];
+  for (int k = 0; k <= nm; ++k) acc[k] = 0.0f;
+  for (int t = 0; t < T; ++t) {
+    // episode_steps = where(active, nstate.info["steps"], episode_steps): an episode that is still active has taken t + 1 steps
+    if (act != 0.0f) steps = (float)(t + 1);
+    for (int k = 0; k < nm; ++k) acc[k] += metrics[((size_t)t * B + b) * nm + k] * act;
+    acc[nm] += reward[(size_t)t * B + b] * act;
+    act *= 1.0f - done[(size_t)t * B + b];
+  }
+  for (int k = 0; k <= nm; ++k) episode_metrics[(size_t)b * (nm + 1) + k] = acc[k];
+  active[b] = act;
+  episode_steps[b] = steps;
+}
+
 // mean and population std of `rows` values (jnp.mean / jnp.std), one block, fixed order
 __global__ void mean_std_kernel(const float* __restrict__ x, int rows, float* __restrict__ out2) {
   __shared__ double r1[32], r2[32];
@@ -425,6 +445,13 @@ int vnl_policy_sample(const float* logits, int ld, const float* eps_a, const flo
   if (!logits || !action || !raw_action || !log_prob || rows <= 0 || nu <= 0 || nu > 32 || ld < 2 * nu) return -1;
   policy_sample_kernel<<<grid_for((size_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(logits, ld, eps_a, rand_action, rows, nu, action, raw_action,
                                                                                           log_prob, rand_log_prob);
+  return rc();
+}
+
+int vnl_eval_metrics(int T, int B, int nm, const float* metrics, const float* reward, const float* done, float* episode_metrics, float* active,
+                     float* episode_steps, void* stream) {
+  if (T <= 0 || B <= 0 || nm < 0 || nm > 15 || !metrics || !reward || !done || !episode_metrics || !active || !episode_steps) return -1;
+  eval_metrics_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(T, B, nm, metrics, reward, done, episode_metrics, active, episode_steps);
   return rc();
 }
 

@@ -65,7 +65,7 @@ class Rollout:
         for t in range(self.T):
             pout = {"action": self.action[t], "raw_action": self.raw_action[t], "logits": self.logits[t],
                     "log_prob": self.log_prob[t], "rand_log_prob": self.rand_log_prob[t]}
-            self.policy(self.traj[t], self.obs[t], self.eps_z[t], self.eps_a[t], out=pout)
+            self.policy(self.traj[t], self.obs[t], self.eps_z[t], None if self.eps_a is None else self.eps_a[t], out=pout)  # eps_a None: the mode
             out = {"obs": self.obs[t + 1], "traj": self.traj[t + 1], "reward": self.reward[t], "done": self.done[t],
                    "metrics": self.metrics[t]}
             self.eng.step_training(self.state[cur], self.action[t], self.state[1 - cur], out, self.first, self.first_obs,
@@ -86,7 +86,7 @@ class Rollout:
             self.eps_z.copy_(eps_z)
         if eps_a is not None:
             self.eps_a.copy_(eps_a)
-        if self.launches:  # the previous unroll's last obs / traj are this one's first
+        if self.launches and not getattr(self, "_fresh", False):  # the previous unroll's last obs / traj are this one's first
             self.obs[0].copy_(self.obs[self.T])
             self.traj[0].copy_(self.traj[self.T])
         if not self.use_graph:
@@ -117,10 +117,28 @@ class Rollout:
                 raise RuntimeError("policy operands moved after the rollout graph was captured")
             self.graph.replay()
         self.launches += 2 * self.T
+        self._fresh = False
         return {"observation": self.obs[:self.T], "next_observation": self.obs[1:], "action": self.action, "reward": self.reward,
                 "discount": 1.0 - self.done, "policy_extras": {"log_prob": self.log_prob, "raw_action": self.raw_action,
                                                                "logits": self.logits},
                 "state_extras": {"truncation": self.truncation, "traj": self.traj[1:]}, "metrics": self.metrics}
+
+    def reset_to(self, first_state) -> None:
+        """Start over from a fresh `env.reset(...)` state WITHOUT changing any buffer address (a captured graph stays valid): the
+        evaluator resets its envs before every evaluation (acting.py:111-113)."""
+        for k, v in first_state.pipeline_state.items():
+            self.first[k].copy_(v)
+            self.state[self.cur][k].copy_(v)
+        self.first_obs.copy_(first_state.obs)
+        self.state[self.cur]["cur_frame"].copy_(first_state.info["cur_frame"])
+        self.state[self.cur]["sub_clip_frame"].copy_(first_state.info["sub_clip_frame"])
+        if "clip_id" in self.state[self.cur] and first_state.info.get("clip_idx") is not None:
+            self.state[self.cur]["clip_id"].copy_(first_state.info["clip_idx"])
+        self.steps.zero_()
+        self.done_prev.zero_()
+        self.obs[0].copy_(first_state.obs)
+        self.traj[0].copy_(first_state.info["traj"])
+        self._fresh = True
 
     # -----------------------------------------------------------------------------------------------------------------
     def _snapshot(self):
