@@ -11,10 +11,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
+RND = os.environ.get("ROUND", "r02")  # file-name prefix of this round's summaries; raw inputs: gpurun_out/<RND>_launches.csv, <RND>_prof.ncu-rep
 
 
 def launch_list():
-    rows = list(csv.reader(open(os.path.join(G, "launches.csv"))))
+    rows = list(csv.reader(open(os.path.join(G, RND + "_launches.csv"))))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr = rows[hi]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
@@ -34,19 +35,19 @@ def launch_list():
            "%-92s %6s %12s %7s" % ("kernel", "count", "total_us", "share")]
     for k, a in sorted(agg.items(), key=lambda x: -x[1][1]):
         out.append("%-92s %6d %12.1f %6.2f%%" % (k, a[0], a[1], 100 * a[1] / tot))
-    open(os.path.join(P, "r01_ncu_launch_list_summary.txt"), "w").write("\n".join(out) + "\n")
-    shutil.copy(os.path.join(G, "launches.csv"), os.path.join(P, "r01_ncu_launches.csv"))
+    open(os.path.join(P, RND + "_ncu_launch_list_summary.txt"), "w").write("\n".join(out) + "\n")
+    shutil.copy(os.path.join(G, RND + "_launches.csv"), os.path.join(P, RND + "_ncu_launches.csv"))
     print("\n".join(out[3:6]))
 
 
 def full_capture():
-    rep = os.path.join(G, "prof.ncu-rep")
-    open(os.path.join(P, "r01_ncu_full_step_kernel_details.txt"), "w").write(
+    rep = os.path.join(G, RND + "_prof.ncu-rep")
+    open(os.path.join(P, RND + "_ncu_full_step_kernel_details.txt"), "w").write(
         subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout)
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
     open("/tmp/src.csv", "w").write(src)
     hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), "/tmp/src.csv", "45"], capture_output=True, text=True).stdout
-    open(os.path.join(P, "r01_ncu_source_hotspots.txt"), "w").write(hot)
+    open(os.path.join(P, RND + "_ncu_source_hotspots.txt"), "w").write(hot)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     d = {k: (rows[2][i], rows[1][i]) for i, k in enumerate(rows[0])}
@@ -57,7 +58,7 @@ def full_capture():
 
     r, w = nbytes("dram__bytes_read.sum"), nbytes("dram__bytes_write.sum")
     json.dump({"envs": 4096, "dram_bytes_per_launch": int(r + w),
-               "source": "profiles/r01_ncu_full_step_kernel_details.txt (ncu --set full, vnl_env_kernel<0>, 4096 envs): "
+               "source": "profiles/" + RND + "_ncu_full_step_kernel_details.txt (ncu --set full, vnl_env_kernel<0>, 4096 envs): "
                          "dram__bytes_read.sum %.3f MB + dram__bytes_write.sum %.3f MB; the algorithmic 35.5 MB per launch and the "
                          "inertia workspace stay in the 126 MB L2" % (r / 1e6, w / 1e6)}, open(os.path.join(P, "traffic.json"), "w"))
     print("dram MB", r / 1e6, w / 1e6, "duration", d["gpu__time_duration.sum"], "inst", d["smsp__inst_executed.sum"])
@@ -79,4 +80,5 @@ def bench_lines():
 if __name__ == "__main__":
     launch_list()
     full_capture()
-    bench_lines()
+    if RND == "r01":
+        bench_lines()
