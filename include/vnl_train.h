@@ -44,9 +44,10 @@ int vnl_obs_normalize(const float* obs, int ld_obs, int rows, int width, const f
  * stats [rows, 2] = (mean, rstd) of relu(pre), kept for the backward pass. */
 int vnl_relu_ln_fwd(const float* pre, int ld_pre, int rows, int n, const float* scale, const float* bias, float* out, int ld_out,
                     float* stats, void* stream);
-/* dpre from dy; dscale / dbias [n] are ACCUMULATED (caller zeroes). */
+/* dpre from dy; dscale / dbias [n] are ACCUMULATED (caller zeroes).  dbias_pre (may be NULL) [n] += column sums of dpre = the bias
+ * gradient of the dense layer in front of the relu, so that it needs no pass of its own. */
 int vnl_relu_ln_bwd(const float* dy, int ld_dy, const float* pre, int ld_pre, const float* stats, const float* scale, int rows, int n,
-                    float* dpre, int ld_dpre, float* dscale, float* dbias, void* stream);
+                    float* dpre, int ld_dpre, float* dscale, float* dbias, float* dbias_pre, void* stream);
 
 /* swish / silu of the brax value MLP (linen.swish), elementwise over n values. */
 int vnl_swish_fwd(const float* pre, size_t n, float* out, void* stream);
@@ -66,6 +67,11 @@ int vnl_colsum(const float* x, int ld, int rows, int n, const float* w, float* o
 int vnl_rowdot(const float* h, int ld, int rows, int n, const float* w, const float* b, float* out, void* stream);
 /* dh[r, c] = dv[r] * w[c]   (value head backward) */
 int vnl_outer(const float* dv, int rows, const float* w, int n, float* dh, int ld, void* stream);
+/* dpre[r, c] = dv[r] * w[c] * swish'(pre[r, c]): vnl_outer followed by vnl_swish_bwd without the intermediate (pre, dpre: ld = n) */
+int vnl_outer_swish_bwd(const float* dv, int rows, const float* w, int n, const float* pre, float* dpre, void* stream);
+/* n <= 4 scalar streams [T, B] of the unroll (reward, discount, truncation, log_prob) gathered by the minibatch's env index list in one
+ * launch: dst[k][t * Bm + j] = src[k][t * B + idx[j]]; src / dst are HOST arrays of n device pointers. */
+int vnl_gather_scalars(int n, const float* const* src, float* const* dst, int T, int B, const int32_t* idx, int Bm, void* stream);
 
 /* Rollout-side sampling of brax NormalTanhDistribution (ppo_imitation/ppo_networks.py:55-83) on fp32 logits [rows, 2 nu]:
  * raw_action = loc + scale * eps_a (eps_a = NULL: the mode, `deterministic=True`), action = tanh(raw_action), log_prob(raw_action),

@@ -54,6 +54,9 @@ def test_learner_reevaluates_the_rollouts_log_probs(gpu_env, rodent, precise):
     assert torch.equal(tr.mb["observation"], data["observation"].reshape(T * B, -1)[rows])
     assert torch.equal(tr.mb["traj"][:, :L.traj], ro.traj[:T].reshape(T * B, -1)[rows]) and float(tr.mb["traj"][:, L.traj:].abs().max()) == 0
     assert torch.equal(tr.mb["next_observation_last"], ro.obs[T][tr.idx.long()])
+    for k, src in (("reward", data["reward"]), ("discount", data["discount"]), ("truncation", data["state_extras"]["truncation"]),
+                   ("log_prob", data["policy_extras"]["log_prob"])):  # the four scalar streams travel in one launch (vnl_gather_scalars)
+        assert torch.equal(tr.mb[k], src.reshape(-1)[rows]), k
     behaviour = data["policy_extras"]["log_prob"].reshape(-1)[rows]
     diff = (L.ws["target_lp"] - behaviour).abs()
     logits_roll = data["policy_extras"]["logits"].reshape(T * B, -1)[rows]

@@ -4,7 +4,9 @@ GEMMs, Adam) with the gradient all-reduce over NCCL at N > 1 -- timed phase by p
 
     python tools/train_bench.py                                             # 1 GPU
     python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/train_bench.py
-  env: ENVS (8192) MINIBATCHES (32) UPDATES (16) STEPS (2) GRAPH (1) X3 (0)"""
+  env: ENVS (8192) MINIBATCHES (32) UPDATES (16) STEPS (2) GRAPH (1) X3 (0)
+  PROFILE=1 (with GRAPH=0): after the warm-up step, ONE eager minibatch update between cudaProfilerStart / Stop and exit -- the region
+  `ncu --profile-from-start off --metrics gpu__time_duration.sum` lists (tools/make_profiles.py summarises the csv)."""
 import importlib
 import json
 import os
@@ -50,6 +52,19 @@ def main():
     ev = lambda: torch.cuda.Event(enable_timing=True)
     m = tr.training_step()  # warm-up: graph captures
     torch.cuda.synchronize()
+    if os.environ.get("PROFILE") == "1":
+        data = tr.rollout.generate_unroll()
+        data = dict(data, state_extras_traj_in=tr.rollout.traj[:unroll])
+        tr.discount_buf.copy_(data["discount"])
+        tr.idx.copy_(torch.randperm(B, device=dev)[:tr.Bm].to(torch.int32))
+        tr.eps.normal_(generator=tr.gen)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        tr._minibatch(data)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled": "one eager minibatch update", "rows": unroll * tr.Bm}), flush=True)
+        return
     sh.barrier()
     t_ro = t_sgd = 0.0
     w0, w1 = ev(), ev()

@@ -125,12 +125,14 @@ class PPOLearner:
             val=f(R + Bm), target_lp=f(R), ent=f(R), termination=f(R), rewards_s=f(R), vs=f(R), adv=f(R),
             dlogits=f(R, 2 * nu), dval=f(R), dd1=f(R, d2), dd1pre=f(R, d2), dd0=f(R, d1), dd0pre=f(R, d1), ddec_in=f(R, L + self.obs),
             dheads=f(R, 2 * L), dh1=f(R, e2), dh1pre=f(R, e2), dh0=f(R, e1), dh0pre=f(R, e1),
-            dv1=f(R, self.vh[1]), dv1pre=f(R, self.vh[1]), dv0=f(R, self.vh[0]), dv0pre=f(R, self.vh[0]),
+            dv1pre=f(R, self.vh[1]), dv0=f(R, self.vh[0]), dv0pre=f(R, self.vh[0]),
             metrics=f(8), scratch2=f(2))
         self.obs_mean, self.obs_std = f(self.obs), t.ones(self.obs, dtype=t.float32, device=dev)
         self.updates = 0
         self.launches = 0
-        self.side = t.cuda.Stream(device=dev)
+        self.side = t.cuda.Stream(device=dev)    # gradient exchange of the policy bucket
+        self.branch = t.cuda.Stream(device=dev)  # the value network's forward / backward, beside the policy's
+        self.leaf_p, self.leaf_v = t.cuda.Stream(device=dev), t.cuda.Stream(device=dev)  # weight / bias gradients: leaves of the backward chains
         self._gae = gae_mod._bind(tk.lib())
         self._pending = None
         del W
@@ -199,7 +201,7 @@ class PPOLearner:
         tiles = ((M + 127) // 128) * ((N + (127 if N > 64 else 63)) // (128 if N > 64 else 64))
         kb = (rows + 31) // 32
         sk = max(self._splitk(rows), min(max(1, 148 // tiles), max(1, kb // 4)))
-        tk.gemm(x, 1, dy, 1, gW, M, N, rows, x3=self.x3, splitk=sk)
+        tk.gemm(x, 1, dy, 1, gW, M, N, rows, x3=self.x3, splitk=sk, zero=False)  # self.grads was zeroed at the top of the evaluation
         self.launches += 1
 
     # ---- one loss + gradient evaluation ------------------------------------------------------------------------------------
@@ -222,10 +224,26 @@ class PPOLearner:
         assert traj.shape == (R, self.ld_traj) and obs.shape == (R, self.obs) and traj.is_contiguous() and obs.is_contiguous()
         # ---- forward: policy --------------------------------------------------------------------------------------------
         Ld = self.L + self.obs
+        # The two networks are independent up to the loss rows and again after them: the value network runs on `self.branch`
+        # (fork / join by stream events, which a CUDA-graph capture records as two parallel chains), so the policy's small,
+        # latency-bound GEMMs (40-80 CTAs each) fill the SMs the value GEMMs leave idle between their waves.
+        main = t.cuda.current_stream(self.device)
+        V = lambda k: p["value/" + k]
+        GV = lambda k: g["value/" + k]
+        RB = R + Bm
+        self.branch.wait_stream(main)
+        with t.cuda.stream(self.branch):
+            sb = tk.stream(self.params)
+            chk(L_.vnl_obs_normalize(ptr(obs), self.obs, R, self.obs, ptr(self.obs_mean), ptr(self.obs_std), ptr(ws["vin"]), self.obs, sb), "normalize")
+            chk(L_.vnl_obs_normalize(ptr(batch["next_observation_last"]), self.obs, Bm, self.obs, ptr(self.obs_mean), ptr(self.obs_std),
+                                     ptr(ws["vin"]) + 4 * R * self.obs, self.obs, sb), "normalize")
+            # value forward (baseline rows + the Bm bootstrap rows in one pass)
+            self._fwd(ws["vin"], RB, V("hidden_0/kernel"), V("hidden_0/bias"), ws["v0pre"])
+            chk(L_.vnl_swish_fwd(ptr(ws["v0pre"]), ws["v0pre"].numel(), ptr(ws["v0"]), sb), "swish")
+            self._fwd(ws["v0"], RB, V("hidden_1/kernel"), V("hidden_1/bias"), ws["v1pre"])
+            chk(L_.vnl_swish_fwd(ptr(ws["v1pre"]), ws["v1pre"].numel(), ptr(ws["v1"]), sb), "swish")
+            chk(L_.vnl_rowdot(ptr(ws["v1"]), self.vh[1], RB, self.vh[1], ptr(V("hidden_2/kernel")), ptr(V("hidden_2/bias")), ptr(ws["val"]), sb), "rowdot")
         chk(L_.vnl_obs_normalize(ptr(obs), self.obs, R, self.obs, ptr(self.obs_mean), ptr(self.obs_std), ptr(ws["dec_in"]) + 4 * self.L, Ld, st), "normalize")
-        chk(L_.vnl_obs_normalize(ptr(obs), self.obs, R, self.obs, ptr(self.obs_mean), ptr(self.obs_std), ptr(ws["vin"]), self.obs, st), "normalize")
-        chk(L_.vnl_obs_normalize(ptr(batch["next_observation_last"]), self.obs, Bm, self.obs, ptr(self.obs_mean), ptr(self.obs_std),
-                                 ptr(ws["vin"]) + 4 * R * self.obs, self.obs, st), "normalize")
 
         def relu_ln(pre, name, out, stats):
             n = pre.shape[1]
@@ -241,15 +259,7 @@ class PPOLearner:
         self._fwd(ws["d0"], R, P("decoder/hidden_1/kernel"), P("decoder/hidden_1/bias"), ws["d1pre"])
         relu_ln(ws["d1pre"], "decoder/LayerNorm_1", ws["d1"], ws["s3"])
         self._fwd(ws["d1"], R, P("decoder/hidden_2/kernel"), P("decoder/hidden_2/bias"), ws["logits"])
-        # ---- forward: value (baseline rows + the Bm bootstrap rows in one pass) ---------------------------------------------------
-        V = lambda k: p["value/" + k]
-        GV = lambda k: g["value/" + k]
-        RB = R + Bm
-        self._fwd(ws["vin"], RB, V("hidden_0/kernel"), V("hidden_0/bias"), ws["v0pre"])
-        chk(L_.vnl_swish_fwd(ptr(ws["v0pre"]), ws["v0pre"].numel(), ptr(ws["v0"]), st), "swish")
-        self._fwd(ws["v0"], RB, V("hidden_1/kernel"), V("hidden_1/bias"), ws["v1pre"])
-        chk(L_.vnl_swish_fwd(ptr(ws["v1pre"]), ws["v1pre"].numel(), ptr(ws["v1"]), st), "swish")
-        chk(L_.vnl_rowdot(ptr(ws["v1"]), self.vh[1], RB, self.vh[1], ptr(V("hidden_2/kernel")), ptr(V("hidden_2/bias")), ptr(ws["val"]), st), "rowdot")
+        main.wait_stream(self.branch)  # join: the loss rows need logits and values
         # ---- loss -------------------------------------------------------------------------------------------------------------
         chk(L_.vnl_ppo_rows(ptr(ws["logits"]), 2 * nu, ptr(batch["raw_action"]), ptr(batch["eps_ent"]), R, nu, ptr(batch["discount"]),
                             ptr(batch["truncation"]), ptr(batch["reward"]), float(hp["reward_scaling"]), ptr(ws["target_lp"]), ptr(ws["ent"]),
@@ -261,52 +271,67 @@ class PPOLearner:
                                 float(hp["entropy_cost"]), int(bool(hp["normalize_advantage"])), ptr(ws["dlogits"]), 2 * nu, ptr(ws["dval"]),
                                 ptr(ws["metrics"]), ptr(ws["scratch2"]), st), "ppo_loss_bwd")
         self.launches += 14
-        # ---- backward: policy (its gradient bucket is complete first: its all-reduce overlaps the value backward) -------------------------
-        colsum = lambda x, n, out, w=None: chk(L_.vnl_colsum(ptr(x), x.shape[1] if x.dim() == 2 else n, R, n, None if w is None else ptr(w), ptr(out), st), "colsum")
+        colsum = lambda x, n, out, w=None: chk(L_.vnl_colsum(ptr(x), x.shape[1] if x.dim() == 2 else n, R, n, None if w is None else ptr(w), ptr(out),
+                                                             tk.stream(self.params)), "colsum")
+        # ---- backward ------------------------------------------------------------------------------------------------------------
+        # Each network's backward is a serial CHAIN (dgrad -> activation backward -> dgrad ...) with LEAVES hanging off it (the weight
+        # and bias gradients of every layer, which nothing downstream reads).  Chains run on `main` (policy) and `self.branch`
+        # (value); leaves go to `leaf_p` / `leaf_v` as soon as their operand exists, so a chain never queues behind a leaf.
+        def leaf(stream, after, fn):
+            stream.wait_stream(after)
+            with t.cuda.stream(stream):
+                fn()
 
-        def relu_ln_bwd(dy, pre, stats, name, dpre):
+        # value (only the R baseline rows carry gradient; the bootstrap rows feed the stop-gradient GAE)
+        self.branch.wait_stream(main)
+
+        def value_head_leaves():
+            sl = tk.stream(self.params)
+            chk(L_.vnl_colsum(ptr(ws["v1"]), self.vh[1], R, self.vh[1], ptr(ws["dval"]), ptr(GV("hidden_2/kernel")), sl), "colsum")
+            chk(L_.vnl_colsum(ptr(ws["dval"]), 1, R, 1, None, ptr(GV("hidden_2/bias")), sl), "colsum")
+        leaf(self.leaf_v, main, value_head_leaves)
+        with t.cuda.stream(self.branch):
+            sb = tk.stream(self.params)
+            chk(L_.vnl_outer_swish_bwd(ptr(ws["dval"]), R, ptr(V("hidden_2/kernel")), self.vh[1], ptr(ws["v1pre"]), ptr(ws["dv1pre"]), sb), "outer_swish_bwd")
+        leaf(self.leaf_v, self.branch, lambda: (self._wgrad(ws["v0"], ws["dv1pre"], R, GV("hidden_1/kernel")),
+                                                colsum(ws["dv1pre"], self.vh[1], GV("hidden_1/bias"))))
+        with t.cuda.stream(self.branch):
+            self._dgrad(ws["dv1pre"], R, V("hidden_1/kernel"), ws["dv0"])
+            chk(L_.vnl_swish_bwd(ptr(ws["dv0"]), ptr(ws["v0pre"]), R * self.vh[0], ptr(ws["dv0pre"]), sb), "swish_bwd")
+            self._wgrad(ws["vin"], ws["dv0pre"], R, GV("hidden_0/kernel"))
+            colsum(ws["dv0pre"], self.vh[0], GV("hidden_0/bias"))
+
+        # policy (its gradient bucket goes to the exchange as soon as it is complete)
+        def relu_ln_bwd(dy, pre, stats, name, dpre, dense):  # also leaves the bias gradient of the dense layer in front (column sums of dpre)
             n = pre.shape[1]
             chk(L_.vnl_relu_ln_bwd(ptr(dy), n, ptr(pre), n, ptr(stats), ptr(P(name + "/scale")), R, n, ptr(dpre), n, ptr(G(name + "/scale")),
-                                   ptr(G(name + "/bias")), st), "relu_ln_bwd")
-        self._wgrad(ws["d1"], ws["dlogits"], R, G("decoder/hidden_2/kernel"))
-        colsum(ws["dlogits"], 2 * nu, G("decoder/hidden_2/bias"))
+                                   ptr(G(name + "/bias")), ptr(G(dense + "/bias")), st), "relu_ln_bwd")
+        lp = lambda fn: leaf(self.leaf_p, main, fn)
+        lp(lambda: (self._wgrad(ws["d1"], ws["dlogits"], R, G("decoder/hidden_2/kernel")), colsum(ws["dlogits"], 2 * nu, G("decoder/hidden_2/bias"))))
         self._dgrad(ws["dlogits"], R, P("decoder/hidden_2/kernel"), ws["dd1"])
-        relu_ln_bwd(ws["dd1"], ws["d1pre"], ws["s3"], "decoder/LayerNorm_1", ws["dd1pre"])
-        self._wgrad(ws["d0"], ws["dd1pre"], R, G("decoder/hidden_1/kernel"))
-        colsum(ws["dd1pre"], self.widths["d2"], G("decoder/hidden_1/bias"))
+        relu_ln_bwd(ws["dd1"], ws["d1pre"], ws["s3"], "decoder/LayerNorm_1", ws["dd1pre"], "decoder/hidden_1")
+        lp(lambda: self._wgrad(ws["d0"], ws["dd1pre"], R, G("decoder/hidden_1/kernel")))
         self._dgrad(ws["dd1pre"], R, P("decoder/hidden_1/kernel"), ws["dd0"])
-        relu_ln_bwd(ws["dd0"], ws["d0pre"], ws["s2"], "decoder/LayerNorm_0", ws["dd0pre"])
-        self._wgrad(ws["dec_in"], ws["dd0pre"], R, G("decoder/hidden_0/kernel"))
-        colsum(ws["dd0pre"], self.widths["d1"], G("decoder/hidden_0/bias"))
+        relu_ln_bwd(ws["dd0"], ws["d0pre"], ws["s2"], "decoder/LayerNorm_0", ws["dd0pre"], "decoder/hidden_0")
+        lp(lambda: self._wgrad(ws["dec_in"], ws["dd0pre"], R, G("decoder/hidden_0/kernel")))
         self._dgrad(ws["dd0pre"], R, P("decoder/hidden_0/kernel"), ws["ddec_in"])
         kl_coef = float(hp["kl_weight"]) / float(R * self.L)
         chk(L_.vnl_heads_bwd(ptr(ws["ddec_in"]), Ld, ptr(ws["heads"]), ptr(batch["eps_z"]), R, self.L, kl_coef, ptr(ws["dheads"]),
                              ptr(ws["metrics"]) + 16, st), "heads_bwd")
-        self._wgrad(ws["h1"], ws["dheads"], R, G("encoder/heads/kernel"))
-        colsum(ws["dheads"], 2 * self.L, G("encoder/heads/bias"))
+        lp(lambda: (self._wgrad(ws["h1"], ws["dheads"], R, G("encoder/heads/kernel")), colsum(ws["dheads"], 2 * self.L, G("encoder/heads/bias"))))
         self._dgrad(ws["dheads"], R, P("encoder/heads/kernel"), ws["dh1"])
-        relu_ln_bwd(ws["dh1"], ws["h1pre"], ws["s1"], "encoder/LayerNorm_1", ws["dh1pre"])
-        self._wgrad(ws["h0"], ws["dh1pre"], R, G("encoder/hidden_1/kernel"))
-        colsum(ws["dh1pre"], self.widths["e2"], G("encoder/hidden_1/bias"))
+        relu_ln_bwd(ws["dh1"], ws["h1pre"], ws["s1"], "encoder/LayerNorm_1", ws["dh1pre"], "encoder/hidden_1")
+        lp(lambda: self._wgrad(ws["h0"], ws["dh1pre"], R, G("encoder/hidden_1/kernel")))
         self._dgrad(ws["dh1pre"], R, P("encoder/hidden_1/kernel"), ws["dh0"])
-        relu_ln_bwd(ws["dh0"], ws["h0pre"], ws["s0"], "encoder/LayerNorm_0", ws["dh0pre"])
+        relu_ln_bwd(ws["dh0"], ws["h0pre"], ws["s0"], "encoder/LayerNorm_0", ws["dh0pre"], "encoder/hidden_0")
         self._wgrad(traj, ws["dh0pre"], R, G("encoder/hidden_0/kernel"))
-        colsum(ws["dh0pre"], self.widths["e1"], G("encoder/hidden_0/bias"))
+        main.wait_stream(self.leaf_p)  # the policy bucket is complete
         self._pending = None
         if exchange:
             self._policy_bucket_ready()
-        # ---- backward: value (only the R baseline rows carry gradient; the bootstrap rows feed the stop-gradient GAE) ------------------------
-        chk(L_.vnl_colsum(ptr(ws["v1"]), self.vh[1], R, self.vh[1], ptr(ws["dval"]), ptr(GV("hidden_2/kernel")), st), "colsum")
-        chk(L_.vnl_colsum(ptr(ws["dval"]), 1, R, 1, None, ptr(GV("hidden_2/bias")), st), "colsum")
-        chk(L_.vnl_outer(ptr(ws["dval"]), R, ptr(V("hidden_2/kernel")), self.vh[1], ptr(ws["dv1"]), self.vh[1], st), "outer")
-        chk(L_.vnl_swish_bwd(ptr(ws["dv1"]), ptr(ws["v1pre"]), R * self.vh[1], ptr(ws["dv1pre"]), st), "swish_bwd")
-        self._wgrad(ws["v0"], ws["dv1pre"], R, GV("hidden_1/kernel"))
-        colsum(ws["dv1pre"], self.vh[1], GV("hidden_1/bias"))
-        self._dgrad(ws["dv1pre"], R, V("hidden_1/kernel"), ws["dv0"])
-        chk(L_.vnl_swish_bwd(ptr(ws["dv0"]), ptr(ws["v0pre"]), R * self.vh[0], ptr(ws["dv0pre"]), st), "swish_bwd")
-        self._wgrad(ws["vin"], ws["dv0pre"], R, GV("hidden_0/kernel"))
-        colsum(ws["dv0pre"], self.vh[0], GV("hidden_0/bias"))
-        self.launches += 24
+        main.wait_stream(self.branch)  # join: all gradients are in self.grads
+        main.wait_stream(self.leaf_v)
+        self.launches += 19
         return ws["metrics"]
 
     # ---- gradient exchange + optimiser ---------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ from typing import Optional
 from . import _lib
 
 TRAIN_EXPORTS = ("vnl_gemm_tf32", "vnl_split_tf32", "vnl_gather_rows", "vnl_obs_normalize", "vnl_relu_ln_fwd", "vnl_relu_ln_bwd",
-                 "vnl_swish_fwd", "vnl_swish_bwd", "vnl_reparam_fwd", "vnl_heads_bwd", "vnl_colsum", "vnl_rowdot", "vnl_outer",
+                 "vnl_swish_fwd", "vnl_swish_bwd", "vnl_reparam_fwd", "vnl_heads_bwd", "vnl_colsum", "vnl_rowdot", "vnl_outer", "vnl_outer_swish_bwd", "vnl_gather_scalars",
                  "vnl_ppo_rows", "vnl_ppo_loss_bwd", "vnl_adam_tick", "vnl_adam", "vnl_policy_sample", "vnl_eval_metrics")
 _bound = None
 
@@ -23,7 +23,7 @@ def lib():
         L.vnl_gather_rows.argtypes = [v, i, i, i, v, i, v, i, v]
         L.vnl_obs_normalize.argtypes = [v, i, i, i, v, v, v, i, v]
         L.vnl_relu_ln_fwd.argtypes = [v, i, i, i, v, v, v, i, v, v]
-        L.vnl_relu_ln_bwd.argtypes = [v, i, v, i, v, v, i, i, v, i, v, v, v]
+        L.vnl_relu_ln_bwd.argtypes = [v, i, v, i, v, v, i, i, v, i, v, v, v, v]
         L.vnl_swish_fwd.argtypes = [v, sz, v, v]
         L.vnl_swish_bwd.argtypes = [v, v, sz, v, v]
         L.vnl_reparam_fwd.argtypes = [v, v, i, i, v, i, v]
@@ -31,6 +31,8 @@ def lib():
         L.vnl_colsum.argtypes = [v, i, i, i, v, v, v]
         L.vnl_rowdot.argtypes = [v, i, i, i, v, v, v, v]
         L.vnl_outer.argtypes = [v, i, v, i, v, i, v]
+        L.vnl_outer_swish_bwd.argtypes = [v, i, v, i, v, v, v]
+        L.vnl_gather_scalars.argtypes = [i, v, v, i, i, v, i, v]
         L.vnl_ppo_rows.argtypes = [v, i, v, v, i, i, v, v, v, f, v, v, v, v, v]
         L.vnl_ppo_loss_bwd.argtypes = [v, i, v, v, i, i, v, v, v, v, v, v, f, f, i, v, i, v, v, v, v]
         L.vnl_policy_sample.argtypes = [v, i, v, v, i, i, v, v, v, v, v]
@@ -69,9 +71,9 @@ def split_into(x, hi, lo):
     return hi, lo
 
 
-def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: bool = False, splitk: int = 1, parts=None):
+def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: bool = False, splitk: int = 1, parts=None, zero: bool = True):
     """C[M, N] (+)= A . B^T (+ bias); operands are 2-D fp32 tensors whose row stride is their ld.  `x3`: 3xTF32 (the operands are
-    split here unless `parts` = ((A_hi, A_lo), (B_hi, B_lo)) is given).  splitk > 1 accumulates into C (zeroed here)."""
+    split here unless `parts` = ((A_hi, A_lo), (B_hi, B_lo)) is given).  splitk > 1 accumulates into C (zeroed here unless the caller says it already is: `zero=False`)."""
     for t in (A, B, C):
         assert t.dim() == 2 and t.stride(1) == 1 and t.dtype.is_floating_point and t.element_size() == 4
     if x3:
@@ -79,7 +81,7 @@ def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: b
         As, Bs = [ah, ah, al], [bh, bl, bh]
     else:
         As, Bs = [A], [B]
-    if splitk > 1:
+    if splitk > 1 and zero:
         C.zero_()
     rc = lib().vnl_gemm_tf32(M, N, K, len(As), _ptrs(As), A.stride(0), int(a_mn), _ptrs(Bs), B.stride(0), int(b_mn), C.data_ptr(), C.stride(0),
                              None if bias is None else bias.data_ptr(), int(splitk), stream(C))

@@ -41,8 +41,13 @@ class Trainer:
         R = self.T * self.Bm
         # static minibatch operands (graph-captured addresses)
         self.idx = t.zeros(self.Bm, dtype=t.int32, device=dev)
+        self.eps = f(R * (L.L + L.nu))  # both noise operands of a minibatch in one buffer: one generator launch per minibatch
         self.mb = dict(traj=f(R, L.ld_traj), observation=f(R, L.obs), next_observation_last=f(self.Bm, L.obs), reward=f(R), discount=f(R),
-                       truncation=f(R), log_prob=f(R), raw_action=f(R, L.nu), eps_z=f(R, L.L), eps_ent=f(R, L.nu))
+                       truncation=f(R), log_prob=f(R), raw_action=f(R, L.nu), eps_z=self.eps[:R * L.L].view(R, L.L),
+                       eps_ent=self.eps[R * L.L:].view(R, L.nu))
+        import ctypes
+        self._scalar_keys = ("reward", "discount", "truncation", "log_prob")
+        self._sdst = (ctypes.c_void_p * 4)(*[self.mb[k].data_ptr() for k in self._scalar_keys])
         self.gen = t.Generator(device=dev).manual_seed(seed)
         self.use_graph, self.graph = bool(use_graph), None
         self.discount_buf = f(self.T, self.B)
@@ -60,10 +65,13 @@ class Trainer:
         g(tr["observation"], lr.obs, mb["observation"], lr.obs)
         g(tr["next_observation"][T - 1:T], lr.obs, mb["next_observation_last"], lr.obs, 1)
         g(tr["policy_extras"]["raw_action"], lr.nu, mb["raw_action"], lr.nu)
-        for k, src in (("reward", tr["reward"]), ("discount", self.discount_buf), ("truncation", tr["state_extras"]["truncation"]),
-                       ("log_prob", tr["policy_extras"]["log_prob"])):
-            g(src, 1, mb[k], 1)
-        self.sgd_launches += 8
+        import ctypes
+        srcs = (tr["reward"], self.discount_buf, tr["state_extras"]["truncation"], tr["policy_extras"]["log_prob"])  # order of _scalar_keys
+        for s_ in srcs:
+            assert s_.is_contiguous() and s_.shape == (T, B) and s_.dtype == self.torch.float32
+        tk.check(L_.vnl_gather_scalars(4, (ctypes.c_void_p * 4)(*[s_.data_ptr() for s_ in srcs]), self._sdst, T, B, self.idx.data_ptr(), Bm, st),
+                 "vnl_gather_scalars")
+        self.sgd_launches += 5
 
     def _minibatch(self, tr):
         self._gather(tr)
@@ -92,8 +100,7 @@ class Trainer:
             perm = t.randperm(self.B, device=self.idx.device, generator=self.gen).to(t.int32)
             for mbi in range(self.num_minibatches):
                 self.idx.copy_(perm[mbi * self.Bm:(mbi + 1) * self.Bm])
-                self.mb["eps_z"].normal_(generator=self.gen)
-                self.mb["eps_ent"].normal_(generator=self.gen)
+                self.eps.normal_(generator=self.gen)
                 if not self.use_graph:
                     self._minibatch(tr)
                     continue
