@@ -573,7 +573,7 @@ def run_train(args, sgd: bool):
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = tr.rollout.launches + tr.learner.launches
+    l0 = tr.rollout.launches + tr.sgd_launches
     sh.barrier()
     e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
@@ -585,7 +585,7 @@ def run_train(args, sgd: bool):
     e2.record()
     torch.cuda.synchronize()
     total = B * world * unroll
-    launches = tr.rollout.launches + tr.learner.launches - l0
+    launches = tr.rollout.launches + tr.sgd_launches - l0  # the captured update's kernels are counted per replay
 
     def line(ms_t, e2e_t, launches_):
         return {"metric": ("rodent PPO training env-steps/s" if sgd else "rodent PPO rollout env-steps/s"), "value": total * K / (ms_t * 1e-3),

@@ -27,6 +27,12 @@ extern "C" {
  * that many slices whose partial tiles are ADDED to C with red.global.add -- the caller zeroes C first. */
 int vnl_gemm_tf32(int M, int N, int K, int npairs, const float* const* A, int lda, int a_mn_major, const float* const* B, int ldb,
                   int b_mn_major, float* C, int ldc, const float* bias, int splitk, void* stream);
+/* The same product with a fused activation epilogue for the swish layers of the value MLP (splitk <= 1, N a multiple of 32,
+ * ldc / ldaux multiples of 4, C / aux 16-byte aligned; else -5):
+ *   epilogue 1: C = pre-activation as above, aux[M, N] = swish(C)            (forward: vnl_swish_fwd without its pass over HBM)
+ *   epilogue 2: C = (A . B^T) * swish'(aux[M, N]), aux = the pre-activation  (dgrad + vnl_swish_bwd in one) */
+int vnl_gemm_tf32_ex(int M, int N, int K, int npairs, const float* const* A, int lda, int a_mn_major, const float* const* B, int ldb,
+                     int b_mn_major, float* C, int ldc, const float* bias, int splitk, int epilogue, float* aux, int ldaux, void* stream);
 
 /* x = hi + lo with hi = x truncated to tf32 (low 13 mantissa bits cleared), lo = x - hi (exact in fp32). */
 int vnl_split_tf32(const float* x, size_t n, float* hi, float* lo, void* stream);

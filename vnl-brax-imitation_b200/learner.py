@@ -185,15 +185,27 @@ class PPOLearner:
         kb = (K + 31) // 32
         return max(1, (kb + 7) // 8) if self.x3 else 1  # 3xTF32: accumulation chains of <= 8 K blocks (the accumulator truncates)
 
-    def _fwd(self, x, rows, W, b, out):  # out[rows, out] = x[rows, in] . W[in, out] + b
+    def _fwd(self, x, rows, W, b, out, act=None):  # out[rows, out] = x[rows, in] . W[in, out] + b;  act = swish(out) from the same epilogue
         K, N = W.shape
         sk = self._splitk(K)
-        tk.gemm(x, 0, W, 1, out, rows, N, K, bias=b, x3=self.x3, splitk=sk)
+        fused = act is not None and sk <= 1 and N % 32 == 0
+        tk.gemm(x, 0, W, 1, out, rows, N, K, bias=b, x3=self.x3, splitk=sk, epilogue=1 if fused else 0, aux=act if fused else None)
         self.launches += 1
+        if act is not None and not fused:
+            tk.check(tk.lib().vnl_swish_fwd(out.data_ptr(), rows * N, act.data_ptr(), tk.stream(out)), "swish")
+            self.launches += 1
 
-    def _dgrad(self, dy, rows, W, out):  # out[rows, in] = dy[rows, out] . W[in, out]^T
+    def _dgrad(self, dy, rows, W, out, pre=None, tmp=None):  # out[rows, in] = dy[rows, out] . W[in, out]^T  (* swish'(pre) in the epilogue)
         N, K = W.shape
-        tk.gemm(dy, 0, W, 0, out, rows, N, K, x3=self.x3, splitk=self._splitk(K))
+        sk = self._splitk(K)
+        if pre is None:
+            tk.gemm(dy, 0, W, 0, out, rows, N, K, x3=self.x3, splitk=sk)
+        elif sk <= 1 and N % 32 == 0:
+            tk.gemm(dy, 0, W, 0, out, rows, N, K, x3=self.x3, splitk=sk, epilogue=2, aux=pre)
+        else:
+            tk.gemm(dy, 0, W, 0, tmp, rows, N, K, x3=self.x3, splitk=sk)
+            tk.check(tk.lib().vnl_swish_bwd(tmp.data_ptr(), pre.data_ptr(), rows * N, out.data_ptr(), tk.stream(out)), "swish_bwd")
+            self.launches += 1
         self.launches += 1
 
     def _wgrad(self, x, dy, rows, gW):  # gW[in, out] = x[rows, in]^T . dy[rows, out]
@@ -201,6 +213,11 @@ class PPOLearner:
         tiles = ((M + 127) // 128) * ((N + (127 if N > 64 else 63)) // (128 if N > 64 else 64))
         kb = (rows + 31) // 32
         sk = max(self._splitk(rows), min(max(1, 148 // tiles), max(1, kb // 4)))
+        if N % 256 == 0 and M >= 256:  # 256 x 256 tiles (vnl_gemm.cu picks them when tiles x splits still fill the machine)
+            tb = ((M + 255) // 256) * (N // 256)
+            skb = min(max(1, 148 // tb), max(1, kb // 4))
+            if tb * skb >= 96:
+                sk = max(self._splitk(rows), skb)
         tk.gemm(x, 1, dy, 1, gW, M, N, rows, x3=self.x3, splitk=sk, zero=False)  # self.grads was zeroed at the top of the evaluation
         self.launches += 1
 
@@ -238,10 +255,8 @@ class PPOLearner:
             chk(L_.vnl_obs_normalize(ptr(batch["next_observation_last"]), self.obs, Bm, self.obs, ptr(self.obs_mean), ptr(self.obs_std),
                                      ptr(ws["vin"]) + 4 * R * self.obs, self.obs, sb), "normalize")
             # value forward (baseline rows + the Bm bootstrap rows in one pass)
-            self._fwd(ws["vin"], RB, V("hidden_0/kernel"), V("hidden_0/bias"), ws["v0pre"])
-            chk(L_.vnl_swish_fwd(ptr(ws["v0pre"]), ws["v0pre"].numel(), ptr(ws["v0"]), sb), "swish")
-            self._fwd(ws["v0"], RB, V("hidden_1/kernel"), V("hidden_1/bias"), ws["v1pre"])
-            chk(L_.vnl_swish_fwd(ptr(ws["v1pre"]), ws["v1pre"].numel(), ptr(ws["v1"]), sb), "swish")
+            self._fwd(ws["vin"], RB, V("hidden_0/kernel"), V("hidden_0/bias"), ws["v0pre"], act=ws["v0"])  # swish in the GEMM epilogue
+            self._fwd(ws["v0"], RB, V("hidden_1/kernel"), V("hidden_1/bias"), ws["v1pre"], act=ws["v1"])
             chk(L_.vnl_rowdot(ptr(ws["v1"]), self.vh[1], RB, self.vh[1], ptr(V("hidden_2/kernel")), ptr(V("hidden_2/bias")), ptr(ws["val"]), sb), "rowdot")
         chk(L_.vnl_obs_normalize(ptr(obs), self.obs, R, self.obs, ptr(self.obs_mean), ptr(self.obs_std), ptr(ws["dec_in"]) + 4 * self.L, Ld, st), "normalize")
 
@@ -259,18 +274,18 @@ class PPOLearner:
         self._fwd(ws["d0"], R, P("decoder/hidden_1/kernel"), P("decoder/hidden_1/bias"), ws["d1pre"])
         relu_ln(ws["d1pre"], "decoder/LayerNorm_1", ws["d1"], ws["s3"])
         self._fwd(ws["d1"], R, P("decoder/hidden_2/kernel"), P("decoder/hidden_2/bias"), ws["logits"])
-        main.wait_stream(self.branch)  # join: the loss rows need logits and values
         # ---- loss -------------------------------------------------------------------------------------------------------------
         chk(L_.vnl_ppo_rows(ptr(ws["logits"]), 2 * nu, ptr(batch["raw_action"]), ptr(batch["eps_ent"]), R, nu, ptr(batch["discount"]),
                             ptr(batch["truncation"]), ptr(batch["reward"]), float(hp["reward_scaling"]), ptr(ws["target_lp"]), ptr(ws["ent"]),
                             ptr(ws["termination"]), ptr(ws["rewards_s"]), st), "ppo_rows")
+        main.wait_stream(self.branch)  # join: GAE needs the values
         chk(self._gae.vnl_gae(self.T, Bm, ptr(batch["truncation"]), ptr(ws["termination"]), ptr(ws["rewards_s"]), ptr(ws["val"]), ptr(ws["val"]) + 4 * R,
                          float(hp["gae_lambda"]), float(hp["discounting"]), ptr(ws["vs"]), ptr(ws["adv"]), st), "gae")
         chk(L_.vnl_ppo_loss_bwd(ptr(ws["logits"]), 2 * nu, ptr(batch["raw_action"]), ptr(batch["eps_ent"]), R, nu, ptr(ws["target_lp"]),
                                 ptr(batch["log_prob"]), ptr(ws["ent"]), ptr(ws["adv"]), ptr(ws["vs"]), ptr(ws["val"]), float(hp["clipping_epsilon"]),
                                 float(hp["entropy_cost"]), int(bool(hp["normalize_advantage"])), ptr(ws["dlogits"]), 2 * nu, ptr(ws["dval"]),
                                 ptr(ws["metrics"]), ptr(ws["scratch2"]), st), "ppo_loss_bwd")
-        self.launches += 14
+        self.launches += 13  # row kernels of the forward pass and the loss (GEMMs count themselves)
         colsum = lambda x, n, out, w=None: chk(L_.vnl_colsum(ptr(x), x.shape[1] if x.dim() == 2 else n, R, n, None if w is None else ptr(w), ptr(out),
                                                              tk.stream(self.params)), "colsum")
         # ---- backward ------------------------------------------------------------------------------------------------------------
@@ -296,8 +311,7 @@ class PPOLearner:
         leaf(self.leaf_v, self.branch, lambda: (self._wgrad(ws["v0"], ws["dv1pre"], R, GV("hidden_1/kernel")),
                                                 colsum(ws["dv1pre"], self.vh[1], GV("hidden_1/bias"))))
         with t.cuda.stream(self.branch):
-            self._dgrad(ws["dv1pre"], R, V("hidden_1/kernel"), ws["dv0"])
-            chk(L_.vnl_swish_bwd(ptr(ws["dv0"]), ptr(ws["v0pre"]), R * self.vh[0], ptr(ws["dv0pre"]), sb), "swish_bwd")
+            self._dgrad(ws["dv1pre"], R, V("hidden_1/kernel"), ws["dv0pre"], pre=ws["v0pre"], tmp=ws["dv0"])  # swish' in the GEMM epilogue
             self._wgrad(ws["vin"], ws["dv0pre"], R, GV("hidden_0/kernel"))
             colsum(ws["dv0pre"], self.vh[0], GV("hidden_0/bias"))
 
@@ -331,7 +345,7 @@ class PPOLearner:
             self._policy_bucket_ready()
         main.wait_stream(self.branch)  # join: all gradients are in self.grads
         main.wait_stream(self.leaf_v)
-        self.launches += 19
+        self.launches += 12  # row kernels of the backward pass
         return ws["metrics"]
 
     # ---- gradient exchange + optimiser ---------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@ from typing import Optional
 
 from . import _lib
 
-TRAIN_EXPORTS = ("vnl_gemm_tf32", "vnl_split_tf32", "vnl_gather_rows", "vnl_obs_normalize", "vnl_relu_ln_fwd", "vnl_relu_ln_bwd",
+TRAIN_EXPORTS = ("vnl_gemm_tf32", "vnl_gemm_tf32_ex", "vnl_split_tf32", "vnl_gather_rows", "vnl_obs_normalize", "vnl_relu_ln_fwd", "vnl_relu_ln_bwd",
                  "vnl_swish_fwd", "vnl_swish_bwd", "vnl_reparam_fwd", "vnl_heads_bwd", "vnl_colsum", "vnl_rowdot", "vnl_outer", "vnl_outer_swish_bwd", "vnl_gather_scalars",
                  "vnl_ppo_rows", "vnl_ppo_loss_bwd", "vnl_adam_tick", "vnl_adam", "vnl_policy_sample", "vnl_eval_metrics")
 _bound = None
@@ -19,6 +19,7 @@ def lib():
         v, i, f, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
         PP = ctypes.POINTER(ctypes.c_void_p)
         L.vnl_gemm_tf32.argtypes = [i, i, i, i, PP, i, i, PP, i, i, v, i, v, i, v]
+        L.vnl_gemm_tf32_ex.argtypes = [i, i, i, i, PP, i, i, PP, i, i, v, i, v, i, i, v, i, v]
         L.vnl_split_tf32.argtypes = [v, sz, v, v, v]
         L.vnl_gather_rows.argtypes = [v, i, i, i, v, i, v, i, v]
         L.vnl_obs_normalize.argtypes = [v, i, i, i, v, v, v, i, v]
@@ -71,9 +72,11 @@ def split_into(x, hi, lo):
     return hi, lo
 
 
-def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: bool = False, splitk: int = 1, parts=None, zero: bool = True):
+def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: bool = False, splitk: int = 1, parts=None, zero: bool = True,
+         epilogue: int = 0, aux=None):
     """C[M, N] (+)= A . B^T (+ bias); operands are 2-D fp32 tensors whose row stride is their ld.  `x3`: 3xTF32 (the operands are
-    split here unless `parts` = ((A_hi, A_lo), (B_hi, B_lo)) is given).  splitk > 1 accumulates into C (zeroed here unless the caller says it already is: `zero=False`)."""
+    split here unless `parts` = ((A_hi, A_lo), (B_hi, B_lo)) is given).  splitk > 1 accumulates into C (zeroed here unless the caller says it already is: `zero=False`).
+    epilogue 1: aux = swish(C) written beside C; 2: C = (A . B^T) * swish'(aux)  (include/vnl_train.h: vnl_gemm_tf32_ex)."""
     for t in (A, B, C):
         assert t.dim() == 2 and t.stride(1) == 1 and t.dtype.is_floating_point and t.element_size() == 4
     if x3:
@@ -83,7 +86,12 @@ def gemm(A, a_mn: int, B, b_mn: int, C, M: int, N: int, K: int, bias=None, x3: b
         As, Bs = [A], [B]
     if splitk > 1 and zero:
         C.zero_()
-    rc = lib().vnl_gemm_tf32(M, N, K, len(As), _ptrs(As), A.stride(0), int(a_mn), _ptrs(Bs), B.stride(0), int(b_mn), C.data_ptr(), C.stride(0),
-                             None if bias is None else bias.data_ptr(), int(splitk), stream(C))
+    if epilogue:
+        assert aux is not None and aux.dim() == 2 and aux.stride(1) == 1 and aux.shape[0] >= M
+        rc = lib().vnl_gemm_tf32_ex(M, N, K, len(As), _ptrs(As), A.stride(0), int(a_mn), _ptrs(Bs), B.stride(0), int(b_mn), C.data_ptr(), C.stride(0),
+                                    None if bias is None else bias.data_ptr(), int(splitk), int(epilogue), aux.data_ptr(), aux.stride(0), stream(C))
+    else:
+        rc = lib().vnl_gemm_tf32(M, N, K, len(As), _ptrs(As), A.stride(0), int(a_mn), _ptrs(Bs), B.stride(0), int(b_mn), C.data_ptr(), C.stride(0),
+                                 None if bias is None else bias.data_ptr(), int(splitk), stream(C))
     check(rc, "vnl_gemm_tf32")
     return C

@@ -74,8 +74,10 @@ class Trainer:
         self.sgd_launches += 5
 
     def _minibatch(self, tr):
+        n0 = self.learner.launches
         self._gather(tr)
         self.learner.update(self.mb)
+        self.sgd_launches += self.learner.launches - n0
 
     def _capture(self, fn):
         """Capture `fn` into a CUDA graph.  The graphs of the SGD phase never contain a collective: with a process group the gradient
@@ -107,10 +109,12 @@ class Trainer:
                 if self.graph is None:
                     side = t.cuda.Stream(device=self.idx.device)  # warm-up outside capture (lazy module loads, attribute sets)
                     side.wait_stream(t.cuda.current_stream(self.idx.device))
+                    l0 = self.sgd_launches
                     with t.cuda.stream(side):
                         self._minibatch(tr)
                     t.cuda.current_stream(self.idx.device).wait_stream(side)
-                    n0 = lr.updates
+                    self._launches_per_update = self.sgd_launches - l0  # kernels one replay of the captured update launches
+                    n0, l1 = lr.updates, self.sgd_launches
                     if dist is None:
                         self.graph = (self._capture(lambda: self._minibatch(tr)),)
                     else:
@@ -118,13 +122,14 @@ class Trainer:
                             self._gather(tr)
                             lr.loss_and_grads(self.mb, exchange=False)
                         self.graph = (self._capture(grads_only), self._capture(lambda: lr.apply_gradients(exchange=False, scale=1.0 / dist.get_world_size())))
-                    lr.updates = n0  # the capture passes went through the host-side counter without executing
+                    lr.updates, self.sgd_launches = n0, l1  # the capture passes went through the host-side counters without executing
                     continue  # this minibatch was the warm-up run
                 self.graph[0].replay()
                 if dist is not None:
                     dist.all_reduce(lr.grads, op=dist.ReduceOp.SUM)  # lax.pmean of the gradients: one NCCL call, 6.5 MB; 1 / world in Adam
                     self.graph[1].replay()
                 lr.updates += 1  # host-side counter (the device-side step counter advanced inside the graph)
+                self.sgd_launches += self._launches_per_update
 
     def training_step(self) -> Dict[str, float]:
         """One `training_step`: unroll, normaliser update, SGD phase, policy refresh.  Returns the last minibatch's loss metrics."""
