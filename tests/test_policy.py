@@ -329,7 +329,7 @@ def test_precise_policy_reloads_in_place_and_is_graph_capturable():
     torch.cuda.synchronize()
     first = out["log_prob"].clone()
     eager = p(traj, obs, eps_z, eps_a)[1]["log_prob"]
-    assert torch.allclose(first, eager, atol=1e-5)  # split-K red.adds: equal to rounding
+    assert torch.allclose(first, eager, atol=1e-4)  # split-K red.adds land in any order: equal to rounding (log-probs of magnitude 10-100)
     new = pol.init_params(np.random.default_rng(99), pol.param_shapes(795, 232, 30), perturb=0.1)
     ptr = p.blob_dev.data_ptr()
     p.load_params(new)

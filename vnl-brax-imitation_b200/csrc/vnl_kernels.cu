@@ -782,6 +782,9 @@ __device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool l
   jtmul_force(so);
   pf.mark(22);
   float v0 = 0.0f, v1 = 0.0f, g = 0.0f;
+  // CG: the gradient goes straight into solve_m's scratch vector (solve_m is safe in place) and is otherwise re-formed as
+  // Ma - qfrc_smooth - qfrc_constraint where it is read: its shared-memory slot holds the previous M^-1 grad instead
+  const int go = c.d.solver == 2 ? L.grad : L.tmpv;
   // reductions: every warp of the env sums ALL elements (same order, same result, no exchange); the grad stores of the
   // warps carry identical values
   for (int r = lane; r < nrow; r += 32) { const float ja = s[L.Jaref + r]; if (ja < 0.0f) v0 += s[L.efcD + r] * ja * ja; }
@@ -789,7 +792,7 @@ __device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool l
     const float ma = s[L.Ma + i], qs = s[L.qfrc_smooth + i];
     v1 += (ma - qs) * (s[L.qacc + i] - s[L.qacc_smooth + i]);
     const float gi = ma - qs - qfrc_con[i];
-    s[L.grad + i] = gi;
+    s[go + i] = gi;
     g += gi * gi;
   }
   v0 = warp_sum(v0); v1 = warp_sum(v1); g = warp_sum(g);
@@ -803,7 +806,7 @@ __device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool l
   if (c.d.iterations != 1) stop |= ((st.prev_cost - st.cost) / scale < c.d.tolerance) || (st.gradnorm / scale < c.d.tolerance);
   if (!stop) {
     if (c.d.solver == 2) newton_mgrad(so);
-    else solve_m(so, L.grad, L.Mgrad);
+    else solve_m(so, L.tmpv, L.Mgrad);
   }
   pf.mark(24);
   return stop;
@@ -1344,7 +1347,9 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
   float* Jaref = s + L.Jaref;
   float* Jv = s + L.Jv;
   const float* efcD = s + L.efcD;
-  float* grad = s + L.grad;
+  float* const Mgp = s + L.grad;  // CG: previous M^-1 grad (Polak-Ribiere) in the gradient's slot (see update_constraint)
+  const float* const qfrc_con = s + L.qfrc_con;
+#define VNL_GRAD(i) (Ma[i] - qfrc_smooth[i] - qfrc_con[i])
   float* Mgrad = s + L.Mgrad;
   float* search = s + L.search;
   float* Mv = s + L.Mv;
@@ -1391,7 +1396,9 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
     bool done = update_constraint(so, st, pf, d.iterations < 1, scale);  // true: converged before the first iteration
-    if (!done) for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
+    // CG: Mgrad = M^-1 grad, so M search needs no mat-vec: M (-Mgrad) = -grad, and Polak-Ribiere's search = -Mgrad + beta search
+    // carries it along as Mv = -grad + beta Mv (MJX multiplies by M every iteration; the two agree to rounding).
+    if (!done) for (int i = tid; i < d.nv; i += kEnvThreads) { search[i] = -Mgrad[i]; Mv[i] = -VNL_GRAD(i); }
     env_sync();
     pf.mark(9);
     for (int itn = 0; itn < d.iterations; ++itn) {
@@ -1403,7 +1410,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       }
       if (done) { if (ls3) continue; break; }
       // ---- _linesearch ----
-      mul_m(so, L.search, L.Mv);
+      if (d.solver == 2) mul_m(so, L.search, L.Mv);  // Newton: Mgrad = H^-1 grad, no such shortcut
       pf.mark(19);
       jmul(so, L.search, L.Jv);
       pf.mark(20);
@@ -1490,9 +1497,11 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       const float alpha = lo.cost < hi.cost ? lo.alpha : hi.alpha;
       const float ia = improved ? alpha : 0.0f * alpha;
       float pg = 0.0f;  // previous grad . Mgrad before they are overwritten
-      for (int i = lane; i < d.nv; i += 32) pg += grad[i] * Mgrad[i];
+      if (d.solver != 2) for (int i = lane; i < d.nv; i += 32) pg += VNL_GRAD(i) * Mgrad[i];
       pg = warp_sum(pg);
-      for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; Mv[i] = Mgrad[i]; }  // Mv <- previous Mgrad
+      env_sync();  // (pg re-forms the gradient from Ma, which the update below advances)
+      if (d.solver == 2) { for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; } }
+      else { for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; Mgp[i] = Mgrad[i]; } }
       for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] += Jv[r] * ia;
       env_sync();
       done = update_constraint(so, st, pf, itn == d.iterations - 1, scale);
@@ -1502,16 +1511,17 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i];
       } else {  // Polak-Ribiere
         float nb = 0.0f;
-        for (int i = lane; i < d.nv; i += 32) nb += grad[i] * (Mgrad[i] - Mv[i]);
+        for (int i = lane; i < d.nv; i += 32) nb += VNL_GRAD(i) * (Mgrad[i] - Mgp[i]);
         nb = warp_sum(nb);
         const float beta = fmaxf(0.0f, nb / fmaxf(VNL_MINVAL, pg));
-        for (int i = tid; i < d.nv; i += kEnvThreads) search[i] = -Mgrad[i] + beta * search[i];
+        for (int i = tid; i < d.nv; i += kEnvThreads) { search[i] = -Mgrad[i] + beta * search[i]; Mv[i] = -VNL_GRAD(i) + beta * Mv[i]; }
       }
       env_sync();
       pf.mark(11);
       ++niter;
     }
   }
+#undef VNL_GRAD
   if (tid == 0) { stats[0] += niter; stats[1] += lsiter; }
   for (int i = tid; i < d.nv; i += kEnvThreads) s[L.warm + i] = qacc[i];  // qacc_warmstart <- qacc
   env_sync();
