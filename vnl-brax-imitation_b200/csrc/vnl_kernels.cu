@@ -830,6 +830,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
   int* ints = (int*)(s + L.ints);
   int* stats = ints + 4;
   const bool ls3 = c.lockstep >= 3;  // CTA-uniform: barriers at every phase boundary
+  const bool lsi = c.lockstep == 3;  // ... and at the top of every solver iteration (VNL_LOCKSTEP=4: phases only)
   const uint8_t* const lvl_start = TB8(lvl_start);
   const uint16_t* const lvl_bp = TB16(lvl_bp);
   const uint8_t* const body_tree = TB8(body_tree);
@@ -1402,13 +1403,13 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     env_sync();
     pf.mark(9);
     for (int itn = 0; itn < d.iterations; ++itn) {
-      if (ls3) __syncthreads();
+      if (lsi) __syncthreads();
       if (!done && d.iterations != 1) {
         const float improvement = (st.prev_cost - st.cost) / scale;
         const float gradient = st.gradnorm / scale;
         done = (improvement < d.tolerance) || (gradient < d.tolerance);
       }
-      if (done) { if (ls3) continue; break; }
+      if (done) { if (lsi) continue; break; }
       // ---- _linesearch ----
       if (d.solver == 2) mul_m(so, L.search, L.Mv);  // Newton: Mgrad = H^-1 grad, no such shortcut
       pf.mark(19);
