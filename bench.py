@@ -442,6 +442,10 @@ def run_ours(args):
         "roofline_fp32": {"bound": "fp32", "achieved": ach_tf, "peak": ffma_tflops, "unit": "TFLOP/s", "frac": ach_tf / ffma_tflops,
                           "peak_source": "FFMA microkernel measured in this run (nominal 74.4)", "flops_per_env_step": flops,
                           "flops_per_env_step_static_max": flops_static,
+                          "flops_note": "SURVEY 8(d) count of the REFERENCE algorithm; it includes one M.search mat-vec per CG iteration "
+                                        "(%.0f flop per env step, %.1f %% of the count) that this kernel replaces by an exact recursion "
+                                        "(DESIGN section 3)" % (nfr * I * 4 * dims["nM"] * (1 if dims.get("solver", 1) != 2 else 0),
+                                                               100.0 * nfr * I * 4 * dims["nM"] * (1 if dims.get("solver", 1) != 2 else 0) / flops),
                           "executed": {"solver_iters_per_substep": I, "ls_iters_per_solver_iter": L,
                                        "active_contacts_per_substep": st[2] / nfr, "active_limits_per_substep": st[3] / nfr}},
     }
