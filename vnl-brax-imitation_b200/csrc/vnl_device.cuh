@@ -90,3 +90,32 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+
+// N = 2, 4 or 8 sums at once, every lane ends with all N totals -- BIT-IDENTICAL to N calls of warp_sum (same pairing order
+// 16, 8, 4, 2, 1; fp addition commutes), with 2 N + 1 - log2 N ... shuffles instead of 5 N: a reduce-scatter (each xor step halves the
+// values a lane carries: it keeps one half and sends the other to its partner) down to one value per lane, the remaining
+// butterfly steps on that value, and one indexed shuffle per total to hand them round.  8 sums: 17 shuffles instead of 40, 4 sums:
+// 10 instead of 20.  The shuffle unit issues one warp instruction per cycle per SM and the lockstep puts all 14 warps of the SM in
+// the same reduction at the same time, so the line search's 9 sums per evaluation were shuffle-throughput bound.
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
+  static_assert(N == 2 || N == 4 || N == 8, "warp_sum_n: N = 2, 4, 8");
+  constexpr int LOG = N == 8 ? 3 : (N == 4 ? 2 : 1);
+  const int lane = threadIdx.x & 31;
+  int o = 16;
+#pragma unroll
+  for (int n = N; n > 1; n >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int k = 0; k < n / 2; ++k) {
+      const float send = up ? v[k] : v[k + n / 2];
+      const float keep = up ? v[k + n / 2] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  float t = v[0];  // total-in-progress of value number (lane >> (5 - LOG))
+#pragma unroll
+  for (int q = 16 >> LOG; q > 0; q >>= 1) t += __shfl_xor_sync(0xffffffffu, t, q);
+#pragma unroll
+  for (int j = 0; j < N; ++j) v[j] = __shfl_sync(0xffffffffu, t, j << (5 - LOG));
+}

@@ -795,7 +795,7 @@ __device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool l
     s[go + i] = gi;
     g += gi * gi;
   }
-  v0 = warp_sum(v0); v1 = warp_sum(v1); g = warp_sum(g);
+  { float a4[4] = {v0, v1, g, 0.0f}; warp_sum_n<4>(a4); v0 = a4[0]; v1 = a4[1]; g = a4[2]; }
   st.gauss = 0.5f * v1;
   st.prev_cost = st.cost;
   st.cost = 0.5f * v0 + st.gauss;
@@ -1420,7 +1420,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
         const float si = search[i];
         q0s += si * si; q1s += si * Ma[i]; q2s += si * qfrc_smooth[i]; q3s += si * Mv[i];
       }
-      q0s = warp_sum(q0s); q1s = warp_sum(q1s); q2s = warp_sum(q2s); q3s = warp_sum(q3s);
+      { float a4[4] = {q0s, q1s, q2s, q3s}; warp_sum_n<4>(a4); q0s = a4[0]; q1s = a4[1]; q2s = a4[2]; q3s = a4[3]; }
       const float gtol = d.tolerance * d.ls_tolerance * (sqrtf(q0s) * scale);
       const float g0 = st.gauss, g1 = q1s - q2s, g2 = 0.5f * q3s;
       // One evaluation site for all line-search points: phase 0 evaluates alpha = 0, phase 1 the Newton step from
@@ -1453,11 +1453,15 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
           if (x + al2 * jv < 0.0f) { acc[6] += q0; acc[7] += q1; acc[8] += q2; }
         }
         if (phase < 2) {  // a single alpha: three sums
-#pragma unroll
-          for (int q = 0; q < 3; ++q) acc[q] = warp_sum(acc[q]);
+          float a4[4] = {acc[0], acc[1], acc[2], 0.0f};
+          warp_sum_n<4>(a4);
+          acc[0] = a4[0]; acc[1] = a4[1]; acc[2] = a4[2];
         } else {
+          float a8[8] = {acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]};
+          warp_sum_n<8>(a8);
 #pragma unroll
-          for (int q = 0; q < 9; ++q) acc[q] = warp_sum(acc[q]);
+          for (int q = 0; q < 8; ++q) acc[q] = a8[q];
+          acc[8] = warp_sum(acc[8]);
         }
         LSP pt[3];
         const float als[3] = {al0, al1, al2};
