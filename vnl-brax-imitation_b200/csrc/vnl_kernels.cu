@@ -169,11 +169,18 @@ constexpr int kCtaFloats = (int)((sizeof(Cta) + 15) / 16 * 4);
 #define TB16(name) reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(smem) + c.o_##name)
 #define TB32(name) reinterpret_cast<const uint32_t*>(reinterpret_cast<const uint8_t*>(smem) + c.o_##name)
 
+// Phase clocks of tools/gpu_prof.py.  The object is passed BY VALUE through the (noinline) phase functions: by reference it had an
+// address, lived in local memory, and every mark() of a production launch paid a local load for its null test (1.1 % of the stall
+// samples, long_scoreboard, 116 of the kernel's 195 local-memory instructions).  The running time stamp sits in the env's `ints` slots.
 struct Prof {
   long long* p;
-  long long t0;
-  __device__ __forceinline__ void mark(int i) {
-    if (p) { env_sync(); if (ETID == 0) { long long t = clock64(); p[i] += t - t0; t0 = t; } }
+  int t0o;  // float offset (in shared memory) of the 8-byte time stamp
+  __device__ __forceinline__ void mark(int i) const {
+    if (p) {
+      extern __shared__ __align__(16) float smem[];
+      env_sync();
+      if (ETID == 0) { long long* t0 = reinterpret_cast<long long*>(smem + t0o); const long long t = clock64(); p[i] += t - *t0; *t0 = t; }
+    }
   }
 };
 
@@ -309,7 +316,7 @@ __device__ __noinline__ void mul_m(int so, int xo, int outo) {
 // L^T D L factorisation in place in the K region, then K = L^-1 in place.  `damp` = false: the region already holds M
 // (forward() builds it there); `damp` = true: M + dt * damping is first put back from the workspace copy and Mdiag.
 // Leaves: K off-diagonals in L.K, 1 / D in the diagonal slots.
-__device__ __noinline__ void factor(int so, bool damp, bool invert, Prof& pf) {
+__device__ __noinline__ void factor(int so, bool damp, bool invert, Prof pf) {
   VNL_SMEM
   const int nv = c.d.nv, nM = c.d.nM, lane = LANE, tid = ETID, maxdepth = c.d.maxdepth;
   float* const F = s + c.L.K;
@@ -766,13 +773,13 @@ __device__ __noinline__ void newton_mgrad(int so) {
 }
 
 // solver state carried between _update_constraint calls
-struct Sol { float cost, prev_cost, gauss, gradnorm; };
+struct Sol { float cost, prev_cost, gauss, gradnorm; bool stop; };  // passed and returned by value: registers, not local memory
 
 // solver._update_constraint + _update_gradient (CG: Mgrad = M^-1 grad)
 // `last`: no iteration can follow (the iteration budget is spent).  Returns true when the solver stops after this update
 // -- budget spent or converged by the test the next loop top would make -- in which case the gradient solve, whose
 // only consumer is the next search direction, is skipped (the reference computes and discards it).
-__device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool last, float scale) {
+__device__ __noinline__ Sol update_constraint(int so, Sol st, Prof pf, bool last, float scale) {
   VNL_SMEM
   const Lay& L = c.L;
   const int* ints = (const int*)(s + L.ints);
@@ -809,7 +816,8 @@ __device__ __noinline__ bool update_constraint(int so, Sol& st, Prof& pf, bool l
     else solve_m(so, L.tmpv, L.Mgrad);
   }
   pf.mark(24);
-  return stop;
+  st.stop = stop;
+  return st;
 }
 
 struct LSP { float alpha, cost, d0, d1; };
@@ -822,7 +830,7 @@ struct LSP { float alpha, cost, d0, d1; };
 // gf -> qfrc_actuator), because their shared-memory homes are recycled by the solver.
 // `kin_only`: stop after smooth.kinematics (the clip-preprocessing mode: process_clip's set_position runs kinematics only).
 template <bool DUMP>
-__device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, float* gq, float* gf, bool kin_only = false) {
+__device__ __noinline__ void forward(int so, float* dump, Prof pf, float* gx, float* gq, float* gf, bool kin_only = false) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
@@ -830,7 +838,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
   int* ints = (int*)(s + L.ints);
   int* stats = ints + 4;
   const bool ls3 = c.lockstep >= 3;  // CTA-uniform: barriers at every phase boundary
-  const bool lsi = c.lockstep == 3;  // ... and at the top of every solver iteration (VNL_LOCKSTEP=4: phases only)
+  const bool lsi = c.lockstep == 3 || c.lockstep == 5;  // ... and at the top of every solver iteration (VNL_LOCKSTEP=4: phases only; 5: every other iteration)
+  const int lsi_mask = c.lockstep == 5 ? 1 : 0;
   const uint8_t* const lvl_start = TB8(lvl_start);
   const uint16_t* const lvl_bp = TB16(lvl_bp);
   const uint8_t* const body_tree = TB8(body_tree);
@@ -1396,14 +1405,16 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
     const float scale = d.meaninertia * (float)max(1, d.nv);
     Sol st;
     st.cost = INFINITY; st.prev_cost = 0.0f; st.gauss = 0.0f; st.gradnorm = 0.0f;
-    bool done = update_constraint(so, st, pf, d.iterations < 1, scale);  // true: converged before the first iteration
+    st.stop = false;
+    st = update_constraint(so, st, pf, d.iterations < 1, scale);
+    bool done = st.stop;  // true: converged before the first iteration
     // CG: Mgrad = M^-1 grad, so M search needs no mat-vec: M (-Mgrad) = -grad, and Polak-Ribiere's search = -Mgrad + beta search
     // carries it along as Mv = -grad + beta Mv (MJX multiplies by M every iteration; the two agree to rounding).
     if (!done) for (int i = tid; i < d.nv; i += kEnvThreads) { search[i] = -Mgrad[i]; Mv[i] = -VNL_GRAD(i); }
     env_sync();
     pf.mark(9);
     for (int itn = 0; itn < d.iterations; ++itn) {
-      if (lsi) __syncthreads();
+      if (lsi && (itn & lsi_mask) == 0) __syncthreads();
       if (!done && d.iterations != 1) {
         const float improvement = (st.prev_cost - st.cost) / scale;
         const float gradient = st.gradnorm / scale;
@@ -1509,7 +1520,8 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
       else { for (int i = tid; i < d.nv; i += kEnvThreads) { qacc[i] += search[i] * ia; Ma[i] += Mv[i] * ia; Mgp[i] = Mgrad[i]; } }
       for (int r = tid; r < nrow; r += kEnvThreads) Jaref[r] += Jv[r] * ia;
       env_sync();
-      done = update_constraint(so, st, pf, itn == d.iterations - 1, scale);
+      st = update_constraint(so, st, pf, itn == d.iterations - 1, scale);
+      done = st.stop;
       if (done) {
         // no further iteration: the search direction is not needed
       } else if (d.solver == 2) {
@@ -1535,7 +1547,7 @@ __device__ __noinline__ void forward(int so, float* dump, Prof& pf, float* gx, f
 // ---------------------------------------------------------------------------------------------------------------------
 // forward.euler (implicit joint damping when enabled) + _advance
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void euler(int so, Prof& pf) {
+__device__ __noinline__ void euler(int so, Prof pf) {
   VNL_SMEM
   const Dims& d = c.d;
   const Lay& L = c.L;
@@ -1629,7 +1641,7 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   const int lane = LANE, tid = ETID;
   if (MODE == 4) {  // preprocessing/mjx_preprocess.py:109-134 `extract_features`: set_position -> smooth.kinematics, per frame
     if (!active) return;  // no CTA-wide barriers on this path
-    Prof pf4; pf4.p = nullptr; pf4.t0 = 0;
+    Prof pf4; pf4.p = nullptr; pf4.t0o = 0;
     for (int i = tid; i < d.nq; i += kEnvThreads) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
     env_sync();
     forward<false>(so, nullptr, pf4, p.out.xpos + (size_t)e * d.nbody * 3, p.out.xquat + (size_t)e * d.nbody * 4, nullptr, true);
@@ -1646,9 +1658,10 @@ __device__ __forceinline__ void env_run(int so, const Params& p, int e, bool act
   }
   Prof pf;
   pf.p = (c.prof && e == c.prof_env) ? c.prof : nullptr;
-  pf.t0 = clock64();
+  pf.t0o = so + c.L.ints + 12;  // ints[12..13]: 8-byte aligned (the slice and every array start on 16 bytes)
   int* ints = (int*)(s + L.ints);
   if (lane < 16) ints[lane] = 0;
+  if (pf.p) { env_sync(); if (ETID == 0) *reinterpret_cast<long long*>(smem + pf.t0o) = clock64(); }
 
   // ---- load state -------------------------------------------------------------------------------------------------------
   for (int i = tid; i < d.nq; i += kEnvThreads) s[L.qpos + i] = p.in.qpos[(size_t)e * d.nq + i];
