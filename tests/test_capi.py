@@ -130,6 +130,20 @@ def test_no_mutable_globals_in_the_abi():
     assert "vnl_register_blob" not in hdr and "vnl_set_workspace" not in hdr
 
 
+def test_env_warps_follow_the_shared_memory_residency(monkeypatch):
+    """model_blob.choose_env_warps: one warp per env unless shared memory leaves <= 8 envs on an SM (then the second warp is free):
+    rodent / humanoid / ant keep one, rodent_pair (nv 146, 6 envs per SM) gets two; VNL_ENV_WARPS overrides."""
+    mb, mj = pkg("model_blob"), pkg("mjcf")
+    monkeypatch.delenv("VNL_ENV_WARPS", raising=False)
+    want = {"rodent": 1, "humanoid": 1, "ant": 1, "rodent_pair": 2}
+    for name, ew in want.items():
+        model = mj.load_model(os.path.join(ROOT, "vnl-brax-imitation_b200", "data", name + "_model.npz"))
+        assert mb.choose_env_warps(model) == ew, name
+        assert mb.read_dims(mb.build_model_blob(model))["env_warps"] == ew, name
+    monkeypatch.setenv("VNL_ENV_WARPS", "1")
+    assert mb.choose_env_warps(model) == 1  # (model = rodent_pair)
+
+
 def test_two_warp_blob_has_wider_lane_programs(rodent):
     mb = pkg("model_blob")
     b1, b2 = mb.build_model_blob(rodent["model"], 1), mb.build_model_blob(rodent["model"], 2)
