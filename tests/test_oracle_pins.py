@@ -384,3 +384,50 @@ def test_limited_hinge_pressed_into_its_stop(oracle_mod):
     tau = mass * 9.81 * l * math.cos(theta)  # gravity along -x on an arm hanging along -z rotated by theta about y
     want = tau * (1 - imp) / (I * k * imp * imp)
     assert abs(abs(r) - want) < 2e-4 * want, (r, want)  # what is left is the solver's stopping tolerance on a 1e-5 N m torque balance
+
+
+def test_implicit_joint_damping_decay(oracle_mod):
+    """forward.euler with eulerdamp (mjx euler: qacc = (M + dt diag(damping))^-1 (qfrc_smooth + qfrc_constraint), with qfrc_smooth
+    carrying the passive -d v): a hinge without gravity coasts as  v' = v I / (I + dt d)  per step -- exactly, whatever dt d / I is;
+    with the flag disabled it is the explicit  v' = v (1 - dt d / I).  Pins the passive damping force, the second factorisation
+    (M + dt D) and its solve."""
+    for ed, damp, n in (("enable", 0.02, 200), ("disable", 0.02, 200), ("enable", 5.0, 3)):  # dt d / I = 0.03, and 8 (stiff: 3 steps)
+        model = mjcf.compile_model(ET.fromstring(PEND.format(ed=ed, damp=str(damp), limit="")), solver="cg", iterations=6, ls_iterations=6)
+        model.gravity = np.zeros(3)
+        A = model.arrays
+        mass, l = A["body_mass"][1], abs(A["body_ipos"][1][2])
+        R = mjcf.quat_to_mat(A["body_iquat"][1])
+        I = (R @ np.diag(A["body_inertia"][1]) @ R.T)[1, 1] + mass * l * l
+        dt, v0 = model.timestep, 1.5
+        fac = I / (I + dt * damp) if ed == "enable" else 1.0 - dt * damp / I
+        (q, v), = _run(oracle_mod, model, [0.0], [v0], n)
+        # the blob stores the model constants (inertia, damping) in fp32: 6e-8 relative each, times up to n dt d / I sensitivity
+        assert abs(v[0] - v0 * fac ** n) < 2e-6 * v0 * fac ** n, (ed, damp, v[0], v0 * fac ** n)
+        theta = dt * v0 * fac * (1 - fac ** n) / (1 - fac)  # semi-implicit Euler: the position advances with the NEW velocity
+        assert abs(q[0] - theta) < 2e-6 * abs(theta)
+        (q32, v32), = _run(oracle_mod, model, [0.0], [v0], n, precision=32)
+        assert abs(v32[0] - v0 * fac ** n) < 2e-5 * v0 * fac ** n
+
+
+MOTOR = '''<mujoco model="motor"><option timestep="0.002"><flag eulerdamp="disable"/></option>
+<worldbody><body name="arm" pos="0 0 1"><joint name="h" type="hinge" axis="0 1 0"/>
+<geom name="g" type="capsule" fromto="0 0 0 0 0 -0.3" size="0.03" density="900"/></body></worldbody>
+<actuator><motor name="m" joint="h" gear="{gear}" ctrllimited="true" ctrlrange="-1 1"/></actuator></mujoco>'''
+
+
+def test_motor_torque_and_ctrl_clamp(oracle_mod):
+    """A torque actuator on a hinge without gravity: qacc = gear clip(ctrl) / I, so v_n = n dt gear u / I and
+    theta_n = dt^2 gear u / I n (n + 1) / 2.  Pins the actuator force (gain x ctrl, gear as the moment arm) and the ctrl clamp."""
+    gear = 3.0
+    model = mjcf.compile_model(ET.fromstring(MOTOR.format(gear=gear)), solver="cg", iterations=6, ls_iterations=6)
+    model.gravity = np.zeros(3)
+    A = model.arrays
+    mass, l = A["body_mass"][1], abs(A["body_ipos"][1][2])
+    R = mjcf.quat_to_mat(A["body_iquat"][1])
+    I = (R @ np.diag(A["body_inertia"][1]) @ R.T)[1, 1] + mass * l * l
+    dt, n = model.timestep, 50
+    for u, ueff in ((0.4, 0.4), (-0.25, -0.25), (2.5, 1.0)):  # the last one is clamped to the ctrl range
+        (q, v), = _run(oracle_mod, model, [0.0], [0.0], n, ctrl=np.array([[u]]))
+        a = gear * ueff / I
+        assert abs(v[0] - n * dt * a) < 2e-7 * abs(n * dt * a), (u, v[0], n * dt * a)  # fp32 constants in the blob
+        assert abs(q[0] - dt * dt * a * n * (n + 1) / 2) < 2e-7 * abs(dt * dt * a * n * n)
