@@ -431,3 +431,74 @@ def test_motor_torque_and_ctrl_clamp(oracle_mod):
         a = gear * ueff / I
         assert abs(v[0] - n * dt * a) < 2e-7 * abs(n * dt * a), (u, v[0], n * dt * a)  # fp32 constants in the blob
         assert abs(q[0] - dt * dt * a * n * (n + 1) / 2) < 2e-7 * abs(dt * dt * a * n * n)
+
+
+def test_sliding_spinning_sphere_against_a_dense_qp_restatement(oracle_mod):
+    """Friction.  A sphere thrown along the floor with spin: every step of the oracle (teacher-forced on its own state) against an
+    independent dense statement of MuJoCo's primal problem for the one pyramidal contact,
+        qacc = argmin 1/2 (a - a0)^T M (a - a0) + sum_i 1/2 D_i min(0, J_i a - aref_i)^2 ,   a0 = M^-1 qfrc_smooth = gravity,
+    solved here by an exact active-set Newton iteration on the 6 x 6 system (numpy, float64).  Rows: J_i = d_i^T [I | -[r]x R] with
+    d_i = n +- mu t_k (k = 1, 2), r = contact point - centre, contact point = centre - n (radius + dist / 2), free-joint angular
+    velocity in the BODY frame (hence R); aref_i = -b J_i v - k imp dist, D = imp / ((1 - imp) w), w = (1/m)(1 + mu^2) 2 mu^2 / impratio.
+    Pins the pyramid directions, the contact point, the rotational block of the contact Jacobian and the solver's convergence with
+    friction rows active (sliding, then rolling)."""
+    mu, rho, rad = 0.7, 800.0, 0.05
+    model = mjcf.compile_model(ET.fromstring(BALL.format(mu=mu, rho=rho, tc=0.02, dr=1.0)), solver="cg", iterations=200, ls_iterations=50)
+    A = model.arrays
+    mass = A["body_mass"][1]
+    Ib = A["body_inertia"][1]
+    assert np.allclose(Ib, 0.4 * mass * rad * rad, rtol=1e-6)  # solid sphere
+    M = np.diag([mass] * 3 + list(Ib))
+    solimp, solref = A["pair_solimp"][0], A["pair_solref"][0]
+    dt, g = model.timestep, 9.81
+    k, b = _kb(solref, solimp, dt)
+    w = (1 / mass) * (1 + mu * mu) * 2 * mu * mu / model.impratio
+    n = np.array([0.0, 0.0, 1.0])
+    tang = (np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0]))  # any orthonormal pair: the set {n +- mu t_k} decides, not the order
+
+    def skew(v):
+        return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+    def qp(qpos, qvel):
+        dist = qpos[2] - rad
+        a0 = np.array([0, 0, -g, 0, 0, 0.0])  # no bias torque: isotropic inertia, omega x I omega = 0
+        if dist >= 0:
+            return a0
+        R = mjcf.quat_to_mat(qpos[3:7])
+        r = -n * (rad + 0.5 * dist)
+        Jp = np.hstack([np.eye(3), -skew(r) @ R])
+        J = np.array([(n + sgn * mu * t) @ Jp for t in tang for sgn in (1.0, -1.0)])
+        imp = _impedance(solimp, dist)
+        D = imp / ((1 - imp) * w)
+        aref = -b * (J @ qvel) - k * imp * dist
+        act = np.ones(4, bool)
+        for _ in range(20):  # active-set Newton: exact for a piecewise-quadratic convex objective once the set is right
+            Ja = J[act]
+            a = np.linalg.solve(M + D * Ja.T @ Ja, M @ a0 + D * Ja.T @ aref[act])
+            new = (J @ a - aref) < 0
+            if (new == act).all():
+                return a
+            act = new
+        raise AssertionError("active set did not settle")
+
+    qpos = np.array([0, 0, rad - 3.0e-4, 1, 0, 0, 0.0])
+    qvel = np.array([0.6, -0.2, 0.0, 3.0, 5.0, -2.0])  # sliding along x / -y with spin about all axes (body frame)
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    st = dict(qpos=qpos[None].copy(), qvel=qvel[None].copy(), act=np.zeros((1, 0)), qacc_warmstart=np.zeros((1, 6)))
+    worst, slid, rolled, errs = 0.0, False, False, []
+    for step in range(400):
+        want = st["qvel"][0] + dt * qp(st["qpos"][0], st["qvel"][0])
+        R = mjcf.quat_to_mat(st["qpos"][0][3:7])
+        vslip = st["qvel"][0][:3] + np.cross(R @ st["qvel"][0][3:], -n * rad)
+        slid |= float(np.hypot(vslip[0], vslip[1])) > 0.1
+        rolled |= step > 50 and float(np.hypot(vslip[0], vslip[1])) < 1e-3
+        st, _ = oracle_mod.pipeline_step(blob, st, None, 1, precision=64, dims=dims)
+        err = float(np.abs(st["qvel"][0] - want).max())
+        worst = max(worst, err)
+        errs.append(err)
+    assert slid and rolled  # the run covers the sliding phase and the rolling one
+    # typical agreement 1e-8 (fp32 model constants in the blob); the worst steps are the first ones of the sliding phase, where the
+    # friction torque on the tiny inertia gives angular accelerations of ~350 rad/s^2 and the CG solver's stopping rule
+    # (improvement / gradient < 1e-8 x meaninertia x nv) leaves 1e-6 rad/s per step
+    assert float(np.median(errs)) < 5e-8 and worst < 5e-6, (float(np.median(errs)), worst)
