@@ -502,3 +502,38 @@ def test_sliding_spinning_sphere_against_a_dense_qp_restatement(oracle_mod):
     # friction torque on the tiny inertia gives angular accelerations of ~350 rad/s^2 and the CG solver's stopping rule
     # (improvement / gradient < 1e-8 x meaninertia x nv) leaves 1e-6 rad/s per step
     assert float(np.median(errs)) < 5e-8 and worst < 5e-6, (float(np.median(errs)), worst)
+
+
+REST = '''<mujoco model="rest"><option timestep="0.002"/>
+<worldbody><geom name="floor" type="plane" size="5 5 .1"/>
+<body name="b" pos="0 0 {z}" {quat}><freejoint/><geom name="g" {geom} density="700"/></body></worldbody></mujoco>'''
+
+
+@pytest.mark.parametrize("geom,bottom,ncon,quat", [
+    ('type="capsule" fromto="-0.08 0 0 0.08 0 0" size="0.03"', 0.03, 2, ""),               # lying flat: one contact under each end sphere
+    ('type="ellipsoid" size="0.08 0.05 0.03"', 0.03, 1, ""),                                # support point under the centre
+    ('type="ellipsoid" size="0.03 0.05 0.08"', 0.05, 1, 'quat="0.5 0.5 0.5 0.5"'),          # 120 deg about (1, 1, 1): local y (0.05) is vertical
+])
+def test_capsule_and_ellipsoid_rest_on_the_plane(oracle_mod, geom, bottom, ncon, quat):
+    """The other two plane colliders of the rodent (plane_capsule: two plane-sphere tests at the end spheres; plane_ellipsoid: support
+    point along -normal in the geom frame).  At rest every contact carries 4 pyramid rows of the same D:
+    (4 ncon) D k imp |r| = m g  with the sphere test's D and w -- which holds only if the colliders report the right distance for
+    the right number of contacts, and the body does not tip (contact points symmetric about the COM)."""
+    mu = 1.0
+    z0 = bottom - 2e-4
+    model = mjcf.compile_model(ET.fromstring(REST.format(z=z0, geom=geom, quat=quat)), solver="cg", iterations=100, ls_iterations=50)
+    A = model.arrays
+    mass = A["body_mass"][1]
+    solimp, solref = A["pair_solimp"][0], A["pair_solref"][0]
+    assert np.allclose(A["pair_friction"][0][:2], mu)
+    k, _ = _kb(solref, solimp, model.timestep)
+    w = A["body_invweight0"][1][0] * (1 + mu * mu) * 2 * mu * mu / model.impratio
+    assert abs(A["body_invweight0"][1][0] - 1 / mass) < 1e-6 / mass  # translational inverse weight of a free body
+    q0 = A["qpos0"].copy()
+    (q, v), = _run(oracle_mod, model, q0, np.zeros(6), 800)
+    r = q[2] - bottom
+    imp = _impedance(solimp, r)
+    lhs = 4 * ncon * (imp / ((1 - imp) * w)) * k * imp * abs(r)
+    assert r < 0 and abs(lhs - mass * 9.81) < 1e-4 * mass * 9.81, (r, lhs, mass * 9.81)
+    assert np.abs(v).max() < 5e-6 and np.abs(q[:2]).max() < 1e-6  # at rest (to the solver's stopping tolerance), not sliding
+    assert np.abs(q[3:7] - q0[3:7]).max() < 1e-6  # and not tipping
