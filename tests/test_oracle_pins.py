@@ -537,3 +537,58 @@ def test_capsule_and_ellipsoid_rest_on_the_plane(oracle_mod, geom, bottom, ncon,
     assert r < 0 and abs(lhs - mass * 9.81) < 1e-4 * mass * 9.81, (r, lhs, mass * 9.81)
     assert np.abs(v).max() < 5e-6 and np.abs(q[:2]).max() < 1e-6  # at rest (to the solver's stopping tolerance), not sliding
     assert np.abs(q[3:7] - q0[3:7]).max() < 1e-6  # and not tipping
+
+
+DPEND = '''<mujoco model="dpend"><option timestep="0.001"/>
+<worldbody><body name="l1" pos="0 0 1"><joint name="h1" type="hinge" axis="0 1 0"/>
+<geom name="g1" type="capsule" fromto="0 0 0 0 0 -0.3" size="0.02" density="1100"/>
+<body name="l2" pos="0 0 -0.3"><joint name="h2" type="hinge" axis="0 1 0"/>
+<geom name="g2" type="capsule" fromto="0 0 0 0 0 -0.22" size="0.015" density="900"/></body></body></worldbody></mujoco>'''
+
+
+def test_double_pendulum_inertia_and_bias_against_the_lagrangian(oracle_mod):
+    """A planar double pendulum: the oracle's composite-rigid-body M(q) and recursive-Newton-Euler bias c(q, v) + g(q) against the
+    textbook Lagrangian
+        M11 = m1 lc1^2 + I1 + m2 (l1^2 + lc2^2 + 2 l1 lc2 cos q2) + I2,  M12 = m2 (lc2^2 + l1 lc2 cos q2) + I2,  M22 = m2 lc2^2 + I2,
+        c = h (-(2 v1 v2 + v2^2), v1^2),  h = m2 l1 lc2 sin q2,
+        g = (m1 g lc1 sin q1 + m2 g (l1 sin q1 + lc2 sin(q1 + q2)),  m2 g lc2 sin(q1 + q2)).
+    Pins the chain part of kinematics / com / cdof / CRB / RNE (Coriolis and centrifugal terms included) without reference to any
+    of the repo's own inertia code; then 300 steps of the oracle against semi-implicit Euler on these equations of motion."""
+    model = mjcf.compile_model(ET.fromstring(DPEND), solver="cg", iterations=6, ls_iterations=6)
+    A = model.arrays
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    m1, m2 = A["body_mass"][1], A["body_mass"][2]
+    lc1, lc2, l1 = abs(A["body_ipos"][1][2]), abs(A["body_ipos"][2][2]), 0.3
+    Iy = lambda b: (mjcf.quat_to_mat(A["body_iquat"][b]) @ np.diag(A["body_inertia"][b]) @ mjcf.quat_to_mat(A["body_iquat"][b]).T)[1, 1]
+    I1, I2, g = Iy(1), Iy(2), 9.81
+
+    def lagr(q, v):
+        c2, s2 = math.cos(q[1]), math.sin(q[1])
+        M = np.array([[m1 * lc1 ** 2 + I1 + m2 * (l1 ** 2 + lc2 ** 2 + 2 * l1 * lc2 * c2) + I2, m2 * (lc2 ** 2 + l1 * lc2 * c2) + I2],
+                      [m2 * (lc2 ** 2 + l1 * lc2 * c2) + I2, m2 * lc2 ** 2 + I2]])
+        h = m2 * l1 * lc2 * s2
+        bias = np.array([-h * (2 * v[0] * v[1] + v[1] ** 2), h * v[0] ** 2])
+        bias += np.array([m1 * g * lc1 * math.sin(q[0]) + m2 * g * (l1 * math.sin(q[0]) + lc2 * math.sin(q[0] + q[1])),
+                          m2 * g * lc2 * math.sin(q[0] + q[1])])
+        V = -m1 * g * lc1 * math.cos(q[0]) - m2 * g * (l1 * math.cos(q[0]) + lc2 * math.cos(q[0] + q[1]))
+        return M, bias, 0.5 * v @ M @ v + V
+
+    rng = np.random.default_rng(4)
+    for _ in range(6):
+        q, v = rng.uniform(-2.5, 2.5, 2), rng.uniform(-6, 6, 2)
+        st = dict(qpos=q[None], qvel=v[None], act=np.zeros((1, 0)), qacc_warmstart=np.zeros((1, 2)))
+        d = oracle_mod.forward_dump(blob, st, None, precision=64, dims=dims)
+        M, bias, _ = lagr(q, v)
+        assert np.abs(d["qM"][0] - M).max() < 1e-6 * np.abs(M).max(), (d["qM"][0], M)  # fp32 model constants in the blob
+        assert np.abs(d["qfrc_bias"][0] - bias).max() < 1e-6 * max(1.0, np.abs(bias).max()), (d["qfrc_bias"][0], bias)
+    # one step = semi-implicit Euler on these equations of motion: v' = v + dt M^-1 (-bias), q' = q + dt v'  (no damping, no constraints);
+    # 300 steps, each predicted from the oracle's own previous state
+    st = dict(qpos=np.array([[1.2, -0.7]]), qvel=np.array([[0.5, 2.0]]), act=np.zeros((1, 0)), qacc_warmstart=np.zeros((1, 2)))
+    dt = model.timestep
+    for _ in range(300):
+        q, v = st["qpos"][0].copy(), st["qvel"][0].copy()
+        M, bias, _ = lagr(q, v)
+        v1 = v + dt * np.linalg.solve(M, -bias)
+        st, _ = oracle_mod.pipeline_step(blob, st, None, 1, precision=64, dims=dims)
+        assert np.abs(st["qvel"][0] - v1).max() < 1e-7 * max(1.0, np.abs(v1).max()) and np.abs(st["qpos"][0] - (q + dt * v1)).max() < 1e-9
