@@ -592,3 +592,43 @@ def test_double_pendulum_inertia_and_bias_against_the_lagrangian(oracle_mod):
         v1 = v + dt * np.linalg.solve(M, -bias)
         st, _ = oracle_mod.pipeline_step(blob, st, None, 1, precision=64, dims=dims)
         assert np.abs(st["qvel"][0] - v1).max() < 1e-7 * max(1.0, np.abs(v1).max()) and np.abs(st["qpos"][0] - (q + dt * v1)).max() < 1e-9
+
+
+TUMBLE = '''<mujoco model="tumble"><option timestep="0.002"/>
+<worldbody><body name="b" pos="0 0 1"><freejoint/><geom name="g" type="ellipsoid" size="0.08 0.05 0.03" density="800"/></body></worldbody></mujoco>'''
+
+
+def test_free_body_tumbles_by_eulers_equations(oracle_mod):
+    """A free asymmetric body: angular velocity in the BODY frame obeys I w' = -(w x I w) (the gyroscopic part of the RNE bias),
+    the quaternion advances by q <- q * exp(dt w_new) (mju_quatIntegrate: right-multiplication by the body-frame rotation), the COM
+    falls with g.  Step by step against semi-implicit Euler on these equations; pins the free joint's rotational dofs end to end."""
+    model = mjcf.compile_model(ET.fromstring(TUMBLE), solver="cg", iterations=6, ls_iterations=6)
+    A = model.arrays
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    Ri = mjcf.quat_to_mat(A["body_iquat"][1])
+    Ib = Ri @ np.diag(A["body_inertia"][1]) @ Ri.T  # inertia in the body frame (the compiler sorts the principal moments)
+    mass = A["body_mass"][1]
+    want = mass / 5 * np.array([0.05 ** 2 + 0.03 ** 2, 0.08 ** 2 + 0.03 ** 2, 0.08 ** 2 + 0.05 ** 2])  # solid ellipsoid
+    assert np.abs(Ib - np.diag(want)).max() < 1e-9 * want.max() and np.abs(A["body_ipos"][1]).max() < 1e-15
+    dt, g = model.timestep, np.array([0, 0, -9.81])
+
+    def quat_exp(w, h):
+        a = np.linalg.norm(w) * h
+        ax = w / max(np.linalg.norm(w), 1e-300)
+        return np.concatenate([[math.cos(a / 2)], math.sin(a / 2) * ax])
+
+    st = dict(qpos=np.array([[0.1, -0.2, 1.0, 0.8, 0.2, -0.4, 0.4]]), qvel=np.array([[0.3, 0.1, -0.2, 3.0, -2.0, 5.0]]), act=np.zeros((1, 0)),
+              qacc_warmstart=np.zeros((1, 6)))
+    st["qpos"][0, 3:7] /= np.linalg.norm(st["qpos"][0, 3:7])
+    for _ in range(300):
+        q, v = st["qpos"][0].copy(), st["qvel"][0].copy()
+        w = v[3:]
+        w1 = w + dt * np.linalg.solve(Ib, -np.cross(w, Ib @ w))
+        vl1 = v[:3] + dt * g
+        q1 = mjcf.quat_mul(q[3:7], quat_exp(w1, dt))
+        q1 /= np.linalg.norm(q1)
+        st, _ = oracle_mod.pipeline_step(blob, st, None, 1, precision=64, dims=dims)
+        assert np.abs(st["qvel"][0][3:] - w1).max() < 1e-6 * np.abs(w1).max(), (st["qvel"][0][3:], w1)  # fp32 inertia constants in the blob
+        assert np.abs(st["qvel"][0][:3] - vl1).max() < 1e-8 and np.abs(st["qpos"][0][:3] - (q[:3] + dt * vl1)).max() < 1e-9  # g, dt are fp32 in the blob
+        assert np.abs(st["qpos"][0][3:7] - q1).max() < 1e-8, (st["qpos"][0][3:7], q1)
