@@ -632,3 +632,51 @@ def test_free_body_tumbles_by_eulers_equations(oracle_mod):
         assert np.abs(st["qvel"][0][3:] - w1).max() < 1e-6 * np.abs(w1).max(), (st["qvel"][0][3:], w1)  # fp32 inertia constants in the blob
         assert np.abs(st["qvel"][0][:3] - vl1).max() < 1e-8 and np.abs(st["qpos"][0][:3] - (q[:3] + dt * vl1)).max() < 1e-9  # g, dt are fp32 in the blob
         assert np.abs(st["qpos"][0][3:7] - q1).max() < 1e-8, (st["qpos"][0][3:7], q1)
+
+
+SPRING = '''<mujoco model="spring"><option timestep="0.001"><flag eulerdamp="disable"/></option>
+<worldbody><body name="arm" pos="0 0 1"><joint name="h" type="hinge" axis="0 1 0" stiffness="{k}" springref="{ref}" armature="{arm}"/>
+<geom name="g" type="capsule" fromto="0 0 0 0 0 -0.3" size="0.03" density="900"/></body></worldbody>
+<actuator><general name="m" joint="h" gear="{gear}" gainprm="{gain}" dyntype="filter" dynprm="{tau}" ctrllimited="true" ctrlrange="-1 1"
+ forcelimited="true" forcerange="-{fmax} {fmax}"/></actuator></mujoco>'''
+
+
+def test_joint_spring_armature_and_filtered_actuator(oracle_mod):
+    """(i) A hinge spring without gravity oscillates with omega^2 = k / (I + armature) about springref (semi-implicit Euler: exactly the
+    recurrence v += dt (-k (q - ref)) / (I + armature), q += dt v).  (ii) A first-order activation filter act' = (ctrl - act) / tau
+    drives force = clip(gain act, forcerange) through the gear; the force of a step uses the activation BEFORE its update.
+    Pins jnt_stiffness / qpos_spring, dof_armature in M, actuator dynamics, gain, force clamp."""
+    k, ref, arm, gear, gain, tau, fmax = 0.8, 15.0, 0.003, 2.0, 4.0, 0.05, 3.0
+    model = mjcf.compile_model(ET.fromstring(SPRING.format(k=k, ref=ref, arm=arm, gear=gear, gain=gain, tau=tau, fmax=fmax)), solver="cg",
+                               iterations=6, ls_iterations=6)
+    model.gravity = np.zeros(3)
+    A = model.arrays
+    mass, l = A["body_mass"][1], abs(A["body_ipos"][1][2])
+    R = mjcf.quat_to_mat(A["body_iquat"][1])
+    I = (R @ np.diag(A["body_inertia"][1]) @ R.T)[1, 1] + mass * l * l + arm
+    dt, qref = model.timestep, math.radians(ref)
+    blob = mb.build_model_blob(model)
+    dims = mb.read_dims(blob)
+    assert model.na == 1 and abs(A["qpos_spring"][0] - qref) < 1e-12
+    # (i) spring, actuator idle
+    q, v = 0.0, 0.0
+    st = dict(qpos=np.array([[q]]), qvel=np.array([[v]]), act=np.zeros((1, 1)), qacc_warmstart=np.zeros((1, 1)))
+    st, _ = oracle_mod.pipeline_step(blob, st, np.zeros((1, 1)), 700, precision=64, dims=dims)
+    for _ in range(700):
+        v += dt * (-k * (q - qref)) / I
+        q += dt * v
+    assert abs(st["qpos"][0, 0] - q) < 2e-6 * abs(qref) and abs(st["qvel"][0, 0] - v) < 2e-6 * math.sqrt(k / I) * abs(qref)
+    assert abs(st["qpos"][0, 0] - qref) <= abs(qref) * 1.001  # it swings about the reference angle
+    # (ii) filtered actuator against the scalar recurrence, spring switched off by starting at the reference with k-force cancelling
+    for u in (0.3, 1.0, -2.0):  # 1.0 saturates the force range (gain x act -> 4 > 3), -2.0 is clamped to -1 first
+        ue = min(max(u, -1.0), 1.0)
+        q, v, act = qref, 0.0, 0.0
+        st = dict(qpos=np.array([[q]]), qvel=np.array([[v]]), act=np.zeros((1, 1)), qacc_warmstart=np.zeros((1, 1)))
+        st, _ = oracle_mod.pipeline_step(blob, st, np.array([[u]]), 300, precision=64, dims=dims)
+        for _ in range(300):
+            force = min(max(gain * act, -fmax), fmax)
+            v += dt * (gear * force - k * (q - qref)) / I
+            q += dt * v
+            act += dt * (ue - act) / tau
+        assert abs(st["act"][0, 0] - act) < 1e-6 * abs(ue), (u, st["act"][0, 0], act)
+        assert abs(st["qvel"][0, 0] - v) < 2e-6 * max(1.0, abs(v)) and abs(st["qpos"][0, 0] - q) < 2e-6 * max(1.0, abs(q)), (u, st["qvel"][0, 0], v)
