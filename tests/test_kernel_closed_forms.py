@@ -122,3 +122,51 @@ def test_pendulum_period():
     assert len(tz) >= 1 and abs(tz[0] - T / 4) / T < 1e-3, (tz, T)  # first downward crossing at a quarter period
     if len(tz) >= 2:
         assert abs((tz[1] - tz[0]) - T) / T < 5e-4
+
+
+def test_free_body_tumbles_by_eulers_equations():
+    """I w' = -(w x I w) in the body frame, q <- q * exp(dt w'), COM falling with g: 200 substeps of the kernel in ONE launch against
+    200 steps of that recurrence in float64 (fp32 kernel: 2e-4 on the angular velocity after 0.4 s of tumbling)."""
+    pins = __import__("test_oracle_pins")
+    mjcf = pkg("mjcf")
+    model, eng = _engine(pins.TUMBLE, iterations=6, ls_iterations=6)
+    A = model.arrays
+    Ri = mjcf.quat_to_mat(A["body_iquat"][1])
+    Ib = Ri @ np.diag(A["body_inertia"][1]) @ Ri.T
+    dt, g = model.timestep, np.array([0, 0, -9.81])
+    q = np.array([0.1, -0.2, 1.0, 0.8, 0.2, -0.4, 0.4]); q[3:] /= np.linalg.norm(q[3:])
+    v = np.array([0.3, 0.1, -0.2, 3.0, -2.0, 5.0])
+    gq, gv = _run(eng, q, v, 200)
+    for _ in range(200):
+        w1 = v[3:] + dt * np.linalg.solve(Ib, -np.cross(v[3:], Ib @ v[3:]))
+        vl1 = v[:3] + dt * g
+        a = np.linalg.norm(w1) * dt
+        dq = np.concatenate([[math.cos(a / 2)], math.sin(a / 2) * w1 / np.linalg.norm(w1)])
+        qq = mjcf.quat_mul(q[3:], dq)
+        q = np.concatenate([q[:3] + dt * vl1, qq / np.linalg.norm(qq)])
+        v = np.concatenate([vl1, w1])
+    assert np.abs(gv[3:] - v[3:]).max() < 2e-4 * np.abs(v[3:]).max(), (gv[3:], v[3:])
+    assert np.abs(gv[:3] - v[:3]).max() < 1e-5 and np.abs(gq[:3] - q[:3]).max() < 1e-5
+    assert min(np.abs(gq[3:] - q[3:]).max(), np.abs(gq[3:] + q[3:]).max()) < 2e-4
+
+
+def test_spring_armature_and_filtered_actuator():
+    """v += dt (gear clip(gain act) - k (q - ref)) / (I + armature); q += dt v; act += dt (ctrl - act) / tau -- 300 substeps in one launch."""
+    pins = __import__("test_oracle_pins")
+    mjcf, mb, libm = pkg("mjcf"), pkg("model_blob"), pkg("_lib")
+    k, ref, arm, gear, gain, tau, fmax = 0.8, 15.0, 0.003, 2.0, 4.0, 0.05, 3.0
+    model = mjcf.compile_model(ET.fromstring(pins.SPRING.format(k=k, ref=ref, arm=arm, gear=gear, gain=gain, tau=tau, fmax=fmax)), solver="cg",
+                               iterations=6, ls_iterations=6)
+    model.gravity = np.zeros(3)
+    eng = libm.Engine(mb.build_model_blob(model), None, device="cuda:0")
+    I, dt, qref = _pivot_inertia(model) + arm, model.timestep, math.radians(ref)
+    for u in (0.0, 0.3, 1.0, -2.0):
+        ue = min(max(u, -1.0), 1.0)
+        q, v, act = 0.05, 0.0, 0.0
+        gq, gv = _run(eng, [q], [v], 300, ctrl=[u])
+        for _ in range(300):
+            force = min(max(gain * act, -fmax), fmax)
+            v += dt * (gear * force - k * (q - qref)) / I
+            q += dt * v
+            act += dt * (ue - act) / tau
+        assert abs(gv[0] - v) < 5e-5 * max(1.0, abs(v)) and abs(gq[0] - q) < 5e-5 * max(1.0, abs(q)), (u, gv[0], v, gq[0], q)
