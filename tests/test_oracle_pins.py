@@ -680,3 +680,34 @@ def test_joint_spring_armature_and_filtered_actuator(oracle_mod):
             act += dt * (ue - act) / tau
         assert abs(st["act"][0, 0] - act) < 1e-6 * abs(ue), (u, st["act"][0, 0], act)
         assert abs(st["qvel"][0, 0] - v) < 2e-6 * max(1.0, abs(v)) and abs(st["qpos"][0, 0] - q) < 2e-6 * max(1.0, abs(q)), (u, st["qvel"][0, 0], v)
+
+
+def test_cg_and_newton_agree_on_the_rodent_in_contact(rodent, oracle_mod):
+    """Two solvers, one convex problem: run to convergence, the oracle's CG path (M^-1-preconditioned Polak-Ribiere) and its Newton path
+    (dense H = M + J^T D J, Cholesky) must give the same constrained acceleration for the rodent pressed into the floor with joint
+    limits active -- two independent code paths of the restatement checking each other on the real model (303 rows, 73 dofs);
+    and the result does not depend on the warm start (it only picks the starting point)."""
+    import copy
+    from conftest import start_states
+    B = 4
+    qpos, qvel, _ = start_states(rodent, B, seed=3)
+    qpos = qpos.astype(np.float64); qvel = qvel.astype(np.float64)
+    qpos[:, 2] -= 0.012  # into the floor: several active contacts per env
+    rng = np.random.default_rng(8)
+    ctrl = rng.uniform(-0.5, 0.5, size=(B, 30))
+    outs = {}
+    for name, solver, iters, warm in (("cg", 1, 300, 0.0), ("newton", 2, 60, 0.0), ("cg_warm", 1, 300, 1.0)):
+        m = copy.copy(rodent["model"])
+        m.solver, m.iterations, m.ls_iterations, m.tolerance = solver, iters, 50, 1e-12
+        blob = mb.build_model_blob(m)
+        dims = mb.read_dims(blob)
+        st = dict(qpos=qpos.copy(), qvel=qvel.copy(), act=np.zeros((B, 30)), qacc_warmstart=warm * 50.0 * rng.standard_normal((B, 73)))
+        d = oracle_mod.forward_dump(blob, st, ctrl, precision=64, dims=dims)
+        outs[name] = d
+        assert (d["counters"][:, 2] >= 3).all() and (d["counters"][:, 3] >= 1).all()  # contacts and limit rows active
+    scale = np.abs(outs["newton"]["qacc"]).max()
+    for other in ("cg", "cg_warm"):
+        err = np.abs(outs[other]["qacc"] - outs["newton"]["qacc"]).max() / scale
+        assert err < 1e-6, (other, err)
+        ferr = np.abs(outs[other]["qfrc_constraint"] - outs["newton"]["qfrc_constraint"]).max() / np.abs(outs["newton"]["qfrc_constraint"]).max()
+        assert ferr < 1e-6, (other, ferr)
