@@ -711,3 +711,77 @@ def test_cg_and_newton_agree_on_the_rodent_in_contact(rodent, oracle_mod):
         assert err < 1e-6, (other, err)
         ferr = np.abs(outs[other]["qfrc_constraint"] - outs["newton"]["qfrc_constraint"]).max() / np.abs(outs["newton"]["qfrc_constraint"]).max()
         assert ferr < 1e-6, (other, ferr)
+
+
+def test_contact_jacobian_rows_are_the_derivative_of_the_forward_kinematics(rodent, oracle_mod):
+    """efc_J of the pyramidal contact rows against central finite differences of the oracle's own forward kinematics (xpos / xmat --
+    which the reference's clip golden pins, tests/test_mjcf_clip.py): for dof i, move the configuration by +-eps along the dof (free
+    joint: world translation, body-frame rotation; hinges: angle), follow the material point of the contact body that sits at the
+    contact position, and project its displacement on n +- mu t_k.  Also: limit rows are -+1 on their dof, and the rows' reference
+    acceleration obeys aref = -b (J v) - k imp pos with (k, b, imp) from the pair's solref / solimp."""
+    from conftest import start_states
+    m = rodent["model"]
+    A = m.arrays
+    qpos, qvel, _ = start_states(rodent, 1, seed=5)
+    qpos = qpos.astype(np.float64); qvel = 0.3 * qvel.astype(np.float64)
+    qpos[:, 2] -= 0.012
+    blob, dims = rodent["model_blob"], rodent["dims"]
+    fd = lambda q: oracle_mod.forward_dump(blob, dict(qpos=q, qvel=qvel, act=np.zeros((1, 30)), qacc_warmstart=np.zeros((1, 73))), None,
+                                           precision=64, dims=dims)
+    d = fd(qpos)
+    J, dist = d["efc_J"][0], d["con_dist"][0]
+    nl = dims["nlimit"]
+    act_con = [c for c in range(dims["ncon"]) if dist[c] < 0]
+    assert len(act_con) >= 3
+
+    def moved(q, i, eps):
+        q = q.copy()
+        if i < 3:
+            q[0, i] += eps
+        elif i < 6:
+            w = np.zeros(3); w[i - 3] = eps
+            dq = np.concatenate([[math.cos(eps / 2)], math.sin(eps / 2) * w / eps])
+            q[0, 3:7] = mjcf.quat_mul(q[0, 3:7], dq)
+        else:
+            q[0, 7 + (i - 6)] += eps
+        return q
+
+    # contact -> (pair, body): contacts are enumerated pair by pair, a plane-capsule pair (type 3) spawns two
+    pair_of = []
+    for p_, t_ in enumerate(A["pair_type"]):
+        pair_of += [p_] * (2 if t_ == 3 else 1)
+    assert len(pair_of) == dims["ncon"]
+    eps = 1e-6
+    Jp = {c: np.zeros((3, 73)) for c in act_con}
+    body_of = {c: int(A["geom_bodyid"][A["pair_geom2"][pair_of[c]]]) for c in act_con}
+    for i in range(73):
+        dp, dm = fd(moved(qpos, i, eps)), fd(moved(qpos, i, -eps))
+        for c in act_con:
+            b, p = body_of[c], d["con_pos"][0][c]
+            loc = d["xmat"][0][b].reshape(3, 3).T @ (p - d["xpos"][0][b])
+            pp = dp["xpos"][0][b] + dp["xmat"][0][b].reshape(3, 3) @ loc
+            pm = dm["xpos"][0][b] + dm["xmat"][0][b].reshape(3, 3) @ loc
+            Jp[c][:, i] = (pp - pm) / (2 * eps)
+    checked = 0
+    for c in act_con:
+        fr = d["con_frame"][0][c].reshape(3, 3)
+        mu = A["pair_friction"][pair_of[c]][0]
+        want = [(fr[0] + sgn * mu * fr[k]) @ Jp[c] for k in (1, 2) for sgn in (1.0, -1.0)]
+        rows = J[nl + 4 * c: nl + 4 * c + 4]
+        assert np.abs(rows).max() > 0
+        for r in rows:  # each dumped row is one of the four pyramid directions (order not assumed)
+            err = min(np.abs(r - w).max() for w in want)
+            assert err < 2e-6 * max(1.0, np.abs(r).max()), (c, err)
+            checked += 1
+    assert checked == 4 * len(act_con)
+    # limit rows: one-hot on their dof; all rows: aref = -b J v - k imp pos
+    pos, aref = d["efc_pos"][0], d["efc_aref"][0]
+    for r in range(nl):
+        if np.abs(J[r]).max() > 0:
+            assert np.count_nonzero(J[r]) == 1 and abs(abs(J[r]).max() - 1.0) < 1e-12
+    for c in act_con:
+        k, b_ = _kb(A["pair_solref"][pair_of[c]], A["pair_solimp"][pair_of[c]], m.timestep)
+        imp = _impedance(A["pair_solimp"][pair_of[c]], dist[c])
+        for r in range(nl + 4 * c, nl + 4 * c + 4):
+            assert abs(pos[r] - dist[c]) < 1e-12
+            assert abs(aref[r] - (-b_ * (J[r] @ qvel[0]) - k * imp * dist[c])) < 1e-6 * max(1.0, abs(aref[r])), (r, aref[r])
