@@ -785,3 +785,48 @@ def test_contact_jacobian_rows_are_the_derivative_of_the_forward_kinematics(rode
         for r in range(nl + 4 * c, nl + 4 * c + 4):
             assert abs(pos[r] - dist[c]) < 1e-12
             assert abs(aref[r] - (-b_ * (J[r] @ qvel[0]) - k * imp * dist[c])) < 1e-6 * max(1.0, abs(aref[r])), (r, aref[r])
+
+
+def test_rodent_inertia_matrix_from_finite_differences_of_the_kinematics(rodent, oracle_mod):
+    """M(q) = sum_b J_b^T diag(m_b 1, R_b I_b R_b^T) J_b + armature with every body Jacobian taken by central finite differences of the
+    oracle's forward kinematics (xipos / ximat) -- against the oracle's composite-rigid-body qM.  The kinematics are pinned by the
+    reference clip, the body inertias by quadrature (above): this closes the chain to the full 73 x 73 inertia of the rodent without
+    any analytic Jacobian code in the loop."""
+    from conftest import start_states
+    m = rodent["model"]
+    A = m.arrays
+    qpos, qvel, _ = start_states(rodent, 1, seed=9)
+    qpos = qpos.astype(np.float64); qvel = qvel.astype(np.float64)
+    blob, dims = rodent["model_blob"], rodent["dims"]
+    nb = dims["nbody"]
+    fd = lambda q: oracle_mod.forward_dump(blob, dict(qpos=q, qvel=qvel, act=np.zeros((1, 30)), qacc_warmstart=np.zeros((1, 73))), None,
+                                           precision=64, dims=dims)
+
+    def moved(q, i, eps):
+        q = q.copy()
+        if i < 3:
+            q[0, i] += eps
+        elif i < 6:
+            w = np.zeros(3); w[i - 3] = 1.0
+            q[0, 3:7] = mjcf.quat_mul(q[0, 3:7], np.concatenate([[math.cos(eps / 2)], math.sin(eps / 2) * w]))
+        else:
+            q[0, 7 + (i - 6)] += eps
+        return q
+
+    d = fd(qpos)
+    eps = 1e-6
+    Jl, Jr = np.zeros((nb, 3, 73)), np.zeros((nb, 3, 73))
+    for i in range(73):
+        dp, dm = fd(moved(qpos, i, eps)), fd(moved(qpos, i, -eps))
+        Jl[:, :, i] = (dp["xipos"][0] - dm["xipos"][0]) / (2 * eps)
+        Rp, Rm, R0 = dp["ximat"][0].reshape(nb, 3, 3), dm["ximat"][0].reshape(nb, 3, 3), d["ximat"][0].reshape(nb, 3, 3)
+        S = np.einsum("bij,bkj->bik", (Rp - Rm) / (2 * eps), R0)  # dR R^T = [w]x
+        Jr[:, 0, i], Jr[:, 1, i], Jr[:, 2, i] = S[:, 2, 1], S[:, 0, 2], S[:, 1, 0]
+    M = np.diag(A["dof_armature"].astype(np.float64))
+    R0 = d["ximat"][0].reshape(nb, 3, 3)
+    for b in range(1, nb):
+        Iw = R0[b] @ np.diag(A["body_inertia"][b]) @ R0[b].T
+        M += A["body_mass"][b] * Jl[b].T @ Jl[b] + Jr[b].T @ Iw @ Jr[b]
+    got = d["qM"][0]
+    assert np.abs(got - M).max() < 2e-6 * np.abs(M).max(), np.abs(got - M).max() / np.abs(M).max()
+    assert np.linalg.eigvalsh(got).min() > 0
