@@ -830,3 +830,41 @@ def test_rodent_inertia_matrix_from_finite_differences_of_the_kinematics(rodent,
     got = d["qM"][0]
     assert np.abs(got - M).max() < 2e-6 * np.abs(M).max(), np.abs(got - M).max() / np.abs(M).max()
     assert np.linalg.eigvalsh(got).min() > 0
+
+
+def test_rodent_bias_forces_balance_the_energy_rate(rodent, oracle_mod):
+    """Power balance of the conservative part of the dynamics, valid in any (quasi-)velocity coordinates:
+    v . qfrc_bias = 1/2 v^T (dM/dt) v + dV/dt  along the motion (from d/dt (1/2 v^T M v + V) = 0 with M v' = -bias), with dM/dt and
+    dV/dt by central differences of the oracle's qM (pinned above) and of V = sum_b m_b g z_b (FK) at q integrated by +-eps v.
+    Pins the power of the recursive-Newton-Euler bias (Coriolis, centrifugal, gyroscopic, gravity) on the full rodent."""
+    from conftest import start_states
+    m = rodent["model"]
+    A = m.arrays
+    blob, dims = rodent["model_blob"], rodent["dims"]
+    mass = A["body_mass"].astype(np.float64)
+    rng = np.random.default_rng(12)
+    for trial in range(4):
+        qpos, _, _ = start_states(rodent, 1, seed=20 + trial)
+        qpos = qpos.astype(np.float64)
+        v = np.concatenate([rng.uniform(-1, 1, 3), rng.uniform(-4, 4, 3), rng.uniform(-6, 6, 67)])
+        fd = lambda q: oracle_mod.forward_dump(blob, dict(qpos=q, qvel=v[None], act=np.zeros((1, 30)), qacc_warmstart=np.zeros((1, 73))), None,
+                                               precision=64, dims=dims)
+
+        def along(q, h):
+            q = q.copy()
+            q[0, :3] += h * v[:3]
+            a = np.linalg.norm(v[3:6]) * h
+            dq = np.concatenate([[math.cos(a / 2)], math.sin(a / 2) * v[3:6] / np.linalg.norm(v[3:6])])
+            q[0, 3:7] = mjcf.quat_mul(q[0, 3:7], dq)
+            q[0, 7:] += h * v[6:]
+            return q
+
+        d0 = fd(qpos)
+        eps = 1e-5
+        dp, dm = fd(along(qpos, eps)), fd(along(qpos, -eps))
+        Mdot = (dp["qM"][0] - dm["qM"][0]) / (2 * eps)
+        V = lambda d: 9.81 * float(mass @ d["xipos"][0][:, 2])
+        rhs = 0.5 * v @ Mdot @ v + (V(dp) - V(dm)) / (2 * eps)
+        lhs = float(v @ d0["qfrc_bias"][0])
+        scale = abs(0.5 * v @ Mdot @ v) + abs((V(dp) - V(dm)) / (2 * eps)) + 1e-9
+        assert abs(lhs - rhs) < 1e-6 * scale, (trial, lhs, rhs, scale)  # measured 3e-8: fp32 constants in the blob, O(eps^2) differences
