@@ -868,3 +868,35 @@ def test_rodent_bias_forces_balance_the_energy_rate(rodent, oracle_mod):
         lhs = float(v @ d0["qfrc_bias"][0])
         scale = abs(0.5 * v @ Mdot @ v) + abs((V(dp) - V(dm)) / (2 * eps)) + 1e-9
         assert abs(lhs - rhs) < 1e-6 * scale, (trial, lhs, rhs, scale)  # measured 3e-8: fp32 constants in the blob, O(eps^2) differences
+
+
+def test_rodent_gravity_forces_are_the_gradient_of_the_potential(rodent, oracle_mod):
+    """At rest the bias force is pure gravity, and by virtual work its i-th component is the derivative of V = sum_b m_b g z_b along
+    dof i (free joint: world translation / body-frame rotation; hinges: angle) -- all 73 components against central differences of
+    the forward kinematics."""
+    from conftest import start_states
+    A = rodent["model"].arrays
+    blob, dims = rodent["model_blob"], rodent["dims"]
+    mass = A["body_mass"].astype(np.float64)
+    qpos, _, _ = start_states(rodent, 1, seed=31)
+    qpos = qpos.astype(np.float64)
+    zero = np.zeros((1, 73))
+    fd = lambda q: oracle_mod.forward_dump(blob, dict(qpos=q, qvel=zero, act=np.zeros((1, 30)), qacc_warmstart=zero), None, precision=64, dims=dims)
+    V = lambda d: 9.81 * float(mass @ d["xipos"][0][:, 2])
+
+    def moved(q, i, eps):
+        q = q.copy()
+        if i < 3:
+            q[0, i] += eps
+        elif i < 6:
+            w = np.zeros(3); w[i - 3] = 1.0
+            q[0, 3:7] = mjcf.quat_mul(q[0, 3:7], np.concatenate([[math.cos(eps / 2)], math.sin(eps / 2) * w]))
+        else:
+            q[0, 7 + (i - 6)] += eps
+        return q
+
+    bias = fd(qpos)["qfrc_bias"][0]
+    eps = 1e-5
+    grad = np.array([(V(fd(moved(qpos, i, eps))) - V(fd(moved(qpos, i, -eps)))) / (2 * eps) for i in range(73)])
+    assert np.abs(bias - grad).max() < 1e-6 * np.abs(grad).max(), np.abs(bias - grad).max() / np.abs(grad).max()
+    assert abs(bias[2] - 9.81 * mass.sum()) < 1e-6 * 9.81 * mass.sum() and np.abs(bias[:2]).max() < 1e-9  # the weight, on the z dof
