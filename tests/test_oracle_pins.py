@@ -782,8 +782,11 @@ def test_contact_jacobian_rows_are_the_derivative_of_the_forward_kinematics(rode
     for c in act_con:
         k, b_ = _kb(A["pair_solref"][pair_of[c]], A["pair_solimp"][pair_of[c]], m.timestep)
         imp = _impedance(A["pair_solimp"][pair_of[c]], dist[c])
+        mu_c = A["pair_friction"][pair_of[c]][0]
+        w_c = A["body_invweight0"][body_of[c]][0] * (1 + mu_c * mu_c) * 2 * mu_c * mu_c / m.impratio  # the plane's body (world) adds 0
         for r in range(nl + 4 * c, nl + 4 * c + 4):
             assert abs(pos[r] - dist[c]) < 1e-12
+            assert abs(d["efc_D"][0][r] - imp / ((1 - imp) * w_c)) < 1e-6 * d["efc_D"][0][r], (r, d["efc_D"][0][r], imp / ((1 - imp) * w_c))
             assert abs(aref[r] - (-b_ * (J[r] @ qvel[0]) - k * imp * dist[c])) < 1e-6 * max(1.0, abs(aref[r])), (r, aref[r])
 
 
