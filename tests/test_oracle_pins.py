@@ -246,6 +246,8 @@ def test_mix_params_rules():
 # ---------------------------------------------------------------------------------------------------------------------
 def _impedance(solimp, r):
     dmin, dmax, width, mid, power = solimp
+    clamp = lambda v: min(max(v, 1e-4), 0.9999)  # mjMINIMP / mjMAXIMP (engine_core_constraint.c: getimpedance)
+    dmin, dmax, mid, power = clamp(dmin), clamp(dmax), clamp(mid), max(1.0, power)
     x = abs(r) / width
     if x >= 1.0:
         return dmax
@@ -903,3 +905,39 @@ def test_rodent_gravity_forces_are_the_gradient_of_the_potential(rodent, oracle_
     grad = np.array([(V(fd(moved(qpos, i, eps))) - V(fd(moved(qpos, i, -eps)))) / (2 * eps) for i in range(73)])
     assert np.abs(bias - grad).max() < 1e-6 * np.abs(grad).max(), np.abs(bias - grad).max() / np.abs(grad).max()
     assert abs(bias[2] - 9.81 * mass.sum()) < 1e-6 * 9.81 * mass.sum() and np.abs(bias[:2]).max() < 1e-9  # the weight, on the z dof
+
+
+def test_rodent_limit_rows(rodent, oracle_mod):
+    """Joint-limit rows of the rodent: J = +1 on the dof at the lower stop (pos = q - lo), -1 at the upper (pos = hi - q);
+    D = imp / ((1 - imp) dof_invweight0), aref = -b (J v) - k imp pos with the joint's solref / solimp."""
+    from conftest import start_states
+    m = rodent["model"]
+    A = m.arrays
+    blob, dims = rodent["model_blob"], rodent["dims"]
+    rng = np.random.default_rng(2)
+    qpos, qvel, _ = start_states(rodent, 1, seed=13)
+    qpos = qpos.astype(np.float64); qvel = qvel.astype(np.float64)
+    lim = [j for j in range(m.njnt) if A["jnt_limited"][j] and A["jnt_type"][j] != 0]
+    for j in lim[::2]:  # push every other limited joint past one of its stops
+        lo, hi = A["jnt_range"][j]
+        qpos[0, A["jnt_qposadr"][j]] = (lo - 0.01) if rng.random() < 0.5 else (hi + 0.02)
+    d = oracle_mod.forward_dump(blob, dict(qpos=qpos, qvel=qvel, act=np.zeros((1, 30)), qacc_warmstart=np.zeros((1, 73))), None,
+                                precision=64, dims=dims)
+    J, pos, D, aref = d["efc_J"][0], d["efc_pos"][0], d["efc_D"][0], d["efc_aref"][0]
+    nl, seen = dims["nlimit"], 0
+    for r in range(nl):
+        if np.abs(J[r]).max() == 0:
+            continue
+        i = int(np.argmax(np.abs(J[r])))
+        assert np.count_nonzero(J[r]) == 1 and abs(abs(J[r][i]) - 1) < 1e-12
+        j = int(A["dof_jntid"][i])
+        q = qpos[0, A["jnt_qposadr"][j]]
+        lo, hi = A["jnt_range"][j]
+        want_pos = (q - lo) if J[r][i] > 0 else (hi - q)
+        assert want_pos < 0 and abs(pos[r] - want_pos) < 1e-7, (r, pos[r], want_pos)  # range stored in fp32
+        k, b = _kb(A["jnt_solref"][j], A["jnt_solimp"][j], m.timestep)
+        imp = _impedance(A["jnt_solimp"][j], pos[r])
+        assert abs(D[r] - imp / ((1 - imp) * A["dof_invweight0"][i])) < 2e-6 * D[r]
+        assert abs(aref[r] - (-b * J[r][i] * qvel[0, i] - k * imp * pos[r])) < 1e-6 * max(1.0, abs(aref[r]))
+        seen += 1
+    assert seen >= len(lim[::2])  # every joint pushed past a stop produced its row
