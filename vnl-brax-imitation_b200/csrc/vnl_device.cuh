@@ -92,7 +92,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // N = 2, 4 or 8 sums at once, every lane ends with all N totals -- BIT-IDENTICAL to N calls of warp_sum (same pairing order
-// 16, 8, 4, 2, 1; fp addition commutes), with 2 N + 1 - log2 N ... shuffles instead of 5 N: a reduce-scatter (each xor step halves the
+// 16, 8, 4, 2, 1; fp addition commutes), with 2 N + 4 - log2 N shuffles instead of 5 N: a reduce-scatter (each xor step halves the
 // values a lane carries: it keeps one half and sends the other to its partner) down to one value per lane, the remaining
 // butterfly steps on that value, and one indexed shuffle per total to hand them round.  8 sums: 17 shuffles instead of 40, 4 sums:
 // 10 instead of 20.  The shuffle unit issues one warp instruction per cycle per SM and the lockstep puts all 14 warps of the SM in
