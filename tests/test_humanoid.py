@@ -113,6 +113,40 @@ def test_oracle_humanoid_reset_and_stand(oracle_mod, humanoid):
     assert (o1["stats"][:, 2] > 0).all()  # feet in contact during the step
 
 
+def test_moving_humanoid_clip(oracle_mod):
+    """The packaged moving clip (tools/build_humanoid_moving_clip.py: rollout states, ping-pong): it moves, stays inside the env's
+    healthy range, its derived fields are consistent with the kinematics, and the oracle env steps on it with the feet in contact --
+    tracking error small when the env starts ON the reference, larger a few frames later under zero action (the reference moves on)."""
+    hum, mb = pkg("envs.humanoid"), pkg("model_blob")
+    model, clip = hum.packaged_humanoid(moving=True)
+    T = clip.position.shape[0]
+    assert T == 256 and clip.body_positions.shape == (256, model.nbody, 3) and clip.center_of_mass.shape == (256, 3)
+    z = clip.position[:, 2]
+    assert z.min() > 1.0 and z.max() < 2.0 and np.ptp(z) > 0.15            # healthy throughout, and it dips by > 15 cm
+    assert float(np.ptp(clip.joints, axis=0).max()) > 1.0                   # arms swing by more than a radian
+    assert np.abs(clip.velocity).max() > 0.3 and np.abs(clip.joints_velocity).max() > 2.0
+    for t in (0, 17, 40, 255):                                              # fields == kinematics of the frame's qpos
+        q = np.concatenate([clip.position[t], clip.quaternion[t], clip.joints[t]]).astype(np.float64)
+        k = mjcf.kinematics(model, q)
+        assert np.abs(k["xpos"] - clip.body_positions[t]).max() < 1e-6
+        assert np.abs(mjcf.subtree_com(model, k["xipos"])[1] - clip.center_of_mass[t]).max() < 1e-6
+    task_blob, obs_size, traj_size = hum.humanoid_task_tables(model, clip)
+    model_blob = mb.build_model_blob(model)
+    kw = dict(precision=64, dims=mb.read_dims(model_blob), obs_size=obs_size, traj_size=traj_size)
+    start = np.array([0, 10, 30, 60], np.int32)
+    qpos = np.hstack([clip.position[start], clip.quaternion[start], clip.joints[start]]).astype(np.float64)
+    qvel = np.hstack([clip.velocity[start], clip.angular_velocity[start], clip.joints_velocity[start]]).astype(np.float64)
+    s, o = oracle_mod.reset(model_blob, task_blob, qpos, qvel, start, **kw)
+    assert (o["done"] == 0).all() and np.abs(o["metrics"][:, 6] - 1.0).max() < 1e-5  # on the reference: zero termination error
+    err = []
+    for _ in range(6):
+        s, o = oracle_mod.step(model_blob, task_blob, s, np.zeros((4, model.nu)), **kw)
+        err.append(1.0 - o["metrics"][:, 6])
+        assert np.isfinite(o["reward"]).all() and np.isfinite(o["obs"]).all()
+    assert (o["stats"][:, 2] > 0).all()                                    # feet on the floor
+    assert (err[-1] > err[0]).all() and (err[-1] > 1e-3).all()             # a limp body does not follow a moving reference
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------------------
 def _rel(a, b):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)

@@ -24,10 +24,14 @@ _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data")
 HUMANOID_ENV_ARGS = dict(solver="cg", iterations=6, ls_iterations=6)  # configs/env_config.yaml:1-8
 
 
-def packaged_humanoid():
-    """(model, clip): humanoid.xml compiled by tools/build_fixtures.py and the synthetic standing clip (the reference's
-    `clips/humanoid_traj_stand.p` is git-ignored and absent): `qpos0` tiled x256, zero velocities."""
+def packaged_humanoid(moving: bool = False):
+    """(model, clip): humanoid.xml compiled by tools/build_fixtures.py and a stand-in for the reference's `clips/humanoid_traj_stand.p`
+    (git-ignored and absent).  Default: `qpos0` tiled x256, zero velocities.  `moving=True`: 256 frames of states of a physics rollout
+    (a PD-held humanoid dipping 20 cm with swinging arms, played forwards and backwards so that it stays inside the healthy range),
+    processed like the rodent's clips -- tools/build_humanoid_moving_clip.py."""
     model = mjcf.load_model(os.path.join(_DATA, "humanoid_model.npz"))
+    if moving:
+        return model, clipm.clip_from_npz(os.path.join(_DATA, "humanoid_moving_clip.npz"))
     return model, clipm.tiled_clip(model, model.arrays["qpos0"], 256)
 
 
